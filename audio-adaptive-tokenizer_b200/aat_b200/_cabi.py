@@ -1,0 +1,128 @@
+"""ctypes binding of ``libaat_b200.so`` (C ABI declared in ``include/aat_b200.h``).
+
+This is the only place the shared library is loaded.  There is no fallback: if the
+library is missing the import of any compute entry point raises, and every compute
+call needs a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libaat_b200.so")
+CSRC_DIR = os.path.join(os.path.dirname(_HERE), "csrc")
+
+AAT_OK = 0
+AAT_ERR_INVALID = -1
+AAT_ERR_UNSUPPORTED = -2
+AAT_ERR_CUDA = -3
+AAT_ERR_CAPACITY = -4
+AAT_ERR_TAIL = -5
+
+AAT_F32, AAT_F64, AAT_F16, AAT_BF16 = 0, 1, 2, 3
+
+c_i32 = ctypes.c_int32
+c_i64 = ctypes.c_int64
+c_void = ctypes.c_void_p
+p_i64 = ctypes.POINTER(ctypes.c_int64)
+p_f64 = ctypes.POINTER(ctypes.c_double)
+p_f32 = ctypes.POINTER(ctypes.c_float)
+
+
+class AatConfig(ctypes.Structure):
+    """``struct aat_config`` (include/aat_b200.h)."""
+
+    _fields_ = [
+        ("sampling_rate", c_i32),
+        ("n_fft", c_i32),
+        ("hop_length", c_i32),
+        ("num_mel_filters", c_i32),
+        ("running_mean_points", c_i32),
+        ("reserved0", c_i32),
+        ("min_segment_frames", c_i64),
+        ("max_segment_frames", c_i64),
+        ("max_amplitude_for_minima", ctypes.c_float),
+        ("reserved1", c_i32),
+    ]
+
+
+class AatError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"aat_b200 status {status}: {message}")
+        self.status = status
+
+
+# every symbol include/aat_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "aat_version": (ctypes.c_int, []),
+    "aat_last_error": (ctypes.c_char_p, []),
+    "aat_kernel_launch_count": (c_i64, []),
+    "aat_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(AatConfig), c_void, c_void, ctypes.POINTER(c_void)]),
+    "aat_destroy": (ctypes.c_int, [c_void]),
+    "aat_get_config": (ctypes.c_int, [c_void, ctypes.POINTER(AatConfig)]),
+    "aat_plan_create": (ctypes.c_int, [c_void, c_i32, c_void, ctypes.POINTER(c_void)]),
+    "aat_plan_destroy": (ctypes.c_int, [c_void]),
+    "aat_plan_total_samples": (c_i64, [c_void]),
+    "aat_plan_total_frames": (c_i64, [c_void]),
+    "aat_plan_total_seg_slots": (c_i64, [c_void]),
+    "aat_plan_offsets": (ctypes.c_int, [c_void, c_void, c_void, c_void]),
+    "aat_logmel": (ctypes.c_int, [c_void, c_void, c_void, ctypes.c_int, c_void, c_void, c_void]),
+    "aat_boundaries": (ctypes.c_int, [c_void] * 11),
+    "aat_process_boarders": (ctypes.c_int, [c_void, c_i64, c_void, c_i64, c_void, c_void, c_i64, c_void, c_void, c_void]),
+    "aat_segment_frame_csr": (ctypes.c_int, [c_void] * 8),
+    "aat_segment_mean_pool": (ctypes.c_int, [c_void, c_void, ctypes.c_int, c_i64, c_i32, c_void, c_i64, c_void, c_void,
+                                             c_void, c_void]),
+    "aat_colsum_accumulate": (ctypes.c_int, [c_void, c_void, c_void, c_i32, c_void]),
+    "aat_colsum_finalize": (ctypes.c_int, [c_void, c_void, c_i32, c_void, c_void]),
+    "aat_host_logmel": (ctypes.c_int, [c_void, c_void, ctypes.c_int, c_i64, c_void]),
+    "aat_host_find_minimas": (ctypes.c_int, [c_void, c_void, c_i64, c_void, c_void]),
+    "aat_host_process_boarders": (ctypes.c_int, [c_void, c_i64, c_void, c_i64, c_void, c_void, c_i64, c_void, c_void]),
+    "aat_host_tokenize": (ctypes.c_int, [c_void, c_void, ctypes.c_int, c_i64, c_void, c_void, c_void, c_void, c_void,
+                                         c_void, c_i64, c_void, c_void]),
+    "aat_host_mean_pool": (ctypes.c_int, [c_void, c_void, ctypes.c_int, c_i64, c_i32, c_void, c_i64, c_void, c_void]),
+    "aat_segment_capacity": (c_i64, [ctypes.POINTER(AatConfig), c_i64]),
+    "aat_num_mel_frames": (c_i64, [ctypes.POINTER(AatConfig), c_i64]),
+}
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile ``libaat_b200.so`` in-tree with nvcc for sm_100a (csrc/Makefile)."""
+    cmd = ["make", "-C", CSRC_DIR, "-j4"]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or proc.returncode != 0:
+        print(proc.stdout)
+    if proc.returncode != 0:
+        raise RuntimeError("building libaat_b200.so failed")
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: the CUDA extension is the product and there is no CPU fallback. "
+                "Build it with `python -c 'import __graft_entry__ as g; g.build()'` or "
+                "`make -C audio-adaptive-tokenizer_b200/csrc`."
+            )
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def check(status: int) -> None:
+    if status != AAT_OK:
+        msg = lib().aat_last_error()
+        raise AatError(status, msg.decode("utf-8", "replace") if msg else "")
+
+
+def launch_count() -> int:
+    return int(lib().aat_kernel_launch_count())

@@ -1,0 +1,124 @@
+// Internal definitions shared by the kernels and the C ABI (not installed).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <vector>
+
+#include "aat_b200.h"
+
+namespace aat {
+
+constexpr int kNfft = 400;          // the FFT kernel is specialised for 400 = 20 x 20
+constexpr int kBins = kNfft / 2 + 1; // 201
+constexpr int kMaxMels = 128;
+constexpr int kMaxRunningMean = 2048; // boundary kernel: chunk (4096) >= running_mean_points + 2
+
+void set_error(const char *fmt, ...);
+extern std::atomic<int64_t> g_launch_count;
+
+#define AAT_CUDA_CHECK(expr)                                                                         \
+    do {                                                                                             \
+        cudaError_t err__ = (expr);                                                                  \
+        if (err__ != cudaSuccess) {                                                                  \
+            aat::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+            return AAT_ERR_CUDA;                                                                     \
+        }                                                                                            \
+    } while (0)
+
+#define AAT_REQUIRE(cond, status, ...)  \
+    do {                                \
+        if (!(cond)) {                  \
+            aat::set_error(__VA_ARGS__); \
+            return (status);            \
+        }                               \
+    } while (0)
+
+#define AAT_LAUNCH_CHECK()                         \
+    do {                                           \
+        aat::g_launch_count.fetch_add(1);          \
+        AAT_CUDA_CHECK(cudaGetLastError());        \
+    } while (0)
+
+// Sparse (CSR by mel filter) form of the dense (bins, mels) float64 filter bank.
+struct MelTable {
+    int n_mels = 0;
+    int nnz = 0;
+    int *row_start = nullptr; // device [n_mels + 1]
+    int *bin = nullptr;       // device [nnz]
+    double *weight = nullptr; // device [nnz]
+};
+
+// Scratch for the pool kernel's cross-CTA partial sums.
+struct PoolScratch {
+    int max_ctas = 0;
+    int max_dim = 0;
+    float *head = nullptr;      // [max_ctas, max_dim]
+    float *tail = nullptr;      // [max_ctas, max_dim]
+    int *head_flag = nullptr;   // [max_ctas]
+    int *tail_flag = nullptr;   // [max_ctas]
+    double *colsum = nullptr;   // [max_ctas, max_dim + 1]
+};
+
+} // namespace aat
+
+struct aat_ctx {
+    int device = 0;
+    int num_sms = 0;
+    aat_config cfg{};
+    double *window_half = nullptr; // device [400], 0.5 * window (exact scaling, folds the /2 of the two-frame split)
+    double2 *twiddle = nullptr;    // device [20 * 20], W_400^(k1 * n2) at [k1 * 20 + n2]
+    aat::MelTable mel{};
+    aat::PoolScratch pool{};
+    // staging for aat_host_* entry points (grown on demand, never inside stream capture)
+    void *dev_scratch = nullptr;
+    size_t dev_scratch_bytes = 0;
+    void *pinned = nullptr;
+    size_t pinned_bytes = 0;
+    cudaStream_t host_stream = nullptr;
+};
+
+struct aat_plan {
+    aat_ctx *ctx = nullptr;
+    int32_t n_utts = 0;
+    int64_t total_samples = 0, total_frames = 0, total_seg_slots = 0;
+    int64_t max_frames = 0;
+    int32_t mel_tiles = 0; // CTAs of the log-mel kernel
+    std::vector<int64_t> h_n_samples, h_wave_off, h_frame_off, h_seg_slot_off;
+    // device tables
+    int64_t *d_n_samples = nullptr;     // [B]
+    int64_t *d_wave_off = nullptr;      // [B+1]
+    int64_t *d_frame_off = nullptr;     // [B+1]
+    int64_t *d_seg_slot_off = nullptr;  // [B+1]
+    int32_t *d_tile_utt = nullptr;      // [mel_tiles] utterance of each tile
+    int32_t *d_tile_first = nullptr;    // [B+1] first tile index of each utterance
+};
+
+namespace aat {
+
+// kernels' host launchers (defined in the .cu files)
+int launch_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave, int wave_dtype, float *mel, float *amp,
+                  cudaStream_t stream);
+int launch_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel, const float *amp, int64_t *seg_start,
+                      int64_t *seg_len, int32_t *seg_count, int64_t *minima, int32_t *minima_count, int32_t *status,
+                      cudaStream_t stream);
+int launch_process_boarders(aat_ctx *ctx, int64_t n_samples, const int64_t *boarders, int64_t n_boarders,
+                            int64_t *seg_start, int64_t *seg_len, int64_t capacity, int32_t *seg_count,
+                            int32_t *status, cudaStream_t stream);
+int launch_segment_frame_csr(aat_ctx *ctx, const aat_plan *plan, const int64_t *seg_len, const int32_t *seg_count,
+                             int64_t *seg_off, int64_t *n_seg, int64_t *utt_seg_off, cudaStream_t stream);
+int launch_mean_pool(aat_ctx *ctx, const void *emb, int emb_dtype, int64_t n_rows, int32_t dim,
+                     const int64_t *seg_off, int64_t n_seg, const int64_t *n_seg_dev, float *out, double *colsum,
+                     cudaStream_t stream);
+int launch_colsum_accumulate(double *acc, const double *colsum, int32_t dim, cudaStream_t stream);
+int launch_colsum_finalize(const double *acc, int32_t dim, float *mean, cudaStream_t stream);
+int pool_scratch_init(aat_ctx *ctx);
+void pool_scratch_free(aat_ctx *ctx);
+
+constexpr int kMelFramesPerTile = 16; // frames one CTA of the log-mel kernel produces
+
+} // namespace aat

@@ -1,0 +1,386 @@
+// K3: amplitude-minima boundary scan + merge/split state machine -> integer segment offsets.
+//
+// Replaces find_amplitude_minimas, pretokenize and process_segments_boarders
+// (ref:src/aat/tokenizer.py:55-92, 121-139, 141-183).  The result is integer and must equal the
+// reference's bit for bit, which pins the float32 arithmetic completely:
+//   amp[t] = -10 * (sum_r mel[r][t], rows added in order, float32) / n_mels   numpy mean(axis=0)
+//   cs[t]  = cs[t-1] + amp[t]                    sequential float32 recurrence numpy cumsum
+//   rm[i]  = (cs[i+n] - cs[i]) / float(n)        float32
+//   minimum at i  <=>  rm[i] > rm[i+1] + 1e-5f  and  rm[i] > rm[i-1] + 1e-5f  and  rm[i] > max_amp
+//                      (argrelextrema order=1 mode='clip': the end points never qualify)
+// Every operation uses an explicit round-to-nearest intrinsic so nothing is contracted into an FMA.
+// A parallel prefix scan would change ~10 % of the minima on long audio (SURVEY.md §7 hard part 1),
+// so the cumsum stays a serial chain on one thread; everything around it (column means, running mean,
+// comparisons, ordered compaction) is thread-parallel.  One CTA per utterance, time axis in chunks.
+#include "aat_internal.cuh"
+
+namespace aat {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kChunk = 4096; // mel frames per pass; must be >= running_mean_points + 2
+
+struct SegState {
+    int64_t prev;
+    int64_t count;
+    int32_t status; // < 0: aat_status error; otherwise bit 0 = the last segment is the zero-padded tail
+};
+
+__device__ __forceinline__ void emit_segment(int64_t start, int64_t len, int64_t *seg_start, int64_t *seg_len,
+                                             int64_t capacity, SegState &st)
+{
+    if (st.count < capacity) {
+        seg_start[st.count] = start;
+        seg_len[st.count] = len;
+    } else {
+        st.status = AAT_ERR_CAPACITY;
+    }
+    ++st.count;
+}
+
+// One iteration of the loop at ref:src/aat/tokenizer.py:154-175.
+__device__ __forceinline__ void push_boarder(int64_t b, int64_t min_frames, int64_t max_frames, int64_t *seg_start,
+                                             int64_t *seg_len, int64_t capacity, SegState &st)
+{
+    const int64_t len = b - st.prev;
+    if (len < min_frames) return; // merge forward: prev stays
+    if (len > max_frames) {
+        const int64_t k = len / max_frames;
+        const int64_t gap = len - k * max_frames;
+        int64_t n_cuts = k;
+        int64_t last_cut = k * max_frames;
+        if (gap == 0)
+            n_cuts = k - 1; // drop last empty segment
+        else if (gap < min_frames)
+            last_cut = len - min_frames; // may fall below the previous cut when min > max
+        int64_t lo = 0;
+        for (int64_t j = 0; j < n_cuts; ++j) { // np.split: a[lo:c] with Python slice clamping
+            const int64_t c = (j == k - 1) ? last_cut : (j + 1) * max_frames;
+            const int64_t a0 = lo < len ? lo : len;
+            const int64_t a1 = c < len ? c : len;
+            emit_segment(st.prev + a0, a1 > a0 ? a1 - a0 : 0, seg_start, seg_len, capacity, st);
+            lo = c;
+        }
+        const int64_t a0 = lo < len ? lo : len;
+        emit_segment(st.prev + a0, len - a0, seg_start, seg_len, capacity, st);
+    } else {
+        emit_segment(st.prev, len, seg_start, seg_len, capacity, st);
+    }
+    st.prev = b;
+}
+
+// ref:src/aat/tokenizer.py:177-181: zero-padded tail of min_segment_frames samples.
+__device__ __forceinline__ void finish_segments(int64_t n_samples, int64_t min_frames, int64_t *seg_start,
+                                                int64_t *seg_len, int64_t capacity, SegState &st)
+{
+    if (st.prev != n_samples) {
+        if (st.status == 0) st.status = (n_samples - st.prev > min_frames) ? AAT_ERR_TAIL : 1;
+        emit_segment(st.prev, min_frames, seg_start, seg_len, capacity, st);
+    }
+}
+
+struct BoundaryParams {
+    const float *mel;
+    const float *amp;
+    const int64_t *n_samples;
+    const int64_t *frame_off;
+    const int64_t *seg_slot_off;
+    int64_t *seg_start;
+    int64_t *seg_len;
+    int32_t *seg_count;
+    int64_t *minima;
+    int32_t *minima_count;
+    int32_t *status;
+    int64_t min_frames, max_frames;
+    int hop, n_mels, npts;
+    float max_amp;
+};
+
+__global__ void __launch_bounds__(kThreads) boundaries_kernel(const BoundaryParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int halo = p.npts + 2;
+    float *s_amp = reinterpret_cast<float *>(smem_raw);     // [kChunk]
+    float *s_cs = s_amp + kChunk;                            // [halo + kChunk]
+    int *s_min = reinterpret_cast<int *>(s_cs + halo + kChunk); // [kChunk] minima of this pass (global frame index)
+    __shared__ int s_warp_count[kThreads / 32];
+    __shared__ int s_total;
+    __shared__ float s_carry;
+
+    const int tid = threadIdx.x;
+    const int utt = blockIdx.x;
+    const int64_t n = p.n_samples[utt];
+    const int64_t T = 1 + n / p.hop;
+    const int64_t fbase = p.frame_off[utt];
+    const float *mel = p.mel ? p.mel + (size_t)p.n_mels * fbase : nullptr;
+    const float *amp_in = p.amp ? p.amp + fbase : nullptr;
+    const int64_t slot0 = p.seg_slot_off[utt];
+    const int64_t capacity = p.seg_slot_off[utt + 1] - slot0;
+    int64_t *seg_start = p.seg_start + slot0;
+    int64_t *seg_len = p.seg_len + slot0;
+    int64_t *minima_out = p.minima ? p.minima + fbase : nullptr;
+
+    const int64_t L = T - p.npts; // running-mean length; minima live in [1, L-2]
+    const float nf = (float)p.npts;
+    SegState st{0, 0, 0};
+    int64_t n_minima = 0;
+    int64_t i_done = 1; // next candidate index to test
+
+    for (int64_t j0 = 0; j0 < T; j0 += kChunk) {
+        const int64_t j1 = (j0 + kChunk < T) ? j0 + kChunk : T;
+        const int len = (int)(j1 - j0);
+
+        // A: amplitude curve of this chunk (thread-parallel over time, sequential down the mel rows)
+        for (int i = tid; i < len; i += kThreads) {
+            const int64_t t = j0 + i;
+            float a;
+            if (amp_in) {
+                a = amp_in[t];
+            } else {
+                float acc = mel[t];
+#pragma unroll 8
+                for (int r = 1; r < p.n_mels; ++r) acc = __fadd_rn(acc, mel[(size_t)r * T + t]);
+                a = __fmul_rn(-10.0f, __fdiv_rn(acc, (float)p.n_mels));
+            }
+            s_amp[i] = a;
+        }
+        __syncthreads();
+
+        // B: the serial float32 cumsum (one thread; loads are independent of the add chain)
+        if (tid == 0) {
+            float run = (j0 == 0) ? 0.0f : s_carry;
+            int i = 0;
+            if (j0 == 0) {
+                run = s_amp[0];
+                s_cs[halo] = run;
+                i = 1;
+            }
+#pragma unroll 8
+            for (; i < len; ++i) {
+                run = __fadd_rn(run, s_amp[i]);
+                s_cs[halo + i] = run;
+            }
+            s_carry = run;
+        }
+        __syncthreads();
+
+        // C: running mean + strict-local-maximum test for every index whose neighbourhood is complete
+        int64_t i_hi = j1 - p.npts - 1; // exclusive: needs cs[i + 1 + npts] < j1
+        if (i_hi > L - 1) i_hi = L - 1;
+        const int64_t range = i_hi > i_done ? i_hi - i_done : 0;
+        const int per = (int)((range + kThreads - 1) / kThreads);
+        unsigned mask = 0;
+        {
+            const int64_t a = i_done + (int64_t)tid * per;
+            // cs index g lives at s_cs[halo + g - j0]
+            const float *cs = s_cs + halo - j0;
+            for (int u = 0; u < per; ++u) {
+                const int64_t i = a + u;
+                if (i >= i_hi) break;
+                const float rl = __fdiv_rn(__fsub_rn(cs[i - 1 + p.npts], cs[i - 1]), nf);
+                const float rc = __fdiv_rn(__fsub_rn(cs[i + p.npts], cs[i]), nf);
+                const float rr = __fdiv_rn(__fsub_rn(cs[i + 1 + p.npts], cs[i + 1]), nf);
+                const bool is_min = rc > __fadd_rn(rr, 1e-5f) && rc > __fadd_rn(rl, 1e-5f) && rc > p.max_amp;
+                if (is_min) mask |= 1u << u;
+            }
+        }
+        // ordered compaction: exclusive scan of per-thread counts
+        const int cnt = __popc(mask);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((tid & 31) >= d) incl += v;
+        }
+        if ((tid & 31) == 31) s_warp_count[tid >> 5] = incl;
+        __syncthreads();
+        if (tid < 32) {
+            int w = (tid < kThreads / 32) ? s_warp_count[tid] : 0;
+            int wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, wi, d);
+                if (tid >= d) wi += v;
+            }
+            if (tid < kThreads / 32) s_warp_count[tid] = wi - w;
+            if (tid == kThreads / 32 - 1) s_total = wi;
+        }
+        __syncthreads();
+        {
+            int pos = s_warp_count[tid >> 5] + incl - cnt;
+            const int64_t a = i_done + (int64_t)tid * per;
+            unsigned m = mask;
+            while (m) {
+                const int u = __ffs(m) - 1;
+                m &= m - 1;
+                s_min[pos++] = (int)(a + u);
+            }
+        }
+        __syncthreads();
+        const int found = s_total;
+
+        // D: publish minima; one thread advances the merge/split state machine over the new boarders
+        if (minima_out)
+            for (int i = tid; i < found; i += kThreads) minima_out[n_minima + i] = s_min[i];
+        if (tid == 0)
+            for (int i = 0; i < found; ++i)
+                push_boarder((int64_t)s_min[i] * p.hop, p.min_frames, p.max_frames, seg_start, seg_len, capacity, st);
+        n_minima += found;
+        if (i_hi > i_done) i_done = i_hi;
+
+        // carry the last `halo` cumsum values into the next pass
+        // (source [kChunk, kChunk + halo) and destination [0, halo) are disjoint because kChunk >= halo)
+        if (j1 < T) {
+            for (int i = tid; i < halo; i += kThreads) s_cs[i] = s_cs[kChunk + i];
+            __syncthreads();
+        }
+    }
+
+    if (tid == 0) {
+        push_boarder(n, p.min_frames, p.max_frames, seg_start, seg_len, capacity, st); // ref:src/aat/tokenizer.py:137
+        finish_segments(n, p.min_frames, seg_start, seg_len, capacity, st);
+        p.seg_count[utt] = (int32_t)(st.count < capacity ? st.count : capacity);
+        if (p.minima_count) p.minima_count[utt] = (int32_t)n_minima;
+        p.status[utt] = st.status;
+    }
+}
+
+__global__ void process_boarders_kernel(int64_t n_samples, const int64_t *boarders, int64_t n_boarders,
+                                        int64_t min_frames, int64_t max_frames, int64_t *seg_start, int64_t *seg_len,
+                                        int64_t capacity, int32_t *seg_count, int32_t *status)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    SegState st{0, 0, 0};
+    for (int64_t i = 0; i < n_boarders; ++i)
+        push_boarder(boarders[i], min_frames, max_frames, seg_start, seg_len, capacity, st);
+    finish_segments(n_samples, min_frames, seg_start, seg_len, capacity, st);
+    *seg_count = (int32_t)(st.count < capacity ? st.count : capacity);
+    *status = st.status;
+}
+
+// Segment lengths -> packed CSR of HuBERT frame offsets (per-segment encode convention).
+// Single CTA: a warp per utterance computes its frame total, the utterance totals are scanned, then each
+// warp writes its utterance's running offsets.
+constexpr int kCsrThreads = 1024;
+
+__device__ __forceinline__ int64_t hubert_frames(int64_t len)
+{
+    const int64_t f = (len - 400) / 320 + 1; // C division truncates toward zero; guard the negative range
+    return (len < 400) ? 0 : f;
+}
+
+__global__ void __launch_bounds__(kCsrThreads)
+segment_frame_csr_kernel(int n_utts, const int64_t *seg_slot_off, const int64_t *seg_len, const int32_t *seg_count,
+                         int64_t *seg_off, int64_t *n_seg_out, int64_t *utt_seg_off_out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int64_t *s_seg = reinterpret_cast<int64_t *>(smem_raw); // [n_utts + 1] packed segment index of each utterance
+    int64_t *s_frm = s_seg + n_utts + 1;                     // [n_utts + 1] first frame of each utterance
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = kCsrThreads / 32;
+
+    for (int b = warp; b < n_utts; b += kWarps) {
+        const int64_t *len = seg_len + seg_slot_off[b];
+        const int cnt = seg_count[b];
+        int64_t sum = 0;
+        for (int i = lane; i < cnt; i += 32) sum += hubert_frames(len[i]);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        if (lane == 0) {
+            s_seg[b + 1] = cnt;
+            s_frm[b + 1] = sum;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) { // n_utts is small (thousands): a serial scan costs microseconds
+        s_seg[0] = 0;
+        s_frm[0] = 0;
+        for (int b = 0; b < n_utts; ++b) {
+            s_seg[b + 1] += s_seg[b];
+            s_frm[b + 1] += s_frm[b];
+        }
+        *n_seg_out = s_seg[n_utts];
+        seg_off[s_seg[n_utts]] = s_frm[n_utts];
+    }
+    __syncthreads();
+    if (utt_seg_off_out)
+        for (int b = tid; b <= n_utts; b += kCsrThreads) utt_seg_off_out[b] = s_seg[b];
+    for (int b = warp; b < n_utts; b += kWarps) {
+        const int64_t *len = seg_len + seg_slot_off[b];
+        const int cnt = seg_count[b];
+        int64_t base = s_frm[b];
+        int64_t *dst = seg_off + s_seg[b];
+        for (int i0 = 0; i0 < cnt; i0 += 32) {
+            const int i = i0 + lane;
+            const int64_t f = (i < cnt) ? hubert_frames(len[i]) : 0;
+            int64_t incl = f;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int64_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            if (i < cnt) dst[i] = base + incl - f;
+            base += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+}
+
+} // namespace
+
+int launch_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel, const float *amp, int64_t *seg_start,
+                      int64_t *seg_len, int32_t *seg_count, int64_t *minima, int32_t *minima_count, int32_t *status,
+                      cudaStream_t stream)
+{
+    if (plan->n_utts == 0) return AAT_OK;
+    BoundaryParams p{};
+    p.mel = mel;
+    p.amp = amp;
+    p.n_samples = plan->d_n_samples;
+    p.frame_off = plan->d_frame_off;
+    p.seg_slot_off = plan->d_seg_slot_off;
+    p.seg_start = seg_start;
+    p.seg_len = seg_len;
+    p.seg_count = seg_count;
+    p.minima = minima;
+    p.minima_count = minima_count;
+    p.status = status;
+    p.min_frames = ctx->cfg.min_segment_frames;
+    p.max_frames = ctx->cfg.max_segment_frames;
+    p.hop = ctx->cfg.hop_length;
+    p.n_mels = ctx->cfg.num_mel_filters;
+    p.npts = ctx->cfg.running_mean_points;
+    p.max_amp = ctx->cfg.max_amplitude_for_minima;
+    const size_t smem = sizeof(float) * (size_t)(kChunk + p.npts + 2 + kChunk) + sizeof(int) * (size_t)kChunk;
+    AAT_CUDA_CHECK(cudaFuncSetAttribute(boundaries_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    boundaries_kernel<<<plan->n_utts, kThreads, smem, stream>>>(p);
+    AAT_LAUNCH_CHECK();
+    return AAT_OK;
+}
+
+int launch_process_boarders(aat_ctx *ctx, int64_t n_samples, const int64_t *boarders, int64_t n_boarders,
+                            int64_t *seg_start, int64_t *seg_len, int64_t capacity, int32_t *seg_count,
+                            int32_t *status, cudaStream_t stream)
+{
+    process_boarders_kernel<<<1, 32, 0, stream>>>(n_samples, boarders, n_boarders, ctx->cfg.min_segment_frames,
+                                                  ctx->cfg.max_segment_frames, seg_start, seg_len, capacity,
+                                                  seg_count, status);
+    AAT_LAUNCH_CHECK();
+    return AAT_OK;
+}
+
+int launch_segment_frame_csr(aat_ctx *ctx, const aat_plan *plan, const int64_t *seg_len, const int32_t *seg_count,
+                             int64_t *seg_off, int64_t *n_seg, int64_t *utt_seg_off, cudaStream_t stream)
+{
+    (void)ctx;
+    const size_t smem = sizeof(int64_t) * 2 * (size_t)(plan->n_utts + 1);
+    AAT_REQUIRE(smem <= 200 * 1024, AAT_ERR_UNSUPPORTED, "aat_segment_frame_csr: at most 12799 utterances per plan");
+    AAT_CUDA_CHECK(
+        cudaFuncSetAttribute(segment_frame_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    segment_frame_csr_kernel<<<1, kCsrThreads, smem, stream>>>(plan->n_utts, plan->d_seg_slot_off, seg_len, seg_count,
+                                                               seg_off, n_seg, utt_seg_off);
+    AAT_LAUNCH_CHECK();
+    return AAT_OK;
+}
+
+} // namespace aat

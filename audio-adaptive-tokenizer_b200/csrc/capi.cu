@@ -1,0 +1,582 @@
+// C ABI of libaat_b200.so (include/aat_b200.h): context and plan management, argument checking,
+// and the aat_host_* entry points that stage host buffers through pinned memory.
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "aat_internal.cuh"
+
+namespace aat {
+
+static thread_local char g_error[512] = "";
+std::atomic<int64_t> g_launch_count{0};
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int device)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            ok = false;
+            return;
+        }
+        if (prev != device && cudaSetDevice(device) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+int upload(T **dst, const T *src, size_t n)
+{
+    AAT_CUDA_CHECK(cudaMalloc(dst, sizeof(T) * (n ? n : 1)));
+    if (n) AAT_CUDA_CHECK(cudaMemcpy(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice));
+    return AAT_OK;
+}
+
+int64_t seg_capacity(const aat_config &cfg, int64_t n)
+{
+    // every accepted boarder consumes >= min samples and emits <= len/max + 1 pieces; + N boarder + padded tail
+    const int64_t by_min = cfg.min_segment_frames > 0 ? n / cfg.min_segment_frames : n / cfg.hop_length + 1;
+    return by_min + n / cfg.max_segment_frames + 4;
+}
+
+// grow-only staging buffers for the aat_host_* entry points
+int ensure_scratch(aat_ctx *ctx, size_t dev_bytes, size_t pinned_bytes)
+{
+    if (dev_bytes > ctx->dev_scratch_bytes) {
+        if (ctx->dev_scratch) cudaFree(ctx->dev_scratch);
+        ctx->dev_scratch = nullptr;
+        ctx->dev_scratch_bytes = 0;
+        const size_t want = dev_bytes + dev_bytes / 4 + 4096;
+        AAT_CUDA_CHECK(cudaMalloc(&ctx->dev_scratch, want));
+        ctx->dev_scratch_bytes = want;
+    }
+    if (pinned_bytes > ctx->pinned_bytes) {
+        if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        ctx->pinned = nullptr;
+        ctx->pinned_bytes = 0;
+        const size_t want = pinned_bytes + pinned_bytes / 4 + 4096;
+        AAT_CUDA_CHECK(cudaMallocHost(&ctx->pinned, want));
+        ctx->pinned_bytes = want;
+    }
+    return AAT_OK;
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+// bump allocator over a scratch block
+struct Arena {
+    unsigned char *base;
+    size_t off = 0;
+    explicit Arena(void *b) : base(static_cast<unsigned char *>(b)) {}
+    template <typename T>
+    T *take(size_t n)
+    {
+        T *p = reinterpret_cast<T *>(base + off);
+        off += align256(sizeof(T) * (n ? n : 1));
+        return p;
+    }
+};
+
+size_t dtype_size(int dt)
+{
+    switch (dt) {
+    case AAT_F32: return 4;
+    case AAT_F64: return 8;
+    case AAT_F16:
+    case AAT_BF16: return 2;
+    default: return 0;
+    }
+}
+
+} // namespace
+} // namespace aat
+
+using namespace aat;
+
+extern "C" {
+
+int aat_version(void) { return AAT_B200_VERSION; }
+const char *aat_last_error(void) { return g_error; }
+int64_t aat_kernel_launch_count(void) { return g_launch_count.load(); }
+
+int64_t aat_segment_capacity(const aat_config *cfg, int64_t n_samples)
+{
+    if (!cfg || n_samples < 0 || cfg->max_segment_frames <= 0 || cfg->hop_length <= 0) return -1;
+    return seg_capacity(*cfg, n_samples);
+}
+
+int64_t aat_num_mel_frames(const aat_config *cfg, int64_t n_samples)
+{
+    if (!cfg || n_samples < 0 || cfg->hop_length <= 0) return -1;
+    return 1 + n_samples / cfg->hop_length;
+}
+
+int aat_create(int device, const aat_config *cfg, const double *window_host, const double *mel_filters_host,
+               aat_ctx **out)
+{
+    AAT_REQUIRE(cfg && window_host && mel_filters_host && out, AAT_ERR_INVALID, "aat_create: NULL argument");
+    AAT_REQUIRE(cfg->n_fft == kNfft, AAT_ERR_UNSUPPORTED,
+                "aat_create: n_fft=%d is not implemented (the FFT kernel is specialised for n_fft=400)", cfg->n_fft);
+    AAT_REQUIRE(cfg->hop_length >= 1 && cfg->hop_length <= kNfft, AAT_ERR_UNSUPPORTED,
+                "aat_create: hop_length=%d outside 1..%d", cfg->hop_length, kNfft);
+    AAT_REQUIRE(cfg->num_mel_filters >= 1 && cfg->num_mel_filters <= kMaxMels, AAT_ERR_UNSUPPORTED,
+                "aat_create: num_mel_filters=%d outside 1..%d", cfg->num_mel_filters, kMaxMels);
+    AAT_REQUIRE(cfg->running_mean_points >= 1 && cfg->running_mean_points <= kMaxRunningMean, AAT_ERR_UNSUPPORTED,
+                "aat_create: running_mean_points=%d outside 1..%d", cfg->running_mean_points, kMaxRunningMean);
+    AAT_REQUIRE(cfg->max_segment_frames > 0, AAT_ERR_INVALID,
+                "aat_create: max_segment_frames must be positive (the reference divides by it)");
+    AAT_REQUIRE(cfg->min_segment_frames >= 0, AAT_ERR_INVALID, "aat_create: min_segment_frames must be >= 0");
+    int n_dev = 0;
+    AAT_CUDA_CHECK(cudaGetDeviceCount(&n_dev));
+    AAT_REQUIRE(device >= 0 && device < n_dev, AAT_ERR_CUDA, "aat_create: no CUDA device %d (%d visible)", device, n_dev);
+    DeviceGuard guard(device);
+    AAT_REQUIRE(guard.ok, AAT_ERR_CUDA, "aat_create: cudaSetDevice(%d) failed", device);
+
+    aat_ctx *ctx = new (std::nothrow) aat_ctx();
+    AAT_REQUIRE(ctx, AAT_ERR_INVALID, "aat_create: out of host memory");
+    ctx->device = device;
+    ctx->cfg = *cfg;
+    cudaDeviceProp prop{};
+    AAT_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    ctx->num_sms = prop.multiProcessorCount;
+
+    // window / 2: the two-frames-per-transform split carries a factor 1/2 (exact power-of-two scaling)
+    std::vector<double> win(kNfft);
+    for (int i = 0; i < kNfft; ++i) win[i] = 0.5 * window_host[i];
+    int rc = upload(&ctx->window_half, win.data(), win.size());
+    if (rc) return rc;
+
+    // W_400^(k1 * n2), evaluated in long double and rounded once
+    std::vector<double2> tw(400);
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for (int k1 = 0; k1 < 20; ++k1)
+        for (int n2 = 0; n2 < 20; ++n2) {
+            const int e = (k1 * n2) % kNfft;
+            const long double a = two_pi * (long double)e / (long double)kNfft;
+            tw[k1 * 20 + n2] = make_double2((double)cosl(a), (double)-sinl(a));
+        }
+    rc = upload(&ctx->twiddle, tw.data(), tw.size());
+    if (rc) return rc;
+
+    // dense (bins, mels) -> CSR by mel, bins ascending (the order a dot product over bins adds them)
+    const int M = cfg->num_mel_filters;
+    std::vector<int> row_start(M + 1, 0), bins;
+    std::vector<double> weights;
+    for (int m = 0; m < M; ++m) {
+        for (int k = 0; k < kBins; ++k) {
+            const double w = mel_filters_host[(size_t)k * M + m];
+            if (w != 0.0) {
+                bins.push_back(k);
+                weights.push_back(w);
+            }
+        }
+        row_start[m + 1] = (int)bins.size();
+    }
+    ctx->mel.n_mels = M;
+    ctx->mel.nnz = (int)bins.size();
+    if ((rc = upload(&ctx->mel.row_start, row_start.data(), row_start.size()))) return rc;
+    if ((rc = upload(&ctx->mel.bin, bins.data(), bins.size()))) return rc;
+    if ((rc = upload(&ctx->mel.weight, weights.data(), weights.size()))) return rc;
+
+    if ((rc = pool_scratch_init(ctx))) return rc;
+    AAT_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking));
+    *out = ctx;
+    return AAT_OK;
+}
+
+int aat_destroy(aat_ctx *ctx)
+{
+    if (!ctx) return AAT_OK;
+    DeviceGuard guard(ctx->device);
+    cudaFree(ctx->window_half);
+    cudaFree(ctx->twiddle);
+    cudaFree(ctx->mel.row_start);
+    cudaFree(ctx->mel.bin);
+    cudaFree(ctx->mel.weight);
+    pool_scratch_free(ctx);
+    if (ctx->dev_scratch) cudaFree(ctx->dev_scratch);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->host_stream) cudaStreamDestroy(ctx->host_stream);
+    delete ctx;
+    return AAT_OK;
+}
+
+int aat_get_config(const aat_ctx *ctx, aat_config *out)
+{
+    AAT_REQUIRE(ctx && out, AAT_ERR_INVALID, "aat_get_config: NULL argument");
+    *out = ctx->cfg;
+    return AAT_OK;
+}
+
+int aat_plan_create(aat_ctx *ctx, int32_t n_utts, const int64_t *n_samples_host, aat_plan **out)
+{
+    AAT_REQUIRE(ctx && out && (n_samples_host || n_utts == 0), AAT_ERR_INVALID, "aat_plan_create: NULL argument");
+    AAT_REQUIRE(n_utts >= 0, AAT_ERR_INVALID, "aat_plan_create: negative n_utts");
+    DeviceGuard guard(ctx->device);
+    aat_plan *plan = new (std::nothrow) aat_plan();
+    AAT_REQUIRE(plan, AAT_ERR_INVALID, "aat_plan_create: out of host memory");
+    plan->ctx = ctx;
+    plan->n_utts = n_utts;
+    plan->h_n_samples.assign(n_samples_host, n_samples_host + n_utts);
+    plan->h_wave_off.assign(n_utts + 1, 0);
+    plan->h_frame_off.assign(n_utts + 1, 0);
+    plan->h_seg_slot_off.assign(n_utts + 1, 0);
+    std::vector<int32_t> tile_first(n_utts + 1, 0), tile_utt;
+    for (int b = 0; b < n_utts; ++b) {
+        const int64_t n = n_samples_host[b];
+        if (n < 1) {
+            delete plan;
+            AAT_REQUIRE(false, AAT_ERR_INVALID,
+                        "aat_plan_create: utterance %d has %lld samples (np.pad(mode='reflect') needs >= 1)", b,
+                        (long long)n);
+        }
+        const int64_t T = 1 + n / ctx->cfg.hop_length;
+        plan->h_wave_off[b + 1] = plan->h_wave_off[b] + n;
+        plan->h_frame_off[b + 1] = plan->h_frame_off[b] + T;
+        plan->h_seg_slot_off[b + 1] = plan->h_seg_slot_off[b] + seg_capacity(ctx->cfg, n);
+        if (T > plan->max_frames) plan->max_frames = T;
+        const int64_t tiles = (T + kMelFramesPerTile - 1) / kMelFramesPerTile;
+        if ((int64_t)tile_utt.size() + tiles > (int64_t)INT32_MAX) {
+            delete plan;
+            AAT_REQUIRE(false, AAT_ERR_UNSUPPORTED, "aat_plan_create: batch too large (mel tiles exceed 2^31)");
+        }
+        tile_first[b + 1] = tile_first[b] + (int32_t)tiles;
+        tile_utt.insert(tile_utt.end(), (size_t)tiles, b);
+    }
+    plan->total_samples = plan->h_wave_off[n_utts];
+    plan->total_frames = plan->h_frame_off[n_utts];
+    plan->total_seg_slots = plan->h_seg_slot_off[n_utts];
+    plan->mel_tiles = (int32_t)tile_utt.size();
+    int rc;
+    if ((rc = upload(&plan->d_n_samples, plan->h_n_samples.data(), (size_t)n_utts)) ||
+        (rc = upload(&plan->d_wave_off, plan->h_wave_off.data(), (size_t)n_utts + 1)) ||
+        (rc = upload(&plan->d_frame_off, plan->h_frame_off.data(), (size_t)n_utts + 1)) ||
+        (rc = upload(&plan->d_seg_slot_off, plan->h_seg_slot_off.data(), (size_t)n_utts + 1)) ||
+        (rc = upload(&plan->d_tile_utt, tile_utt.data(), tile_utt.size())) ||
+        (rc = upload(&plan->d_tile_first, tile_first.data(), tile_first.size()))) {
+        aat_plan_destroy(plan);
+        return rc;
+    }
+    *out = plan;
+    return AAT_OK;
+}
+
+int aat_plan_destroy(aat_plan *plan)
+{
+    if (!plan) return AAT_OK;
+    DeviceGuard guard(plan->ctx->device);
+    cudaFree(plan->d_n_samples);
+    cudaFree(plan->d_wave_off);
+    cudaFree(plan->d_frame_off);
+    cudaFree(plan->d_seg_slot_off);
+    cudaFree(plan->d_tile_utt);
+    cudaFree(plan->d_tile_first);
+    delete plan;
+    return AAT_OK;
+}
+
+int64_t aat_plan_total_samples(const aat_plan *plan) { return plan ? plan->total_samples : -1; }
+int64_t aat_plan_total_frames(const aat_plan *plan) { return plan ? plan->total_frames : -1; }
+int64_t aat_plan_total_seg_slots(const aat_plan *plan) { return plan ? plan->total_seg_slots : -1; }
+
+int aat_plan_offsets(const aat_plan *plan, int64_t *wave_off_host, int64_t *frame_off_host, int64_t *seg_slot_off_host)
+{
+    AAT_REQUIRE(plan, AAT_ERR_INVALID, "aat_plan_offsets: NULL plan");
+    const size_t bytes = sizeof(int64_t) * ((size_t)plan->n_utts + 1);
+    if (wave_off_host) memcpy(wave_off_host, plan->h_wave_off.data(), bytes);
+    if (frame_off_host) memcpy(frame_off_host, plan->h_frame_off.data(), bytes);
+    if (seg_slot_off_host) memcpy(seg_slot_off_host, plan->h_seg_slot_off.data(), bytes);
+    return AAT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ device API
+int aat_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave_dev, int wave_dtype, float *mel_dev,
+               float *amp_dev, void *stream)
+{
+    AAT_REQUIRE(ctx && plan && wave_dev && mel_dev, AAT_ERR_INVALID, "aat_logmel: NULL argument");
+    AAT_REQUIRE(plan->ctx == ctx, AAT_ERR_INVALID, "aat_logmel: plan belongs to another context");
+    return launch_logmel(ctx, plan, wave_dev, wave_dtype, mel_dev, amp_dev, static_cast<cudaStream_t>(stream));
+}
+
+int aat_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel_dev, const float *amp_dev,
+                   int64_t *seg_start_dev, int64_t *seg_len_dev, int32_t *seg_count_dev, int64_t *minima_dev,
+                   int32_t *minima_count_dev, int32_t *status_dev, void *stream)
+{
+    AAT_REQUIRE(ctx && plan && seg_start_dev && seg_len_dev && seg_count_dev && status_dev, AAT_ERR_INVALID,
+                "aat_boundaries: NULL argument");
+    AAT_REQUIRE(mel_dev || amp_dev, AAT_ERR_INVALID, "aat_boundaries: need mel_dev or amp_dev");
+    AAT_REQUIRE(plan->ctx == ctx, AAT_ERR_INVALID, "aat_boundaries: plan belongs to another context");
+    return launch_boundaries(ctx, plan, mel_dev, amp_dev, seg_start_dev, seg_len_dev, seg_count_dev, minima_dev,
+                             minima_count_dev, status_dev, static_cast<cudaStream_t>(stream));
+}
+
+int aat_process_boarders(aat_ctx *ctx, int64_t n_samples, const int64_t *boarders_dev, int64_t n_boarders,
+                         int64_t *seg_start_dev, int64_t *seg_len_dev, int64_t capacity, int32_t *seg_count_dev,
+                         int32_t *status_dev, void *stream)
+{
+    AAT_REQUIRE(ctx && (boarders_dev || n_boarders == 0) && seg_start_dev && seg_len_dev && seg_count_dev && status_dev,
+                AAT_ERR_INVALID, "aat_process_boarders: NULL argument");
+    AAT_REQUIRE(n_samples >= 0 && n_boarders >= 0 && capacity >= 0, AAT_ERR_INVALID, "aat_process_boarders: negative size");
+    return launch_process_boarders(ctx, n_samples, boarders_dev, n_boarders, seg_start_dev, seg_len_dev, capacity,
+                                   seg_count_dev, status_dev, static_cast<cudaStream_t>(stream));
+}
+
+int aat_segment_frame_csr(aat_ctx *ctx, const aat_plan *plan, const int64_t *seg_len_dev, const int32_t *seg_count_dev,
+                          int64_t *seg_off_dev, int64_t *n_seg_dev, int64_t *utt_seg_off_dev, void *stream)
+{
+    AAT_REQUIRE(ctx && plan && seg_len_dev && seg_count_dev && seg_off_dev && n_seg_dev, AAT_ERR_INVALID,
+                "aat_segment_frame_csr: NULL argument");
+    return launch_segment_frame_csr(ctx, plan, seg_len_dev, seg_count_dev, seg_off_dev, n_seg_dev, utt_seg_off_dev,
+                                    static_cast<cudaStream_t>(stream));
+}
+
+int aat_segment_mean_pool(aat_ctx *ctx, const void *emb_dev, int emb_dtype, int64_t n_rows, int32_t dim,
+                          const int64_t *seg_off_dev, int64_t n_seg, const int64_t *n_seg_dev, float *out_dev,
+                          double *colsum_dev, void *stream)
+{
+    AAT_REQUIRE(ctx, AAT_ERR_INVALID, "aat_segment_mean_pool: NULL context");
+    return launch_mean_pool(ctx, emb_dev, emb_dtype, n_rows, dim, seg_off_dev, n_seg, n_seg_dev, out_dev, colsum_dev,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int aat_colsum_accumulate(aat_ctx *ctx, double *acc_dev, const double *colsum_dev, int32_t dim, void *stream)
+{
+    AAT_REQUIRE(ctx && acc_dev && colsum_dev && dim > 0, AAT_ERR_INVALID, "aat_colsum_accumulate: bad argument");
+    return launch_colsum_accumulate(acc_dev, colsum_dev, dim, static_cast<cudaStream_t>(stream));
+}
+
+int aat_colsum_finalize(aat_ctx *ctx, const double *acc_dev, int32_t dim, float *mean_dev, void *stream)
+{
+    AAT_REQUIRE(ctx && acc_dev && mean_dev && dim > 0, AAT_ERR_INVALID, "aat_colsum_finalize: bad argument");
+    return launch_colsum_finalize(acc_dev, dim, mean_dev, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ host API
+// One utterance, host buffers in / host buffers out: H2D -> kernels -> D2H on the context's own stream.
+
+static int host_pipeline(aat_ctx *ctx, const void *wave_host, int wave_dtype, int64_t n_samples,
+                         const float *mel_in_host, bool want_boundaries, float *mel_out_host, int64_t *minima_host,
+                         int64_t *n_minima_host, int64_t *seg_start_host, int64_t *seg_len_host, int64_t capacity,
+                         int64_t *n_segments_host, int32_t *padded_tail_host)
+{
+    DeviceGuard guard(ctx->device);
+    AAT_REQUIRE(guard.ok, AAT_ERR_CUDA, "cudaSetDevice(%d) failed", ctx->device);
+    aat_plan *plan = nullptr;
+    int rc = aat_plan_create(ctx, 1, &n_samples, &plan);
+    if (rc) return rc;
+    const int M = ctx->cfg.num_mel_filters;
+    const int64_t T = plan->total_frames;
+    const int64_t slots = plan->total_seg_slots;
+    const size_t wsize = dtype_size(wave_dtype);
+    const bool need_wave = mel_in_host == nullptr;
+
+    size_t dev_bytes = align256(need_wave ? wsize * n_samples : 0) + align256(sizeof(float) * M * T) +
+                       align256(sizeof(float) * T) + 2 * align256(sizeof(int64_t) * slots) +
+                       align256(sizeof(int64_t) * T) + 3 * 256;
+    size_t pin_bytes = dev_bytes;
+    rc = ensure_scratch(ctx, dev_bytes, pin_bytes);
+    if (rc) {
+        aat_plan_destroy(plan);
+        return rc;
+    }
+    Arena d(ctx->dev_scratch), h(ctx->pinned);
+    unsigned char *d_wave = d.take<unsigned char>(need_wave ? wsize * n_samples : 0);
+    float *d_mel = d.take<float>((size_t)M * T);
+    float *d_amp = d.take<float>(T);
+    int64_t *d_seg_start = d.take<int64_t>(slots);
+    int64_t *d_seg_len = d.take<int64_t>(slots);
+    int64_t *d_minima = d.take<int64_t>(T);
+    int32_t *d_seg_count = d.take<int32_t>(1);
+    int32_t *d_min_count = d.take<int32_t>(1);
+    int32_t *d_status = d.take<int32_t>(1);
+    unsigned char *h_wave = h.take<unsigned char>(need_wave ? wsize * n_samples : 0);
+    float *h_mel = h.take<float>((size_t)M * T);
+    (void)h.take<float>(T);
+    int64_t *h_seg_start = h.take<int64_t>(slots);
+    int64_t *h_seg_len = h.take<int64_t>(slots);
+    int64_t *h_minima = h.take<int64_t>(T);
+    int32_t *h_seg_count = h.take<int32_t>(1);
+    int32_t *h_min_count = h.take<int32_t>(1);
+    int32_t *h_status = h.take<int32_t>(1);
+    cudaStream_t st = ctx->host_stream;
+
+    auto fail = [&](int code) {
+        aat_plan_destroy(plan);
+        return code;
+    };
+#define AAT_TRY_CUDA(expr)                                                                            \
+    do {                                                                                              \
+        cudaError_t e__ = (expr);                                                                     \
+        if (e__ != cudaSuccess) {                                                                     \
+            set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__);   \
+            return fail(AAT_ERR_CUDA);                                                                \
+        }                                                                                             \
+    } while (0)
+
+    if (need_wave) {
+        memcpy(h_wave, wave_host, wsize * n_samples);
+        AAT_TRY_CUDA(cudaMemcpyAsync(d_wave, h_wave, wsize * n_samples, cudaMemcpyHostToDevice, st));
+        rc = launch_logmel(ctx, plan, d_wave, wave_dtype, d_mel, want_boundaries ? d_amp : nullptr, st);
+        if (rc) return fail(rc);
+        if (mel_out_host) AAT_TRY_CUDA(cudaMemcpyAsync(h_mel, d_mel, sizeof(float) * M * T, cudaMemcpyDeviceToHost, st));
+    } else {
+        memcpy(h_mel, mel_in_host, sizeof(float) * M * T);
+        AAT_TRY_CUDA(cudaMemcpyAsync(d_mel, h_mel, sizeof(float) * M * T, cudaMemcpyHostToDevice, st));
+    }
+    if (want_boundaries) {
+        rc = launch_boundaries(ctx, plan, d_mel, need_wave ? d_amp : nullptr, d_seg_start, d_seg_len, d_seg_count,
+                               d_minima, d_min_count, d_status, st);
+        if (rc) return fail(rc);
+        AAT_TRY_CUDA(cudaMemcpyAsync(h_seg_count, d_seg_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        AAT_TRY_CUDA(cudaMemcpyAsync(h_min_count, d_min_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        AAT_TRY_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        AAT_TRY_CUDA(cudaMemcpyAsync(h_seg_start, d_seg_start, sizeof(int64_t) * slots, cudaMemcpyDeviceToHost, st));
+        AAT_TRY_CUDA(cudaMemcpyAsync(h_seg_len, d_seg_len, sizeof(int64_t) * slots, cudaMemcpyDeviceToHost, st));
+        if (minima_host) AAT_TRY_CUDA(cudaMemcpyAsync(h_minima, d_minima, sizeof(int64_t) * T, cudaMemcpyDeviceToHost, st));
+    }
+    AAT_TRY_CUDA(cudaStreamSynchronize(st));
+#undef AAT_TRY_CUDA
+    if (mel_out_host) memcpy(mel_out_host, h_mel, sizeof(float) * M * T);
+    if (want_boundaries) {
+        if (*h_status < 0) {
+            set_error(*h_status == AAT_ERR_TAIL ? "tail longer than min_segment_frames (reference raises ValueError)"
+                                                : "segment capacity exceeded");
+            return fail(*h_status);
+        }
+        if (padded_tail_host) *padded_tail_host = *h_status & 1;
+        const int64_t n_seg = *h_seg_count;
+        if (n_seg > capacity) {
+            set_error("aat_host_tokenize: %lld segments exceed the caller's capacity %lld", (long long)n_seg,
+                      (long long)capacity);
+            return fail(AAT_ERR_CAPACITY);
+        }
+        if (seg_start_host) memcpy(seg_start_host, h_seg_start, sizeof(int64_t) * n_seg);
+        if (seg_len_host) memcpy(seg_len_host, h_seg_len, sizeof(int64_t) * n_seg);
+        if (n_segments_host) *n_segments_host = n_seg;
+        if (minima_host) memcpy(minima_host, h_minima, sizeof(int64_t) * (*h_min_count));
+        if (n_minima_host) *n_minima_host = *h_min_count;
+    }
+    aat_plan_destroy(plan);
+    return AAT_OK;
+}
+
+int aat_host_logmel(aat_ctx *ctx, const void *wave_host, int wave_dtype, int64_t n_samples, float *mel_host)
+{
+    AAT_REQUIRE(ctx && wave_host && mel_host, AAT_ERR_INVALID, "aat_host_logmel: NULL argument");
+    AAT_REQUIRE(wave_dtype == AAT_F32 || wave_dtype == AAT_F64, AAT_ERR_UNSUPPORTED,
+                "aat_host_logmel: waveform dtype must be AAT_F32 or AAT_F64");
+    return host_pipeline(ctx, wave_host, wave_dtype, n_samples, nullptr, false, mel_host, nullptr, nullptr, nullptr,
+                         nullptr, 0, nullptr, nullptr);
+}
+
+int aat_host_find_minimas(aat_ctx *ctx, const float *mel_host, int64_t n_frames, int64_t *minima_host,
+                          int64_t *n_minima_host)
+{
+    AAT_REQUIRE(ctx && mel_host && minima_host && n_minima_host, AAT_ERR_INVALID, "aat_host_find_minimas: NULL argument");
+    AAT_REQUIRE(n_frames >= 1, AAT_ERR_INVALID, "aat_host_find_minimas: need at least one frame");
+    // any sample count with 1 + n/hop == n_frames reproduces the layout; the segments are discarded
+    const int64_t n_samples = (n_frames - 1) * ctx->cfg.hop_length + (n_frames == 1 ? 1 : 0);
+    std::vector<int64_t> seg((size_t)seg_capacity(ctx->cfg, n_samples) * 2);
+    int64_t n_seg = 0;
+    return host_pipeline(ctx, nullptr, AAT_F32, n_samples, mel_host, true, nullptr, minima_host, n_minima_host,
+                         seg.data(), seg.data() + seg.size() / 2, (int64_t)seg.size() / 2, &n_seg, nullptr);
+}
+
+int aat_host_process_boarders(aat_ctx *ctx, int64_t n_samples, const int64_t *boarders_host, int64_t n_boarders,
+                              int64_t *seg_start_host, int64_t *seg_len_host, int64_t capacity, int64_t *n_segments_host,
+                              int32_t *padded_tail_host)
+{
+    AAT_REQUIRE(ctx && (boarders_host || n_boarders == 0) && seg_start_host && seg_len_host && n_segments_host,
+                AAT_ERR_INVALID, "aat_host_process_boarders: NULL argument");
+    AAT_REQUIRE(n_samples >= 0 && n_boarders >= 0 && capacity >= 0, AAT_ERR_INVALID,
+                "aat_host_process_boarders: negative size");
+    DeviceGuard guard(ctx->device);
+    size_t bytes = align256(sizeof(int64_t) * n_boarders) + 2 * align256(sizeof(int64_t) * capacity) + 2 * 256;
+    int rc = ensure_scratch(ctx, bytes, bytes);
+    if (rc) return rc;
+    Arena d(ctx->dev_scratch), h(ctx->pinned);
+    int64_t *d_b = d.take<int64_t>(n_boarders), *d_s = d.take<int64_t>(capacity), *d_l = d.take<int64_t>(capacity);
+    int32_t *d_cnt = d.take<int32_t>(1), *d_status = d.take<int32_t>(1);
+    int64_t *h_b = h.take<int64_t>(n_boarders), *h_s = h.take<int64_t>(capacity), *h_l = h.take<int64_t>(capacity);
+    int32_t *h_cnt = h.take<int32_t>(1), *h_status = h.take<int32_t>(1);
+    cudaStream_t st = ctx->host_stream;
+    if (n_boarders) memcpy(h_b, boarders_host, sizeof(int64_t) * n_boarders);
+    AAT_CUDA_CHECK(cudaMemcpyAsync(d_b, h_b, sizeof(int64_t) * n_boarders, cudaMemcpyHostToDevice, st));
+    rc = launch_process_boarders(ctx, n_samples, d_b, n_boarders, d_s, d_l, capacity, d_cnt, d_status, st);
+    if (rc) return rc;
+    AAT_CUDA_CHECK(cudaMemcpyAsync(h_s, d_s, sizeof(int64_t) * capacity, cudaMemcpyDeviceToHost, st));
+    AAT_CUDA_CHECK(cudaMemcpyAsync(h_l, d_l, sizeof(int64_t) * capacity, cudaMemcpyDeviceToHost, st));
+    AAT_CUDA_CHECK(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    AAT_CUDA_CHECK(cudaMemcpyAsync(h_status, d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    AAT_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (*h_status < 0) {
+        set_error(*h_status == AAT_ERR_TAIL ? "tail longer than min_segment_frames (reference raises ValueError)"
+                                            : "segment capacity exceeded");
+        return *h_status;
+    }
+    if (padded_tail_host) *padded_tail_host = *h_status & 1;
+    memcpy(seg_start_host, h_s, sizeof(int64_t) * (*h_cnt));
+    memcpy(seg_len_host, h_l, sizeof(int64_t) * (*h_cnt));
+    *n_segments_host = *h_cnt;
+    return AAT_OK;
+}
+
+int aat_host_tokenize(aat_ctx *ctx, const void *wave_host, int wave_dtype, int64_t n_samples, const float *mel_in_host,
+                      float *mel_out_host, int64_t *minima_host, int64_t *n_minima_host, int64_t *seg_start_host,
+                      int64_t *seg_len_host, int64_t capacity, int64_t *n_segments_host, int32_t *padded_tail_host)
+{
+    AAT_REQUIRE(ctx && (wave_host || mel_in_host) && seg_len_host && n_segments_host, AAT_ERR_INVALID,
+                "aat_host_tokenize: NULL argument");
+    AAT_REQUIRE(mel_in_host || wave_dtype == AAT_F32 || wave_dtype == AAT_F64, AAT_ERR_UNSUPPORTED,
+                "aat_host_tokenize: waveform dtype must be AAT_F32 or AAT_F64");
+    return host_pipeline(ctx, wave_host, wave_dtype, n_samples, mel_in_host, true, mel_out_host, minima_host,
+                         n_minima_host, seg_start_host, seg_len_host, capacity, n_segments_host, padded_tail_host);
+}
+
+int aat_host_mean_pool(aat_ctx *ctx, const void *emb_host, int emb_dtype, int64_t n_rows, int32_t dim,
+                       const int64_t *seg_off_host, int64_t n_seg, float *out_host, double *colsum_host)
+{
+    AAT_REQUIRE(ctx && (emb_host || n_rows == 0) && seg_off_host && (out_host || n_seg == 0), AAT_ERR_INVALID,
+                "aat_host_mean_pool: NULL argument");
+    AAT_REQUIRE(n_rows >= 0 && n_seg >= 0 && dim > 0, AAT_ERR_INVALID, "aat_host_mean_pool: negative size");
+    const size_t esize = dtype_size(emb_dtype);
+    AAT_REQUIRE(emb_dtype == AAT_F32 || emb_dtype == AAT_F16 || emb_dtype == AAT_BF16, AAT_ERR_UNSUPPORTED,
+                "aat_host_mean_pool: embedding dtype must be F32, F16 or BF16");
+    DeviceGuard guard(ctx->device);
+    const size_t emb_bytes = esize * (size_t)n_rows * dim, out_bytes = sizeof(float) * (size_t)n_seg * dim;
+    const size_t off_bytes = sizeof(int64_t) * ((size_t)n_seg + 1), cs_bytes = sizeof(double) * ((size_t)dim + 1);
+    // embeddings are copied straight from the caller's buffer (registering/pinning is the caller's choice)
+    const size_t dev_bytes = align256(emb_bytes) + align256(out_bytes) + align256(off_bytes) + align256(cs_bytes);
+    int rc = ensure_scratch(ctx, dev_bytes, align256(off_bytes) + align256(cs_bytes));
+    if (rc) return rc;
+    Arena d(ctx->dev_scratch);
+    unsigned char *d_emb = d.take<unsigned char>(emb_bytes);
+    float *d_out = d.take<float>((size_t)n_seg * dim);
+    int64_t *d_off = d.take<int64_t>((size_t)n_seg + 1);
+    double *d_cs = d.take<double>((size_t)dim + 1);
+    cudaStream_t st = ctx->host_stream;
+    if (emb_bytes) AAT_CUDA_CHECK(cudaMemcpyAsync(d_emb, emb_host, emb_bytes, cudaMemcpyHostToDevice, st));
+    AAT_CUDA_CHECK(cudaMemcpyAsync(d_off, seg_off_host, off_bytes, cudaMemcpyHostToDevice, st));
+    rc = launch_mean_pool(ctx, d_emb, emb_dtype, n_rows, dim, d_off, n_seg, nullptr, d_out, colsum_host ? d_cs : nullptr, st);
+    if (rc) return rc;
+    if (out_bytes) AAT_CUDA_CHECK(cudaMemcpyAsync(out_host, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    if (colsum_host) AAT_CUDA_CHECK(cudaMemcpyAsync(colsum_host, d_cs, cs_bytes, cudaMemcpyDeviceToHost, st));
+    AAT_CUDA_CHECK(cudaStreamSynchronize(st));
+    return AAT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,612 @@
+// K4: ragged per-segment mean-pool of frame embeddings — the HBM-streaming kernel.
+//
+// Replaces `torch.cat([x.mean(dim=1, keepdim=True).to(float32) for x in embs], dim=1)`
+// (ref:scripts/mean_hubert_embeddings.py:19-20) on the packed layout emb[n_rows, dim] + CSR
+// seg_off[S+1].  Pure streaming reduction (~0.25 flop/B): the only roofline is HBM bandwidth, so the
+// design is about bytes in flight and balance, not arithmetic:
+//
+//   * work is tiled by BYTES, not by segment: the row range [0, n_rows) is split evenly over a
+//     persistent grid (CTAs-per-SM x 148 SMs), so 6-frame and 74-frame segments cost the same per byte
+//     and a giant segment cannot serialise on one SM;
+//   * each CTA's rows are one contiguous byte range, streamed once through a ring of shared-memory
+//     stages by 1-D bulk async copies (cp.async.bulk.shared.global -> SASS UBLKCP) issued by a single
+//     producer thread and tracked by mbarrier transaction counts — tens of KB in flight per SM without
+//     spending registers or address arithmetic on it;
+//   * consumer threads own one 16-byte column slab each (128-bit conflict-free shared loads), walk the
+//     rows of a stage, keep four interleaved float32 accumulators and flush at every segment boundary
+//     with a coalesced float4 store of sum / n;
+//   * a segment cut by a CTA boundary is finished deterministically: the CTAs that hold its beginning
+//     and middle publish partial sums (+ release flag); the CTA that holds its end adds them in CTA
+//     order.  Dependencies only point to lower CTA indices and the whole grid is co-resident, so the
+//     wait cannot deadlock; flags are reset by their single consumer, so CUDA-graph replays are safe;
+//   * optional epilogue: float64 column sums of the pooled vectors (input of the dataset-mean
+//     allreduce) are accumulated per CTA and reduced in CTA order by a second tiny kernel.
+//
+// Algorithmic bytes per launch: n_rows*dim*e + S*dim*4 + (S+1)*8  (SURVEY.md §8d).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "aat_internal.cuh"
+
+namespace aat {
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kStageBytes = 24 * 1024; // 8 rows of 768 fp32, 6 rows of 1024 fp32
+constexpr int kMaxConsumers = 256;
+constexpr int kMaxSlabs = 4; // 16-byte column slabs per consumer thread -> dim*e <= 16 KB
+
+// ---------------------------------------------------------------- PTX helpers (mbarrier + bulk copy)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (TMA engine, no tensor map)
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void consumer_barrier(int n_consumers)
+{
+    asm volatile("bar.sync 1, %0;" ::"r"(n_consumers) : "memory");
+}
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---------------------------------------------------------------- element traits: one 16-byte slab
+template <typename T>
+struct Slab;
+template <>
+struct Slab<float> {
+    static constexpr int kCols = 4;
+    __device__ static void load(const void *p, float (&v)[4])
+    {
+        const float4 x = *reinterpret_cast<const float4 *>(p);
+        v[0] = x.x, v[1] = x.y, v[2] = x.z, v[3] = x.w;
+    }
+    // torch: sum.div_(n) in float32
+    __device__ static float finish(float sum, float n) { return __fdiv_rn(sum, n); }
+};
+template <>
+struct Slab<__half> {
+    static constexpr int kCols = 8;
+    __device__ static void load(const void *p, float (&v)[8])
+    {
+        const uint4 x = *reinterpret_cast<const uint4 *>(p);
+        const __half2 *h = reinterpret_cast<const __half2 *>(&x);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(h[i]);
+            v[2 * i] = f.x, v[2 * i + 1] = f.y;
+        }
+    }
+    // torch CPU: float32 accumulate, sum stored as half, div_ in half (computed in float32, rounded to half)
+    __device__ static float finish(float sum, float n)
+    {
+        const float s = __half2float(__float2half_rn(sum));
+        return __half2float(__float2half_rn(__fdiv_rn(s, n)));
+    }
+};
+template <>
+struct Slab<__nv_bfloat16> {
+    static constexpr int kCols = 8;
+    __device__ static void load(const void *p, float (&v)[8])
+    {
+        const uint4 x = *reinterpret_cast<const uint4 *>(p);
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[2 * i] = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    __device__ static float finish(float sum, float n)
+    {
+        const float s = __bfloat162float(__float2bfloat16_rn(sum));
+        return __bfloat162float(__float2bfloat16_rn(__fdiv_rn(s, n)));
+    }
+};
+
+struct PoolParams {
+    const unsigned char *emb;
+    const int64_t *seg_off;
+    const int64_t *n_seg_dev;
+    float *out;
+    float *head;      // [G, dim] partial sums of a segment that began in an earlier CTA
+    float *tail;      // [G, dim] partial sums of a segment that continues into a later CTA
+    int *head_flag;   // [G]
+    int *tail_flag;   // [G]
+    double *colsum;   // [G, dim] per-CTA column sums of pooled vectors (optional)
+    int64_t n_rows;
+    int64_t n_seg;
+    int dim;
+    int row_bytes;
+    int rows_per_stage;
+    int slabs_per_row; // row_bytes / 16
+    int n_consumers;
+};
+
+__device__ __forceinline__ int64_t cta_row_begin(int64_t c, int64_t n_rows, int64_t G) { return (c * n_rows) / G; }
+
+// Number of entries of off[0..count) that are <= key, found cooperatively by the consumer threads.
+__device__ int64_t coop_upper_bound(const int64_t *off, int64_t count, int64_t key, int tid, int n_consumers,
+                                    int *s_votes)
+{
+    int64_t lo = 0, hi = count; // entries < lo are <= key; entries >= hi are > key
+    while (lo < hi) {
+        const int64_t span = hi - lo;
+        const int64_t step = (span + n_consumers - 1) / n_consumers;
+        const int64_t q = lo + (int64_t)(tid + 1) * step - 1;
+        const bool pred = (q < hi) && (off[q] <= key);
+        const unsigned ballot = __ballot_sync(0xffffffffu, pred);
+        if ((tid & 31) == 0) s_votes[tid >> 5] = __popc(ballot);
+        consumer_barrier(n_consumers);
+        int c = 0;
+        for (int w = 0; w < n_consumers / 32; ++w) c += s_votes[w];
+        consumer_barrier(n_consumers);
+        const int64_t new_lo = lo + (int64_t)c * step;
+        int64_t new_hi = lo + (int64_t)(c + 1) * step - 1;
+        if (new_hi > hi) new_hi = hi;
+        lo = new_lo < hi ? new_lo : hi;
+        hi = new_hi;
+    }
+    return lo;
+}
+
+template <typename EmbT, int kSlabs, bool kColsum>
+__global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolParams p)
+{
+    using S = Slab<EmbT>;
+    constexpr int kCols = S::kCols;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_full[kStages];
+    __shared__ __align__(8) uint64_t s_empty[kStages];
+    __shared__ int s_votes[kMaxConsumers / 32];
+
+    const int tid = threadIdx.x;
+    const int n_consumers = p.n_consumers;
+    const int64_t G = gridDim.x;
+    const int64_t c = blockIdx.x;
+    const int64_t r0 = cta_row_begin(c, p.n_rows, G);
+    const int64_t r1 = cta_row_begin(c + 1, p.n_rows, G);
+    const int64_t n_chunks = (r1 - r0 + p.rows_per_stage - 1) / p.rows_per_stage;
+    const size_t stage_stride = (size_t)p.rows_per_stage * p.row_bytes;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_empty[s], n_consumers / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= n_consumers) {
+        // ============================== producer warp ==============================
+        const int lane = tid - n_consumers;
+        if (lane == 0) {
+            const int64_t S_prod = p.n_seg_dev ? min(*p.n_seg_dev, p.n_seg) : p.n_seg;
+            for (int64_t ch = 0; ch < (S_prod > 0 ? n_chunks : 0); ++ch) {
+                const int s = (int)(ch % kStages);
+                const int64_t use = ch / kStages;
+                if (use > 0) mbar_wait(&s_empty[s], (uint32_t)((use - 1) & 1));
+                const int64_t row = r0 + ch * p.rows_per_stage;
+                const int64_t rows = (r1 - row < p.rows_per_stage) ? r1 - row : p.rows_per_stage;
+                const uint32_t bytes = (uint32_t)(rows * p.row_bytes);
+                mbar_expect_tx(&s_full[s], bytes);
+                bulk_g2s(smem_raw + s * stage_stride, p.emb + (size_t)row * p.row_bytes, bytes, &s_full[s]);
+            }
+        } else {
+            // idle lanes: empty segments never meet a row, so they are written here (torch: mean of
+            // an empty slice is NaN).  Grid-stride over all segments, 31 lanes per CTA.
+            const int64_t S_total = p.n_seg_dev ? min(*p.n_seg_dev, p.n_seg) : p.n_seg;
+            const float nan = __int_as_float(0x7fc00000);
+            for (int64_t s = c * 31 + (lane - 1); s < S_total; s += G * 31) {
+                if (p.seg_off[s] == p.seg_off[s + 1]) {
+                    float *o = p.out + (size_t)s * p.dim;
+                    for (int d = 0; d < p.dim; ++d) o[d] = nan;
+                }
+            }
+        }
+        return;
+    }
+
+    // ================================ consumers ================================
+    const int64_t S_total = p.n_seg_dev ? min(*p.n_seg_dev, p.n_seg) : p.n_seg;
+    float acc[kSlabs][4][kCols];
+    double csum[kColsum ? kSlabs : 1][kCols];
+#pragma unroll
+    for (int j = 0; j < kSlabs; ++j)
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < kCols; ++k) acc[j][u][k] = 0.0f;
+    if (kColsum) {
+#pragma unroll
+        for (int j = 0; j < kSlabs; ++j)
+#pragma unroll
+            for (int k = 0; k < kCols; ++k) csum[j][k] = 0.0;
+    }
+
+    if (r0 < r1 && S_total > 0) {
+        // current segment: last s with seg_off[s] <= r0 (cooperative k-ary search, overlaps the first copies)
+        const int64_t idx = coop_upper_bound(p.seg_off, S_total + 1, r0, tid, n_consumers, s_votes);
+        int64_t seg = idx - 1; // -1: rows before the first segment; S_total: rows after the last one
+        int64_t seg_begin, seg_end;
+        bool in_gap;
+        auto load_segment = [&]() {
+            if (seg < 0) {
+                in_gap = true, seg_begin = r0, seg_end = p.seg_off[0];
+            } else if (seg >= S_total) {
+                in_gap = true, seg_begin = r0, seg_end = INT64_MAX;
+            } else {
+                in_gap = false, seg_begin = p.seg_off[seg], seg_end = p.seg_off[seg + 1];
+            }
+        };
+        load_segment();
+
+        auto reduce_acc = [&](int j, int k) { return (acc[j][0][k] + acc[j][1][k]) + (acc[j][2][k] + acc[j][3][k]); };
+        auto clear_acc = [&]() {
+#pragma unroll
+            for (int j = 0; j < kSlabs; ++j)
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int k = 0; k < kCols; ++k) acc[j][u][k] = 0.0f;
+        };
+        auto write_pooled = [&](int j, const float (&sum)[kCols], float nrows) {
+            const int slab = tid + j * n_consumers;
+            if (slab < p.slabs_per_row) {
+                float *o = p.out + (size_t)seg * p.dim + (size_t)slab * kCols;
+                float r[kCols];
+#pragma unroll
+                for (int k = 0; k < kCols; ++k) {
+                    r[k] = S::finish(sum[k], nrows);
+                    if (kColsum) csum[kColsum ? j : 0][k] += (double)r[k];
+                }
+#pragma unroll
+                for (int k = 0; k < kCols; k += 4)
+                    *reinterpret_cast<float4 *>(o + k) = make_float4(r[k], r[k + 1], r[k + 2], r[k + 3]);
+            }
+        };
+
+        // flush the accumulators for the segment that ends (or is cut) at `row_end`
+        auto flush = [&](int64_t row_end) {
+            if (!in_gap) {
+                const bool starts_before = seg_begin < r0;
+                const bool ends_after = seg_end > row_end; // only possible when row_end == r1
+                const float nrows = (float)(seg_end - seg_begin);
+                if (!starts_before && !ends_after) {
+#pragma unroll
+                    for (int j = 0; j < kSlabs; ++j) {
+                        float sum[kCols];
+#pragma unroll
+                        for (int k = 0; k < kCols; ++k) sum[k] = reduce_acc(j, k);
+                        write_pooled(j, sum, nrows);
+                    }
+                } else if (ends_after) {
+                    // publish a partial: "tail" if the segment began here, "head" (a middle piece) otherwise
+                    float *dst = (starts_before ? p.head : p.tail) + (size_t)c * p.dim;
+#pragma unroll
+                    for (int j = 0; j < kSlabs; ++j) {
+                        const int slab = tid + j * n_consumers;
+                        if (slab < p.slabs_per_row)
+#pragma unroll
+                            for (int k = 0; k < kCols; ++k) dst[(size_t)slab * kCols + k] = reduce_acc(j, k);
+                    }
+                    __threadfence();
+                    consumer_barrier(n_consumers);
+                    if (tid == 0) st_release((starts_before ? p.head_flag : p.tail_flag) + c, 1);
+                } else {
+                    // the segment ends here but began in an earlier CTA: add the published pieces in CTA order
+                    int64_t cs = (seg_begin * G) / (p.n_rows > 0 ? p.n_rows : 1);
+                    while (cs + 1 < G && cta_row_begin(cs + 1, p.n_rows, G) <= seg_begin) ++cs;
+                    while (cs > 0 && cta_row_begin(cs, p.n_rows, G) > seg_begin) --cs;
+                    if (tid == 0) {
+                        while (ld_acquire(p.tail_flag + cs) == 0) {}
+                        p.tail_flag[cs] = 0;
+                        for (int64_t m = cs + 1; m < c; ++m) {
+                            if (cta_row_begin(m, p.n_rows, G) == cta_row_begin(m + 1, p.n_rows, G)) continue;
+                            while (ld_acquire(p.head_flag + m) == 0) {}
+                            p.head_flag[m] = 0;
+                        }
+                    }
+                    consumer_barrier(n_consumers);
+#pragma unroll
+                    for (int j = 0; j < kSlabs; ++j) {
+                        const int slab = tid + j * n_consumers;
+                        float sum[kCols];
+                        if (slab < p.slabs_per_row) {
+#pragma unroll
+                            for (int k = 0; k < kCols; ++k) sum[k] = __ldcg(p.tail + (size_t)cs * p.dim + slab * kCols + k);
+                            for (int64_t m = cs + 1; m < c; ++m) {
+                                if (cta_row_begin(m, p.n_rows, G) == cta_row_begin(m + 1, p.n_rows, G)) continue;
+#pragma unroll
+                                for (int k = 0; k < kCols; ++k)
+                                    sum[k] += __ldcg(p.head + (size_t)m * p.dim + slab * kCols + k);
+                            }
+#pragma unroll
+                            for (int k = 0; k < kCols; ++k) sum[k] += reduce_acc(j, k);
+                        }
+                        write_pooled(j, sum, nrows);
+                    }
+                }
+            }
+            clear_acc();
+        };
+
+        int64_t row = r0;
+        for (int64_t ch = 0; ch < n_chunks; ++ch) {
+            const int s = (int)(ch % kStages);
+            mbar_wait(&s_full[s], (uint32_t)((ch / kStages) & 1));
+            const unsigned char *stage = smem_raw + s * stage_stride;
+            const int64_t chunk_end = (row + p.rows_per_stage < r1) ? row + p.rows_per_stage : r1;
+            int rr = 0; // row within the stage
+            while (row < chunk_end) {
+                while (row >= seg_end) { // crossed a boundary: finish the segment, move to the next non-empty one
+                    flush(row);
+                    do {
+                        ++seg;
+                        load_segment();
+                    } while (!in_gap && seg_end == seg_begin);
+                }
+                const int64_t stop = seg_end < chunk_end ? seg_end : chunk_end;
+                const int run = (int)(stop - row);
+                if (!in_gap) {
+                    const unsigned char *base = stage + (size_t)rr * p.row_bytes + (size_t)tid * 16;
+                    int i = 0;
+                    for (; i + 4 <= run; i += 4) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+#pragma unroll
+                            for (int j = 0; j < kSlabs; ++j) {
+                                if (tid + j * n_consumers < p.slabs_per_row) {
+                                    float v[kCols];
+                                    S::load(base + (size_t)(i + u) * p.row_bytes + (size_t)j * n_consumers * 16, v);
+#pragma unroll
+                                    for (int k = 0; k < kCols; ++k) acc[j][u][k] += v[k];
+                                }
+                            }
+                    }
+                    for (; i < run; ++i)
+#pragma unroll
+                        for (int j = 0; j < kSlabs; ++j) {
+                            if (tid + j * n_consumers < p.slabs_per_row) {
+                                float v[kCols];
+                                S::load(base + (size_t)i * p.row_bytes + (size_t)j * n_consumers * 16, v);
+#pragma unroll
+                                for (int k = 0; k < kCols; ++k) acc[j][0][k] += v[k];
+                            }
+                        }
+                }
+                row += run;
+                rr += run;
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&s_empty[s]);
+        }
+        flush(r1); // the segment still open at the end of this CTA's rows
+    }
+
+    if (kColsum) {
+#pragma unroll
+        for (int j = 0; j < kSlabs; ++j) {
+            const int slab = tid + j * n_consumers;
+            if (slab < p.slabs_per_row)
+#pragma unroll
+                for (int k = 0; k < kCols; ++k) p.colsum[(size_t)c * p.dim + (size_t)slab * kCols + k] = csum[kColsum ? j : 0][k];
+        }
+    }
+}
+
+// colsum_out[d] = sum over CTAs (in CTA order) of the per-CTA sums; colsum_out[dim] = S.
+__global__ void colsum_reduce_kernel(const double *partial, int n_ctas, int dim, int64_t n_seg,
+                                     const int64_t *n_seg_dev, double *out)
+{
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < dim) {
+        double s = 0.0;
+        for (int c = 0; c < n_ctas; ++c) s += partial[(size_t)c * dim + d];
+        out[d] = s;
+    } else if (d == dim) {
+        out[dim] = (double)(n_seg_dev ? min(*n_seg_dev, n_seg) : n_seg);
+    }
+}
+
+__global__ void colsum_accumulate_kernel(double *acc, const double *colsum, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) acc[i] += colsum[i];
+}
+
+__global__ void colsum_finalize_kernel(const double *acc, int dim, float *mean)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < dim) mean[i] = (float)(acc[i] / acc[dim]);
+}
+
+template <typename EmbT, int kSlabs>
+int launch_typed(aat_ctx *ctx, const PoolParams &p, int grid, size_t smem, bool colsum, cudaStream_t stream)
+{
+    const int threads = p.n_consumers + 32;
+    if (colsum) {
+        AAT_CUDA_CHECK(cudaFuncSetAttribute(pool_kernel<EmbT, kSlabs, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pool_kernel<EmbT, kSlabs, true><<<grid, threads, smem, stream>>>(p);
+    } else {
+        AAT_CUDA_CHECK(cudaFuncSetAttribute(pool_kernel<EmbT, kSlabs, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pool_kernel<EmbT, kSlabs, false><<<grid, threads, smem, stream>>>(p);
+    }
+    (void)ctx;
+    AAT_LAUNCH_CHECK();
+    return AAT_OK;
+}
+
+template <typename EmbT>
+int launch_slabs(aat_ctx *ctx, const PoolParams &p, int slabs, int grid, size_t smem, bool colsum, cudaStream_t stream)
+{
+    switch (slabs) {
+    case 1: return launch_typed<EmbT, 1>(ctx, p, grid, smem, colsum, stream);
+    case 2: return launch_typed<EmbT, 2>(ctx, p, grid, smem, colsum, stream);
+    default: return launch_typed<EmbT, 4>(ctx, p, grid, smem, colsum, stream);
+    }
+}
+
+} // namespace
+
+int pool_scratch_init(aat_ctx *ctx)
+{
+    PoolScratch &ps = ctx->pool;
+    ps.max_ctas = ctx->num_sms * 2; // launch_mean_pool never uses more than two CTAs per SM
+    ps.max_dim = 4096;
+    AAT_CUDA_CHECK(cudaMalloc(&ps.head, sizeof(float) * (size_t)ps.max_ctas * ps.max_dim));
+    AAT_CUDA_CHECK(cudaMalloc(&ps.tail, sizeof(float) * (size_t)ps.max_ctas * ps.max_dim));
+    AAT_CUDA_CHECK(cudaMalloc(&ps.head_flag, sizeof(int) * (size_t)ps.max_ctas));
+    AAT_CUDA_CHECK(cudaMalloc(&ps.tail_flag, sizeof(int) * (size_t)ps.max_ctas));
+    AAT_CUDA_CHECK(cudaMalloc(&ps.colsum, sizeof(double) * (size_t)ps.max_ctas * ps.max_dim));
+    AAT_CUDA_CHECK(cudaMemset(ps.head_flag, 0, sizeof(int) * (size_t)ps.max_ctas));
+    AAT_CUDA_CHECK(cudaMemset(ps.tail_flag, 0, sizeof(int) * (size_t)ps.max_ctas));
+    return AAT_OK;
+}
+
+void pool_scratch_free(aat_ctx *ctx)
+{
+    PoolScratch &ps = ctx->pool;
+    cudaFree(ps.head);
+    cudaFree(ps.tail);
+    cudaFree(ps.head_flag);
+    cudaFree(ps.tail_flag);
+    cudaFree(ps.colsum);
+    ps = PoolScratch{};
+}
+
+int launch_mean_pool(aat_ctx *ctx, const void *emb, int emb_dtype, int64_t n_rows, int32_t dim,
+                     const int64_t *seg_off, int64_t n_seg, const int64_t *n_seg_dev, float *out, double *colsum,
+                     cudaStream_t stream)
+{
+    int esize;
+    switch (emb_dtype) {
+    case AAT_F32: esize = 4; break;
+    case AAT_F16:
+    case AAT_BF16: esize = 2; break;
+    default:
+        AAT_REQUIRE(false, AAT_ERR_UNSUPPORTED, "aat_segment_mean_pool: embedding dtype must be F32, F16 or BF16");
+    }
+    AAT_REQUIRE(dim > 0 && n_rows >= 0 && n_seg >= 0, AAT_ERR_INVALID, "aat_segment_mean_pool: negative size");
+    const int64_t row_bytes = (int64_t)dim * esize;
+    AAT_REQUIRE(row_bytes % 16 == 0, AAT_ERR_UNSUPPORTED,
+                "aat_segment_mean_pool: dim * sizeof(element) = %lld must be a multiple of 16", (long long)row_bytes);
+    AAT_REQUIRE(row_bytes <= 16 * kMaxConsumers * kMaxSlabs && dim <= ctx->pool.max_dim, AAT_ERR_UNSUPPORTED,
+                "aat_segment_mean_pool: dim %d too large (row must be <= %d bytes, dim <= %d)", dim,
+                16 * kMaxConsumers * kMaxSlabs, ctx->pool.max_dim);
+    AAT_REQUIRE((reinterpret_cast<uintptr_t>(emb) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                AAT_ERR_INVALID, "aat_segment_mean_pool: emb_dev and out_dev must be 16-byte aligned");
+    if (n_seg == 0) {
+        if (colsum) AAT_CUDA_CHECK(cudaMemsetAsync(colsum, 0, sizeof(double) * (size_t)(dim + 1), stream));
+        return AAT_OK;
+    }
+    AAT_REQUIRE(emb != nullptr || n_rows == 0, AAT_ERR_INVALID, "aat_segment_mean_pool: emb_dev is NULL");
+    AAT_REQUIRE(seg_off != nullptr && out != nullptr, AAT_ERR_INVALID, "aat_segment_mean_pool: NULL seg_off/out");
+
+    PoolParams p{};
+    p.emb = static_cast<const unsigned char *>(emb);
+    p.seg_off = seg_off;
+    p.n_seg_dev = n_seg_dev;
+    p.out = out;
+    p.head = ctx->pool.head;
+    p.tail = ctx->pool.tail;
+    p.head_flag = ctx->pool.head_flag;
+    p.tail_flag = ctx->pool.tail_flag;
+    p.colsum = ctx->pool.colsum;
+    p.n_rows = n_rows;
+    p.n_seg = n_seg;
+    p.dim = dim;
+    p.row_bytes = (int)row_bytes;
+    p.slabs_per_row = (int)(row_bytes / 16);
+    int consumers = ((p.slabs_per_row + 31) / 32) * 32;
+    int slabs = 1;
+    while (consumers > kMaxConsumers) {
+        slabs *= 2;
+        consumers = (((p.slabs_per_row + slabs - 1) / slabs + 31) / 32) * 32;
+    }
+    p.n_consumers = consumers;
+    p.rows_per_stage = (int)(kStageBytes / row_bytes);
+    if (p.rows_per_stage < 1) p.rows_per_stage = 1;
+    const size_t smem = (size_t)kStages * p.rows_per_stage * row_bytes;
+    // persistent grid: every CTA must be resident at once (cross-CTA carry waits on lower CTA indices)
+    const int ctas_per_sm = (int)((220 * 1024) / (smem + 1024)) < 2 ? 1 : 2;
+    int grid = ctx->num_sms * ctas_per_sm;
+    if (grid > ctx->pool.max_ctas) grid = ctx->pool.max_ctas;
+
+    int rc;
+    const bool want_colsum = colsum != nullptr;
+    if (emb_dtype == AAT_F32)
+        rc = launch_slabs<float>(ctx, p, slabs, grid, smem, want_colsum, stream);
+    else if (emb_dtype == AAT_F16)
+        rc = launch_slabs<__half>(ctx, p, slabs, grid, smem, want_colsum, stream);
+    else
+        rc = launch_slabs<__nv_bfloat16>(ctx, p, slabs, grid, smem, want_colsum, stream);
+    if (rc != AAT_OK) return rc;
+    if (want_colsum) {
+        const int threads = 128;
+        colsum_reduce_kernel<<<(dim + 1 + threads - 1) / threads, threads, 0, stream>>>(ctx->pool.colsum, grid, dim,
+                                                                                        n_seg, n_seg_dev, colsum);
+        AAT_LAUNCH_CHECK();
+    }
+    return AAT_OK;
+}
+
+int launch_colsum_accumulate(double *acc, const double *colsum, int32_t dim, cudaStream_t stream)
+{
+    colsum_accumulate_kernel<<<(dim + 1 + 127) / 128, 128, 0, stream>>>(acc, colsum, dim + 1);
+    AAT_LAUNCH_CHECK();
+    return AAT_OK;
+}
+
+int launch_colsum_finalize(const double *acc, int32_t dim, float *mean, cudaStream_t stream)
+{
+    colsum_finalize_kernel<<<(dim + 127) / 128, 128, 0, stream>>>(acc, dim, mean);
+    AAT_LAUNCH_CHECK();
+    return AAT_OK;
+}
+
+} // namespace aat

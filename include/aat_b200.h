@@ -1,0 +1,220 @@
+/*
+ * aat_b200.h — C ABI of the B200-native tokenization front end.
+ *
+ * Drop-in boundary for the hot path of mrsndmn/audio-adaptive-tokenizer:
+ * log-mel -> adaptive segment boundaries -> ragged per-segment mean-pool.
+ * The reference is pure Python; the binding a maintainer adds is a ctypes stub
+ * (INTEGRATION.md).  Every entry point names the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no C++/torch types; `void *stream` is a cudaStream_t
+ *     (NULL = legacy default stream).
+ *   - return value: 0 = AAT_OK, negative = aat_status; aat_last_error() gives a message
+ *     (thread-local).  No exceptions cross the ABI.
+ *   - `*_dev` pointers are device memory owned by the caller (e.g. torch tensors);
+ *     `*_host` pointers are host memory.  The library never frees or reallocates
+ *     caller memory.  Device entry points are asynchronous on `stream` and
+ *     allocate nothing (safe inside CUDA-graph capture); `aat_host_*` entry
+ *     points copy host<->device themselves and synchronise before returning.
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with
+ *     AAT_ERR_CUDA.
+ *
+ * Packed batch layout ("plan"): a batch of B utterances with n_samples[b] samples each.
+ *   wave      : concatenated samples, utterance b at wave_off[b] = sum_{i<b} n_samples[i]
+ *   mel       : utterance b is a C-contiguous (n_mels, T_b) float32 block starting at
+ *               element n_mels * frame_off[b], T_b = 1 + n_samples[b] / hop
+ *               (for equal lengths this is exactly a [B, n_mels, T] tensor)
+ *   amp       : float32 per mel frame, utterance b at frame_off[b]
+ *   segments  : utterance b owns slots [seg_slot_off[b], seg_slot_off[b+1]) of
+ *               seg_start / seg_len; seg_count[b] of them are valid
+ */
+#ifndef AAT_B200_H
+#define AAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define AAT_B200_VERSION 100 /* 0.1.0 */
+
+typedef enum aat_status {
+    AAT_OK = 0,
+    AAT_ERR_INVALID = -1,     /* bad argument (NULL, negative size, misaligned pointer) */
+    AAT_ERR_UNSUPPORTED = -2, /* configuration outside what the kernels implement   */
+    AAT_ERR_CUDA = -3,        /* CUDA runtime error / no device                      */
+    AAT_ERR_CAPACITY = -4,    /* an output buffer was too small (segments, minima)   */
+    AAT_ERR_TAIL = -5         /* reference would raise: tail longer than min_segment_frames
+                                 (ref:src/aat/tokenizer.py:102-105 broadcast error)  */
+} aat_status;
+
+typedef enum aat_dtype {
+    AAT_F32 = 0,
+    AAT_F64 = 1,
+    AAT_F16 = 2,
+    AAT_BF16 = 3
+} aat_dtype;
+
+/* Constructor arguments of AdaptiveAudioAmplitudeTokenizer (ref:src/aat/tokenizer.py:15-38),
+ * with the two derived frame counts already evaluated by the caller
+ * (milliseconds_to_frames, ref:src/aat/tokenizer.py:94-95). */
+typedef struct aat_config {
+    int32_t sampling_rate;          /* 16000 */
+    int32_t n_fft;                  /* 400 (the only length the FFT kernel implements) */
+    int32_t hop_length;             /* 160; 1..n_fft */
+    int32_t num_mel_filters;        /* 64; 1..128 */
+    int32_t running_mean_points;    /* 12; 1..2048 */
+    int32_t reserved0;
+    int64_t min_segment_frames;     /* 2000 */
+    int64_t max_segment_frames;     /* 24000; > 0 */
+    float max_amplitude_for_minima; /* 15 */
+    int32_t reserved1;
+} aat_config;
+
+typedef struct aat_ctx aat_ctx;   /* per-device constant tables + scratch; immutable after create */
+typedef struct aat_plan aat_plan; /* device-resident layout tables of one batch shape           */
+
+/* ------------------------------------------------------------------ library */
+int aat_version(void);
+const char *aat_last_error(void);
+/* Number of CUDA kernels this library has launched in the calling process (bench.py's gpu_launches). */
+int64_t aat_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------ context
+ * Replaces AdaptiveAudioAmplitudeTokenizer.__init__ (ref:src/aat/tokenizer.py:15-53).
+ * window_host      : n_fft float64, the analysis window (window_function(n_fft,"hann"), ref :51)
+ * mel_filters_host : (n_fft/2+1, num_mel_filters) float64 row-major (mel_filter_bank, ref :41-49)
+ * Both tables are uploaded as given, so the device uses bit-identical constants to the
+ * tokenizer attributes `window_fn` / `mel_filters`. */
+int aat_create(int device, const aat_config *cfg, const double *window_host, const double *mel_filters_host,
+               aat_ctx **out);
+int aat_destroy(aat_ctx *ctx);
+int aat_get_config(const aat_ctx *ctx, aat_config *out);
+
+/* ------------------------------------------------------------------ plan
+ * Layout tables for a batch of n_utts utterances (sizes live on the host, as array shapes
+ * do in the reference).  Creation uploads a few small tables and synchronises; reuse the
+ * plan for every batch of the same shape. */
+int aat_plan_create(aat_ctx *ctx, int32_t n_utts, const int64_t *n_samples_host, aat_plan **out);
+int aat_plan_destroy(aat_plan *plan);
+int64_t aat_plan_total_samples(const aat_plan *plan);
+int64_t aat_plan_total_frames(const aat_plan *plan);    /* sum of T_b                                */
+int64_t aat_plan_total_seg_slots(const aat_plan *plan); /* sum of per-utterance segment capacities   */
+/* Copies host-side copies of the tables: each array has n_utts+1 entries. NULL = skip. */
+int aat_plan_offsets(const aat_plan *plan, int64_t *wave_off_host, int64_t *frame_off_host,
+                     int64_t *seg_slot_off_host);
+
+/* ------------------------------------------------------------------ K1+K2: log-mel
+ * Replaces get_melspec -> transformers.audio_utils.spectrogram(power=2, mel_filters, "log10")
+ * (ref:src/aat/tokenizer.py:107-119, TF:audio_utils.py:769-830): reflect pad n_fft/2, frames of
+ * n_fft at hop, window, real DFT in float64, spectrum rounded to complex64, |.|^2 in float64,
+ * mel projection, max(1e-10, .), log10, float32.
+ * wave_dev   : packed samples, AAT_F32 or AAT_F64
+ * mel_dev    : packed (n_mels, T_b) float32 blocks (see layout above)
+ * amp_dev    : optional (may be NULL) float32 per frame: -10 * mean over mels of the float32
+ *              log-mel, accumulated in the order numpy uses (ref:src/aat/tokenizer.py:67) */
+int aat_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave_dev, int wave_dtype, float *mel_dev,
+               float *amp_dev, void *stream);
+
+/* ------------------------------------------------------------------ K3: boundaries
+ * Replaces find_amplitude_minimas + pretokenize + process_segments_boarders
+ * (ref:src/aat/tokenizer.py:55-92, 121-139, 141-183).  Bit-exact: sequential float32
+ * column mean / cumsum / running mean, strict local maxima with the 1e-5 epsilon,
+ * loudness gate, x hop, append N, merge < min, split > max (np.split clamp semantics), padded tail.
+ * mel_dev        : packed log-mel as written by aat_logmel (or the reference's own mel); may be
+ *                  NULL when amp_dev is given
+ * amp_dev        : optional precomputed amplitude curve (from aat_logmel); NULL = derive from mel_dev
+ * seg_start_dev,
+ * seg_len_dev    : int64, aat_plan_total_seg_slots entries; start sample and length of each segment
+ * seg_count_dev  : int32 [n_utts]
+ * minima_dev     : optional int64, packed per utterance at frame_off[b] (capacity T_b); mel-frame indices
+ * minima_count_dev : optional int32 [n_utts]
+ * status_dev     : int32 [n_utts]; negative = aat_status (AAT_ERR_CAPACITY / AAT_ERR_TAIL) for that utterance,
+ *                  otherwise bit 0 is set when the last segment is the zero-padded tail
+ *                  (ref:src/aat/tokenizer.py:177-181) */
+int aat_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel_dev, const float *amp_dev,
+                   int64_t *seg_start_dev, int64_t *seg_len_dev, int32_t *seg_count_dev, int64_t *minima_dev,
+                   int32_t *minima_count_dev, int32_t *status_dev, void *stream);
+
+/* Replaces process_segments_boarders alone (ref:src/aat/tokenizer.py:141-183) for one utterance:
+ * boarders_dev [n_boarders] int64 -> (seg_start, seg_len)[capacity], *seg_count_dev, *status_dev. */
+int aat_process_boarders(aat_ctx *ctx, int64_t n_samples, const int64_t *boarders_dev, int64_t n_boarders,
+                         int64_t *seg_start_dev, int64_t *seg_len_dev, int64_t capacity, int32_t *seg_count_dev,
+                         int32_t *status_dev, void *stream);
+
+/* Segment lengths (samples) -> CSR offsets in HuBERT-frame units for the pool kernel, on device.
+ * Per-segment encode convention consumed by ref:scripts/mean_hubert_embeddings.py:18-20:
+ * n_i = max(0, (L_i - 400) / 320 + 1) frames (TF:models/hubert/modeling_hubert.py:675-688).
+ * seg_off_dev   : int64 [total_seg_slots + 1]; entries [0, S] are written
+ * n_seg_dev     : int64 [1]; S = total number of segments in the batch
+ * utt_seg_off_dev : optional int64 [n_utts+1]; first packed segment index of each utterance */
+int aat_segment_frame_csr(aat_ctx *ctx, const aat_plan *plan, const int64_t *seg_len_dev,
+                          const int32_t *seg_count_dev, int64_t *seg_off_dev, int64_t *n_seg_dev,
+                          int64_t *utt_seg_off_dev, void *stream);
+
+/* ------------------------------------------------------------------ K4: ragged mean-pool
+ * Replaces `torch.cat([x.mean(dim=1, keepdim=True).to(float32) for x in embs], dim=1)`
+ * (ref:scripts/mean_hubert_embeddings.py:19-20) on the packed layout
+ *   emb_dev [n_rows, dim] row-major (AAT_F32 / AAT_F16 / AAT_BF16) + seg_off_dev [S+1] (frame units).
+ * out_dev   : float32 [S, dim]; an empty segment yields NaN, as torch's mean does
+ * n_seg     : S when n_seg_dev is NULL; otherwise an upper bound and S is read from n_seg_dev[0]
+ * colsum_dev: optional float64 [dim+1]: column sums over the S pooled vectors and, last, S itself
+ *             (input of the dataset-level mean allreduce); overwritten, not accumulated
+ * One pass over emb; dim * sizeof(element) must be a multiple of 16 and emb_dev 16-byte aligned. */
+int aat_segment_mean_pool(aat_ctx *ctx, const void *emb_dev, int emb_dtype, int64_t n_rows, int32_t dim,
+                          const int64_t *seg_off_dev, int64_t n_seg, const int64_t *n_seg_dev, float *out_dev,
+                          double *colsum_dev, void *stream);
+
+/* acc_dev[0..dim] += colsum_dev[0..dim] (float64), for accumulating over batches before the allreduce. */
+int aat_colsum_accumulate(aat_ctx *ctx, double *acc_dev, const double *colsum_dev, int32_t dim, void *stream);
+/* mean_dev[d] = float32(acc_dev[d] / acc_dev[dim]) — after the SUM allreduce of acc_dev over ranks. */
+int aat_colsum_finalize(aat_ctx *ctx, const double *acc_dev, int32_t dim, float *mean_dev, void *stream);
+
+/* ------------------------------------------------------------------ host-buffer entry points
+ * Same operations for callers that hold numpy arrays, exactly like the reference's methods:
+ * the library stages host<->device copies in its own scratch and synchronises. */
+
+/* get_melspec (ref:src/aat/tokenizer.py:107): wave_host [n_samples] -> mel_host (n_mels, 1+n/hop) float32 */
+int aat_host_logmel(aat_ctx *ctx, const void *wave_host, int wave_dtype, int64_t n_samples, float *mel_host);
+
+/* find_amplitude_minimas (ref:src/aat/tokenizer.py:55): mel_host (n_mels, n_frames) C-contiguous float32
+ * -> minima_host (capacity n_frames), *n_minima_host */
+int aat_host_find_minimas(aat_ctx *ctx, const float *mel_host, int64_t n_frames, int64_t *minima_host,
+                          int64_t *n_minima_host);
+
+/* process_segments_boarders (ref:src/aat/tokenizer.py:141) */
+int aat_host_process_boarders(aat_ctx *ctx, int64_t n_samples, const int64_t *boarders_host, int64_t n_boarders,
+                              int64_t *seg_start_host, int64_t *seg_len_host, int64_t capacity,
+                              int64_t *n_segments_host, int32_t *padded_tail_host);
+
+/* tokenize / pretokenize+process_segments_boarders (ref:src/aat/tokenizer.py:121-200) for one utterance.
+ * mel_in_host  : optional precomputed mel (the `melspec=` argument); NULL = compute from wave
+ * mel_out_host : optional, receives the mel that was used
+ * minima_host  : optional (capacity n_frames)
+ * padded_tail_host : optional; 1 when the last segment is the zero-padded tail */
+int aat_host_tokenize(aat_ctx *ctx, const void *wave_host, int wave_dtype, int64_t n_samples,
+                      const float *mel_in_host, float *mel_out_host, int64_t *minima_host,
+                      int64_t *n_minima_host, int64_t *seg_start_host, int64_t *seg_len_host, int64_t capacity,
+                      int64_t *n_segments_host, int32_t *padded_tail_host);
+
+/* mean_hubert_embeddings pooling (ref:scripts/mean_hubert_embeddings.py:19-20) on host buffers */
+int aat_host_mean_pool(aat_ctx *ctx, const void *emb_host, int emb_dtype, int64_t n_rows, int32_t dim,
+                       const int64_t *seg_off_host, int64_t n_seg, float *out_host, double *colsum_host);
+
+/* Upper bound on the segments one utterance can produce (slot capacity used by plans). */
+int64_t aat_segment_capacity(const aat_config *cfg, int64_t n_samples);
+/* 1 + n_samples / hop (TF:audio_utils.py:778 with centre padding). */
+int64_t aat_num_mel_frames(const aat_config *cfg, int64_t n_samples);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* AAT_B200_H */
