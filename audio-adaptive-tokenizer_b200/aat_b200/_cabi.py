@@ -61,6 +61,8 @@ SIGNATURES = {
     "aat_kernel_launch_count": (c_i64, []),
     "aat_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(AatConfig), c_void, c_void, ctypes.POINTER(c_void)]),
     "aat_destroy": (ctypes.c_int, [c_void]),
+    "aat_profile_enable": (ctypes.c_int, [c_void, ctypes.c_uint32]),
+    "aat_profile_summary": (ctypes.c_int, [c_void, c_void, c_void]),
     "aat_get_config": (ctypes.c_int, [c_void, ctypes.POINTER(AatConfig)]),
     "aat_plan_create": (ctypes.c_int, [c_void, c_i32, c_void, ctypes.POINTER(c_void)]),
     "aat_plan_destroy": (ctypes.c_int, [c_void]),
@@ -122,6 +124,24 @@ def check(status: int) -> None:
     if status != AAT_OK:
         msg = lib().aat_last_error()
         raise AatError(status, msg.decode("utf-8", "replace") if msg else "")
+
+
+KERNEL_NAMES = ("logmel", "boundaries", "frame_csr", "pool")
+
+
+def profile_enable(ctx_handle, names=KERNEL_NAMES) -> None:
+    mask = 0
+    for n in names:
+        mask |= 1 << KERNEL_NAMES.index(n)
+    check(lib().aat_profile_enable(ctx_handle, mask))
+
+
+def profile_summary(ctx_handle) -> dict:
+    """{kernel name: (launches, total_ms)} of the launches recorded since the last enable."""
+    n = (ctypes.c_int64 * len(KERNEL_NAMES))()
+    ms = (ctypes.c_double * len(KERNEL_NAMES))()
+    check(lib().aat_profile_summary(ctx_handle, n, ms))
+    return {name: (int(n[i]), float(ms[i])) for i, name in enumerate(KERNEL_NAMES)}
 
 
 def launch_count() -> int:

@@ -64,6 +64,14 @@ struct PoolScratch {
     double *colsum = nullptr;   // [max_ctas, max_dim + 1]
 };
 
+// Event-pair ring for aat_profile_* (created lazily on enable).
+struct Profiler {
+    uint32_t mask = 0;
+    std::vector<cudaEvent_t> start, stop;
+    std::vector<int> kernel;
+    size_t used = 0;
+};
+
 } // namespace aat
 
 struct aat_ctx {
@@ -80,6 +88,7 @@ struct aat_ctx {
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
     cudaStream_t host_stream = nullptr;
+    aat::Profiler prof{};
 };
 
 struct aat_plan {
@@ -120,5 +129,27 @@ int pool_scratch_init(aat_ctx *ctx);
 void pool_scratch_free(aat_ctx *ctx);
 
 constexpr int kMelFramesPerTile = 16; // frames one CTA of the log-mel kernel produces
+
+// RAII helper: records an event pair around one launch when profiling is enabled for `id`.
+struct ProfileScope {
+    aat_ctx *ctx;
+    cudaStream_t stream;
+    long slot = -1;
+    ProfileScope(aat_ctx *c, int id, cudaStream_t s) : ctx(c), stream(s)
+    {
+        Profiler &p = c->prof;
+        if ((p.mask >> id) & 1u) {
+            if (p.used < p.start.size()) {
+                slot = (long)p.used++;
+                p.kernel[slot] = id;
+                cudaEventRecord(p.start[slot], stream);
+            }
+        }
+    }
+    ~ProfileScope()
+    {
+        if (slot >= 0) cudaEventRecord(ctx->prof.stop[slot], stream);
+    }
+};
 
 } // namespace aat

@@ -353,6 +353,7 @@ int launch_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel, cons
     p.max_amp = ctx->cfg.max_amplitude_for_minima;
     const size_t smem = sizeof(float) * (size_t)(kChunk + p.npts + 2 + kChunk) + sizeof(int) * (size_t)kChunk;
     AAT_CUDA_CHECK(cudaFuncSetAttribute(boundaries_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfileScope prof(ctx, AAT_K_BOUNDARIES, stream);
     boundaries_kernel<<<plan->n_utts, kThreads, smem, stream>>>(p);
     AAT_LAUNCH_CHECK();
     return AAT_OK;
@@ -372,11 +373,11 @@ int launch_process_boarders(aat_ctx *ctx, int64_t n_samples, const int64_t *boar
 int launch_segment_frame_csr(aat_ctx *ctx, const aat_plan *plan, const int64_t *seg_len, const int32_t *seg_count,
                              int64_t *seg_off, int64_t *n_seg, int64_t *utt_seg_off, cudaStream_t stream)
 {
-    (void)ctx;
     const size_t smem = sizeof(int64_t) * 2 * (size_t)(plan->n_utts + 1);
     AAT_REQUIRE(smem <= 200 * 1024, AAT_ERR_UNSUPPORTED, "aat_segment_frame_csr: at most 12799 utterances per plan");
     AAT_CUDA_CHECK(
         cudaFuncSetAttribute(segment_frame_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfileScope prof(ctx, AAT_K_FRAME_CSR, stream);
     segment_frame_csr_kernel<<<1, kCsrThreads, smem, stream>>>(plan->n_utts, plan->d_seg_slot_off, seg_len, seg_count,
                                                                seg_off, n_seg, utt_seg_off);
     AAT_LAUNCH_CHECK();

@@ -211,7 +211,45 @@ int aat_destroy(aat_ctx *ctx)
     if (ctx->dev_scratch) cudaFree(ctx->dev_scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->host_stream) cudaStreamDestroy(ctx->host_stream);
+    for (cudaEvent_t e : ctx->prof.start) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->prof.stop) cudaEventDestroy(e);
     delete ctx;
+    return AAT_OK;
+}
+
+int aat_profile_enable(aat_ctx *ctx, uint32_t kernel_mask)
+{
+    AAT_REQUIRE(ctx, AAT_ERR_INVALID, "aat_profile_enable: NULL context");
+    DeviceGuard guard(ctx->device);
+    Profiler &p = ctx->prof;
+    constexpr size_t kSlots = 16384;
+    if (kernel_mask != 0 && p.start.empty()) {
+        p.start.resize(kSlots);
+        p.stop.resize(kSlots);
+        p.kernel.assign(kSlots, 0);
+        for (size_t i = 0; i < kSlots; ++i) {
+            AAT_CUDA_CHECK(cudaEventCreate(&p.start[i]));
+            AAT_CUDA_CHECK(cudaEventCreate(&p.stop[i]));
+        }
+    }
+    p.mask = kernel_mask;
+    p.used = 0;
+    return AAT_OK;
+}
+
+int aat_profile_summary(aat_ctx *ctx, int64_t *launches, double *total_ms)
+{
+    AAT_REQUIRE(ctx && launches && total_ms, AAT_ERR_INVALID, "aat_profile_summary: NULL argument");
+    DeviceGuard guard(ctx->device);
+    Profiler &p = ctx->prof;
+    for (int k = 0; k < AAT_K_COUNT; ++k) launches[k] = 0, total_ms[k] = 0.0;
+    for (size_t i = 0; i < p.used; ++i) {
+        AAT_CUDA_CHECK(cudaEventSynchronize(p.stop[i]));
+        float ms = 0.f;
+        AAT_CUDA_CHECK(cudaEventElapsedTime(&ms, p.start[i], p.stop[i]));
+        launches[p.kernel[i]] += 1;
+        total_ms[p.kernel[i]] += ms;
+    }
     return AAT_OK;
 }
 

@@ -267,6 +267,7 @@ int launch_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave, int wave
     p.nnz = ctx->mel.nnz;
     p.stage_len = (kFrames - 1) * p.hop + kNfft;
     const size_t smem = logmel_smem_bytes(p.hop, p.n_mels, p.nnz);
+    ProfileScope prof(ctx, AAT_K_LOGMEL, stream);
     if (wave_dtype == AAT_F32) {
         AAT_CUDA_CHECK(cudaFuncSetAttribute(logmel_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         logmel_kernel<float><<<plan->mel_tiles, kThreads, smem, stream>>>(p);

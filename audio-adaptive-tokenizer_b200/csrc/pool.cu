@@ -579,12 +579,15 @@ int launch_mean_pool(aat_ctx *ctx, const void *emb, int emb_dtype, int64_t n_row
 
     int rc;
     const bool want_colsum = colsum != nullptr;
-    if (emb_dtype == AAT_F32)
-        rc = launch_slabs<float>(ctx, p, slabs, grid, smem, want_colsum, stream);
-    else if (emb_dtype == AAT_F16)
-        rc = launch_slabs<__half>(ctx, p, slabs, grid, smem, want_colsum, stream);
-    else
-        rc = launch_slabs<__nv_bfloat16>(ctx, p, slabs, grid, smem, want_colsum, stream);
+    {
+        ProfileScope prof(ctx, AAT_K_POOL, stream); // the streaming kernel alone (not the colsum reduce)
+        if (emb_dtype == AAT_F32)
+            rc = launch_slabs<float>(ctx, p, slabs, grid, smem, want_colsum, stream);
+        else if (emb_dtype == AAT_F16)
+            rc = launch_slabs<__half>(ctx, p, slabs, grid, smem, want_colsum, stream);
+        else
+            rc = launch_slabs<__nv_bfloat16>(ctx, p, slabs, grid, smem, want_colsum, stream);
+    }
     if (rc != AAT_OK) return rc;
     if (want_colsum) {
         const int threads = 128;

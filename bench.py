@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""Benchmark of the tokenization front end: audio-hours/s tokenized (log-mel + segment + pool).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3|c4]
+
+A *step* is one pass of the whole hot path over one batch of synthetic input: K1+K2 log-mel,
+K3 boundaries, frame-CSR, K4 mean-pool (with the column-sum epilogue feeding the dataset mean).
+The default workload is BASELINE.json configs[1]: 64 x 16 s utterances, HuBERT-base 768-d embeddings
+on one B200; with N GPUs every rank runs that batch on its own shard (weak scaling, no data-path
+collective) and the ranks meet once, in the dataset-mean allreduce, at the end of the timed region.
+
+One JSON line on stdout (rank 0).  `value` = whole-job audio-hours/s with inputs resident in HBM;
+`e2e` = the same metric through the public batched API with HOST (pinned) buffers, H2D/D2H inside the
+timed region; `roofline` = the pool kernel's algorithmic bytes / its CUDA-event duration measured in
+the timed region, against MEASURED_PEAKS.json; `cpu_baseline` = the oracle port of the reference's
+CPU path on a bounded sample.  `--impl reference` times that CPU path alone with all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "audio-adaptive-tokenizer_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "audio_hours_per_sec_tokenized"
+UNIT = "audio-hours/s"
+WORKLOADS = {
+    # name: (batch, samples per utterance, embedding dim, BASELINE.json config index)
+    "c2": (64, 256_000, 768, 1),
+    "c3": (256, 320_000, 1024, 2),
+    "c4": (8, 28_800_000, 768, 3),
+}
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def workload_name(name):
+    b, n, d, idx = WORKLOADS[name]
+    return f"configs[{idx}]: batch {b} x {n / 16000:g} s synthetic 16 kHz utterances, {d}-d HuBERT-shaped embeddings"
+
+
+def make_waves(name, rank):
+    from aat_b200 import synth
+
+    b, n, _, idx = WORKLOADS[name]
+    if name == "c4":  # a 30-min stream takes seconds to synthesise: tile two distinct streams
+        base = [synth.bursty_speech(n, synth.seed_for(4, i)) for i in range(2)]
+        return [base[i % 2] for i in range(b)]
+    return [synth.bursty_speech(n, synth.seed_for(idx + 1, rank * b + i)) for i in range(b)]
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.samples = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.samples.append(parts)
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, reasons, sm_max = [], set(), None
+        for p in self.samples:
+            try:
+                sm.append(float(p[0]))
+                sm_max = float(p[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": sm_max, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- CPU baseline
+def _cpu_tokenize_one(args):
+    """Reference CPU path for one utterance: log-mel + minima + merge/split + per-segment mean-pool."""
+    wave, dim, seed = args
+    import torch
+
+    from aat_b200 import synth
+    from oracle import ref_port
+
+    tok = _cpu_tokenize_one.tok = getattr(_cpu_tokenize_one, "tok", None) or ref_port.RefTokenizer()
+    lengths, _, _ = tok.segment_lengths(wave)
+    frames = synth.hubert_frames(lengths)
+    g = torch.Generator().manual_seed(seed)
+    embs = [torch.randn(1, int(f), dim, generator=g) for f in frames]
+    t0 = time.perf_counter()
+    ref_port.mean_pool_segments(embs)
+    return time.perf_counter() - t0
+
+
+def _cpu_worker_init():
+    """One BLAS / torch thread per worker process: the pool already uses every core."""
+    try:
+        import threadpoolctl
+
+        _cpu_worker_init.limit = threadpoolctl.threadpool_limits(1)
+    except Exception:
+        pass
+    import torch
+
+    torch.set_num_threads(1)
+
+
+def cpu_reference_throughput(name, n_utts, processes, pool=None):
+    """Audio-hours/s of the oracle port (reference algorithm, same third-party calls) on host cores.
+    A worker pool created by the caller is reused so that its start-up is not billed to the reference."""
+    from aat_b200 import synth
+
+    _, n, dim, idx = WORKLOADS[name]
+    n = min(n, 4_800_000)  # 30-min streams: time a 5-min slice per item, throughput is linear in length
+    waves = [(synth.bursty_speech(n, synth.seed_for(idx + 1, 5000 + i)).astype(np.float64), dim, i) for i in range(n_utts)]
+    _cpu_tokenize_one(waves[0])  # warm imports
+    t0 = time.perf_counter()
+    if pool is not None:
+        pool.map(_cpu_tokenize_one, waves, chunksize=1)
+    else:
+        for w in waves:
+            _cpu_tokenize_one(w)
+    dt = time.perf_counter() - t0
+    return (n_utts * n / 16000 / 3600) / dt, dt
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path (oracle port: the reference
+    is pure Python and /root/reference does not travel), all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    _, n, dim, _ = WORKLOADS[args.workload]
+    # size the per-step sample so that warm-up + K steps end within ~2.5 minutes whatever K is
+    _, t1 = cpu_reference_throughput(args.workload, 1, 1)
+    budget_s = 150.0
+    per_step = int(budget_s * cores / max(t1, 1e-3) / max(args.steps + args.warmup, 1))
+    per_step = max(1, min(4 * cores, per_step))
+    procs = min(cores, per_step)
+    import multiprocessing as mp
+
+    with mp.get_context("fork").Pool(procs, initializer=_cpu_worker_init) as pool:
+        for _ in range(args.warmup):
+            cpu_reference_throughput(args.workload, per_step, procs, pool)
+        vals, t_total = [], 0.0
+        for _ in range(args.steps):
+            v, dt = cpu_reference_throughput(args.workload, per_step, procs, pool)
+            vals.append(v)
+            t_total += dt
+    value = float(np.mean(vals))
+    sample = f"{per_step} utterances of {min(n, 4_800_000) / 16000:g} s per step, multiprocessing.Pool({procs})"
+    cores = procs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload), "host": "cpu"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from aat_b200 import AdaptiveAudioAmplitudeTokenizer, _cabi
+    from aat_b200.pooling import DatasetMean
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, N, D, _ = WORKLOADS[args.workload]
+    tok = AdaptiveAudioAmplitudeTokenizer(device=local_rank)
+    waves = make_waves(args.workload, rank)
+    batch = tok.plan([N] * B)
+    host_wave = torch.from_numpy(np.concatenate(waves)).pin_memory()
+    R = args.rotate  # rotating input sets so that no step finds its inputs in the 126 MB L2
+    wave_sets = [host_wave.to(dev) for _ in range(R)]
+
+    # one untimed pass fixes the segmentation, hence the embedding shape
+    batch.logmel(wave_sets[0]), batch.boundaries(), batch.frame_csr()
+    torch.cuda.synchronize()
+    assert int(batch.status.min().item()) >= 0
+    n_seg = int(batch.n_seg.item())
+    n_rows = int(batch.seg_off[n_seg].item())
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    emb_sets = [torch.randn(n_rows, D, device=dev, generator=gen) for _ in range(R)]
+    out = torch.empty(batch.total_seg_slots, D, device=dev)
+    dm = DatasetMean(D, device=local_rank)
+    audio_hours_per_step = B * N / 16000 / 3600
+
+    def step(i):
+        s = i % R
+        batch.logmel(wave_sets[s])
+        batch.boundaries()
+        batch.frame_csr()
+        batch.pool(emb_sets[s], out, colsum=dm.colsum_buffer())
+        dm.accumulate()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+
+    # ---- timed region: K steps + the one collective
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    _cabi.profile_enable(batch.ctx.handle, ("pool",))
+    launches0 = _cabi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step(i)
+    dm.allreduce()
+    mean_vec = dm.result()
+    ev1.record()
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = _cabi.launch_count() - launches0
+    prof = _cabi.profile_summary(batch.ctx.handle)
+    _cabi.profile_enable(batch.ctx.handle, ())
+    clocks = sampler.stop()
+    assert bool(torch.isfinite(mean_vec).all())
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = world * audio_hours_per_step * args.steps / (elapsed_ms / 1e3)
+
+    # ---- per-kernel breakdown (untimed extra pass with every kernel instrumented)
+    _cabi.profile_enable(batch.ctx.handle, _cabi.KERNEL_NAMES)
+    for i in range(min(args.steps, 50)):
+        step(i)
+    torch.cuda.synchronize()
+    breakdown = {k: (ms / n * 1e3 if n else None) for k, (n, ms) in _cabi.profile_summary(batch.ctx.handle).items()}
+    _cabi.profile_enable(batch.ctx.handle, ())
+
+    # ---- roofline of the pool kernel (algorithmic bytes)
+    pool_launches, pool_ms = prof["pool"]
+    pool_bytes = n_rows * D * 4 + n_seg * D * 4 + (n_seg + 1) * 8
+    pool_us = pool_ms / max(pool_launches, 1) * 1e3
+    achieved = pool_bytes / (pool_us * 1e-6) / 1e9
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+    else:
+        peak, peak_src = FALLBACK_HBM_GBS, "fallback of B200_PROFILING.md"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "pool_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload)
+    roofline = {"kernel": "pool_kernel<float,1,true>", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "bytes_per_launch": pool_bytes,
+                "us_per_launch": pool_us, "launches_timed": pool_launches, "peak_source": peak_src}
+
+    # ---- e2e: same step through the public batched API with host (pinned) buffers
+    e2e = run_e2e(torch, dev, tok, batch, host_wave, emb_sets[0], out, n_seg, D, args, world, audio_hours_per_step)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 (log-mel) / f32 (boundaries, pool)", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload), "batch_per_gpu": B, "samples_per_utterance": N, "dim": D,
+                   "segments_per_batch": n_seg, "hubert_frames_per_batch": n_rows,
+                   "parallelism": f"utterance-sharded dp{world}, one allreduce of {D + 1} f64",
+                   "l2": f"inputs rotate over {R} buffer sets ({R * (host_wave.numel() * 4 + n_rows * D * 4) / 1e6:.0f} MB) > 126 MB L2"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "kernel_us": breakdown,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            n_sample = 64 if args.workload != "c4" else 8
+            v, dt = cpu_reference_throughput(args.workload, n_sample, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"{n_sample} utterances of the workload, single process "
+                                              f"(datasets.map without num_proc), {dt:.1f} s of CPU work"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(torch, dev, tok, batch, host_wave, emb_dev, out, n_seg, D, args, world, audio_hours_per_step):
+    """Host buffers in, host buffers out: every step copies its waveforms and embeddings from pinned host
+    memory, runs the path, and reads segment lengths and pooled vectors back.  Two streams ping-pong so
+    the next step's H2D overlaps this step's kernels (throughput metric over K steps)."""
+    import torch.distributed as dist
+
+    host_emb = emb_dev.cpu().pin_memory()
+    n_slots = batch.total_seg_slots
+    bufs = []
+    for _ in range(2):
+        bufs.append({
+            "stream": torch.cuda.Stream(device=dev),
+            "wave": torch.empty_like(host_wave, device=dev),
+            "emb": torch.empty_like(emb_dev),
+            "pooled_host": torch.empty((n_seg, D), dtype=torch.float32).pin_memory(),
+            "len_host": torch.empty(n_slots, dtype=torch.int64).pin_memory(),
+            "count_host": torch.empty(batch.n_utts, dtype=torch.int32).pin_memory(),
+        })
+    h2d = host_wave.numel() * 4 + host_emb.numel() * 4
+    d2h = n_seg * D * 4 + n_slots * 8 + batch.n_utts * 4
+    compute = torch.cuda.Stream(device=dev)  # kernels share the plan's output buffers: keep them on one stream
+
+    def e2e_step(i):
+        b = bufs[i % 2]
+        with torch.cuda.stream(b["stream"]):
+            b["wave"].copy_(host_wave, non_blocking=True)
+            b["emb"].copy_(host_emb, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record()
+        with torch.cuda.stream(compute):
+            compute.wait_event(ready)
+            batch.logmel(b["wave"]), batch.boundaries(), batch.frame_csr()
+            batch.pool(b["emb"], out)
+            b["pooled_host"].copy_(out[:n_seg], non_blocking=True)
+            b["len_host"].copy_(batch.seg_len, non_blocking=True)
+            b["count_host"].copy_(batch.seg_count, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+        b["stream"].wait_event(done)  # the next reuse of this buffer pair waits for this step
+
+    steps = max(4, min(args.steps, 40))
+    for i in range(2):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(steps):
+        e2e_step(i)
+    compute.synchronize()
+    torch.cuda.synchronize()
+    ev1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    t = torch.tensor([wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall = float(t.item())
+    assert int(bufs[0]["count_host"].sum()) == n_seg
+    return {"value": world * audio_hours_per_step * steps / wall, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": 1e3 * wall / steps,
+            "api": "PackedBatch.logmel/boundaries/frame_csr/pool on pinned host tensors, 2-deep copy/compute pipeline"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
+    ap.add_argument("--rotate", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = 3 if args.steps is None else args.steps
+        args.warmup = 1 if args.warmup is None else args.warmup
+        run_reference(args)
+    else:
+        args.steps = 200 if args.steps is None else args.steps
+        args.warmup = max(3, 10 if args.warmup is None else args.warmup)
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

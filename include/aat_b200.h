@@ -85,6 +85,24 @@ const char *aat_last_error(void);
 /* Number of CUDA kernels this library has launched in the calling process (bench.py's gpu_launches). */
 int64_t aat_kernel_launch_count(void);
 
+/* ------------------------------------------------------------------ profiling
+ * Optional CUDA-event timing of the library's own kernels, recorded on the launching stream
+ * immediately before and after each launch (so a caller can attribute time to one kernel even
+ * though the launch sits inside a C call).  Kernel ids: */
+typedef enum aat_kernel_id {
+    AAT_K_LOGMEL = 0,
+    AAT_K_BOUNDARIES = 1,
+    AAT_K_FRAME_CSR = 2,
+    AAT_K_POOL = 3,
+    AAT_K_COUNT = 4
+} aat_kernel_id;
+/* kernel_mask: bit i enables kernel id i; 0 disables.  Resets the counters.  Must not be enabled
+ * while a stream capture is in progress.  At most 16384 launches are recorded per enable. */
+int aat_profile_enable(aat_ctx *ctx, uint32_t kernel_mask);
+/* Synchronises the recorded events and returns, per kernel id, the number of recorded launches and
+ * the sum of their durations in milliseconds (arrays of AAT_K_COUNT entries). */
+int aat_profile_summary(aat_ctx *ctx, int64_t *launches, double *total_ms);
+
 /* ------------------------------------------------------------------ context
  * Replaces AdaptiveAudioAmplitudeTokenizer.__init__ (ref:src/aat/tokenizer.py:15-53).
  * window_host      : n_fft float64, the analysis window (window_function(n_fft,"hann"), ref :51)

@@ -1,0 +1,464 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the oracle and the committed goldens.
+
+Bars (BASELINE.json north_star):
+  * segment boundaries / offsets: bit-exact when fed the reference's mel frames;
+  * log-mel: |a - b| <= 1e-5 * max(1, |ref|) elementwise (float32) — in practice the float64 pipeline
+    is bit-identical on > 99.99 % of the elements, which the tests also assert;
+  * pooled embeddings: ||a - b||_2 / ||ref||_2 <= 1e-5 per segment vector and
+    |a - b| <= 1e-5 * max(|ref|, rms(ref)) elementwise.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+MEL_TOL = 1e-5
+POOL_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def tok():
+    from aat_b200 import AdaptiveAudioAmplitudeTokenizer
+
+    return AdaptiveAudioAmplitudeTokenizer()
+
+
+def assert_mel_close(got, ref, min_exact=0.9999):
+    assert got.shape == ref.shape and got.dtype == np.float32
+    err = np.abs(got.astype(np.float64) - ref.astype(np.float64))
+    assert np.all(err <= MEL_TOL * np.maximum(1.0, np.abs(ref))), float(err.max())
+    assert np.mean(got == ref) >= min_exact, float(np.mean(got == ref))
+
+
+def assert_pooled_close(got, ref):
+    got = np.asarray(got, dtype=np.float64).reshape(-1, ref.shape[-1])
+    ref = np.asarray(ref, dtype=np.float64).reshape(-1, ref.shape[-1])
+    assert got.shape == ref.shape
+    norm = np.linalg.norm(ref, axis=1)
+    rel = np.linalg.norm(got - ref, axis=1) / np.where(norm > 0, norm, 1.0)
+    assert rel.max() <= POOL_TOL, float(rel.max())
+    rms = np.sqrt(np.mean(ref * ref, axis=1, keepdims=True))
+    assert np.all(np.abs(got - ref) <= POOL_TOL * np.maximum(np.abs(ref), rms))
+
+
+# ----------------------------------------------------------------------------------------- K1 + K2
+MEL_CASES = ["c1_10s", "c2_16s_u0", "c2_16s_znorm", "silence_2s", "edge_100", "edge_201", "edge_1919", "edge_1920",
+             "edge_1999", "edge_2000", "edge_2080"]
+
+
+@pytest.mark.parametrize("case", MEL_CASES)
+def test_logmel_matches_reference_golden(tok, golden, case):
+    got = tok.get_melspec(golden.wave(case))
+    assert_mel_close(got, golden.get(case, "mel"))
+
+
+def test_logmel_other_dtypes_follow_float64_promotion(tok, golden):
+    from oracle import restate
+
+    wave = golden.wave("c1_10s")[:40000]
+    i16 = np.round(wave * 20000).astype(np.int16)
+    assert_mel_close(tok.get_melspec(i16), restate.logmel(i16))
+    f16 = wave.astype(np.float16)
+    assert_mel_close(tok.get_melspec(f16), restate.logmel(f16))
+
+
+def test_logmel_argument_errors(tok):
+    with pytest.raises(ValueError):
+        tok.get_melspec(np.zeros((2, 100)))
+    with pytest.raises(ValueError):
+        tok.get_melspec(np.zeros(0))
+
+
+def test_logmel_tiny_inputs_reflect_repeatedly(tok):
+    """N <= 200 makes numpy's reflect padding wrap several times."""
+    from oracle import restate
+
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 3, 7, 100, 159, 160, 161, 199, 200, 201, 399, 400, 401):
+        w = rng.standard_normal(n)
+        if n == 1:
+            continue  # np.pad(mode="reflect") on a single sample is ill-defined across numpy versions
+        assert_mel_close(tok.get_melspec(w), restate.logmel(w), min_exact=0.999)
+
+
+# ----------------------------------------------------------------------------------------- K3
+@pytest.mark.parametrize("case", MEL_CASES)
+def test_minima_bit_exact_on_reference_mel(tok, golden, case):
+    got = tok.find_amplitude_minimas(golden.get(case, "mel"))
+    assert got.dtype == np.int64
+    assert np.array_equal(got, golden.get(case, "minima"))
+
+
+@pytest.mark.parametrize("case", MEL_CASES)
+def test_segments_bit_exact_on_reference_mel(tok, golden, case):
+    wave = golden.wave(case)
+    boarders, mel = tok.pretokenize(wave, melspec=golden.get(case, "mel"))
+    assert boarders == golden.get(case, "boarders").tolist()
+    segs = tok.process_segments_boarders(wave, boarders)
+    assert [s.shape[-1] for s in segs] == golden.get(case, "lengths").tolist()
+    assert tok.segment_lengths(wave, melspec=golden.get(case, "mel")).tolist() == golden.get(case, "lengths").tolist()
+
+
+ALL_CASES = MEL_CASES + ["c2_16s_u1", "c3_20s", "noise_10s", "edge_24000", "edge_24001", "edge_25999", "edge_26000",
+                         "edge_48000", "edge_50000"]
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_end_to_end_tokenize_matches_reference(tok, golden, case):
+    """Own mel -> own boundaries: must reproduce the reference's segment lengths."""
+    from aat_b200 import AudioWaveform
+
+    wave = golden.wave(case)
+    segments, mel = tok.tokenize(AudioWaveform(wave, 16000))
+    assert [s.waveform.shape[-1] for s in segments] == golden.get(case, "lengths").tolist()
+    assert mel.shape == tuple(golden.cases[case]["mel_shape"])
+    boarders, _ = tok.pretokenize(wave)
+    assert boarders == golden.get(case, "boarders").tolist()
+    # segments are views of the caller's array except the zero-padded tail
+    total = sum(s.waveform.shape[-1] for s in segments)
+    assert total >= wave.shape[-1]
+    if total == wave.shape[-1]:
+        assert all(np.shares_memory(s.waveform, wave) for s in segments if s.waveform.size)
+
+
+def test_min_greater_than_max_configuration(golden):
+    from aat_b200 import AdaptiveAudioAmplitudeTokenizer
+
+    t = AdaptiveAudioAmplitudeTokenizer(min_segment_duration_milliseconds=500, max_segment_duration_milliseconds=250)
+    wave = golden.wave("minmax_16s")
+    assert t.segment_lengths(wave).tolist() == golden.get("minmax_16s", "lengths").tolist()
+
+
+SM_CASES = ["sm_25000", "sm_49000", "sm_48000", "sm_160000", "sm_merge_a", "sm_merge_b", "sm_100", "sm_1999",
+            "sm_mm_20000", "sm_mm_12000", "sm_mm_9000", "sm_mm_17000"]
+
+
+@pytest.mark.parametrize("case", SM_CASES)
+def test_state_machine_known_answers(golden, case):
+    from aat_b200 import AdaptiveAudioAmplitudeTokenizer
+
+    info = golden.cases[case]
+    t = AdaptiveAudioAmplitudeTokenizer(
+        min_segment_duration_milliseconds=info["min_segment_frames"] / 16, max_segment_duration_milliseconds=info["max_segment_frames"] / 16)
+    assert (t.min_segment_frames, t.max_segment_frames) == (info["min_segment_frames"], info["max_segment_frames"])
+    wave = np.zeros(info["n_samples"])
+    segs = t.process_segments_boarders(wave, golden.get(case, "boarders").tolist())
+    assert [s.shape[-1] for s in segs] == golden.get(case, "lengths").tolist()
+
+
+def test_state_machine_matches_oracle_on_random_boarders(c_oracle):
+    from aat_b200 import AdaptiveAudioAmplitudeTokenizer
+
+    rng = np.random.default_rng(11)
+    for min_ms, max_ms in ((125, 1500), (500, 250), (10, 30), (1000, 1000)):
+        t = AdaptiveAudioAmplitudeTokenizer(min_segment_duration_milliseconds=min_ms, max_segment_duration_milliseconds=max_ms)
+        for _ in range(25):
+            n = int(rng.integers(1, 400000))
+            k = int(rng.integers(0, 40))
+            boarders = np.sort(rng.integers(0, n, size=k)).tolist() + [n]
+            want_s, want_l, _ = c_oracle.state_machine(n, boarders, t.min_segment_frames, t.max_segment_frames)
+            starts, lengths, _ = t._process_boarders(n, boarders)
+            assert lengths.tolist() == want_l.tolist() and starts.tolist() == want_s.tolist()
+
+
+def test_tail_longer_than_min_raises_like_reference(tok):
+    with pytest.raises(ValueError):
+        tok.process_segments_boarders(np.zeros(10000), [5000])
+
+
+def test_tokenize_assertions(tok):
+    from aat_b200 import AudioWaveform
+
+    with pytest.raises(AssertionError):
+        tok.tokenize(AudioWaveform(np.zeros(16000), 8000))
+    # stale intended invariants of ref:src/aat/tokenizer_test.py:18-34: silence has no minima
+    boarders, mel = tok.pretokenize(np.zeros(32000))
+    assert boarders == [32000] and mel.shape == (64, 201) and np.all(mel == -10.0)
+    segs, _ = tok.tokenize(AudioWaveform(np.zeros(32000), 16000))
+    assert [s.waveform.shape[-1] for s in segs] == [24000, 8000]
+
+
+def test_segment_length_invariants_on_bursty_audio(tok):
+    """The four inequalities of ref:src/aat/tokenizer_test.py:46-52, on synthetic speech-like audio."""
+    from aat_b200 import AudioWaveform, synth
+
+    segs, _ = tok.tokenize(AudioWaveform(synth.bursty_speech(256000, 77), 16000))
+    frames = [s.waveform.shape[0] for s in segs]
+    assert min(frames) != max(frames)
+    assert min(frames) >= tok.min_segment_frames and min(frames) < tok.max_segment_frames * 0.5
+    assert max(frames) <= tok.max_segment_frames and max(frames) > tok.min_segment_frames * 2
+
+
+def test_long_form_30min_stream(tok, golden):
+    """Config 4 shape: T_mel = 180 001; the serial float32 chain must survive 44 chunk hand-overs."""
+    from oracle import restate
+
+    wave = golden.wave("c4_30min")
+    ref_mel = restate.logmel(wave)
+    assert hashlib.sha256(ref_mel.tobytes()).hexdigest() == golden.cases["c4_30min"]["mel_sha256"]
+    assert np.array_equal(tok.find_amplitude_minimas(ref_mel), golden.get("c4_30min", "minima"))
+    assert tok.segment_lengths(wave, melspec=ref_mel).tolist() == golden.get("c4_30min", "lengths").tolist()
+    got_mel = tok.get_melspec(wave)
+    assert_mel_close(got_mel, ref_mel)
+    assert tok.segment_lengths(wave).tolist() == golden.get("c4_30min", "lengths").tolist()
+
+
+# ----------------------------------------------------------------------------------------- K4
+@pytest.mark.parametrize("case", ["c1_10s", "c2_16s_u0", "c3_20s"])
+def test_pool_matches_reference_golden(golden, case):
+    import torch
+
+    from aat_b200 import mean_pool_segments
+
+    info = golden.cases[case]
+    off = golden.get(case, "frame_off")
+    emb = np.random.default_rng(info["pool_seed"]).standard_normal((int(off[-1]), info["pool_dim"]), dtype=np.float32)
+    ref = golden.get(case, "pooled")
+    te = torch.from_numpy(emb)
+    # the reference's own calling convention: a list of [1, n_i, D] tensors (host)
+    lst = [te[off[i]:off[i + 1]].unsqueeze(0) for i in range(off.size - 1)]
+    got = mean_pool_segments(lst)
+    assert tuple(got.shape) == ref.shape and got.dtype == torch.float32
+    assert_pooled_close(got.numpy(), ref)
+    # packed CUDA form
+    got2 = mean_pool_segments(te.cuda(), off)
+    assert_pooled_close(got2.cpu().numpy(), ref)
+
+
+def _random_offsets(rng, n_rows, lo, hi):
+    cuts = [0]
+    while cuts[-1] < n_rows:
+        cuts.append(min(n_rows, cuts[-1] + int(rng.integers(lo, hi + 1))))
+    return np.asarray(cuts, dtype=np.int64)
+
+
+@pytest.mark.parametrize("dim", [768, 1024, 64, 200, 2048, 4096])
+def test_pool_ragged_against_oracle(c_oracle, dim):
+    import torch
+
+    from aat_b200 import mean_pool_segments
+
+    rng = np.random.default_rng(dim)
+    n_rows = 6000 if dim <= 1024 else 1500
+    emb = rng.standard_normal((n_rows, dim), dtype=np.float32)
+    mixes = {"all_min": (6, 6), "all_max": (74, 74), "uniform": (6, 74), "tiny": (1, 3), "giant": (n_rows, n_rows)}
+    for name, (lo, hi) in mixes.items():
+        off = _random_offsets(rng, n_rows, lo, hi)
+        ref = c_oracle.mean_pool_f64(emb, off)
+        got = mean_pool_segments(torch.from_numpy(emb).cuda(), off).cpu().numpy()[0]
+        assert_pooled_close(got, ref)
+    # alternating 6 / 74
+    lens = np.tile([6, 74], n_rows // 80 + 1)
+    off = np.minimum(np.concatenate([[0], np.cumsum(lens)]), n_rows)
+    off = off[: int(np.argmax(off == n_rows)) + 1].astype(np.int64)
+    got = mean_pool_segments(torch.from_numpy(emb).cuda(), off).cpu().numpy()[0]
+    assert_pooled_close(got, c_oracle.mean_pool_f64(emb, off))
+
+
+def test_pool_empty_segments_gaps_and_degenerate_shapes(c_oracle):
+    import torch
+
+    from aat_b200 import mean_pool_segments
+
+    rng = np.random.default_rng(5)
+    emb = rng.standard_normal((300, 768), dtype=np.float32)
+    off = np.asarray([0, 0, 10, 10, 10, 150, 300, 300], dtype=np.int64)  # empty segments at the start, middle and end
+    got = mean_pool_segments(torch.from_numpy(emb).cuda(), off).cpu().numpy()[0]
+    ref = c_oracle.mean_pool_f64(emb, off)
+    empty = np.diff(off) == 0
+    assert np.all(np.isnan(got[empty])) and np.all(np.isnan(ref[empty]))  # torch: mean of an empty slice is NaN
+    assert_pooled_close(got[~empty], ref[~empty])
+    # rows outside [off[0], off[S]) belong to no segment
+    off2 = np.asarray([20, 60, 200], dtype=np.int64)
+    got2 = mean_pool_segments(torch.from_numpy(emb).cuda(), off2).cpu().numpy()[0]
+    assert_pooled_close(got2, c_oracle.mean_pool_f64(emb, off2))
+    # fewer rows than CTAs
+    small = emb[:5]
+    off3 = np.asarray([0, 2, 5], dtype=np.int64)
+    got3 = mean_pool_segments(torch.from_numpy(small).cuda(), off3).cpu().numpy()[0]
+    assert_pooled_close(got3, c_oracle.mean_pool_f64(small, off3))
+
+
+def test_pool_is_deterministic_and_graph_safe(c_oracle):
+    import torch
+
+    from aat_b200 import mean_pool_segments
+
+    rng = np.random.default_rng(9)
+    emb = torch.from_numpy(rng.standard_normal((20000, 768), dtype=np.float32)).cuda()
+    off = _random_offsets(rng, 20000, 300, 900)  # long segments: every CTA boundary cuts one
+    a = mean_pool_segments(emb, off).clone()
+    for _ in range(5):
+        assert torch.equal(mean_pool_segments(emb, off), a)
+    assert_pooled_close(a.cpu().numpy()[0], c_oracle.mean_pool_f64(emb.cpu().numpy(), off))
+
+
+def test_pool_half_precision_follows_torch(c_oracle):
+    import torch
+
+    from aat_b200 import mean_pool_segments
+    from oracle import ref_port
+
+    rng = np.random.default_rng(21)
+    off = _random_offsets(rng, 3000, 6, 74)
+    for dtype in (torch.float16, torch.bfloat16):
+        emb = torch.from_numpy(rng.standard_normal((3000, 768), dtype=np.float32)).to(dtype)
+        ref = ref_port.mean_pool_csr(emb, off).numpy()[0]
+        got = mean_pool_segments(emb.cuda(), off).cpu().numpy()[0]
+        # the reference rounds the mean to the input dtype: agree to one unit in the last place of that dtype
+        ulp = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
+        assert np.all(np.abs(got - ref) <= ulp * np.maximum(np.abs(ref), 2.0 ** -14))
+        assert np.mean(got == ref) > 0.95
+
+
+def test_pool_colsum_and_dataset_mean(c_oracle):
+    import torch
+
+    from aat_b200 import mean_pool_segments
+    from aat_b200.pooling import DatasetMean
+
+    rng = np.random.default_rng(31)
+    dm = DatasetMean(768)
+    pooled_all = []
+    for b in range(3):
+        emb = torch.from_numpy(rng.standard_normal((4000 + 500 * b, 768), dtype=np.float32)).cuda()
+        off = _random_offsets(rng, emb.shape[0], 6, 74)
+        out = mean_pool_segments(emb, off, colsum=dm.colsum_buffer())
+        dm.accumulate()
+        pooled_all.append(out[0].double().cpu())
+    dm.allreduce()
+    cat = torch.cat(pooled_all)
+    assert dm.count == cat.shape[0]
+    want = cat.mean(dim=0).float().numpy()
+    np.testing.assert_allclose(dm.result().cpu().numpy(), want, rtol=1e-6, atol=1e-7)
+
+
+# ----------------------------------------------------------------------------------------- batched path
+def test_packed_batch_matches_per_utterance_path(tok, golden):
+    import torch
+
+    from aat_b200 import synth
+
+    lengths = [160000, 256000, 100, 2080, 31999, 48000]
+    waves = [synth.bursty_speech(n, 500 + i) for i, n in enumerate(lengths)]
+    batch = tok.plan(lengths)
+    packed = batch.pack([torch.from_numpy(w) for w in waves])
+    batch.logmel(packed)
+    batch.boundaries()
+    batch.frame_csr()
+    torch.cuda.synchronize()
+    assert int(batch.status.min().item()) >= 0
+    total = 0
+    for b, w in enumerate(waves):
+        mel = tok.get_melspec(w)
+        assert np.array_equal(batch.mel_of(b).cpu().numpy(), mel)
+        assert np.array_equal(batch.minima_of(b), tok.find_amplitude_minimas(mel))
+        starts, lens, tail = batch.segments_of(b)
+        assert lens.tolist() == tok.segment_lengths(w).tolist()
+        so = int(batch.utt_seg_off[b].item())
+        off = batch.seg_off[so: so + len(lens) + 1].cpu().numpy()
+        assert np.array_equal(np.diff(off), synth.hubert_frames(lens))
+        total += len(lens)
+    assert int(batch.n_seg.item()) == total
+    # the fused amplitude curve and the one recomputed from the mel give identical segments
+    before = batch.seg_len.clone(), batch.seg_count.clone()
+    batch.boundaries(use_amp=False)
+    torch.cuda.synchronize()
+    assert torch.equal(batch.seg_len, before[0]) and torch.equal(batch.seg_count, before[1])
+
+
+def test_packed_batch_segments_reference_mel(tok, golden):
+    """Device path fed the reference's own mel frames: bit-exact offsets."""
+    import torch
+
+    cases = ["c1_10s", "c2_16s_u0", "silence_2s", "edge_2080"]
+    lengths = [golden.cases[c]["n_samples"] for c in cases]
+    batch = tok.plan(lengths)
+    mel = torch.cat([torch.from_numpy(golden.get(c, "mel")).reshape(-1) for c in cases]).cuda()
+    batch.boundaries(mel=mel)
+    torch.cuda.synchronize()
+    for b, c in enumerate(cases):
+        assert np.array_equal(batch.minima_of(b), golden.get(c, "minima"))
+        assert batch.segments_of(b)[1].tolist() == golden.get(c, "lengths").tolist()
+
+
+def test_pipeline_replays_in_a_cuda_graph(tok):
+    import torch
+
+    from aat_b200 import synth
+
+    lengths = [64000] * 8
+    batch = tok.plan(lengths)
+    wave = batch.pack([torch.from_numpy(synth.bursty_speech(n, 900 + i)) for i, n in enumerate(lengths)])
+    batch.logmel(wave), batch.boundaries(), batch.frame_csr()
+    torch.cuda.synchronize()
+    n_seg = int(batch.n_seg.item())
+    n_rows = int(batch.seg_off[n_seg].item())
+    emb = torch.randn(n_rows, 768, device="cuda")
+    out = torch.empty(batch.total_seg_slots, 768, device="cuda")
+    batch.pool(emb, out)
+    torch.cuda.synchronize()
+    want = out[:n_seg].clone()
+    want_len = batch.seg_len.clone()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            batch.logmel(wave), batch.boundaries(), batch.frame_csr(), batch.pool(emb, out)
+    for _ in range(3):
+        out.zero_()
+        batch.seg_len.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out[:n_seg], want) and torch.equal(batch.seg_len, want_len)
+
+
+# ----------------------------------------------------------------------------------------- full-size properties
+def test_config2_full_size_properties(tok):
+    """BASELINE config 2 (64 x 16 s, D = 768): size-independent properties on the whole batch plus
+    oracle parity on a sample of utterances."""
+    import torch
+
+    from aat_b200 import synth
+    from oracle import ref_port
+
+    B, N, D = 64, 256000, 768
+    waves = [synth.bursty_speech(N, synth.seed_for(2, i)) for i in range(B)]
+    batch = tok.plan([N] * B)
+    batch.logmel(batch.pack([torch.from_numpy(w) for w in waves]))
+    batch.boundaries()
+    batch.frame_csr()
+    torch.cuda.synchronize()
+    assert int(batch.status.min().item()) >= 0
+    n_seg = int(batch.n_seg.item())
+    seg_off = batch.seg_off[: n_seg + 1].cpu().numpy()
+    assert np.all(np.diff(seg_off) >= 0) and seg_off[0] == 0
+    ref = ref_port.RefTokenizer()
+    for b in range(B):
+        starts, lens, tail = batch.segments_of(b)
+        assert lens.sum() >= N and (lens.sum() > N) == tail
+        assert lens.min() >= tok.min_segment_frames and lens.max() <= tok.max_segment_frames
+        assert np.array_equal(starts[1:], np.cumsum(lens)[:-1])
+        if b % 16 == 0:
+            want, _, mel = ref.segment_lengths(waves[b])
+            assert lens.tolist() == want
+            assert_mel_close(batch.mel_of(b).cpu().numpy(), mel)
+    # pooling: linearity and the frame-weighted checksum  sum_s n_s * pooled[s] == column sums of E
+    n_rows = int(seg_off[-1])
+    g = torch.Generator(device="cuda").manual_seed(1)
+    e1 = torch.randn(n_rows, D, device="cuda", generator=g)
+    e2 = torch.randn(n_rows, D, device="cuda", generator=g)
+    out = torch.empty(batch.total_seg_slots, D, device="cuda")
+    p1 = batch.pool(e1, out)[:n_seg].clone()
+    p2 = batch.pool(e2, out)[:n_seg].clone()
+    p3 = batch.pool(2.0 * e1 + e2, out)[:n_seg].clone()
+    torch.cuda.synchronize()
+    assert torch.allclose(p3, 2.0 * p1 + p2, rtol=1e-5, atol=1e-5)
+    counts = torch.from_numpy(np.diff(seg_off)).cuda().double()
+    lhs = (p1.double() * counts[:, None]).sum(dim=0)
+    rhs = e1.double().sum(dim=0)
+    assert torch.allclose(lhs, rhs, rtol=1e-6, atol=1e-3)
+    want = ref_port.mean_pool_csr(e1[: seg_off[40]].cpu(), seg_off[:41]).numpy()[0]
+    assert_pooled_close(p1[:40].cpu().numpy(), want)
