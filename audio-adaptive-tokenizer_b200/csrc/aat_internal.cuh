@@ -58,9 +58,7 @@ struct PoolScratch {
     int max_ctas = 0;
     int max_dim = 0;
     float *head = nullptr;      // [max_ctas, max_dim]
-    float *tail = nullptr;      // [max_ctas, max_dim]
     int *head_flag = nullptr;   // [max_ctas]
-    int *tail_flag = nullptr;   // [max_ctas]
     double *colsum = nullptr;   // [max_ctas, max_dim + 1]
 };
 

@@ -101,9 +101,10 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel(const BoundaryPara
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int halo = p.npts + 2;
+    const int halo_pad = (halo + 3) & ~3; // keeps the chunk part of s_cs 16-byte aligned
     float *s_amp = reinterpret_cast<float *>(smem_raw);     // [kChunk]
-    float *s_cs = s_amp + kChunk;                            // [halo + kChunk]
-    int *s_min = reinterpret_cast<int *>(s_cs + halo + kChunk); // [kChunk] minima of this pass (global frame index)
+    float *s_cs = s_amp + kChunk;                            // [halo_pad + kChunk]; cs index g at [halo_pad + g - j0]
+    int *s_min = reinterpret_cast<int *>(s_cs + halo_pad + kChunk); // [kChunk] minima of this pass (global frame index)
     __shared__ int s_warp_count[kThreads / 32];
     __shared__ int s_total;
     __shared__ float s_carry;
@@ -147,19 +148,26 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel(const BoundaryPara
         }
         __syncthreads();
 
-        // B: the serial float32 cumsum (one thread; loads are independent of the add chain)
+        // B: the serial float32 cumsum.  One thread; values are fetched 16 at a time into registers so the
+        // shared-memory latency is paid once per batch and the chain itself runs at the FADD latency.
         if (tid == 0) {
             float run = (j0 == 0) ? 0.0f : s_carry;
+            const float4 *src = reinterpret_cast<const float4 *>(s_amp);
+            float4 *dst = reinterpret_cast<float4 *>(s_cs + halo_pad);
             int i = 0;
-            if (j0 == 0) {
-                run = s_amp[0];
-                s_cs[halo] = run;
-                i = 1;
+            for (; i + 16 <= len; i += 16) {
+                float4 a = src[i / 4], b = src[i / 4 + 1], c4 = src[i / 4 + 2], d = src[i / 4 + 3];
+                a.x = (j0 == 0 && i == 0) ? a.x : __fadd_rn(run, a.x);
+                a.y = __fadd_rn(a.x, a.y), a.z = __fadd_rn(a.y, a.z), a.w = __fadd_rn(a.z, a.w);
+                b.x = __fadd_rn(a.w, b.x), b.y = __fadd_rn(b.x, b.y), b.z = __fadd_rn(b.y, b.z), b.w = __fadd_rn(b.z, b.w);
+                c4.x = __fadd_rn(b.w, c4.x), c4.y = __fadd_rn(c4.x, c4.y), c4.z = __fadd_rn(c4.y, c4.z), c4.w = __fadd_rn(c4.z, c4.w);
+                d.x = __fadd_rn(c4.w, d.x), d.y = __fadd_rn(d.x, d.y), d.z = __fadd_rn(d.y, d.z), d.w = __fadd_rn(d.z, d.w);
+                dst[i / 4] = a, dst[i / 4 + 1] = b, dst[i / 4 + 2] = c4, dst[i / 4 + 3] = d;
+                run = d.w;
             }
-#pragma unroll 8
             for (; i < len; ++i) {
-                run = __fadd_rn(run, s_amp[i]);
-                s_cs[halo + i] = run;
+                run = (j0 == 0 && i == 0) ? s_amp[0] : __fadd_rn(run, s_amp[i]);
+                s_cs[halo_pad + i] = run;
             }
             s_carry = run;
         }
@@ -173,8 +181,7 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel(const BoundaryPara
         unsigned mask = 0;
         {
             const int64_t a = i_done + (int64_t)tid * per;
-            // cs index g lives at s_cs[halo + g - j0]
-            const float *cs = s_cs + halo - j0;
+            const float *cs = s_cs + halo_pad - j0;
             for (int u = 0; u < per; ++u) {
                 const int64_t i = a + u;
                 if (i >= i_hi) break;
@@ -232,7 +239,7 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel(const BoundaryPara
         // carry the last `halo` cumsum values into the next pass
         // (source [kChunk, kChunk + halo) and destination [0, halo) are disjoint because kChunk >= halo)
         if (j1 < T) {
-            for (int i = tid; i < halo; i += kThreads) s_cs[i] = s_cs[kChunk + i];
+            for (int i = tid; i < halo_pad; i += kThreads) s_cs[i] = s_cs[kChunk + i];
             __syncthreads();
         }
     }
@@ -351,7 +358,7 @@ int launch_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel, cons
     p.n_mels = ctx->cfg.num_mel_filters;
     p.npts = ctx->cfg.running_mean_points;
     p.max_amp = ctx->cfg.max_amplitude_for_minima;
-    const size_t smem = sizeof(float) * (size_t)(kChunk + p.npts + 2 + kChunk) + sizeof(int) * (size_t)kChunk;
+    const size_t smem = sizeof(float) * (size_t)(kChunk + ((p.npts + 2 + 3) & ~3) + kChunk) + sizeof(int) * (size_t)kChunk;
     AAT_CUDA_CHECK(cudaFuncSetAttribute(boundaries_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfileScope prof(ctx, AAT_K_BOUNDARIES, stream);
     boundaries_kernel<<<plan->n_utts, kThreads, smem, stream>>>(p);

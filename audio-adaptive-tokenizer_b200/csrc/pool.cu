@@ -15,10 +15,11 @@
 //   * consumer threads own one 16-byte column slab each (128-bit conflict-free shared loads), walk the
 //     rows of a stage, keep four interleaved float32 accumulators and flush at every segment boundary
 //     with a coalesced float4 store of sum / n;
-//   * a segment cut by a CTA boundary is finished deterministically: the CTAs that hold its beginning
-//     and middle publish partial sums (+ release flag); the CTA that holds its end adds them in CTA
-//     order.  Dependencies only point to lower CTA indices and the whole grid is co-resident, so the
-//     wait cannot deadlock; flags are reset by their single consumer, so CUDA-graph replays are safe;
+//   * a segment cut by a CTA boundary is finished deterministically: the CTA that holds its first row
+//     owns it; the CTAs that hold its middle and end publish their partial sums (+ release flag) as
+//     soon as they have them and never wait first; the owner adds them in CTA order at the very end
+//     of its own rows.  No CTA waits on a waiter and the whole grid is co-resident, so there is neither
+//     a dependency chain nor a deadlock; flags are reset by their single consumer (graph-replay safe);
 //   * optional epilogue: float64 column sums of the pooled vectors (input of the dataset-mean
 //     allreduce) are accumulated per CTA and reduced in CTA order by a second tiny kernel.
 //
@@ -36,6 +37,7 @@ constexpr int kStages = 4;
 constexpr int kStageBytes = 24 * 1024; // 8 rows of 768 fp32, 6 rows of 1024 fp32
 constexpr int kMaxConsumers = 256;
 constexpr int kMaxSlabs = 4; // 16-byte column slabs per consumer thread -> dim*e <= 16 KB
+constexpr int kMaxCtasPerSm = 2;
 
 // ---------------------------------------------------------------- PTX helpers (mbarrier + bulk copy)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -120,12 +122,9 @@ struct Slab<__half> {
             v[2 * i] = f.x, v[2 * i + 1] = f.y;
         }
     }
-    // torch CPU: float32 accumulate, sum stored as half, div_ in half (computed in float32, rounded to half)
-    __device__ static float finish(float sum, float n)
-    {
-        const float s = __half2float(__float2half_rn(sum));
-        return __half2float(__float2half_rn(__fdiv_rn(s, n)));
-    }
+    // torch: mean of a half tensor accumulates and divides in float32 and rounds once to half
+    // (verified against torch 2.11 CPU: half(sum_f32 / n) reproduces x.mean(dim=1) bit for bit)
+    __device__ static float finish(float sum, float n) { return __half2float(__float2half_rn(__fdiv_rn(sum, n))); }
 };
 template <>
 struct Slab<__nv_bfloat16> {
@@ -142,8 +141,7 @@ struct Slab<__nv_bfloat16> {
     }
     __device__ static float finish(float sum, float n)
     {
-        const float s = __bfloat162float(__float2bfloat16_rn(sum));
-        return __bfloat162float(__float2bfloat16_rn(__fdiv_rn(s, n)));
+        return __bfloat162float(__float2bfloat16_rn(__fdiv_rn(sum, n)));
     }
 };
 
@@ -152,10 +150,8 @@ struct PoolParams {
     const int64_t *seg_off;
     const int64_t *n_seg_dev;
     float *out;
-    float *head;      // [G, dim] partial sums of a segment that began in an earlier CTA
-    float *tail;      // [G, dim] partial sums of a segment that continues into a later CTA
+    float *head;      // [G, dim] this CTA's piece of a segment that began in an earlier CTA
     int *head_flag;   // [G]
-    int *tail_flag;   // [G]
     double *colsum;   // [G, dim] per-CTA column sums of pooled vectors (optional)
     int64_t n_rows;
     int64_t n_seg;
@@ -310,23 +306,18 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
             }
         };
 
-        // flush the accumulators for the segment that ends (or is cut) at `row_end`
+        // flush the accumulators for the segment that ends (or is cut) at `row_end`.
+        // Ownership rule for a segment cut by CTA boundaries: the CTA that holds its FIRST row owns it.
+        // Every other CTA publishes its piece as soon as it has it and never waits before publishing;
+        // the owner waits only at the very end of its own rows.  So no CTA ever waits on a waiter.
         auto flush = [&](int64_t row_end) {
             if (!in_gap) {
                 const bool starts_before = seg_begin < r0;
                 const bool ends_after = seg_end > row_end; // only possible when row_end == r1
                 const float nrows = (float)(seg_end - seg_begin);
-                if (!starts_before && !ends_after) {
-#pragma unroll
-                    for (int j = 0; j < kSlabs; ++j) {
-                        float sum[kCols];
-#pragma unroll
-                        for (int k = 0; k < kCols; ++k) sum[k] = reduce_acc(j, k);
-                        write_pooled(j, sum, nrows);
-                    }
-                } else if (ends_after) {
-                    // publish a partial: "tail" if the segment began here, "head" (a middle piece) otherwise
-                    float *dst = (starts_before ? p.head : p.tail) + (size_t)c * p.dim;
+                if (starts_before) {
+                    // end piece (or, when it also ends_after, a middle piece) of an earlier CTA's segment
+                    float *dst = p.head + (size_t)c * p.dim;
 #pragma unroll
                     for (int j = 0; j < kSlabs; ++j) {
                         const int slab = tid + j * n_consumers;
@@ -336,19 +327,26 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
                     }
                     __threadfence();
                     consumer_barrier(n_consumers);
-                    if (tid == 0) st_release((starts_before ? p.head_flag : p.tail_flag) + c, 1);
+                    if (tid == 0) st_release(p.head_flag + c, 1);
+                } else if (!ends_after) {
+#pragma unroll
+                    for (int j = 0; j < kSlabs; ++j) {
+                        float sum[kCols];
+#pragma unroll
+                        for (int k = 0; k < kCols; ++k) sum[k] = reduce_acc(j, k);
+                        write_pooled(j, sum, nrows);
+                    }
                 } else {
-                    // the segment ends here but began in an earlier CTA: add the published pieces in CTA order
-                    int64_t cs = (seg_begin * G) / (p.n_rows > 0 ? p.n_rows : 1);
-                    while (cs + 1 < G && cta_row_begin(cs + 1, p.n_rows, G) <= seg_begin) ++cs;
-                    while (cs > 0 && cta_row_begin(cs, p.n_rows, G) > seg_begin) --cs;
+                    // this CTA owns a segment that continues into later CTAs: add their pieces in CTA order
+                    const int64_t last_row = seg_end - 1;
+                    int64_t ce = p.n_rows > 0 ? (last_row < p.n_rows ? (last_row * G) / p.n_rows : G - 1) : G - 1;
+                    while (ce + 1 < G && cta_row_begin(ce + 1, p.n_rows, G) <= last_row) ++ce;
+                    while (ce > c && cta_row_begin(ce, p.n_rows, G) > last_row) --ce;
                     if (tid == 0) {
-                        while (ld_acquire(p.tail_flag + cs) == 0) {}
-                        p.tail_flag[cs] = 0;
-                        for (int64_t m = cs + 1; m < c; ++m) {
+                        for (int64_t m = c + 1; m <= ce; ++m) {
                             if (cta_row_begin(m, p.n_rows, G) == cta_row_begin(m + 1, p.n_rows, G)) continue;
                             while (ld_acquire(p.head_flag + m) == 0) {}
-                            p.head_flag[m] = 0;
+                            p.head_flag[m] = 0; // single consumer resets: safe for CUDA-graph replays
                         }
                     }
                     consumer_barrier(n_consumers);
@@ -358,15 +356,13 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
                         float sum[kCols];
                         if (slab < p.slabs_per_row) {
 #pragma unroll
-                            for (int k = 0; k < kCols; ++k) sum[k] = __ldcg(p.tail + (size_t)cs * p.dim + slab * kCols + k);
-                            for (int64_t m = cs + 1; m < c; ++m) {
+                            for (int k = 0; k < kCols; ++k) sum[k] = reduce_acc(j, k);
+                            for (int64_t m = c + 1; m <= ce; ++m) {
                                 if (cta_row_begin(m, p.n_rows, G) == cta_row_begin(m + 1, p.n_rows, G)) continue;
 #pragma unroll
                                 for (int k = 0; k < kCols; ++k)
                                     sum[k] += __ldcg(p.head + (size_t)m * p.dim + slab * kCols + k);
                             }
-#pragma unroll
-                            for (int k = 0; k < kCols; ++k) sum[k] += reduce_acc(j, k);
                         }
                         write_pooled(j, sum, nrows);
                     }
@@ -466,28 +462,33 @@ __global__ void colsum_finalize_kernel(const double *acc, int dim, float *mean)
 }
 
 template <typename EmbT, int kSlabs>
-int launch_typed(aat_ctx *ctx, const PoolParams &p, int grid, size_t smem, bool colsum, cudaStream_t stream)
+int launch_typed(aat_ctx *ctx, PoolParams &p, size_t smem, bool colsum, cudaStream_t stream, int *grid_out)
 {
     const int threads = p.n_consumers + 32;
-    if (colsum) {
-        AAT_CUDA_CHECK(cudaFuncSetAttribute(pool_kernel<EmbT, kSlabs, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        pool_kernel<EmbT, kSlabs, true><<<grid, threads, smem, stream>>>(p);
-    } else {
-        AAT_CUDA_CHECK(cudaFuncSetAttribute(pool_kernel<EmbT, kSlabs, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        pool_kernel<EmbT, kSlabs, false><<<grid, threads, smem, stream>>>(p);
-    }
-    (void)ctx;
+    auto kernel = colsum ? pool_kernel<EmbT, kSlabs, true> : pool_kernel<EmbT, kSlabs, false>;
+    AAT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // persistent grid: the cross-CTA carry needs every CTA resident at once, so size it from the
+    // occupancy the driver reports for this very instantiation
+    int per_sm = 0;
+    AAT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    AAT_REQUIRE(per_sm >= 1, AAT_ERR_UNSUPPORTED, "aat_segment_mean_pool: kernel does not fit on an SM");
+    if (per_sm > kMaxCtasPerSm) per_sm = kMaxCtasPerSm;
+    int grid = ctx->num_sms * per_sm;
+    if (grid > ctx->pool.max_ctas) grid = ctx->pool.max_ctas;
+    *grid_out = grid;
+    ProfileScope prof(ctx, AAT_K_POOL, stream); // the streaming kernel alone (not the colsum reduce)
+    kernel<<<grid, threads, smem, stream>>>(p);
     AAT_LAUNCH_CHECK();
     return AAT_OK;
 }
 
 template <typename EmbT>
-int launch_slabs(aat_ctx *ctx, const PoolParams &p, int slabs, int grid, size_t smem, bool colsum, cudaStream_t stream)
+int launch_slabs(aat_ctx *ctx, PoolParams &p, int slabs, size_t smem, bool colsum, cudaStream_t stream, int *grid_out)
 {
     switch (slabs) {
-    case 1: return launch_typed<EmbT, 1>(ctx, p, grid, smem, colsum, stream);
-    case 2: return launch_typed<EmbT, 2>(ctx, p, grid, smem, colsum, stream);
-    default: return launch_typed<EmbT, 4>(ctx, p, grid, smem, colsum, stream);
+    case 1: return launch_typed<EmbT, 1>(ctx, p, smem, colsum, stream, grid_out);
+    case 2: return launch_typed<EmbT, 2>(ctx, p, smem, colsum, stream, grid_out);
+    default: return launch_typed<EmbT, 4>(ctx, p, smem, colsum, stream, grid_out);
     }
 }
 
@@ -496,15 +497,12 @@ int launch_slabs(aat_ctx *ctx, const PoolParams &p, int slabs, int grid, size_t 
 int pool_scratch_init(aat_ctx *ctx)
 {
     PoolScratch &ps = ctx->pool;
-    ps.max_ctas = ctx->num_sms * 2; // launch_mean_pool never uses more than two CTAs per SM
+    ps.max_ctas = ctx->num_sms * kMaxCtasPerSm;
     ps.max_dim = 4096;
     AAT_CUDA_CHECK(cudaMalloc(&ps.head, sizeof(float) * (size_t)ps.max_ctas * ps.max_dim));
-    AAT_CUDA_CHECK(cudaMalloc(&ps.tail, sizeof(float) * (size_t)ps.max_ctas * ps.max_dim));
     AAT_CUDA_CHECK(cudaMalloc(&ps.head_flag, sizeof(int) * (size_t)ps.max_ctas));
-    AAT_CUDA_CHECK(cudaMalloc(&ps.tail_flag, sizeof(int) * (size_t)ps.max_ctas));
     AAT_CUDA_CHECK(cudaMalloc(&ps.colsum, sizeof(double) * (size_t)ps.max_ctas * ps.max_dim));
     AAT_CUDA_CHECK(cudaMemset(ps.head_flag, 0, sizeof(int) * (size_t)ps.max_ctas));
-    AAT_CUDA_CHECK(cudaMemset(ps.tail_flag, 0, sizeof(int) * (size_t)ps.max_ctas));
     return AAT_OK;
 }
 
@@ -512,9 +510,7 @@ void pool_scratch_free(aat_ctx *ctx)
 {
     PoolScratch &ps = ctx->pool;
     cudaFree(ps.head);
-    cudaFree(ps.tail);
     cudaFree(ps.head_flag);
-    cudaFree(ps.tail_flag);
     cudaFree(ps.colsum);
     ps = PoolScratch{};
 }
@@ -553,9 +549,7 @@ int launch_mean_pool(aat_ctx *ctx, const void *emb, int emb_dtype, int64_t n_row
     p.n_seg_dev = n_seg_dev;
     p.out = out;
     p.head = ctx->pool.head;
-    p.tail = ctx->pool.tail;
     p.head_flag = ctx->pool.head_flag;
-    p.tail_flag = ctx->pool.tail_flag;
     p.colsum = ctx->pool.colsum;
     p.n_rows = n_rows;
     p.n_seg = n_seg;
@@ -572,22 +566,15 @@ int launch_mean_pool(aat_ctx *ctx, const void *emb, int emb_dtype, int64_t n_row
     p.rows_per_stage = (int)(kStageBytes / row_bytes);
     if (p.rows_per_stage < 1) p.rows_per_stage = 1;
     const size_t smem = (size_t)kStages * p.rows_per_stage * row_bytes;
-    // persistent grid: every CTA must be resident at once (cross-CTA carry waits on lower CTA indices)
-    const int ctas_per_sm = (int)((220 * 1024) / (smem + 1024)) < 2 ? 1 : 2;
-    int grid = ctx->num_sms * ctas_per_sm;
-    if (grid > ctx->pool.max_ctas) grid = ctx->pool.max_ctas;
 
-    int rc;
+    int rc, grid = 0;
     const bool want_colsum = colsum != nullptr;
-    {
-        ProfileScope prof(ctx, AAT_K_POOL, stream); // the streaming kernel alone (not the colsum reduce)
-        if (emb_dtype == AAT_F32)
-            rc = launch_slabs<float>(ctx, p, slabs, grid, smem, want_colsum, stream);
-        else if (emb_dtype == AAT_F16)
-            rc = launch_slabs<__half>(ctx, p, slabs, grid, smem, want_colsum, stream);
-        else
-            rc = launch_slabs<__nv_bfloat16>(ctx, p, slabs, grid, smem, want_colsum, stream);
-    }
+    if (emb_dtype == AAT_F32)
+        rc = launch_slabs<float>(ctx, p, slabs, smem, want_colsum, stream, &grid);
+    else if (emb_dtype == AAT_F16)
+        rc = launch_slabs<__half>(ctx, p, slabs, smem, want_colsum, stream, &grid);
+    else
+        rc = launch_slabs<__nv_bfloat16>(ctx, p, slabs, smem, want_colsum, stream, &grid);
     if (rc != AAT_OK) return rc;
     if (want_colsum) {
         const int threads = 128;
