@@ -78,6 +78,7 @@ struct aat_ctx {
     aat_config cfg{};
     double *window_half = nullptr; // device [400], 0.5 * window (exact scaling, folds the /2 of the two-frame split)
     double2 *twiddle = nullptr;    // device [20 * 20], W_400^(k1 * n2) at [k1 * 20 + n2]
+    double2 *log_table = nullptr;  // device [128], (1/c_i, -log10(1/c_i)) for the log-mel kernel's log10
     aat::MelTable mel{};
     aat::PoolScratch pool{};
     // staging for aat_host_* entry points (grown on demand, never inside stream capture)
@@ -123,6 +124,7 @@ int launch_mean_pool(aat_ctx *ctx, const void *emb, int emb_dtype, int64_t n_row
                      cudaStream_t stream);
 int launch_colsum_accumulate(double *acc, const double *colsum, int32_t dim, cudaStream_t stream);
 int launch_colsum_finalize(const double *acc, int32_t dim, float *mean, cudaStream_t stream);
+int logmel_tables_init(aat_ctx *ctx);
 int pool_scratch_init(aat_ctx *ctx);
 void pool_scratch_free(aat_ctx *ctx);
 

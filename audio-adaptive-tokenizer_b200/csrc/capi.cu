@@ -192,6 +192,7 @@ int aat_create(int device, const aat_config *cfg, const double *window_host, con
     if ((rc = upload(&ctx->mel.bin, bins.data(), bins.size()))) return rc;
     if ((rc = upload(&ctx->mel.weight, weights.data(), weights.size()))) return rc;
 
+    if ((rc = logmel_tables_init(ctx))) return rc;
     if ((rc = pool_scratch_init(ctx))) return rc;
     AAT_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking));
     *out = ctx;
@@ -204,6 +205,7 @@ int aat_destroy(aat_ctx *ctx)
     DeviceGuard guard(ctx->device);
     cudaFree(ctx->window_half);
     cudaFree(ctx->twiddle);
+    cudaFree(ctx->log_table);
     cudaFree(ctx->mel.row_start);
     cudaFree(ctx->mel.bin);
     cudaFree(ctx->mel.weight);

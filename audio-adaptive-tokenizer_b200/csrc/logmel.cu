@@ -19,7 +19,12 @@
 //   * optional fused epilogue: amp[t] = -10 * mean_m(mel[m][t]) in numpy's sequential float32 order
 //     (ref:src/aat/tokenizer.py:67), so the boundary kernel does not have to re-read the mel.
 //
-// One CTA = 16 consecutive frames of one utterance (8 frame pairs x 20 threads = 160 threads).
+// Execution shape: persistent CTAs (grid = resident CTAs), each looping over tiles of 16 consecutive
+// frames of one utterance (8 frame pairs x 20 threads = 160 threads).  The raw samples of the NEXT
+// tile are fetched with cp.async (LDGSTS, no registers) into the other half of a double buffer while
+// the current tile is transformed, so the global-load latency that dominated the first version of
+// this kernel (ncu: 37 % of stall samples on the load->convert dependency, profiles/) is hidden; the
+// window / twiddle / filter-bank / log tables are loaded into shared memory once per CTA.
 #include "aat_internal.cuh"
 
 namespace aat {
@@ -32,6 +37,7 @@ constexpr int kThreads = kPairs * 20;        // 160
 constexpr int kRow = 21;                     // padded row (double2 units): 21 is odd -> conflict-free columns
 constexpr int kPairStride = 20 * kRow;       // 420 double2; 420 % 8 == 4 keeps neighbouring pairs on distinct banks
 constexpr int kPowStride = kBins;            // 201 doubles (odd)
+constexpr int kLogTable = 128;               // entries of the log10 table
 
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
@@ -90,6 +96,57 @@ __device__ __forceinline__ int64_t reflect_index(int64_t g, int64_t n)
     return m < n ? m : period - m;
 }
 
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int kBytes>
+__device__ __forceinline__ void cp_async(void *dst_smem, const void *src_gmem)
+{
+    if constexpr (kBytes == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst_smem)), "l"(src_gmem) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "n"(kBytes)
+                     : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+
+// log10 of a positive finite double to full double accuracy, table driven:
+//   x = 2^e * m, m in [1, 2); i = top 7 mantissa bits; r = m * inv_c[i] - 1 (|r| < 2^-7, one FMA);
+//   log10(x) = e * log10(2) + (-log10(inv_c[i])) + log1p(r) / ln(10)
+// The table stores inv_c[i] = double(1 / c_i) and -log10 of that ROUNDED value, so the identity is
+// exact and the only errors are the final roundings (~1e-16 relative), far below float32 resolution.
+__device__ __forceinline__ double fast_log10(double x, const double2 *__restrict__ table)
+{
+    const long long bits = __double_as_longlong(x);
+    const int hi = (int)(bits >> 32);
+    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log10(x); // zero, subnormal, inf, nan, negative
+    const int e = (hi >> 20) - 1023;
+    const int idx = (hi >> 13) & (kLogTable - 1);
+    const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+    const double2 t = table[idx];
+    const double r = fma(m, t.x, -1.0);
+    // log1p(r)/ln(10) = r * (c1 + r * (c2 + ...)), c_k = (-1)^(k+1) / (k ln 10)
+    constexpr double k1 = 0.43429448190325182765112891891661;  //  1/ln10
+    constexpr double k2 = -0.21714724095162591382556445945830; // -1/(2 ln10)
+    constexpr double k3 = 0.14476482730108394255037630630554;  //  1/(3 ln10)
+    constexpr double k4 = -0.10857362047581295691278222972915; // -1/(4 ln10)
+    constexpr double k5 = 0.08685889638065036553022578378332;  //  1/(5 ln10)
+    constexpr double k6 = -0.07238241365054197127518815315277; // -1/(6 ln10)
+    constexpr double k7 = 0.06204206884332168966444698841666;  //  1/(7 ln10)
+    constexpr double k8 = -0.05428681023790647845639111486458; // -1/(8 ln10)
+    double q = k8;
+    q = fma(q, r, k7);
+    q = fma(q, r, k6);
+    q = fma(q, r, k5);
+    q = fma(q, r, k4);
+    q = fma(q, r, k3);
+    q = fma(q, r, k2);
+    q = fma(q, r, k1);
+    constexpr double log10_2 = 0.30102999566398119521373889472449;
+    return fma((double)e, log10_2, fma(q, r, t.y));
+}
+
 struct LogmelParams {
     const void *wave;
     float *mel;
@@ -101,146 +158,220 @@ struct LogmelParams {
     const int32_t *tile_first;
     const double *window_half;
     const double2 *twiddle;
+    const double2 *log_table;
     const int *mel_row_start;
     const int *mel_bin;
     const double *mel_weight;
+    int n_tiles;
     int hop;
     int n_mels;
     int nnz;
     int stage_len; // (kFrames - 1) * hop + 400
+    int stage_pad; // stage_len rounded up to 16 bytes worth of samples
 };
 
+struct SmemLayout {
+    size_t raw, win, tw, logt, mw, mbin, mrow, ex, mel, total;
+};
+
+__host__ __device__ inline SmemLayout smem_layout(int stage_pad, int wave_bytes, int n_mels, int nnz)
+{
+    SmemLayout L{};
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        size_t at = o;
+        o += (bytes + 15) & ~size_t(15);
+        return at;
+    };
+    L.ex = take(sizeof(double2) * kPairs * kPairStride); // exchange matrix; later the power spectra (16 x 201 doubles)
+    L.raw = take((size_t)2 * stage_pad * wave_bytes);
+    L.win = take(sizeof(double) * kNfft);
+    L.tw = take(sizeof(double2) * 400);
+    L.logt = take(sizeof(double2) * kLogTable);
+    L.mw = take(sizeof(double) * nnz);
+    L.mbin = take(sizeof(int) * nnz);
+    L.mrow = take(sizeof(int) * (n_mels + 1));
+    L.mel = take(sizeof(float) * kFrames * (n_mels + 1));
+    L.total = o;
+    return L;
+}
+
 template <typename WaveT>
-__global__ void __launch_bounds__(kThreads) logmel_kernel(const LogmelParams p)
+__global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // region A: wave staging + window, later overlaid by the power spectra
-    double *s_wave = reinterpret_cast<double *>(smem_raw);
-    double *s_win = s_wave + p.stage_len;
-    double *s_pow = reinterpret_cast<double *>(smem_raw);
-    size_t region_a = sizeof(double) * (size_t)max(p.stage_len + kNfft, kFrames * kPowStride);
-    region_a = (region_a + 15) & ~size_t(15);
-    double2 *s_ex = reinterpret_cast<double2 *>(smem_raw + region_a);
-    double2 *s_tw = s_ex + kPairs * kPairStride;
-    double *s_mw = reinterpret_cast<double *>(s_tw + 400);
-    int *s_mbin = reinterpret_cast<int *>(s_mw + p.nnz);
-    int *s_mrow = s_mbin + p.nnz;
-    float *s_mel = reinterpret_cast<float *>(s_mrow + p.n_mels + 1);
+    const SmemLayout L = smem_layout(p.stage_pad, (int)sizeof(WaveT), p.n_mels, p.nnz);
+    double2 *s_ex = reinterpret_cast<double2 *>(smem_raw + L.ex);
+    double *s_pow = reinterpret_cast<double *>(smem_raw + L.ex);
+    WaveT *s_rawbuf = reinterpret_cast<WaveT *>(smem_raw + L.raw);
+    double *s_win = reinterpret_cast<double *>(smem_raw + L.win);
+    double2 *s_tw = reinterpret_cast<double2 *>(smem_raw + L.tw);
+    double2 *s_logt = reinterpret_cast<double2 *>(smem_raw + L.logt);
+    double *s_mw = reinterpret_cast<double *>(smem_raw + L.mw);
+    int *s_mbin = reinterpret_cast<int *>(smem_raw + L.mbin);
+    int *s_mrow = reinterpret_cast<int *>(smem_raw + L.mrow);
+    float *s_mel = reinterpret_cast<float *>(smem_raw + L.mel);
 
     const int tid = threadIdx.x;
-    const int utt = p.tile_utt[blockIdx.x];
-    const int tile = blockIdx.x - p.tile_first[utt];
-    const int64_t n = p.n_samples[utt];
-    const int64_t T = 1 + n / p.hop;
-    const int64_t f0 = (int64_t)tile * kFrames;
-    const WaveT *wave = reinterpret_cast<const WaveT *>(p.wave) + p.wave_off[utt];
+    constexpr int kVec = 16 / (int)sizeof(WaveT); // samples per 16-byte copy
 
-    // ---- stage 0: constants and the tile's samples (reflect padding, TF:audio_utils.py:769-771) ----
+    // Asynchronous fetch of one tile's raw samples (reflect padding resolved per element,
+    // TF:audio_utils.py:769-771); interior, 16-byte aligned tiles move 16 bytes per copy.
+    auto prefetch = [&](int tile_id, int buf) {
+        if (tile_id < p.n_tiles) {
+            const int utt = p.tile_utt[tile_id];
+            const int64_t n = p.n_samples[utt];
+            const int64_t woff = p.wave_off[utt];
+            const int64_t g0 = (int64_t)(tile_id - p.tile_first[utt]) * kFrames * p.hop - kNfft / 2;
+            const WaveT *wave = reinterpret_cast<const WaveT *>(p.wave) + woff;
+            WaveT *dst = s_rawbuf + (size_t)buf * p.stage_pad;
+            const bool interior = g0 >= 0 && g0 + p.stage_pad <= n;
+            const bool aligned = ((woff + g0) % kVec) == 0 && (reinterpret_cast<uintptr_t>(p.wave) & 15) == 0;
+            if (interior && aligned) {
+                for (int i = tid * kVec; i < p.stage_pad; i += kThreads * kVec) cp_async<16>(dst + i, wave + g0 + i);
+            } else {
+                for (int i = tid; i < p.stage_len; i += kThreads)
+                    cp_async<(int)sizeof(WaveT)>(dst + i, wave + reflect_index(g0 + i, n));
+            }
+        }
+        cp_async_commit();
+    };
+
+    prefetch(blockIdx.x, 0);
     for (int i = tid; i < kNfft; i += kThreads) {
         s_win[i] = p.window_half[i];
         s_tw[i] = p.twiddle[i];
     }
+    for (int i = tid; i < kLogTable; i += kThreads) s_logt[i] = p.log_table[i];
     for (int i = tid; i < p.nnz; i += kThreads) {
         s_mw[i] = p.mel_weight[i];
         s_mbin[i] = p.mel_bin[i];
     }
     for (int i = tid; i <= p.n_mels; i += kThreads) s_mrow[i] = p.mel_row_start[i];
-    {
-        const int64_t g0 = f0 * p.hop - kNfft / 2;
-        for (int i = tid; i < p.stage_len; i += kThreads)
-            s_wave[i] = (double)wave[reflect_index(g0 + i, n)];
-    }
-    __syncthreads();
 
     const int pair = tid / 20;
     const int lane20 = tid - pair * 20;
     double2 *ex = s_ex + pair * kPairStride;
+    const int mel_stride = p.n_mels + 1;
 
-    // ---- stage 1: thread n2 transforms x[20 n1 + n2] over n1, applies W_400^(n2 k1) ----
-    {
-        double2 v[20];
-        const double *wa = s_wave + (2 * pair) * p.hop + lane20;
-        const double *wb = wa + p.hop;
+    int buf = 0;
+    for (int tile_id = blockIdx.x; tile_id < p.n_tiles; tile_id += gridDim.x, buf ^= 1) {
+        const int utt = p.tile_utt[tile_id];
+        const int64_t T = 1 + p.n_samples[utt] / p.hop;
+        const int64_t f0 = (int64_t)(tile_id - p.tile_first[utt]) * kFrames;
+        const int64_t fbase = p.frame_off[utt];
+
+        prefetch(tile_id + gridDim.x, buf ^ 1); // lands while this tile is transformed
+        cp_async_wait<1>();                     // this tile's samples (older group) have arrived
+        __syncthreads();                        // ... for every thread; also fences the previous tile's smem reuse
+
+        // ---- pass 1: thread n2 transforms x[20 n1 + n2] over n1, applies W_400^(n2 k1) ----
+        {
+            double2 v[20];
+            const WaveT *wa = s_rawbuf + (size_t)buf * p.stage_pad + (2 * pair) * p.hop + lane20;
+            const WaveT *wb = wa + p.hop;
 #pragma unroll
-        for (int n1 = 0; n1 < 20; ++n1) {
-            const double w = s_win[20 * n1 + lane20];
-            v[n1] = make_double2(wa[20 * n1] * w, wb[20 * n1] * w);
+            for (int n1 = 0; n1 < 20; ++n1) {
+                const double w = s_win[20 * n1 + lane20];
+                v[n1] = make_double2((double)wa[20 * n1] * w, (double)wb[20 * n1] * w);
+            }
+            dft20(v);
+            ex[lane20] = v[0];
+#pragma unroll
+            for (int k1 = 1; k1 < 20; ++k1) ex[k1 * kRow + lane20] = cmul(v[k1], s_tw[k1 * 20 + lane20]);
         }
-        dft20(v);
-        ex[lane20] = v[0];
-#pragma unroll
-        for (int k1 = 1; k1 < 20; ++k1) ex[k1 * kRow + lane20] = cmul(v[k1], s_tw[k1 * 20 + lane20]);
-    }
-    __syncthreads();
-
-    // ---- stage 2: thread k1 transforms row k1 over n2; Z[k1 + 20 k2] goes back into its own row ----
-    {
-        double2 v[20];
-        double2 *row = ex + lane20 * kRow;
-#pragma unroll
-        for (int n2 = 0; n2 < 20; ++n2) v[n2] = row[n2];
-        dft20(v);
-#pragma unroll
-        for (int k2 = 0; k2 < 20; ++k2) row[k2] = v[k2];
-    }
-    __syncthreads();
-
-    // ---- split into the two real spectra, round to complex64, power in float64 ----
-    for (int item = tid; item < kPairs * kBins; item += kThreads) {
-        const int pr = item / kBins;
-        const int k = item - pr * kBins;
-        const double2 *e = s_ex + pr * kPairStride;
-        const int kk = (k == 0) ? 0 : kNfft - k;
-        const double2 z = e[(k % 20) * kRow + k / 20];
-        const double2 y = e[(kk % 20) * kRow + kk / 20];
-        // X_a = (z + conj y), X_b = (z - conj y) / i   (the 1/2 lives in the window table)
-        const float ar = (float)(z.x + y.x), ai = (float)(z.y - y.y);
-        const float br = (float)(z.y + y.y), bi = (float)(y.x - z.x);
-        s_pow[(2 * pr) * kPowStride + k] = (double)ar * (double)ar + (double)ai * (double)ai;
-        s_pow[(2 * pr + 1) * kPowStride + k] = (double)br * (double)br + (double)bi * (double)bi;
-    }
-    __syncthreads();
-
-    // ---- mel projection (sparse rows), floor, log10, float32 store ----
-    float *mel_out = p.mel + (size_t)p.n_mels * p.frame_off[utt];
-    for (int item = tid; item < p.n_mels * kFrames; item += kThreads) {
-        const int m = item / kFrames;
-        const int f = item - m * kFrames;
-        const double *pw = s_pow + f * kPowStride;
-        double acc = 0.0;
-        for (int j = s_mrow[m]; j < s_mrow[m + 1]; ++j) acc = fma(s_mw[j], pw[s_mbin[j]], acc);
-        const float out = (float)log10(fmax(acc, 1e-10));
-        if (f0 + f < T) mel_out[(size_t)m * T + f0 + f] = out;
-        s_mel[f * (p.n_mels + 1) + m] = out;
-    }
-
-    // ---- fused amplitude curve: numpy's mean(axis=0) adds the rows in order in float32 ----
-    if (p.amp != nullptr) {
         __syncthreads();
-        if (tid < kFrames && f0 + tid < T) {
-            const float *col = s_mel + tid * (p.n_mels + 1);
-            float acc = col[0];
-            for (int m = 1; m < p.n_mels; ++m) acc = __fadd_rn(acc, col[m]);
-            const float mean = __fdiv_rn(acc, (float)p.n_mels);
-            p.amp[p.frame_off[utt] + f0 + tid] = __fmul_rn(-10.0f, mean);
-        }
-    }
-}
 
-size_t logmel_smem_bytes(int hop, int n_mels, int nnz)
-{
-    const int stage_len = (kFrames - 1) * hop + kNfft;
-    size_t region_a = sizeof(double) * (size_t)((stage_len + kNfft) > kFrames * kPowStride ? (stage_len + kNfft)
-                                                                                              : kFrames * kPowStride);
-    region_a = (region_a + 15) & ~size_t(15);
-    size_t bytes = region_a;
-    bytes += sizeof(double2) * (kPairs * kPairStride + 400);
-    bytes += sizeof(double) * nnz + sizeof(int) * (nnz + n_mels + 1);
-    bytes += sizeof(float) * kFrames * (n_mels + 1);
-    return bytes;
+        // ---- pass 2: thread k1 transforms row k1 over n2; Z[k1 + 20 k2] goes back into its own row ----
+        {
+            double2 v[20];
+            double2 *row = ex + lane20 * kRow;
+#pragma unroll
+            for (int n2 = 0; n2 < 20; ++n2) v[n2] = row[n2];
+            dft20(v);
+#pragma unroll
+            for (int k2 = 0; k2 < 20; ++k2) row[k2] = v[k2];
+        }
+        __syncthreads();
+
+        // ---- split into the two real spectra, round to complex64, power in float64 ----
+        // thread (pair, r) owns bins k = r + 20 j: Z[k] sits at row r, column j; its mirror Z[400 - k] at
+        // row (20 - r) % 20, column 19 - j (r > 0) or 20 - j (r = 0).  No divisions, no bank conflicts.
+        {
+            double pa[11], pb[11];
+            const int mrow = (lane20 == 0) ? 0 : 20 - lane20;
+            const int mcol0 = (lane20 == 0) ? 20 : 19;
+#pragma unroll
+            for (int j = 0; j < 11; ++j) {
+                if (j < 10 || lane20 == 0) {
+                    const double2 z = ex[lane20 * kRow + j];
+                    const int mc = mcol0 - j; // 20 only for k = 0, whose mirror is Z[0] itself
+                    const double2 y = (mc == 20) ? z : ex[mrow * kRow + mc];
+                    // X_a = (z + conj y), X_b = (z - conj y) / i   (the 1/2 lives in the window table)
+                    const float ar = (float)(z.x + y.x), ai = (float)(z.y - y.y);
+                    const float br = (float)(z.y + y.y), bi = (float)(y.x - z.x);
+                    pa[j] = (double)ar * (double)ar + (double)ai * (double)ai;
+                    pb[j] = (double)br * (double)br + (double)bi * (double)bi;
+                }
+            }
+            __syncthreads(); // every thread has read the exchange matrix: overlay it with the power spectra
+            double *rowa = s_pow + (2 * pair) * kPowStride + lane20;
+#pragma unroll
+            for (int j = 0; j < 11; ++j) {
+                if (j < 10 || lane20 == 0) {
+                    rowa[20 * j] = pa[j];
+                    rowa[kPowStride + 20 * j] = pb[j];
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- mel projection (sparse rows), floor, log10, float32 store ----
+        float *mel_out = p.mel + (size_t)p.n_mels * fbase;
+        for (int item = tid; item < p.n_mels * kFrames; item += kThreads) {
+            const int m = item / kFrames;
+            const int f = item % kFrames;
+            const double *pw = s_pow + f * kPowStride;
+            double acc = 0.0;
+            const int j1 = s_mrow[m + 1];
+            for (int j = s_mrow[m]; j < j1; ++j) acc = fma(s_mw[j], pw[s_mbin[j]], acc);
+            acc = (acc < 1e-10) ? 1e-10 : acc; // np.maximum(mel_floor, .): NaN propagates
+            const float out = (float)fast_log10(acc, s_logt);
+            if (f0 + f < T) mel_out[(size_t)m * T + f0 + f] = out;
+            s_mel[f * mel_stride + m] = out;
+        }
+
+        // ---- fused amplitude curve: numpy's mean(axis=0) adds the rows in order in float32 ----
+        if (p.amp != nullptr) {
+            __syncthreads();
+            if (tid < kFrames && f0 + tid < T) {
+                const float *col = s_mel + tid * mel_stride;
+                float acc = col[0];
+                for (int m = 1; m < p.n_mels; ++m) acc = __fadd_rn(acc, col[m]);
+                const float mean = __fdiv_rn(acc, (float)p.n_mels);
+                p.amp[fbase + f0 + tid] = __fmul_rn(-10.0f, mean);
+            }
+        }
+        // the next iteration's first __syncthreads orders these reads before the next overwrite
+    }
+    cp_async_wait<0>();
 }
 
 } // namespace
+
+int logmel_tables_init(aat_ctx *ctx)
+{
+    // inv_c[i] = double(1 / c_i), c_i = 1 + (i + 0.5) / 128;  y = -log10(inv_c[i]) of the ROUNDED inverse
+    std::vector<double2> t(kLogTable);
+    for (int i = 0; i < kLogTable; ++i) {
+        const long double c = 1.0L + ((long double)i + 0.5L) / (long double)kLogTable;
+        const double inv = (double)(1.0L / c);
+        t[i] = make_double2(inv, (double)(-log10l((long double)inv)));
+    }
+    AAT_CUDA_CHECK(cudaMalloc(&ctx->log_table, sizeof(double2) * kLogTable));
+    AAT_CUDA_CHECK(cudaMemcpy(ctx->log_table, t.data(), sizeof(double2) * kLogTable, cudaMemcpyHostToDevice));
+    return AAT_OK;
+}
 
 int launch_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave, int wave_dtype, float *mel, float *amp,
                   cudaStream_t stream)
@@ -259,22 +390,28 @@ int launch_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave, int wave
     p.tile_first = plan->d_tile_first;
     p.window_half = ctx->window_half;
     p.twiddle = ctx->twiddle;
+    p.log_table = ctx->log_table;
     p.mel_row_start = ctx->mel.row_start;
     p.mel_bin = ctx->mel.bin;
     p.mel_weight = ctx->mel.weight;
+    p.n_tiles = plan->mel_tiles;
     p.hop = ctx->cfg.hop_length;
     p.n_mels = ctx->mel.n_mels;
     p.nnz = ctx->mel.nnz;
     p.stage_len = (kFrames - 1) * p.hop + kNfft;
-    const size_t smem = logmel_smem_bytes(p.hop, p.n_mels, p.nnz);
+    const int wave_bytes = wave_dtype == AAT_F32 ? 4 : 8;
+    const int vec = 16 / wave_bytes;
+    p.stage_pad = (p.stage_len + vec - 1) / vec * vec;
+    const size_t smem = smem_layout(p.stage_pad, wave_bytes, p.n_mels, p.nnz).total;
+    auto kernel = wave_dtype == AAT_F32 ? logmel_kernel<float> : logmel_kernel<double>;
+    AAT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    AAT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
+    AAT_REQUIRE(per_sm >= 1, AAT_ERR_UNSUPPORTED, "aat_logmel: kernel does not fit on an SM (%zu bytes of shared memory)", smem);
+    int grid = ctx->num_sms * per_sm;
+    if (grid > plan->mel_tiles) grid = plan->mel_tiles;
     ProfileScope prof(ctx, AAT_K_LOGMEL, stream);
-    if (wave_dtype == AAT_F32) {
-        AAT_CUDA_CHECK(cudaFuncSetAttribute(logmel_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        logmel_kernel<float><<<plan->mel_tiles, kThreads, smem, stream>>>(p);
-    } else {
-        AAT_CUDA_CHECK(cudaFuncSetAttribute(logmel_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        logmel_kernel<double><<<plan->mel_tiles, kThreads, smem, stream>>>(p);
-    }
+    kernel<<<grid, kThreads, smem, stream>>>(p);
     AAT_LAUNCH_CHECK();
     return AAT_OK;
 }

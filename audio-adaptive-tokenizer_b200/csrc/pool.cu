@@ -38,6 +38,7 @@ constexpr int kStageBytes = 24 * 1024; // 8 rows of 768 fp32, 6 rows of 1024 fp3
 constexpr int kMaxConsumers = 256;
 constexpr int kMaxSlabs = 4; // 16-byte column slabs per consumer thread -> dim*e <= 16 KB
 constexpr int kMaxCtasPerSm = 2;
+constexpr int kOffCache = 256; // segment offsets of the CTA's neighbourhood kept in shared memory
 
 // ---------------------------------------------------------------- PTX helpers (mbarrier + bulk copy)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -198,6 +199,7 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
     __shared__ __align__(8) uint64_t s_full[kStages];
     __shared__ __align__(8) uint64_t s_empty[kStages];
     __shared__ int s_votes[kMaxConsumers / 32];
+    __shared__ int64_t s_off[kOffCache];
 
     const int tid = threadIdx.x;
     const int n_consumers = p.n_consumers;
@@ -270,17 +272,30 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
         int64_t seg = idx - 1; // -1: rows before the first segment; S_total: rows after the last one
         int64_t seg_begin, seg_end;
         bool in_gap;
+        // window of seg_off kept in shared memory: s_off[i] = seg_off[cache_base + i], i < cache_n.
+        // `seg` is uniform across the consumer threads, so refills are collective.
+        int64_t cache_base = 0;
+        int cache_n = 0;
+        auto fill_cache = [&](int64_t first) {
+            consumer_barrier(n_consumers); // nobody still reads the old window
+            cache_base = first;
+            const int64_t avail = S_total + 1 - first;
+            cache_n = (int)(avail < kOffCache ? avail : kOffCache);
+            for (int i = tid; i < cache_n; i += n_consumers) s_off[i] = p.seg_off[first + i];
+            consumer_barrier(n_consumers);
+        };
         auto load_segment = [&]() {
             if (seg < 0) {
-                in_gap = true, seg_begin = r0, seg_end = p.seg_off[0];
+                if (cache_n == 0 || cache_base != 0) fill_cache(0);
+                in_gap = true, seg_begin = r0, seg_end = s_off[0];
             } else if (seg >= S_total) {
                 in_gap = true, seg_begin = r0, seg_end = INT64_MAX;
             } else {
-                in_gap = false, seg_begin = p.seg_off[seg], seg_end = p.seg_off[seg + 1];
+                if (seg < cache_base || seg + 1 >= cache_base + cache_n) fill_cache(seg);
+                in_gap = false, seg_begin = s_off[seg - cache_base], seg_end = s_off[seg + 1 - cache_base];
             }
         };
         load_segment();
-
         auto reduce_acc = [&](int j, int k) { return (acc[j][0][k] + acc[j][1][k]) + (acc[j][2][k] + acc[j][3][k]); };
         auto clear_acc = [&]() {
 #pragma unroll
