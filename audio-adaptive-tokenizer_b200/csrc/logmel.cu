@@ -19,12 +19,12 @@
 //   * optional fused epilogue: amp[t] = -10 * mean_m(mel[m][t]) in numpy's sequential float32 order
 //     (ref:src/aat/tokenizer.py:67), so the boundary kernel does not have to re-read the mel.
 //
-// Execution shape: persistent CTAs (grid = resident CTAs), each looping over tiles of 16 consecutive
-// frames of one utterance (8 frame pairs x 20 threads = 160 threads).  The raw samples of the NEXT
-// tile are fetched with cp.async (LDGSTS, no registers) into the other half of a double buffer while
-// the current tile is transformed, so the global-load latency that dominated the first version of
-// this kernel (ncu: 37 % of stall samples on the load->convert dependency, profiles/) is hidden; the
-// window / twiddle / filter-bank / log tables are loaded into shared memory once per CTA.
+// Execution shape: persistent CTAs (grid = resident CTAs, three per SM), each looping over tiles of 16
+// consecutive frames of one utterance (8 frame pairs x 20 threads = 160 threads).  The raw samples of
+// the NEXT tile are fetched with cp.async (LDGSTS, no registers) as soon as pass 1 has consumed the
+// current ones, so the global-load latency that dominated the first version of this kernel (ncu: 37 %
+// of stall samples on the load->convert dependency, profiles/) hides behind pass 2, the split and the
+// mel projection; the filter-bank and log tables are loaded into shared memory once per CTA.
 #include "aat_internal.cuh"
 
 namespace aat {
@@ -184,9 +184,9 @@ __host__ __device__ inline SmemLayout smem_layout(int stage_pad, int wave_bytes,
         return at;
     };
     L.ex = take(sizeof(double2) * kPairs * kPairStride); // exchange matrix; later the power spectra (16 x 201 doubles)
-    L.raw = take((size_t)2 * stage_pad * wave_bytes);
-    L.win = take(sizeof(double) * kNfft);
-    L.tw = take(sizeof(double2) * 400);
+    L.raw = take((size_t)stage_pad * wave_bytes);
+    L.win = 0; // window and twiddles are read through the read-only L1 path (coalesced, hot in every CTA):
+    L.tw = 0;  // keeping them out of shared memory is what lets three CTAs share an SM
     L.logt = take(sizeof(double2) * kLogTable);
     L.mw = take(sizeof(double) * nnz);
     L.mbin = take(sizeof(int) * nnz);
@@ -197,15 +197,15 @@ __host__ __device__ inline SmemLayout smem_layout(int stage_pad, int wave_bytes,
 }
 
 template <typename WaveT>
-__global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams p)
+__global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SmemLayout L = smem_layout(p.stage_pad, (int)sizeof(WaveT), p.n_mels, p.nnz);
     double2 *s_ex = reinterpret_cast<double2 *>(smem_raw + L.ex);
     double *s_pow = reinterpret_cast<double *>(smem_raw + L.ex);
     WaveT *s_rawbuf = reinterpret_cast<WaveT *>(smem_raw + L.raw);
-    double *s_win = reinterpret_cast<double *>(smem_raw + L.win);
-    double2 *s_tw = reinterpret_cast<double2 *>(smem_raw + L.tw);
+    const double *__restrict__ g_win = p.window_half;
+    const double2 *__restrict__ g_tw = p.twiddle;
     double2 *s_logt = reinterpret_cast<double2 *>(smem_raw + L.logt);
     double *s_mw = reinterpret_cast<double *>(smem_raw + L.mw);
     int *s_mbin = reinterpret_cast<int *>(smem_raw + L.mbin);
@@ -217,14 +217,14 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
 
     // Asynchronous fetch of one tile's raw samples (reflect padding resolved per element,
     // TF:audio_utils.py:769-771); interior, 16-byte aligned tiles move 16 bytes per copy.
-    auto prefetch = [&](int tile_id, int buf) {
+    auto prefetch = [&](int tile_id) {
         if (tile_id < p.n_tiles) {
             const int utt = p.tile_utt[tile_id];
             const int64_t n = p.n_samples[utt];
             const int64_t woff = p.wave_off[utt];
             const int64_t g0 = (int64_t)(tile_id - p.tile_first[utt]) * kFrames * p.hop - kNfft / 2;
             const WaveT *wave = reinterpret_cast<const WaveT *>(p.wave) + woff;
-            WaveT *dst = s_rawbuf + (size_t)buf * p.stage_pad;
+            WaveT *dst = s_rawbuf;
             const bool interior = g0 >= 0 && g0 + p.stage_pad <= n;
             const bool aligned = ((woff + g0) % kVec) == 0 && (reinterpret_cast<uintptr_t>(p.wave) & 15) == 0;
             if (interior && aligned) {
@@ -237,11 +237,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
         cp_async_commit();
     };
 
-    prefetch(blockIdx.x, 0);
-    for (int i = tid; i < kNfft; i += kThreads) {
-        s_win[i] = p.window_half[i];
-        s_tw[i] = p.twiddle[i];
-    }
+    prefetch(blockIdx.x);
     for (int i = tid; i < kLogTable; i += kThreads) s_logt[i] = p.log_table[i];
     for (int i = tid; i < p.nnz; i += kThreads) {
         s_mw[i] = p.mel_weight[i];
@@ -254,33 +250,32 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
     double2 *ex = s_ex + pair * kPairStride;
     const int mel_stride = p.n_mels + 1;
 
-    int buf = 0;
-    for (int tile_id = blockIdx.x; tile_id < p.n_tiles; tile_id += gridDim.x, buf ^= 1) {
+    for (int tile_id = blockIdx.x; tile_id < p.n_tiles; tile_id += gridDim.x) {
         const int utt = p.tile_utt[tile_id];
         const int64_t T = 1 + p.n_samples[utt] / p.hop;
         const int64_t f0 = (int64_t)(tile_id - p.tile_first[utt]) * kFrames;
         const int64_t fbase = p.frame_off[utt];
 
-        prefetch(tile_id + gridDim.x, buf ^ 1); // lands while this tile is transformed
-        cp_async_wait<1>();                     // this tile's samples (older group) have arrived
-        __syncthreads();                        // ... for every thread; also fences the previous tile's smem reuse
+        cp_async_wait<0>(); // this tile's samples have arrived
+        __syncthreads();    // ... for every thread; also fences the previous tile's shared-memory reuse
 
         // ---- pass 1: thread n2 transforms x[20 n1 + n2] over n1, applies W_400^(n2 k1) ----
         {
             double2 v[20];
-            const WaveT *wa = s_rawbuf + (size_t)buf * p.stage_pad + (2 * pair) * p.hop + lane20;
+            const WaveT *wa = s_rawbuf + (2 * pair) * p.hop + lane20;
             const WaveT *wb = wa + p.hop;
 #pragma unroll
             for (int n1 = 0; n1 < 20; ++n1) {
-                const double w = s_win[20 * n1 + lane20];
+                const double w = __ldg(g_win + 20 * n1 + lane20);
                 v[n1] = make_double2((double)wa[20 * n1] * w, (double)wb[20 * n1] * w);
             }
             dft20(v);
             ex[lane20] = v[0];
 #pragma unroll
-            for (int k1 = 1; k1 < 20; ++k1) ex[k1 * kRow + lane20] = cmul(v[k1], s_tw[k1 * 20 + lane20]);
+            for (int k1 = 1; k1 < 20; ++k1) ex[k1 * kRow + lane20] = cmul(v[k1], __ldg(g_tw + k1 * 20 + lane20));
         }
         __syncthreads();
+        prefetch(tile_id + gridDim.x); // the raw buffer is free again: the next tile lands during the rest of this one
 
         // ---- pass 2: thread k1 transforms row k1 over n2; Z[k1 + 20 k2] goes back into its own row ----
         {
