@@ -44,12 +44,13 @@ extern std::atomic<int64_t> g_launch_count;
         AAT_CUDA_CHECK(cudaGetLastError());        \
     } while (0)
 
-// Sparse (CSR by mel filter) form of the dense (bins, mels) float64 filter bank.
+// Banded form of the dense (bins, mels) float64 filter bank: filter m covers the consecutive bins
+// [bin[m], bin[m] + row_start[m+1] - row_start[m]) with weights weight[row_start[m] ...].
 struct MelTable {
     int n_mels = 0;
-    int nnz = 0;
+    int nnz = 0;              // total band length
     int *row_start = nullptr; // device [n_mels + 1]
-    int *bin = nullptr;       // device [nnz]
+    int *bin = nullptr;       // device [n_mels] first bin of each filter
     double *weight = nullptr; // device [nnz]
 };
 

@@ -172,24 +172,28 @@ int aat_create(int device, const aat_config *cfg, const double *window_host, con
     rc = upload(&ctx->twiddle, tw.data(), tw.size());
     if (rc) return rc;
 
-    // dense (bins, mels) -> CSR by mel, bins ascending (the order a dot product over bins adds them)
+    // dense (bins, mels) -> banded rows: filter m covers bins [first_m, last_m] (its first and last non-zero
+    // weight; interior zeros, if any, are kept so the row stays contiguous), weights stored densely
     const int M = cfg->num_mel_filters;
-    std::vector<int> row_start(M + 1, 0), bins;
+    std::vector<int> row_start(M + 1, 0), first_bin(M, 0);
     std::vector<double> weights;
     for (int m = 0; m < M; ++m) {
-        for (int k = 0; k < kBins; ++k) {
-            const double w = mel_filters_host[(size_t)k * M + m];
-            if (w != 0.0) {
-                bins.push_back(k);
-                weights.push_back(w);
+        int lo = -1, hi = -1;
+        for (int k = 0; k < kBins; ++k)
+            if (mel_filters_host[(size_t)k * M + m] != 0.0) {
+                if (lo < 0) lo = k;
+                hi = k;
             }
+        if (lo >= 0) {
+            first_bin[m] = lo;
+            for (int k = lo; k <= hi; ++k) weights.push_back(mel_filters_host[(size_t)k * M + m]);
         }
-        row_start[m + 1] = (int)bins.size();
+        row_start[m + 1] = (int)weights.size();
     }
     ctx->mel.n_mels = M;
-    ctx->mel.nnz = (int)bins.size();
+    ctx->mel.nnz = (int)weights.size();
     if ((rc = upload(&ctx->mel.row_start, row_start.data(), row_start.size()))) return rc;
-    if ((rc = upload(&ctx->mel.bin, bins.data(), bins.size()))) return rc;
+    if ((rc = upload(&ctx->mel.bin, first_bin.data(), first_bin.size()))) return rc;
     if ((rc = upload(&ctx->mel.weight, weights.data(), weights.size()))) return rc;
 
     if ((rc = logmel_tables_init(ctx))) return rc;

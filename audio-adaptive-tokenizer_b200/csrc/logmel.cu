@@ -14,8 +14,9 @@
 //     transpose with the W_400 twiddles between the two passes
 //   * split: X_a[k] = (Z[k] + conj Z[400-k]) / 2,  X_b[k] = (Z[k] - conj Z[400-k]) / 2i
 //     (the 1/2 is folded into the window table: an exact power-of-two scaling)
-//   * power (float64 of the float32-rounded re/im), sparse triangular mel (<= 2 filters per bin,
-//     388 non-zeros: a gather, not a dense contraction -> CUDA cores, no tensor cores), log10, float32
+//   * power (float64 of the float32-rounded re/im), banded triangular mel (each filter touches 2-18
+//     consecutive bins, 388 non-zeros of 12 864: a gather, not a dense contraction -> CUDA cores, no
+//     tensor cores), log10, float32
 //   * optional fused epilogue: amp[t] = -10 * mean_m(mel[m][t]) in numpy's sequential float32 order
 //     (ref:src/aat/tokenizer.py:67), so the boundary kernel does not have to re-read the mel.
 //
@@ -37,7 +38,7 @@ constexpr int kThreads = kPairs * 20;        // 160
 constexpr int kRow = 21;                     // padded row (double2 units): 21 is odd -> conflict-free columns
 constexpr int kPairStride = 20 * kRow;       // 420 double2; 420 % 8 == 4 keeps neighbouring pairs on distinct banks
 constexpr int kPowStride = kBins;            // 201 doubles (odd)
-constexpr int kLogTable = 128;               // entries of the log10 table
+constexpr int kLogTable = 64;                // entries of the log10 table (|r| < 2^-7, degree-8 series)
 
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
@@ -112,7 +113,7 @@ template <int kPending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
 // log10 of a positive finite double to full double accuracy, table driven:
-//   x = 2^e * m, m in [1, 2); i = top 7 mantissa bits; r = m * inv_c[i] - 1 (|r| < 2^-7, one FMA);
+//   x = 2^e * m, m in [1, 2); i = top 6 mantissa bits; r = m * inv_c[i] - 1 (|r| < 2^-7, one FMA);
 //   log10(x) = e * log10(2) + (-log10(inv_c[i])) + log1p(r) / ln(10)
 // The table stores inv_c[i] = double(1 / c_i) and -log10 of that ROUNDED value, so the identity is
 // exact and the only errors are the final roundings (~1e-16 relative), far below float32 resolution.
@@ -122,7 +123,7 @@ __device__ __forceinline__ double fast_log10(double x, const double2 *__restrict
     const int hi = (int)(bits >> 32);
     if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log10(x); // zero, subnormal, inf, nan, negative
     const int e = (hi >> 20) - 1023;
-    const int idx = (hi >> 13) & (kLogTable - 1);
+    const int idx = (hi >> 14) & (kLogTable - 1);
     const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
     const double2 t = table[idx];
     const double r = fma(m, t.x, -1.0);
@@ -185,13 +186,13 @@ __host__ __device__ inline SmemLayout smem_layout(int stage_pad, int wave_bytes,
     };
     L.ex = take(sizeof(double2) * kPairs * kPairStride); // exchange matrix; later the power spectra (16 x 201 doubles)
     L.raw = take((size_t)stage_pad * wave_bytes);
-    L.win = 0; // window and twiddles are read through the read-only L1 path (coalesced, hot in every CTA):
-    L.tw = 0;  // keeping them out of shared memory is what lets three CTAs share an SM
+    L.win = 0; // the window is read through the read-only L1 path (20 coalesced loads at the top of pass 1)
+    L.tw = take(sizeof(double2) * 400);
     L.logt = take(sizeof(double2) * kLogTable);
     L.mw = take(sizeof(double) * nnz);
-    L.mbin = take(sizeof(int) * nnz);
+    L.mbin = take(sizeof(int) * n_mels);
     L.mrow = take(sizeof(int) * (n_mels + 1));
-    L.mel = take(sizeof(float) * kFrames * (n_mels + 1));
+    L.mel = L.ex; // float32 mel tile for the amplitude epilogue: overlays the power spectra once they are dead
     L.total = o;
     return L;
 }
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
     double *s_pow = reinterpret_cast<double *>(smem_raw + L.ex);
     WaveT *s_rawbuf = reinterpret_cast<WaveT *>(smem_raw + L.raw);
     const double *__restrict__ g_win = p.window_half;
-    const double2 *__restrict__ g_tw = p.twiddle;
+    double2 *s_tw = reinterpret_cast<double2 *>(smem_raw + L.tw);
     double2 *s_logt = reinterpret_cast<double2 *>(smem_raw + L.logt);
     double *s_mw = reinterpret_cast<double *>(smem_raw + L.mw);
     int *s_mbin = reinterpret_cast<int *>(smem_raw + L.mbin);
@@ -238,11 +239,10 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
     };
 
     prefetch(blockIdx.x);
+    for (int i = tid; i < 400; i += kThreads) s_tw[i] = p.twiddle[i];
     for (int i = tid; i < kLogTable; i += kThreads) s_logt[i] = p.log_table[i];
-    for (int i = tid; i < p.nnz; i += kThreads) {
-        s_mw[i] = p.mel_weight[i];
-        s_mbin[i] = p.mel_bin[i];
-    }
+    for (int i = tid; i < p.nnz; i += kThreads) s_mw[i] = p.mel_weight[i];
+    for (int i = tid; i < p.n_mels; i += kThreads) s_mbin[i] = p.mel_bin[i];
     for (int i = tid; i <= p.n_mels; i += kThreads) s_mrow[i] = p.mel_row_start[i];
 
     const int pair = tid / 20;
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
             dft20(v);
             ex[lane20] = v[0];
 #pragma unroll
-            for (int k1 = 1; k1 < 20; ++k1) ex[k1 * kRow + lane20] = cmul(v[k1], __ldg(g_tw + k1 * 20 + lane20));
+            for (int k1 = 1; k1 < 20; ++k1) ex[k1 * kRow + lane20] = cmul(v[k1], s_tw[k1 * 20 + lane20]);
         }
         __syncthreads();
         prefetch(tile_id + gridDim.x); // the raw buffer is free again: the next tile lands during the rest of this one
@@ -321,23 +321,61 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
         }
         __syncthreads();
 
-        // ---- mel projection (sparse rows), floor, log10, float32 store ----
-        float *mel_out = p.mel + (size_t)p.n_mels * fbase;
-        for (int item = tid; item < p.n_mels * kFrames; item += kThreads) {
-            const int m = item / kFrames;
-            const int f = item % kFrames;
+        // ---- mel projection (banded rows), floor, log10, float32 store ----
+        // thread (f, q): frame f = tid % 16, filters q, q + 10, ...  Half-warps share a filter, so the
+        // weights are broadcast reads and the 16 frames hit 16 different banks (row stride 201 doubles).
+        // Two filters are evaluated together so that two independent dependency chains are in flight.
+        constexpr int kGroups = kThreads / kFrames; // 10
+        constexpr int kMaxPerThread = (kMaxMels + kGroups - 1) / kGroups;
+        float outs[kMaxPerThread];
+        {
+            const int f = tid & (kFrames - 1);
+            const int q = tid / kFrames;
             const double *pw = s_pow + f * kPowStride;
-            double acc = 0.0;
-            const int j1 = s_mrow[m + 1];
-            for (int j = s_mrow[m]; j < j1; ++j) acc = fma(s_mw[j], pw[s_mbin[j]], acc);
-            acc = (acc < 1e-10) ? 1e-10 : acc; // np.maximum(mel_floor, .): NaN propagates
-            const float out = (float)fast_log10(acc, s_logt);
-            if (f0 + f < T) mel_out[(size_t)m * T + f0 + f] = out;
-            s_mel[f * mel_stride + m] = out;
+            float *dst = p.mel + (size_t)p.n_mels * fbase + f0 + f;
+            const bool live = f0 + f < T;
+            const int Ti = (int)T;
+            auto band = [&](int m) {
+                const int j0 = s_mrow[m];
+                const int n = s_mrow[m + 1] - j0;
+                const double *ww = s_mw + j0;
+                const double *pp = pw + s_mbin[m];
+                double acc = 0.0;
+#pragma unroll 1
+                for (int t = 0; t < n; ++t) acc = fma(ww[t], pp[t], acc);
+                return (acc < 1e-10) ? 1e-10 : acc; // np.maximum(mel_floor, .): NaN propagates
+            };
+#pragma unroll
+            for (int i = 0; i < kMaxPerThread; i += 2) {
+                const int m0 = q + i * kGroups, m1 = m0 + kGroups;
+                if (m0 < p.n_mels) {
+                    const bool two = m1 < p.n_mels;
+                    const double a0 = band(m0);
+                    const double a1 = two ? band(m1) : 1.0;
+                    const float o0 = (float)fast_log10(a0, s_logt);
+                    const float o1 = (float)fast_log10(a1, s_logt);
+                    outs[i] = o0;
+                    if (i + 1 < kMaxPerThread) outs[i + 1] = o1;
+                    if (live) {
+                        dst[(unsigned)(m0 * Ti)] = o0;
+                        if (two) dst[(unsigned)(m1 * Ti)] = o1;
+                    }
+                }
+            }
         }
 
         // ---- fused amplitude curve: numpy's mean(axis=0) adds the rows in order in float32 ----
         if (p.amp != nullptr) {
+            __syncthreads(); // the power spectra are dead: stage the float32 tile over them
+            {
+                const int f = tid & (kFrames - 1);
+                const int q = tid / kFrames;
+#pragma unroll
+                for (int i = 0; i < kMaxPerThread; ++i) {
+                    const int m = q + i * kGroups;
+                    if (m < p.n_mels) s_mel[f * mel_stride + m] = outs[i];
+                }
+            }
             __syncthreads();
             if (tid < kFrames && f0 + tid < T) {
                 const float *col = s_mel + tid * mel_stride;
