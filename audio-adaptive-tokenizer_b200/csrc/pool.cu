@@ -450,18 +450,38 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
     }
 }
 
-// colsum_out[d] = sum over CTAs (in CTA order) of the per-CTA sums; colsum_out[dim] = S.
-__global__ void colsum_reduce_kernel(const double *partial, int n_ctas, int dim, int64_t n_seg,
-                                     const int64_t *n_seg_dev, double *out)
+// colsum_out[d] = sum over the pool CTAs of their per-CTA column sums; colsum_out[dim] = S.
+// Block = 32 columns x 8 slices of the CTA axis (coalesced 256-byte rows); the slice partials are then
+// added in slice order, so the result does not depend on scheduling.
+constexpr int kReduceSlices = 8;
+__global__ void __launch_bounds__(32 * kReduceSlices)
+colsum_reduce_kernel(const double *partial, int n_ctas, int dim, int64_t n_seg, const int64_t *n_seg_dev, double *out)
 {
-    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double s_part[kReduceSlices][33];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int d = blockIdx.x * 32 + lane;
+    const int per = (n_ctas + kReduceSlices - 1) / kReduceSlices;
+    const int c0 = slice * per, c1 = min(n_ctas, c0 + per);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     if (d < dim) {
-        double s = 0.0;
-        for (int c = 0; c < n_ctas; ++c) s += partial[(size_t)c * dim + d];
-        out[d] = s;
-    } else if (d == dim) {
-        out[dim] = (double)(n_seg_dev ? min(*n_seg_dev, n_seg) : n_seg);
+        int c = c0;
+        for (; c + 4 <= c1; c += 4) {
+            s0 += partial[(size_t)c * dim + d];
+            s1 += partial[(size_t)(c + 1) * dim + d];
+            s2 += partial[(size_t)(c + 2) * dim + d];
+            s3 += partial[(size_t)(c + 3) * dim + d];
+        }
+        for (; c < c1; ++c) s0 += partial[(size_t)c * dim + d];
     }
+    s_part[slice][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (slice == 0 && d < dim) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < kReduceSlices; ++k) s += s_part[k][lane];
+        out[d] = s;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[dim] = (double)(n_seg_dev ? min(*n_seg_dev, n_seg) : n_seg);
 }
 
 __global__ void colsum_accumulate_kernel(double *acc, const double *colsum, int n)
@@ -592,9 +612,8 @@ int launch_mean_pool(aat_ctx *ctx, const void *emb, int emb_dtype, int64_t n_row
         rc = launch_slabs<__nv_bfloat16>(ctx, p, slabs, smem, want_colsum, stream, &grid);
     if (rc != AAT_OK) return rc;
     if (want_colsum) {
-        const int threads = 128;
-        colsum_reduce_kernel<<<(dim + 1 + threads - 1) / threads, threads, 0, stream>>>(ctx->pool.colsum, grid, dim,
-                                                                                        n_seg, n_seg_dev, colsum);
+        colsum_reduce_kernel<<<(dim + 31) / 32, 32 * kReduceSlices, 0, stream>>>(ctx->pool.colsum, grid, dim, n_seg,
+                                                                                 n_seg_dev, colsum);
         AAT_LAUNCH_CHECK();
     }
     return AAT_OK;
