@@ -333,9 +333,11 @@ class PackedBatch:
                                            self.amp.data_ptr() if with_amp else None, self._stream()))
         return self.mel
 
-    def boundaries(self, mel=None, use_amp: bool = True, with_minima: bool = True):
+    def boundaries(self, mel=None, use_amp: bool = True, with_minima: bool = True, with_csr: bool = True):
         """K3.  ``mel=None`` uses this batch's own mel (and the fused amplitude curve when ``use_amp``);
-        pass a packed float32 CUDA tensor to segment somebody else's mel (e.g. the reference's)."""
+        pass a packed float32 CUDA tensor to segment somebody else's mel (e.g. the reference's).
+        ``with_csr`` also fills ``seg_off`` / ``n_seg`` / ``utt_seg_off`` (what :meth:`frame_csr` computes)
+        from the kernel's own tail, saving a launch."""
         mel_ptr, amp_ptr = self.mel.data_ptr(), (self.amp.data_ptr() if use_amp else None)
         if mel is not None:
             if mel.numel() != self.n_mels * self.total_frames or not mel.is_cuda or not mel.is_contiguous():
@@ -344,7 +346,9 @@ class PackedBatch:
         _cabi.check(_cabi.lib().aat_boundaries(
             self.ctx.handle, self.handle, mel_ptr, amp_ptr, self.seg_start.data_ptr(), self.seg_len.data_ptr(),
             self.seg_count.data_ptr(), self.minima.data_ptr() if with_minima else None,
-            self.minima_count.data_ptr() if with_minima else None, self.status.data_ptr(), self._stream()))
+            self.minima_count.data_ptr() if with_minima else None, self.status.data_ptr(),
+            self.seg_off.data_ptr() if with_csr else None, self.n_seg.data_ptr() if with_csr else None,
+            self.utt_seg_off.data_ptr() if with_csr else None, self._stream()))
         return self.seg_len, self.seg_count
 
     def frame_csr(self):

@@ -79,6 +79,7 @@ struct aat_ctx {
     aat_config cfg{};
     double *window_half = nullptr; // device [400], 0.5 * window (exact scaling, folds the /2 of the two-frame split)
     double2 *twiddle = nullptr;    // device [20 * 20], W_400^(k1 * n2) at [k1 * 20 + n2]
+    unsigned *ticket = nullptr;    // device [1], "last CTA done" counter of the boundaries kernel (self-resetting)
     double2 *log_table = nullptr;  // device [128], (1/c_i, -log10(1/c_i)) for the log-mel kernel's log10
     aat::MelTable mel{};
     aat::PoolScratch pool{};
@@ -105,6 +106,9 @@ struct aat_plan {
     int64_t *d_seg_slot_off = nullptr;  // [B+1]
     int32_t *d_tile_utt = nullptr;      // [mel_tiles] utterance of each tile
     int32_t *d_tile_first = nullptr;    // [B+1] first tile index of each utterance
+    // scratch written by the boundaries kernel for its fused frame-CSR epilogue
+    int64_t *d_seg_local = nullptr;     // [total_seg_slots]
+    int64_t *d_utt_frames = nullptr;    // [B]
 };
 
 namespace aat {
@@ -114,7 +118,7 @@ int launch_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave, int wave
                   cudaStream_t stream);
 int launch_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel, const float *amp, int64_t *seg_start,
                       int64_t *seg_len, int32_t *seg_count, int64_t *minima, int32_t *minima_count, int32_t *status,
-                      cudaStream_t stream);
+                      int64_t *seg_off, int64_t *n_seg, int64_t *utt_seg_off, cudaStream_t stream);
 int launch_process_boarders(aat_ctx *ctx, int64_t n_samples, const int64_t *boarders, int64_t n_boarders,
                             int64_t *seg_start, int64_t *seg_len, int64_t capacity, int32_t *seg_count,
                             int32_t *status, cudaStream_t stream);

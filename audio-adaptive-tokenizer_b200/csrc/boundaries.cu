@@ -24,8 +24,15 @@ constexpr int kChunk = 4096; // mel frames per pass; must be >= running_mean_poi
 struct SegState {
     int64_t prev;
     int64_t count;
-    int32_t status; // < 0: aat_status error; otherwise bit 0 = the last segment is the zero-padded tail
+    int32_t status;   // < 0: aat_status error; otherwise bit 0 = the last segment is the zero-padded tail
+    int64_t frames;   // HuBERT frames of the segments emitted so far (per-segment encode convention)
+    int64_t *local;   // optional: local[i] = frames before segment i of this utterance
 };
+
+__device__ __forceinline__ int64_t hubert_frames(int64_t len)
+{
+    return (len < 400) ? 0 : (len - 400) / 320 + 1; // TF:models/hubert/modeling_hubert.py:675-688, closed form
+}
 
 __device__ __forceinline__ void emit_segment(int64_t start, int64_t len, int64_t *seg_start, int64_t *seg_len,
                                              int64_t capacity, SegState &st)
@@ -33,6 +40,8 @@ __device__ __forceinline__ void emit_segment(int64_t start, int64_t len, int64_t
     if (st.count < capacity) {
         seg_start[st.count] = start;
         seg_len[st.count] = len;
+        if (st.local) st.local[st.count] = st.frames;
+        st.frames += hubert_frames(len);
     } else {
         st.status = AAT_ERR_CAPACITY;
     }
@@ -80,6 +89,158 @@ __device__ __forceinline__ void finish_segments(int64_t n_samples, int64_t min_f
     }
 }
 
+
+__device__ __forceinline__ int64_t ld_cg(const int64_t *p) { return __ldcg(reinterpret_cast<const long long *>(p)); }
+
+// Segment lengths -> packed CSR of HuBERT frame offsets (per-segment encode convention), by ONE CTA.
+// s_seg / s_frm: shared scratch of n_utts + 1 int64 each.  Loads bypass L1 (the lengths may have been
+// written by other CTAs of the same launch).
+__device__ void build_frame_csr(int n_utts, const int64_t *seg_slot_off, const int64_t *seg_len,
+                                const int32_t *seg_count, int64_t *seg_off, int64_t *n_seg_out,
+                                int64_t *utt_seg_off_out, int64_t *s_seg, int64_t *s_frm)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_threads = blockDim.x, n_warps = n_threads >> 5;
+    __shared__ int64_t s_wsum[2][32];
+    // per-utterance totals (a warp per utterance)
+    for (int b = warp; b < n_utts; b += n_warps) {
+        const int64_t *len = seg_len + seg_slot_off[b];
+        const int cnt = __ldcg(seg_count + b);
+        int64_t sum = 0;
+        for (int i = lane; i < cnt; i += 32) sum += hubert_frames(ld_cg(len + i));
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        if (lane == 0) {
+            s_seg[b + 1] = cnt;
+            s_frm[b + 1] = sum;
+        }
+    }
+    if (tid == 0) s_seg[0] = 0, s_frm[0] = 0;
+    __syncthreads();
+    // block-wide inclusive scan of both arrays: contiguous chunk per thread, shuffle scan of the chunk totals
+    const int per = (n_utts + n_threads - 1) / n_threads;
+    const int b0 = 1 + tid * per, b1 = min(n_utts + 1, b0 + per);
+    int64_t a = 0, f = 0;
+    for (int b = b0; b < b1; ++b) a += s_seg[b], f += s_frm[b];
+    int64_t ia = a, jf = f;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int64_t va = __shfl_up_sync(0xffffffffu, ia, d), vf = __shfl_up_sync(0xffffffffu, jf, d);
+        if (lane >= d) ia += va, jf += vf;
+    }
+    if (lane == 31) s_wsum[0][warp] = ia, s_wsum[1][warp] = jf;
+    __syncthreads();
+    if (warp == 0) {
+        int64_t wa = lane < n_warps ? s_wsum[0][lane] : 0, wf = lane < n_warps ? s_wsum[1][lane] : 0;
+        int64_t xa = wa, xf = wf;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int64_t va = __shfl_up_sync(0xffffffffu, xa, d), vf = __shfl_up_sync(0xffffffffu, xf, d);
+            if (lane >= d) xa += va, xf += vf;
+        }
+        s_wsum[0][lane] = xa - wa, s_wsum[1][lane] = xf - wf; // exclusive warp offsets
+    }
+    __syncthreads();
+    {
+        int64_t ra = s_wsum[0][warp] + ia - a, rf = s_wsum[1][warp] + jf - f; // exclusive prefix of this chunk
+        for (int b = b0; b < b1; ++b) {
+            ra += s_seg[b], rf += s_frm[b];
+            s_seg[b] = ra, s_frm[b] = rf;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        *n_seg_out = s_seg[n_utts];
+        seg_off[s_seg[n_utts]] = s_frm[n_utts];
+    }
+    if (utt_seg_off_out)
+        for (int b = tid; b <= n_utts; b += n_threads) utt_seg_off_out[b] = s_seg[b];
+    // running offsets inside each utterance (a warp per utterance)
+    for (int b = warp; b < n_utts; b += n_warps) {
+        const int64_t *len = seg_len + seg_slot_off[b];
+        const int cnt = __ldcg(seg_count + b);
+        int64_t base = s_frm[b];
+        int64_t *dst = seg_off + s_seg[b];
+        for (int i0 = 0; i0 < cnt; i0 += 32) {
+            const int i = i0 + lane;
+            const int64_t fr = (i < cnt) ? hubert_frames(ld_cg(len + i)) : 0;
+            int64_t incl = fr;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int64_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            if (i < cnt) dst[i] = base + incl - fr;
+            base += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+}
+
+// Fused form used by the boundaries kernel's last CTA: every utterance's CTA has already written its frame
+// total and the local (within-utterance) frame offset of each segment, so what is left is one scan over the
+// utterances and a rebase — two rounds of independent loads instead of a per-utterance dependency chain.
+__device__ void rebase_frame_csr(int n_utts, const int64_t *seg_slot_off, const int64_t *seg_local,
+                                 const int64_t *utt_frames, const int32_t *seg_count, int64_t *seg_off,
+                                 int64_t *n_seg_out, int64_t *utt_seg_off_out, int64_t *s_seg, int64_t *s_frm)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_threads = blockDim.x, n_warps = n_threads >> 5;
+    __shared__ int64_t s_wsum[2][32];
+    for (int b = tid; b < n_utts; b += n_threads) {
+        s_seg[b + 1] = __ldcg(seg_count + b);
+        s_frm[b + 1] = ld_cg(utt_frames + b);
+    }
+    if (tid == 0) s_seg[0] = 0, s_frm[0] = 0;
+    __syncthreads();
+    const int per = (n_utts + n_threads - 1) / n_threads;
+    const int b0 = 1 + tid * per, b1 = min(n_utts + 1, b0 + per);
+    int64_t a = 0, f = 0;
+    for (int b = b0; b < b1; ++b) a += s_seg[b], f += s_frm[b];
+    int64_t ia = a, jf = f;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int64_t va = __shfl_up_sync(0xffffffffu, ia, d), vf = __shfl_up_sync(0xffffffffu, jf, d);
+        if (lane >= d) ia += va, jf += vf;
+    }
+    if (lane == 31) s_wsum[0][warp] = ia, s_wsum[1][warp] = jf;
+    __syncthreads();
+    if (warp == 0) {
+        int64_t wa = lane < n_warps ? s_wsum[0][lane] : 0, wf = lane < n_warps ? s_wsum[1][lane] : 0;
+        int64_t xa = wa, xf = wf;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int64_t va = __shfl_up_sync(0xffffffffu, xa, d), vf = __shfl_up_sync(0xffffffffu, xf, d);
+            if (lane >= d) xa += va, xf += vf;
+        }
+        s_wsum[0][lane] = xa - wa, s_wsum[1][lane] = xf - wf;
+    }
+    __syncthreads();
+    {
+        int64_t ra = s_wsum[0][warp] + ia - a, rf = s_wsum[1][warp] + jf - f;
+        for (int b = b0; b < b1; ++b) {
+            ra += s_seg[b], rf += s_frm[b];
+            s_seg[b] = ra, s_frm[b] = rf;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        *n_seg_out = s_seg[n_utts];
+        seg_off[s_seg[n_utts]] = s_frm[n_utts];
+    }
+    if (utt_seg_off_out)
+        for (int b = tid; b <= n_utts; b += n_threads) utt_seg_off_out[b] = s_seg[b];
+    // rebase: half-warps take utterances round-robin; loads of successive utterances are independent
+    const int half = tid >> 4, hl = tid & 15, n_halves = n_threads >> 4;
+#pragma unroll 4
+    for (int b = half; b < n_utts; b += n_halves) {
+        const int cnt = (int)(s_seg[b + 1] - s_seg[b]);
+        const int64_t *src = seg_local + seg_slot_off[b];
+        int64_t *dst = seg_off + s_seg[b];
+        const int64_t base = s_frm[b];
+        for (int i = hl; i < cnt; i += 16) dst[i] = base + ld_cg(src + i);
+    }
+}
+
 struct BoundaryParams {
     const float *mel;
     const float *amp;
@@ -92,6 +253,14 @@ struct BoundaryParams {
     int64_t *minima;
     int32_t *minima_count;
     int32_t *status;
+    // optional fused frame CSR (built by the last CTA to finish)
+    int64_t *seg_off;
+    int64_t *n_seg;
+    int64_t *utt_seg_off;
+    int64_t *seg_local;   // [total_seg_slots] plan scratch: within-utterance frame offsets
+    int64_t *utt_frames;  // [n_utts] plan scratch: frames per utterance
+    unsigned *ticket;
+    int n_utts;
     int64_t min_frames, max_frames;
     int hop, n_mels, npts;
     float max_amp;
@@ -124,7 +293,7 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel(const BoundaryPara
 
     const int64_t L = T - p.npts; // running-mean length; minima live in [1, L-2]
     const float nf = (float)p.npts;
-    SegState st{0, 0, 0};
+    SegState st{0, 0, 0, 0, p.seg_off ? p.seg_local + slot0 : nullptr};
     int64_t n_minima = 0;
     int64_t i_done = 1; // next candidate index to test
 
@@ -250,6 +419,25 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel(const BoundaryPara
         p.seg_count[utt] = (int32_t)(st.count < capacity ? st.count : capacity);
         if (p.minima_count) p.minima_count[utt] = (int32_t)n_minima;
         p.status[utt] = st.status;
+        if (p.seg_off) p.utt_frames[utt] = st.frames;
+    }
+
+    // ---- fused epilogue: the last CTA to finish turns all segment lengths into the packed frame CSR ----
+    if (p.seg_off != nullptr) {
+        __shared__ int s_last;
+        if (tid == 0) {
+            __threadfence(); // this CTA's segment writes (all by thread 0) are visible before the ticket
+            s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            int64_t *s_seg = reinterpret_cast<int64_t *>(smem_raw); // the chunk buffers are free now
+            int64_t *s_frm = s_seg + p.n_utts + 1;
+            rebase_frame_csr(p.n_utts, p.seg_slot_off, p.seg_local, p.utt_frames, p.seg_count, p.seg_off, p.n_seg,
+                             p.utt_seg_off, s_seg, s_frm);
+            if (tid == 0) *p.ticket = 0; // ready for the next launch (graph replays included)
+        }
     }
 }
 
@@ -258,7 +446,7 @@ __global__ void process_boarders_kernel(int64_t n_samples, const int64_t *boarde
                                         int64_t capacity, int32_t *seg_count, int32_t *status)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    SegState st{0, 0, 0};
+    SegState st{0, 0, 0, 0, nullptr};
     for (int64_t i = 0; i < n_boarders; ++i)
         push_boarder(boarders[i], min_frames, max_frames, seg_start, seg_len, capacity, st);
     finish_segments(n_samples, min_frames, seg_start, seg_len, capacity, st);
@@ -266,78 +454,24 @@ __global__ void process_boarders_kernel(int64_t n_samples, const int64_t *boarde
     *status = st.status;
 }
 
-// Segment lengths -> packed CSR of HuBERT frame offsets (per-segment encode convention).
-// Single CTA: a warp per utterance computes its frame total, the utterance totals are scanned, then each
-// warp writes its utterance's running offsets.
+// Stand-alone form of the same CSR construction (one CTA).
 constexpr int kCsrThreads = 1024;
-
-__device__ __forceinline__ int64_t hubert_frames(int64_t len)
-{
-    const int64_t f = (len - 400) / 320 + 1; // C division truncates toward zero; guard the negative range
-    return (len < 400) ? 0 : f;
-}
 
 __global__ void __launch_bounds__(kCsrThreads)
 segment_frame_csr_kernel(int n_utts, const int64_t *seg_slot_off, const int64_t *seg_len, const int32_t *seg_count,
                          int64_t *seg_off, int64_t *n_seg_out, int64_t *utt_seg_off_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int64_t *s_seg = reinterpret_cast<int64_t *>(smem_raw); // [n_utts + 1] packed segment index of each utterance
-    int64_t *s_frm = s_seg + n_utts + 1;                     // [n_utts + 1] first frame of each utterance
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int kWarps = kCsrThreads / 32;
-
-    for (int b = warp; b < n_utts; b += kWarps) {
-        const int64_t *len = seg_len + seg_slot_off[b];
-        const int cnt = seg_count[b];
-        int64_t sum = 0;
-        for (int i = lane; i < cnt; i += 32) sum += hubert_frames(len[i]);
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
-        if (lane == 0) {
-            s_seg[b + 1] = cnt;
-            s_frm[b + 1] = sum;
-        }
-    }
-    __syncthreads();
-    if (tid == 0) { // n_utts is small (thousands): a serial scan costs microseconds
-        s_seg[0] = 0;
-        s_frm[0] = 0;
-        for (int b = 0; b < n_utts; ++b) {
-            s_seg[b + 1] += s_seg[b];
-            s_frm[b + 1] += s_frm[b];
-        }
-        *n_seg_out = s_seg[n_utts];
-        seg_off[s_seg[n_utts]] = s_frm[n_utts];
-    }
-    __syncthreads();
-    if (utt_seg_off_out)
-        for (int b = tid; b <= n_utts; b += kCsrThreads) utt_seg_off_out[b] = s_seg[b];
-    for (int b = warp; b < n_utts; b += kWarps) {
-        const int64_t *len = seg_len + seg_slot_off[b];
-        const int cnt = seg_count[b];
-        int64_t base = s_frm[b];
-        int64_t *dst = seg_off + s_seg[b];
-        for (int i0 = 0; i0 < cnt; i0 += 32) {
-            const int i = i0 + lane;
-            const int64_t f = (i < cnt) ? hubert_frames(len[i]) : 0;
-            int64_t incl = f;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int64_t v = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += v;
-            }
-            if (i < cnt) dst[i] = base + incl - f;
-            base += __shfl_sync(0xffffffffu, incl, 31);
-        }
-    }
+    int64_t *s_seg = reinterpret_cast<int64_t *>(smem_raw);
+    build_frame_csr(n_utts, seg_slot_off, seg_len, seg_count, seg_off, n_seg_out, utt_seg_off_out, s_seg,
+                    s_seg + n_utts + 1);
 }
 
 } // namespace
 
 int launch_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel, const float *amp, int64_t *seg_start,
                       int64_t *seg_len, int32_t *seg_count, int64_t *minima, int32_t *minima_count, int32_t *status,
-                      cudaStream_t stream)
+                      int64_t *seg_off, int64_t *n_seg, int64_t *utt_seg_off, cudaStream_t stream)
 {
     if (plan->n_utts == 0) return AAT_OK;
     BoundaryParams p{};
@@ -358,11 +492,24 @@ int launch_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel, cons
     p.n_mels = ctx->cfg.num_mel_filters;
     p.npts = ctx->cfg.running_mean_points;
     p.max_amp = ctx->cfg.max_amplitude_for_minima;
+    p.n_utts = plan->n_utts;
+    p.ticket = ctx->ticket;
+    const size_t csr_smem = sizeof(int64_t) * 2 * (size_t)(plan->n_utts + 1);
+    const bool fuse_csr = seg_off != nullptr && csr_smem <= sizeof(float) * 2 * kChunk;
+    p.seg_off = fuse_csr ? seg_off : nullptr;
+    p.n_seg = n_seg;
+    p.utt_seg_off = utt_seg_off;
+    p.seg_local = plan->d_seg_local;
+    p.utt_frames = plan->d_utt_frames;
     const size_t smem = sizeof(float) * (size_t)(kChunk + ((p.npts + 2 + 3) & ~3) + kChunk) + sizeof(int) * (size_t)kChunk;
     AAT_CUDA_CHECK(cudaFuncSetAttribute(boundaries_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ProfileScope prof(ctx, AAT_K_BOUNDARIES, stream);
-    boundaries_kernel<<<plan->n_utts, kThreads, smem, stream>>>(p);
-    AAT_LAUNCH_CHECK();
+    {
+        ProfileScope prof(ctx, AAT_K_BOUNDARIES, stream);
+        boundaries_kernel<<<plan->n_utts, kThreads, smem, stream>>>(p);
+        AAT_LAUNCH_CHECK();
+    }
+    if (seg_off != nullptr && !fuse_csr) // batch too large for the fused epilogue's scratch: separate kernel
+        return launch_segment_frame_csr(ctx, plan, seg_len, seg_count, seg_off, n_seg, utt_seg_off, stream);
     return AAT_OK;
 }
 

@@ -196,6 +196,8 @@ int aat_create(int device, const aat_config *cfg, const double *window_host, con
     if ((rc = upload(&ctx->mel.bin, first_bin.data(), first_bin.size()))) return rc;
     if ((rc = upload(&ctx->mel.weight, weights.data(), weights.size()))) return rc;
 
+    AAT_CUDA_CHECK(cudaMalloc(&ctx->ticket, sizeof(unsigned)));
+    AAT_CUDA_CHECK(cudaMemset(ctx->ticket, 0, sizeof(unsigned)));
     if ((rc = logmel_tables_init(ctx))) return rc;
     if ((rc = pool_scratch_init(ctx))) return rc;
     AAT_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking));
@@ -210,6 +212,7 @@ int aat_destroy(aat_ctx *ctx)
     cudaFree(ctx->window_half);
     cudaFree(ctx->twiddle);
     cudaFree(ctx->log_table);
+    cudaFree(ctx->ticket);
     cudaFree(ctx->mel.row_start);
     cudaFree(ctx->mel.bin);
     cudaFree(ctx->mel.weight);
@@ -315,6 +318,11 @@ int aat_plan_create(aat_ctx *ctx, int32_t n_utts, const int64_t *n_samples_host,
         aat_plan_destroy(plan);
         return rc;
     }
+    if (cudaMalloc(&plan->d_seg_local, sizeof(int64_t) * (size_t)(plan->total_seg_slots ? plan->total_seg_slots : 1)) != cudaSuccess ||
+        cudaMalloc(&plan->d_utt_frames, sizeof(int64_t) * (size_t)(n_utts ? n_utts : 1)) != cudaSuccess) {
+        aat_plan_destroy(plan);
+        AAT_REQUIRE(false, AAT_ERR_CUDA, "aat_plan_create: out of device memory");
+    }
     *out = plan;
     return AAT_OK;
 }
@@ -329,6 +337,8 @@ int aat_plan_destroy(aat_plan *plan)
     cudaFree(plan->d_seg_slot_off);
     cudaFree(plan->d_tile_utt);
     cudaFree(plan->d_tile_first);
+    cudaFree(plan->d_seg_local);
+    cudaFree(plan->d_utt_frames);
     delete plan;
     return AAT_OK;
 }
@@ -358,14 +368,18 @@ int aat_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave_dev, int wav
 
 int aat_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel_dev, const float *amp_dev,
                    int64_t *seg_start_dev, int64_t *seg_len_dev, int32_t *seg_count_dev, int64_t *minima_dev,
-                   int32_t *minima_count_dev, int32_t *status_dev, void *stream)
+                   int32_t *minima_count_dev, int32_t *status_dev, int64_t *seg_off_dev, int64_t *n_seg_dev,
+                   int64_t *utt_seg_off_dev, void *stream)
 {
+    AAT_REQUIRE(seg_off_dev == nullptr || n_seg_dev != nullptr, AAT_ERR_INVALID,
+                "aat_boundaries: seg_off_dev needs n_seg_dev");
     AAT_REQUIRE(ctx && plan && seg_start_dev && seg_len_dev && seg_count_dev && status_dev, AAT_ERR_INVALID,
                 "aat_boundaries: NULL argument");
     AAT_REQUIRE(mel_dev || amp_dev, AAT_ERR_INVALID, "aat_boundaries: need mel_dev or amp_dev");
     AAT_REQUIRE(plan->ctx == ctx, AAT_ERR_INVALID, "aat_boundaries: plan belongs to another context");
     return launch_boundaries(ctx, plan, mel_dev, amp_dev, seg_start_dev, seg_len_dev, seg_count_dev, minima_dev,
-                             minima_count_dev, status_dev, static_cast<cudaStream_t>(stream));
+                             minima_count_dev, status_dev, seg_off_dev, n_seg_dev, utt_seg_off_dev,
+                             static_cast<cudaStream_t>(stream));
 }
 
 int aat_process_boarders(aat_ctx *ctx, int64_t n_samples, const int64_t *boarders_dev, int64_t n_boarders,
@@ -483,7 +497,7 @@ static int host_pipeline(aat_ctx *ctx, const void *wave_host, int wave_dtype, in
     }
     if (want_boundaries) {
         rc = launch_boundaries(ctx, plan, d_mel, need_wave ? d_amp : nullptr, d_seg_start, d_seg_len, d_seg_count,
-                               d_minima, d_min_count, d_status, st);
+                               d_minima, d_min_count, d_status, nullptr, nullptr, nullptr, st);
         if (rc) return fail(rc);
         AAT_TRY_CUDA(cudaMemcpyAsync(h_seg_count, d_seg_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         AAT_TRY_CUDA(cudaMemcpyAsync(h_min_count, d_min_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));

@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3|c4]
 
 A *step* is one pass of the whole hot path over one batch of synthetic input: K1+K2 log-mel,
-K3 boundaries, frame-CSR, K4 mean-pool (with the column-sum epilogue feeding the dataset mean).
+K3 boundaries (+ frame CSR in its tail), K4 mean-pool (with the column-sum epilogue feeding the dataset mean).
 The default workload is BASELINE.json configs[1]: 64 x 16 s utterances, HuBERT-base 768-d embeddings
 on one B200; with N GPUs every rank runs that batch on its own shard (weak scaling, no data-path
 collective) and the ranks meet once, in the dataset-mean allreduce, at the end of the timed region.
@@ -231,7 +231,7 @@ def run_b200(args):
     wave_sets = [host_wave.to(dev) for _ in range(R)]
 
     # one untimed pass fixes the segmentation, hence the embedding shape
-    batch.logmel(wave_sets[0]), batch.boundaries(), batch.frame_csr()
+    batch.logmel(wave_sets[0]), batch.boundaries()
     torch.cuda.synchronize()
     assert int(batch.status.min().item()) >= 0
     n_seg = int(batch.n_seg.item())
@@ -245,8 +245,7 @@ def run_b200(args):
     def step(i):
         s = i % R
         batch.logmel(wave_sets[s])
-        batch.boundaries()
-        batch.frame_csr()
+        batch.boundaries()  # also emits the packed frame CSR from the kernel's tail
         batch.pool(emb_sets[s], out, colsum=dm.colsum_buffer())
         dm.accumulate()
 
@@ -370,7 +369,7 @@ def run_e2e(torch, dev, tok, batch, host_wave, emb_dev, out, n_seg, D, args, wor
             ready.record()
         with torch.cuda.stream(compute):
             compute.wait_event(ready)
-            batch.logmel(b["wave"]), batch.boundaries(), batch.frame_csr()
+            batch.logmel(b["wave"]), batch.boundaries()
             batch.pool(b["emb"], out)
             b["pooled_host"].copy_(out[:n_seg], non_blocking=True)
             b["len_host"].copy_(batch.seg_len, non_blocking=True)
@@ -402,7 +401,7 @@ def run_e2e(torch, dev, tok, batch, host_wave, emb_dev, out, n_seg, D, args, wor
     assert int(bufs[0]["count_host"].sum()) == n_seg
     return {"value": world * audio_hours_per_step * steps / wall, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": 1e3 * wall / steps,
-            "api": "PackedBatch.logmel/boundaries/frame_csr/pool on pinned host tensors, 2-deep copy/compute pipeline"}
+            "api": "PackedBatch.logmel/boundaries/pool on pinned host tensors, 2-deep copy/compute pipeline"}
 
 
 def main():

@@ -362,11 +362,15 @@ def test_packed_batch_matches_per_utterance_path(tok, golden):
         assert np.array_equal(np.diff(off), synth.hubert_frames(lens))
         total += len(lens)
     assert int(batch.n_seg.item()) == total
-    # the fused amplitude curve and the one recomputed from the mel give identical segments
-    before = batch.seg_len.clone(), batch.seg_count.clone()
-    batch.boundaries(use_amp=False)
+    # the fused amplitude curve and the one recomputed from the mel give identical segments; the frame CSR
+    # built in the boundary kernel's tail equals the stand-alone kernel's
+    before = batch.seg_len.clone(), batch.seg_count.clone(), batch.seg_off.clone(), batch.utt_seg_off.clone()
+    batch.seg_off.zero_(), batch.n_seg.zero_(), batch.utt_seg_off.zero_()
+    batch.boundaries(use_amp=False, with_csr=True)
     torch.cuda.synchronize()
     assert torch.equal(batch.seg_len, before[0]) and torch.equal(batch.seg_count, before[1])
+    assert int(batch.n_seg.item()) == total
+    assert torch.equal(batch.seg_off[: total + 1], before[2][: total + 1]) and torch.equal(batch.utt_seg_off, before[3])
 
 
 def test_packed_batch_segments_reference_mel(tok, golden):
@@ -406,7 +410,7 @@ def test_pipeline_replays_in_a_cuda_graph(tok):
     side = torch.cuda.Stream()
     with torch.cuda.stream(side):
         with torch.cuda.graph(g, stream=side):
-            batch.logmel(wave), batch.boundaries(), batch.frame_csr(), batch.pool(emb, out)
+            batch.logmel(wave), batch.boundaries(), batch.pool(emb, out)
     for _ in range(3):
         out.zero_()
         batch.seg_len.zero_()
