@@ -267,13 +267,10 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
     }
 
     if (r0 < r1 && S_total > 0) {
-        // current segment: last s with seg_off[s] <= r0 (cooperative k-ary search, overlaps the first copies)
-        const int64_t idx = coop_upper_bound(p.seg_off, S_total + 1, r0, tid, n_consumers, s_votes);
-        int64_t seg = idx - 1; // -1: rows before the first segment; S_total: rows after the last one
-        int64_t seg_begin, seg_end;
-        bool in_gap;
-        // window of seg_off kept in shared memory: s_off[i] = seg_off[cache_base + i], i < cache_n.
-        // `seg` is uniform across the consumer threads, so refills are collective.
+        // current segment: last s with seg_off[s] <= r0.  Segments have a typical length, so the answer is
+        // near r0 * S / n_rows: load a window of offsets around that guess into shared memory (ONE global
+        // round trip, and the window doubles as the boundary cache) and finish with a binary search in shared
+        // memory; only if the guess misses fall back to the cooperative k-ary search over global memory.
         int64_t cache_base = 0;
         int cache_n = 0;
         auto fill_cache = [&](int64_t first) {
@@ -284,6 +281,30 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
             for (int i = tid; i < cache_n; i += n_consumers) s_off[i] = p.seg_off[first + i];
             consumer_barrier(n_consumers);
         };
+        int64_t idx;
+        {
+            int64_t guess = (int64_t)((double)r0 / (double)p.n_rows * (double)S_total);
+            int64_t w0 = guess - kOffCache / 2;
+            const int64_t w_max = S_total + 1 - kOffCache;
+            if (w0 > w_max) w0 = w_max;
+            if (w0 < 0) w0 = 0;
+            fill_cache(w0);
+            const bool lower_ok = w0 == 0 || s_off[0] <= r0;
+            const bool upper_ok = w0 + cache_n == S_total + 1 || s_off[cache_n - 1] > r0;
+            if (lower_ok && upper_ok) {
+                int lo = 0, hi = cache_n; // entries of the window that are <= r0
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_off[mid] <= r0) lo = mid + 1; else hi = mid;
+                }
+                idx = w0 + lo;
+            } else {
+                idx = coop_upper_bound(p.seg_off, S_total + 1, r0, tid, n_consumers, s_votes);
+            }
+        }
+        int64_t seg = idx - 1; // -1: rows before the first segment; S_total: rows after the last one
+        int64_t seg_begin, seg_end;
+        bool in_gap;
         auto load_segment = [&]() {
             if (seg < 0) {
                 if (cache_n == 0 || cache_base != 0) fill_cache(0);
@@ -340,8 +361,9 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
 #pragma unroll
                             for (int k = 0; k < kCols; ++k) dst[(size_t)slab * kCols + k] = reduce_acc(j, k);
                     }
-                    __threadfence();
                     consumer_barrier(n_consumers);
+                    // release store by one thread after the barrier: the release is cumulative, so it also
+                    // covers the other consumers' partial-sum stores that the barrier ordered before it
                     if (tid == 0) st_release(p.head_flag + c, 1);
                 } else if (!ends_after) {
 #pragma unroll
@@ -510,6 +532,11 @@ int launch_typed(aat_ctx *ctx, PoolParams &p, size_t smem, bool colsum, cudaStre
     if (per_sm > kMaxCtasPerSm) per_sm = kMaxCtasPerSm;
     int grid = ctx->num_sms * per_sm;
     if (grid > ctx->pool.max_ctas) grid = ctx->pool.max_ctas;
+    // small inputs: give every CTA at least two stages of rows, otherwise one segment spans dozens of CTAs
+    // and its owner spends longer collecting pieces than streaming
+    const int64_t min_rows = 2 * (int64_t)p.rows_per_stage;
+    const int64_t by_rows = (p.n_rows + min_rows - 1) / min_rows;
+    if (by_rows < grid) grid = by_rows < 1 ? 1 : (int)by_rows;
     *grid_out = grid;
     ProfileScope prof(ctx, AAT_K_POOL, stream); // the streaming kernel alone (not the colsum reduce)
     kernel<<<grid, threads, smem, stream>>>(p);
