@@ -16,7 +16,7 @@ namespace aat {
 constexpr int kNfft = 400;          // the FFT kernel is specialised for 400 = 20 x 20
 constexpr int kBins = kNfft / 2 + 1; // 201
 constexpr int kMaxMels = 128;
-constexpr int kMaxRunningMean = 2048; // boundary kernel: chunk (4096) >= running_mean_points + 2
+constexpr int kMaxRunningMean = 2040; // boundary kernel: cumsum ring (8192) >= running_mean_points + 2 + 3 chunks
 
 void set_error(const char *fmt, ...);
 extern std::atomic<int64_t> g_launch_count;

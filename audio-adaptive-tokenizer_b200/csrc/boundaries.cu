@@ -11,7 +11,8 @@
 // Every operation uses an explicit round-to-nearest intrinsic so nothing is contracted into an FMA.
 // A parallel prefix scan would change ~10 % of the minima on long audio (SURVEY.md §7 hard part 1),
 // so the cumsum stays a serial chain on one thread; everything around it (column means, running mean,
-// comparisons, ordered compaction) is thread-parallel.  One CTA per utterance, time axis in chunks.
+// comparisons, ordered compaction) is thread-parallel and runs concurrently with the chain in a four-stage
+// software pipeline.  One CTA per utterance.
 #include "aat_internal.cuh"
 
 namespace aat {
@@ -19,29 +20,43 @@ namespace aat {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kChunk = 4096; // mel frames per pass; must be >= running_mean_points + 2
+constexpr int kChunk = 512; // mel frames per pipeline stage
 
-struct SegState {
-    int64_t prev;
-    int64_t count;
+// The merge/split state machine runs on ONE thread and is sequential in `prev`, so its cost per boarder is
+// instruction latency.  It is templated on the index type: 32-bit arithmetic (no carry chains, single-instruction
+// compares, multiply-high divisions) whenever every quantity fits in 31 bits — any utterance shorter than
+// 37 hours at 16 kHz — and 64-bit otherwise.  Outputs are always written as int64.
+template <typename I>
+struct SegStateT {
+    I prev;
+    I count;
     int32_t status;   // < 0: aat_status error; otherwise bit 0 = the last segment is the zero-padded tail
-    int64_t frames;   // HuBERT frames of the segments emitted so far (per-segment encode convention)
+    I frames;         // HuBERT frames of the segments emitted so far (per-segment encode convention)
     int64_t *local;   // optional: local[i] = frames before segment i of this utterance
 };
+using SegState = SegStateT<int64_t>;
 
+template <typename I>
+__device__ __forceinline__ I hubert_frames_t(I len)
+{
+    // TF:models/hubert/modeling_hubert.py:675-688, closed form
+    return (len < 400) ? (I)0 : (I)((len - 400) / 320 + 1);
+}
 __device__ __forceinline__ int64_t hubert_frames(int64_t len)
 {
-    return (len < 400) ? 0 : (len - 400) / 320 + 1; // TF:models/hubert/modeling_hubert.py:675-688, closed form
+    if (len <= 0x7fffffffLL) return (int64_t)hubert_frames_t<int32_t>((int32_t)len);
+    return hubert_frames_t<int64_t>(len);
 }
 
-__device__ __forceinline__ void emit_segment(int64_t start, int64_t len, int64_t *seg_start, int64_t *seg_len,
-                                             int64_t capacity, SegState &st)
+template <typename I>
+__device__ __forceinline__ void emit_segment(I start, I len, int64_t *seg_start, int64_t *seg_len, I capacity,
+                                             SegStateT<I> &st)
 {
     if (st.count < capacity) {
-        seg_start[st.count] = start;
-        seg_len[st.count] = len;
-        if (st.local) st.local[st.count] = st.frames;
-        st.frames += hubert_frames(len);
+        seg_start[st.count] = (int64_t)start;
+        seg_len[st.count] = (int64_t)len;
+        if (st.local) st.local[st.count] = (int64_t)st.frames;
+        st.frames += hubert_frames_t<I>(len);
     } else {
         st.status = AAT_ERR_CAPACITY;
     }
@@ -49,43 +64,45 @@ __device__ __forceinline__ void emit_segment(int64_t start, int64_t len, int64_t
 }
 
 // One iteration of the loop at ref:src/aat/tokenizer.py:154-175.
-__device__ __forceinline__ void push_boarder(int64_t b, int64_t min_frames, int64_t max_frames, int64_t *seg_start,
-                                             int64_t *seg_len, int64_t capacity, SegState &st)
+template <typename I>
+__device__ __forceinline__ void push_boarder(I b, I min_frames, I max_frames, int64_t *seg_start, int64_t *seg_len,
+                                             I capacity, SegStateT<I> &st)
 {
-    const int64_t len = b - st.prev;
+    const I len = b - st.prev;
     if (len < min_frames) return; // merge forward: prev stays
     if (len > max_frames) {
-        const int64_t k = len / max_frames;
-        const int64_t gap = len - k * max_frames;
-        int64_t n_cuts = k;
-        int64_t last_cut = k * max_frames;
+        const I k = len / max_frames;
+        const I gap = len - k * max_frames;
+        I n_cuts = k;
+        I last_cut = k * max_frames;
         if (gap == 0)
             n_cuts = k - 1; // drop last empty segment
         else if (gap < min_frames)
             last_cut = len - min_frames; // may fall below the previous cut when min > max
-        int64_t lo = 0;
-        for (int64_t j = 0; j < n_cuts; ++j) { // np.split: a[lo:c] with Python slice clamping
-            const int64_t c = (j == k - 1) ? last_cut : (j + 1) * max_frames;
-            const int64_t a0 = lo < len ? lo : len;
-            const int64_t a1 = c < len ? c : len;
-            emit_segment(st.prev + a0, a1 > a0 ? a1 - a0 : 0, seg_start, seg_len, capacity, st);
+        I lo = 0;
+        for (I j = 0; j < n_cuts; ++j) { // np.split: a[lo:c] with Python slice clamping
+            const I c = (j == k - 1) ? last_cut : (I)((j + 1) * max_frames);
+            const I a0 = lo < len ? lo : len;
+            const I a1 = c < len ? c : len;
+            emit_segment<I>(st.prev + a0, a1 > a0 ? (I)(a1 - a0) : (I)0, seg_start, seg_len, capacity, st);
             lo = c;
         }
-        const int64_t a0 = lo < len ? lo : len;
-        emit_segment(st.prev + a0, len - a0, seg_start, seg_len, capacity, st);
+        const I a0 = lo < len ? lo : len;
+        emit_segment<I>(st.prev + a0, len - a0, seg_start, seg_len, capacity, st);
     } else {
-        emit_segment(st.prev, len, seg_start, seg_len, capacity, st);
+        emit_segment<I>(st.prev, len, seg_start, seg_len, capacity, st);
     }
     st.prev = b;
 }
 
 // ref:src/aat/tokenizer.py:177-181: zero-padded tail of min_segment_frames samples.
-__device__ __forceinline__ void finish_segments(int64_t n_samples, int64_t min_frames, int64_t *seg_start,
-                                                int64_t *seg_len, int64_t capacity, SegState &st)
+template <typename I>
+__device__ __forceinline__ void finish_segments(I n_samples, I min_frames, int64_t *seg_start, int64_t *seg_len,
+                                                I capacity, SegStateT<I> &st)
 {
     if (st.prev != n_samples) {
         if (st.status == 0) st.status = (n_samples - st.prev > min_frames) ? AAT_ERR_TAIL : 1;
-        emit_segment(st.prev, min_frames, seg_start, seg_len, capacity, st);
+        emit_segment<I>(st.prev, min_frames, seg_start, seg_len, capacity, st);
     }
 }
 
@@ -266,17 +283,26 @@ struct BoundaryParams {
     float max_amp;
 };
 
+// Four-stage software pipeline over chunks of kChunk mel frames, one __syncthreads per iteration:
+//     iteration `it`:   load chunk it      (worker warps)   amplitude curve -> s_amp[it & 1]
+//                       scan chunk it - 1  (thread 0)        serial float32 cumsum -> s_cs ring
+//                       test chunk it - 2  (worker warps)    running mean, local-max test, ordered compaction
+//                       emit chunk it - 3  (thread 224)      merge/split state machine over the new boarders
+// so the only thing on the critical path is the serial chain itself (~4-5 cycles per frame).
+constexpr int kWorkers = 192;        // warps 1..6
+constexpr int kEmitThread = 224;     // warp 7, lane 0
+constexpr int kRing = 8192;          // cumsum ring (power of two) >= running_mean_points + 2 + 3 * kChunk
+
+__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(kWorkers) : "memory"); }
+
 __global__ void __launch_bounds__(kThreads) boundaries_kernel(const BoundaryParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int halo = p.npts + 2;
-    const int halo_pad = (halo + 3) & ~3; // keeps the chunk part of s_cs 16-byte aligned
-    float *s_amp = reinterpret_cast<float *>(smem_raw);     // [kChunk]
-    float *s_cs = s_amp + kChunk;                            // [halo_pad + kChunk]; cs index g at [halo_pad + g - j0]
-    int *s_min = reinterpret_cast<int *>(s_cs + halo_pad + kChunk); // [kChunk] minima of this pass (global frame index)
-    __shared__ int s_warp_count[kThreads / 32];
-    __shared__ int s_total;
-    __shared__ float s_carry;
+    float *s_amp = reinterpret_cast<float *>(smem_raw);          // [2][kChunk]
+    float *s_cs = s_amp + 2 * kChunk;                             // [kRing]: cs index g lives at s_cs[g & (kRing - 1)]
+    int *s_min = reinterpret_cast<int *>(s_cs + kRing);           // [2][kChunk] minima (global frame index) per chunk
+    __shared__ int s_wcount[kWorkers / 32];
+    __shared__ int s_found[2];
 
     const int tid = threadIdx.x;
     const int utt = blockIdx.x;
@@ -293,146 +319,208 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel(const BoundaryPara
 
     const int64_t L = T - p.npts; // running-mean length; minima live in [1, L-2]
     const float nf = (float)p.npts;
-    SegState st{0, 0, 0, 0, p.seg_off ? p.seg_local + slot0 : nullptr};
-    int64_t n_minima = 0;
-    int64_t i_done = 1; // next candidate index to test
+    const int64_t n_chunks = (T + kChunk - 1) / kChunk;
+    // candidate range [lo, hi) whose neighbourhood is complete once chunk c has been scanned
+    auto cand_hi = [&](int64_t c) {
+        const int64_t j1 = ((c + 1) * kChunk < T) ? (c + 1) * kChunk : T;
+        int64_t hi = j1 - p.npts - 1; // needs cs[i + 1 + npts] < j1
+        if (hi > L - 1) hi = L - 1;
+        return hi < 1 ? (int64_t)1 : hi;
+    };
 
-    for (int64_t j0 = 0; j0 < T; j0 += kChunk) {
-        const int64_t j1 = (j0 + kChunk < T) ? j0 + kChunk : T;
-        const int len = (int)(j1 - j0);
-
-        // A: amplitude curve of this chunk (thread-parallel over time, sequential down the mel rows)
-        for (int i = tid; i < len; i += kThreads) {
-            const int64_t t = j0 + i;
-            float a;
-            if (amp_in) {
-                a = amp_in[t];
-            } else {
-                float acc = mel[t];
-#pragma unroll 8
-                for (int r = 1; r < p.n_mels; ++r) acc = __fadd_rn(acc, mel[(size_t)r * T + t]);
-                a = __fmul_rn(-10.0f, __fdiv_rn(acc, (float)p.n_mels));
-            }
-            s_amp[i] = a;
+    constexpr int kPre = (kChunk + kWorkers - 1) / kWorkers; // amplitude values each worker prefetches per chunk
+    float pre[kPre];
+    auto prefetch = [&](int64_t c) {
+        const int64_t j0 = c * kChunk;
+        const int w = tid - 32;
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) {
+            const int64_t t = j0 + w + k * kWorkers;
+            pre[k] = (c < n_chunks && w + k * kWorkers < kChunk && t < T) ? amp_in[t] : 0.0f;
         }
-        __syncthreads();
+    };
+    if (amp_in && tid >= 32 && tid < 32 + kWorkers) prefetch(0);
 
-        // B: the serial float32 cumsum.  One thread; values are fetched 16 at a time into registers so the
-        // shared-memory latency is paid once per batch and the chain itself runs at the FADD latency.
+    // merge/split state of the emit thread, in the narrowest index type that holds every quantity
+    int64_t *local_ptr = p.seg_off ? p.seg_local + slot0 : nullptr;
+    const int64_t kLim = 0x3fffffffLL;
+    const bool narrow = n < kLim && p.min_frames < kLim && p.max_frames < kLim && capacity < kLim;
+    SegStateT<int32_t> st32{0, 0, 0, 0, local_ptr};
+    SegStateT<int64_t> st64{0, 0, 0, 0, local_ptr};
+    int64_t n_minima = 0;                                                // workers and emit thread keep their own copy
+    float run = 0.0f;                                                    // scan thread's carry
+
+    for (int64_t it = 0; it < n_chunks + 3; ++it) {
         if (tid == 0) {
-            float run = (j0 == 0) ? 0.0f : s_carry;
-            const float4 *src = reinterpret_cast<const float4 *>(s_amp);
-            float4 *dst = reinterpret_cast<float4 *>(s_cs + halo_pad);
-            int i = 0;
-            for (; i + 16 <= len; i += 16) {
-                float4 a = src[i / 4], b = src[i / 4 + 1], c4 = src[i / 4 + 2], d = src[i / 4 + 3];
-                a.x = (j0 == 0 && i == 0) ? a.x : __fadd_rn(run, a.x);
-                a.y = __fadd_rn(a.x, a.y), a.z = __fadd_rn(a.y, a.z), a.w = __fadd_rn(a.z, a.w);
-                b.x = __fadd_rn(a.w, b.x), b.y = __fadd_rn(b.x, b.y), b.z = __fadd_rn(b.y, b.z), b.w = __fadd_rn(b.z, b.w);
-                c4.x = __fadd_rn(b.w, c4.x), c4.y = __fadd_rn(c4.x, c4.y), c4.z = __fadd_rn(c4.y, c4.z), c4.w = __fadd_rn(c4.z, c4.w);
-                d.x = __fadd_rn(c4.w, d.x), d.y = __fadd_rn(d.x, d.y), d.z = __fadd_rn(d.y, d.z), d.w = __fadd_rn(d.z, d.w);
-                dst[i / 4] = a, dst[i / 4 + 1] = b, dst[i / 4 + 2] = c4, dst[i / 4 + 3] = d;
-                run = d.w;
+            // ---------------- scan: chunk it - 1 ----------------
+            const int64_t c = it - 1;
+            if (c >= 0 && c < n_chunks) {
+                const int64_t j0 = c * kChunk;
+                const int len = (int)(((j0 + kChunk < T) ? j0 + kChunk : T) - j0);
+                const float *src_s = s_amp + (c & 1) * kChunk;
+                float *dst_s = s_cs + (j0 & (kRing - 1));
+                // 0.0f + x == x bit for bit (up to the sign of zero, which no later operation can see), so the
+                // chain simply starts from run = 0 and numpy's cs[0] = x[0] needs no special case.
+                const float4 *src = reinterpret_cast<const float4 *>(src_s);
+                float4 *dst = reinterpret_cast<float4 *>(dst_s);
+                const int nb = len / 16;
+                float4 n0, n1, n2, n3;
+                if (nb > 0) n0 = src[0], n1 = src[1], n2 = src[2], n3 = src[3];
+#pragma unroll 2
+                for (int bi = 0; bi < nb; ++bi) {
+                    float4 a = n0, b = n1, c4 = n2, d = n3;
+                    const int nx = (bi + 1 < nb) ? bi + 1 : bi; // next batch's loads fly while this batch's adds run
+                    n0 = src[4 * nx], n1 = src[4 * nx + 1], n2 = src[4 * nx + 2], n3 = src[4 * nx + 3];
+                    a.x = __fadd_rn(run, a.x);
+                    a.y = __fadd_rn(a.x, a.y), a.z = __fadd_rn(a.y, a.z), a.w = __fadd_rn(a.z, a.w);
+                    b.x = __fadd_rn(a.w, b.x), b.y = __fadd_rn(b.x, b.y), b.z = __fadd_rn(b.y, b.z), b.w = __fadd_rn(b.z, b.w);
+                    c4.x = __fadd_rn(b.w, c4.x), c4.y = __fadd_rn(c4.x, c4.y), c4.z = __fadd_rn(c4.y, c4.z), c4.w = __fadd_rn(c4.z, c4.w);
+                    d.x = __fadd_rn(c4.w, d.x), d.y = __fadd_rn(d.x, d.y), d.z = __fadd_rn(d.y, d.z), d.w = __fadd_rn(d.z, d.w);
+                    dst[4 * bi] = a, dst[4 * bi + 1] = b, dst[4 * bi + 2] = c4, dst[4 * bi + 3] = d;
+                    run = d.w;
+                }
+                for (int i = nb * 16; i < len; ++i) {
+                    run = __fadd_rn(run, src_s[i]);
+                    dst_s[i] = run;
+                }
             }
-            for (; i < len; ++i) {
-                run = (j0 == 0 && i == 0) ? s_amp[0] : __fadd_rn(run, s_amp[i]);
-                s_cs[halo_pad + i] = run;
-            }
-            s_carry = run;
-        }
-        __syncthreads();
-
-        // C: running mean + strict-local-maximum test for every index whose neighbourhood is complete
-        int64_t i_hi = j1 - p.npts - 1; // exclusive: needs cs[i + 1 + npts] < j1
-        if (i_hi > L - 1) i_hi = L - 1;
-        const int64_t range = i_hi > i_done ? i_hi - i_done : 0;
-        const int per = (int)((range + kThreads - 1) / kThreads);
-        unsigned mask = 0;
-        {
-            const int64_t a = i_done + (int64_t)tid * per;
-            const float *cs = s_cs + halo_pad - j0;
-            for (int u = 0; u < per; ++u) {
-                const int64_t i = a + u;
-                if (i >= i_hi) break;
-                const float rl = __fdiv_rn(__fsub_rn(cs[i - 1 + p.npts], cs[i - 1]), nf);
-                const float rc = __fdiv_rn(__fsub_rn(cs[i + p.npts], cs[i]), nf);
-                const float rr = __fdiv_rn(__fsub_rn(cs[i + 1 + p.npts], cs[i + 1]), nf);
-                const bool is_min = rc > __fadd_rn(rr, 1e-5f) && rc > __fadd_rn(rl, 1e-5f) && rc > p.max_amp;
-                if (is_min) mask |= 1u << u;
-            }
-        }
-        // ordered compaction: exclusive scan of per-thread counts
-        const int cnt = __popc(mask);
-        int incl = cnt;
+        } else if (tid >= 32 && tid < 32 + kWorkers) {
+            const int w = tid - 32;
+            // ---------------- test: chunk it - 2 ----------------
+            {
+                const int64_t c = it - 2;
+                if (c >= 0 && c < n_chunks) {
+                    const int64_t lo = (c == 0) ? 1 : cand_hi(c - 1);
+                    const int64_t hi = cand_hi(c);
+                    const int64_t range = hi > lo ? hi - lo : 0;
+                    const int per = (int)((range + kWorkers - 1) / kWorkers); // <= 3 (< 32 mask bits)
+                    const int64_t a = lo + (int64_t)w * per;
+                    unsigned mask = 0;
+                    if (per > 0 && a < hi) {
+                        auto rm = [&](int64_t i) {
+                            return __fdiv_rn(__fsub_rn(s_cs[(i + p.npts) & (kRing - 1)], s_cs[i & (kRing - 1)]), nf);
+                        };
+                        float rl = rm(a - 1), rc = rm(a);
+                        for (int u = 0; u < per; ++u) {
+                            const int64_t i = a + u;
+                            if (i >= hi) break;
+                            const float rr = rm(i + 1);
+                            if (rc > __fadd_rn(rr, 1e-5f) && rc > __fadd_rn(rl, 1e-5f) && rc > p.max_amp) mask |= 1u << u;
+                            rl = rc, rc = rr;
+                        }
+                    }
+                    // ordered compaction over the 192 workers
+                    const int cnt = __popc(mask);
+                    int incl = cnt;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, d);
-            if ((tid & 31) >= d) incl += v;
-        }
-        if ((tid & 31) == 31) s_warp_count[tid >> 5] = incl;
-        __syncthreads();
-        if (tid < 32) {
-            int w = (tid < kThreads / 32) ? s_warp_count[tid] : 0;
-            int wi = w;
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                        if ((w & 31) >= d) incl += v;
+                    }
+                    if ((w & 31) == 31) s_wcount[w >> 5] = incl;
+                    worker_barrier();
+                    int base = 0, total = 0;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, wi, d);
-                if (tid >= d) wi += v;
+                    for (int k = 0; k < kWorkers / 32; ++k) {
+                        const int v = s_wcount[k];
+                        if (k < (w >> 5)) base += v;
+                        total += v;
+                    }
+                    int *mq = s_min + (c & 1) * kChunk;
+                    int pos = base + incl - cnt;
+                    unsigned m = mask;
+                    while (m) {
+                        const int u = __ffs(m) - 1;
+                        m &= m - 1;
+                        mq[pos] = (int)(a + u);
+                        if (minima_out) minima_out[n_minima + pos] = a + u;
+                        ++pos;
+                    }
+                    if (w == 0) s_found[c & 1] = total;
+                    n_minima += total;
+                    worker_barrier(); // s_wcount is reused next iteration
+                }
             }
-            if (tid < kThreads / 32) s_warp_count[tid] = wi - w;
-            if (tid == kThreads / 32 - 1) s_total = wi;
+            // ---------------- load: chunk it ----------------
+            // With a precomputed amplitude curve the values were fetched into registers one iteration ago (so
+            // the global-memory latency hides behind a whole pipeline iteration); the fetch for chunk it + 1
+            // is issued now and consumed next time round.
+            {
+                const int64_t c = it;
+                if (c < n_chunks) {
+                    const int64_t j0 = c * kChunk;
+                    const int len = (int)(((j0 + kChunk < T) ? j0 + kChunk : T) - j0);
+                    float *dst = s_amp + (c & 1) * kChunk;
+                    if (amp_in) {
+#pragma unroll
+                        for (int k = 0; k < kPre; ++k) {
+                            const int i = w + k * kWorkers;
+                            if (i < len) dst[i] = pre[k];
+                        }
+                    } else { // numpy mean(axis=0): rows added in order, float32 (ref:src/aat/tokenizer.py:67)
+                        for (int i = w; i < len; i += kWorkers) {
+                            const int64_t t = j0 + i;
+                            float acc = mel[t];
+#pragma unroll 8
+                            for (int r = 1; r < p.n_mels; ++r) acc = __fadd_rn(acc, mel[(size_t)r * T + t]);
+                            dst[i] = __fmul_rn(-10.0f, __fdiv_rn(acc, (float)p.n_mels));
+                        }
+                    }
+                }
+                if (amp_in) prefetch(it + 1);
+            }
+        } else if (tid == kEmitThread) {
+            // ---------------- emit: chunk it - 3 ----------------
+            const int64_t c = it - 3;
+            if (c >= 0 && c < n_chunks) {
+                const int found = s_found[c & 1];
+                const int *mq = s_min + (c & 1) * kChunk;
+                if (narrow) {
+                    const int32_t mn = (int32_t)p.min_frames, mx = (int32_t)p.max_frames, cap = (int32_t)capacity;
+                    for (int i = 0; i < found; ++i)
+                        push_boarder<int32_t>(mq[i] * p.hop, mn, mx, seg_start, seg_len, cap, st32);
+                } else {
+                    for (int i = 0; i < found; ++i)
+                        push_boarder<int64_t>((int64_t)mq[i] * p.hop, p.min_frames, p.max_frames, seg_start, seg_len,
+                                              capacity, st64);
+                }
+                n_minima += found;
+            }
         }
         __syncthreads();
-        {
-            int pos = s_warp_count[tid >> 5] + incl - cnt;
-            const int64_t a = i_done + (int64_t)tid * per;
-            unsigned m = mask;
-            while (m) {
-                const int u = __ffs(m) - 1;
-                m &= m - 1;
-                s_min[pos++] = (int)(a + u);
-            }
-        }
-        __syncthreads();
-        const int found = s_total;
-
-        // D: publish minima; one thread advances the merge/split state machine over the new boarders
-        if (minima_out)
-            for (int i = tid; i < found; i += kThreads) minima_out[n_minima + i] = s_min[i];
-        if (tid == 0)
-            for (int i = 0; i < found; ++i)
-                push_boarder((int64_t)s_min[i] * p.hop, p.min_frames, p.max_frames, seg_start, seg_len, capacity, st);
-        n_minima += found;
-        if (i_hi > i_done) i_done = i_hi;
-
-        // carry the last `halo` cumsum values into the next pass
-        // (source [kChunk, kChunk + halo) and destination [0, halo) are disjoint because kChunk >= halo)
-        if (j1 < T) {
-            for (int i = tid; i < halo_pad; i += kThreads) s_cs[i] = s_cs[kChunk + i];
-            __syncthreads();
-        }
     }
 
-    if (tid == 0) {
-        push_boarder(n, p.min_frames, p.max_frames, seg_start, seg_len, capacity, st); // ref:src/aat/tokenizer.py:137
-        finish_segments(n, p.min_frames, seg_start, seg_len, capacity, st);
-        p.seg_count[utt] = (int32_t)(st.count < capacity ? st.count : capacity);
+    if (tid == kEmitThread) {
+        int64_t count, frames;
+        int32_t status;
+        if (narrow) {
+            const int32_t mn = (int32_t)p.min_frames, mx = (int32_t)p.max_frames, cap = (int32_t)capacity;
+            push_boarder<int32_t>((int32_t)n, mn, mx, seg_start, seg_len, cap, st32); // ref:src/aat/tokenizer.py:137
+            finish_segments<int32_t>((int32_t)n, mn, seg_start, seg_len, cap, st32);
+            count = st32.count, frames = st32.frames, status = st32.status;
+        } else {
+            push_boarder<int64_t>(n, p.min_frames, p.max_frames, seg_start, seg_len, capacity, st64);
+            finish_segments<int64_t>(n, p.min_frames, seg_start, seg_len, capacity, st64);
+            count = st64.count, frames = st64.frames, status = st64.status;
+        }
+        p.seg_count[utt] = (int32_t)(count < capacity ? count : capacity);
         if (p.minima_count) p.minima_count[utt] = (int32_t)n_minima;
-        p.status[utt] = st.status;
-        if (p.seg_off) p.utt_frames[utt] = st.frames;
+        p.status[utt] = status;
+        if (p.seg_off) p.utt_frames[utt] = frames;
     }
 
     // ---- fused epilogue: the last CTA to finish turns all segment lengths into the packed frame CSR ----
     if (p.seg_off != nullptr) {
         __shared__ int s_last;
-        if (tid == 0) {
-            __threadfence(); // this CTA's segment writes (all by thread 0) are visible before the ticket
+        __syncthreads();
+        if (tid == kEmitThread) {
+            __threadfence(); // this CTA's segment writes (all by this thread) are visible before the ticket
             s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
         }
         __syncthreads();
         if (s_last) {
             __threadfence();
-            int64_t *s_seg = reinterpret_cast<int64_t *>(smem_raw); // the chunk buffers are free now
+            int64_t *s_seg = reinterpret_cast<int64_t *>(smem_raw); // the pipeline buffers are free now
             int64_t *s_frm = s_seg + p.n_utts + 1;
             rebase_frame_csr(p.n_utts, p.seg_slot_off, p.seg_local, p.utt_frames, p.seg_count, p.seg_off, p.n_seg,
                              p.utt_seg_off, s_seg, s_frm);
@@ -446,10 +534,10 @@ __global__ void process_boarders_kernel(int64_t n_samples, const int64_t *boarde
                                         int64_t capacity, int32_t *seg_count, int32_t *status)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    SegState st{0, 0, 0, 0, nullptr};
+    SegState st{0, 0, 0, 0, nullptr}; // caller-supplied boarders may be anything: keep the 64-bit machine here
     for (int64_t i = 0; i < n_boarders; ++i)
-        push_boarder(boarders[i], min_frames, max_frames, seg_start, seg_len, capacity, st);
-    finish_segments(n_samples, min_frames, seg_start, seg_len, capacity, st);
+        push_boarder<int64_t>(boarders[i], min_frames, max_frames, seg_start, seg_len, capacity, st);
+    finish_segments<int64_t>(n_samples, min_frames, seg_start, seg_len, capacity, st);
     *seg_count = (int32_t)(st.count < capacity ? st.count : capacity);
     *status = st.status;
 }
@@ -495,13 +583,13 @@ int launch_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel, cons
     p.n_utts = plan->n_utts;
     p.ticket = ctx->ticket;
     const size_t csr_smem = sizeof(int64_t) * 2 * (size_t)(plan->n_utts + 1);
-    const bool fuse_csr = seg_off != nullptr && csr_smem <= sizeof(float) * 2 * kChunk;
+    const bool fuse_csr = seg_off != nullptr && csr_smem <= sizeof(float) * (size_t)(2 * kChunk + kRing);
     p.seg_off = fuse_csr ? seg_off : nullptr;
     p.n_seg = n_seg;
     p.utt_seg_off = utt_seg_off;
     p.seg_local = plan->d_seg_local;
     p.utt_frames = plan->d_utt_frames;
-    const size_t smem = sizeof(float) * (size_t)(kChunk + ((p.npts + 2 + 3) & ~3) + kChunk) + sizeof(int) * (size_t)kChunk;
+    const size_t smem = sizeof(float) * (size_t)(2 * kChunk + kRing) + sizeof(int) * (size_t)(2 * kChunk);
     AAT_CUDA_CHECK(cudaFuncSetAttribute(boundaries_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         ProfileScope prof(ctx, AAT_K_BOUNDARIES, stream);

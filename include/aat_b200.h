@@ -68,7 +68,7 @@ typedef struct aat_config {
     int32_t n_fft;                  /* 400 (the only length the FFT kernel implements) */
     int32_t hop_length;             /* 160; 1..n_fft */
     int32_t num_mel_filters;        /* 64; 1..128 */
-    int32_t running_mean_points;    /* 12; 1..2048 */
+    int32_t running_mean_points;    /* 12; 1..2040 */
     int32_t reserved0;
     int64_t min_segment_frames;     /* 2000 */
     int64_t max_segment_frames;     /* 24000; > 0 */
