@@ -277,7 +277,12 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
         __syncthreads();
         prefetch(tile_id + gridDim.x); // the raw buffer is free again: the next tile lands during the rest of this one
 
-        // ---- pass 2: thread k1 transforms row k1 over n2; Z[k1 + 20 k2] goes back into its own row ----
+        // ---- pass 2 + split: thread k1 transforms row k1 over n2 and keeps Z[k1 + 20 k2] in registers ----
+        // It owns the bins k = k1 + 20 j (j = 0..9, and j = 10 for k1 = 0).  The mirror Z[400 - k] of those bins
+        // sits in row (20 - k1) % 20 at k2 = 19 - j (k1 > 0) or 20 - j (k1 = 0), i.e. always in the UPPER half
+        // (k2 >= 10) of the partner row — so only that half goes back through shared memory, and each thread
+        // reads 10 mirror values instead of re-reading both operands (-40 % exchange traffic, no division,
+        // no bank conflicts).  Round to complex64, power in float64 (TF:audio_utils.py:781,803,808).
         {
             double2 v[20];
             double2 *row = ex + lane20 * kRow;
@@ -285,23 +290,19 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
             for (int n2 = 0; n2 < 20; ++n2) v[n2] = row[n2];
             dft20(v);
 #pragma unroll
-            for (int k2 = 0; k2 < 20; ++k2) row[k2] = v[k2];
-        }
-        __syncthreads();
-
-        // ---- split into the two real spectra, round to complex64, power in float64 ----
-        // thread (pair, r) owns bins k = r + 20 j: Z[k] sits at row r, column j; its mirror Z[400 - k] at
-        // row (20 - r) % 20, column 19 - j (r > 0) or 20 - j (r = 0).  No divisions, no bank conflicts.
-        {
+            for (int k2 = 10; k2 < 20; ++k2) row[k2] = v[k2]; // a thread reads and rewrites only its own row
+            __syncthreads();
             double pa[11], pb[11];
-            const int mrow = (lane20 == 0) ? 0 : 20 - lane20;
-            const int mcol0 = (lane20 == 0) ? 20 : 19;
+            const double2 *mir = ex + ((lane20 == 0) ? 0 : 20 - lane20) * kRow;
 #pragma unroll
             for (int j = 0; j < 11; ++j) {
                 if (j < 10 || lane20 == 0) {
-                    const double2 z = ex[lane20 * kRow + j];
-                    const int mc = mcol0 - j; // 20 only for k = 0, whose mirror is Z[0] itself
-                    const double2 y = (mc == 20) ? z : ex[mrow * kRow + mc];
+                    const double2 z = v[j];
+                    double2 y;
+                    if (lane20 == 0)
+                        y = (j == 0) ? z : ((j == 10) ? z : mir[20 - j]); // Z[0] and Z[200] mirror themselves
+                    else
+                        y = mir[19 - j];
                     // X_a = (z + conj y), X_b = (z - conj y) / i   (the 1/2 lives in the window table)
                     const float ar = (float)(z.x + y.x), ai = (float)(z.y - y.y);
                     const float br = (float)(z.y + y.y), bi = (float)(y.x - z.x);
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
                     pb[j] = (double)br * (double)br + (double)bi * (double)bi;
                 }
             }
-            __syncthreads(); // every thread has read the exchange matrix: overlay it with the power spectra
+            __syncthreads(); // every thread has read its mirror values: overlay the matrix with the power spectra
             double *rowa = s_pow + (2 * pair) * kPowStride + lane20;
 #pragma unroll
             for (int j = 0; j < 11; ++j) {
