@@ -22,6 +22,7 @@ AAT_ERR_CAPACITY = -4
 AAT_ERR_TAIL = -5
 
 AAT_F32, AAT_F64, AAT_F16, AAT_BF16 = 0, 1, 2, 3
+AAT_NORM_ZSCORE, AAT_NORM_W2V2 = 0, 1
 
 c_i32 = ctypes.c_int32
 c_i64 = ctypes.c_int64
@@ -78,6 +79,11 @@ SIGNATURES = {
                                              c_void, c_void]),
     "aat_colsum_accumulate": (ctypes.c_int, [c_void, c_void, c_void, c_i32, c_void]),
     "aat_colsum_finalize": (ctypes.c_int, [c_void, c_void, c_i32, c_void, c_void]),
+    "aat_normalize": (ctypes.c_int, [c_void, c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, ctypes.c_int, c_void, c_void]),
+    "aat_pad_segment_boarders": (ctypes.c_int, [c_void, c_void, c_void, c_void, c_i64, c_void, c_void, c_void, c_void]),
+    "aat_scatter_segments": (ctypes.c_int, [c_void, c_void, c_i64, c_i32, c_void, c_i64, c_i64, c_void, c_void, c_void,
+                                            c_void]),
+    "aat_scatter_mel_segments": (ctypes.c_int, [c_void, c_void, c_void, c_void, c_i64, c_i64, c_void, c_void, c_void]),
     "aat_host_logmel": (ctypes.c_int, [c_void, c_void, ctypes.c_int, c_i64, c_void]),
     "aat_host_find_minimas": (ctypes.c_int, [c_void, c_void, c_i64, c_void, c_void]),
     "aat_host_process_boarders": (ctypes.c_int, [c_void, c_i64, c_void, c_i64, c_void, c_void, c_i64, c_void, c_void]),

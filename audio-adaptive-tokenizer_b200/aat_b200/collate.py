@@ -1,0 +1,108 @@
+"""GPU versions of the collator-side data movement either side of the hot path.
+
+The reference's ``TokenizedAudioWaveformCollator.__call__`` builds these tensors with a double Python loop
+in DataLoader workers (ref:src/aat/training/collate.py:242-253, 291-346; "todo vectorize", :248); here they
+are produced on the device from the boundary kernel's outputs, so the training collator can stay
+GPU-resident.  All functions enqueue on the current torch stream and return CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes
+
+from . import _cabi
+from .tokenizer import PackedBatch
+
+
+def _stream():
+    import torch
+
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _raise_on_status(status, what):
+    import torch
+
+    bad = torch.nonzero(status < 0).flatten()
+    if bad.numel():
+        code = int(status[bad[0]].item())
+        raise _cabi.AatError(code, f"{what}: utterance {int(bad[0])} (the reference raises here: segment longer than "
+                                   "the tile, boarders not increasing, or a slice past the padded waveform)")
+
+
+def normalize_waveforms(batch: PackedBatch, wave, mode: str = "zscore", out_dtype=None, return_stats: bool = False):
+    """Per-utterance normalisation of a packed waveform tensor.
+
+    mode="zscore": ``(x - x.mean()) / (x.std() + 1e-6)`` — what the reference applies before ``get_melspec`` /
+    ``tokenize`` (ref:scripts/audio_tokenization_melspec.py:40, ref:src/aat/training/collate.py:135-152).
+    mode="w2v2": ``(x - x.mean()) / sqrt(x.var() + 1e-7)`` in float32 — the Wav2Vec2 feature extractor's
+    ``zero_mean_unit_var_norm`` (ref:src/aat/training/collate.py:301)."""
+    import torch
+
+    modes = {"zscore": _cabi.AAT_NORM_ZSCORE, "w2v2": _cabi.AAT_NORM_W2V2}
+    if mode not in modes:
+        raise ValueError(f"mode must be one of {sorted(modes)}")
+    codes = {torch.float32: _cabi.AAT_F32, torch.float64: _cabi.AAT_F64}
+    if wave.dtype not in codes or not wave.is_cuda or not wave.is_contiguous() or wave.numel() != batch.total_samples:
+        raise TypeError("wave must be a contiguous packed CUDA tensor (float32 or float64) matching the plan")
+    if out_dtype is None:
+        out_dtype = torch.float32 if mode == "w2v2" else torch.float64
+    out = torch.empty(batch.total_samples, dtype=out_dtype, device=wave.device)
+    stats = torch.empty(2 * batch.n_utts, dtype=torch.float64, device=wave.device)
+    _cabi.check(_cabi.lib().aat_normalize(batch.ctx.handle, batch.handle, wave.data_ptr(), codes[wave.dtype], modes[mode],
+                                          out.data_ptr(), codes[out_dtype], stats.data_ptr(), _stream()))
+    return (out, stats.view(batch.n_utts, 2)) if return_stats else out
+
+
+def pad_segment_boarders(batch: PackedBatch, s_max=None):
+    """``_make_padded_segments_boarders`` on the device: ``(segments_boarders_padded, attention_mask)``,
+    both ``[B, S_max]`` int64.  ``s_max=None`` reads the largest segment count back from the device (one sync)."""
+    import torch
+
+    if s_max is None:
+        s_max = int(batch.seg_count.max().item())
+    padded = torch.empty((batch.n_utts, s_max), dtype=torch.int64, device=batch.device)
+    mask = torch.empty_like(padded)
+    status = torch.empty(batch.n_utts, dtype=torch.int32, device=batch.device)
+    _cabi.check(_cabi.lib().aat_pad_segment_boarders(batch.ctx.handle, batch.handle, batch.seg_len.data_ptr(),
+                                                     batch.seg_count.data_ptr(), s_max, padded.data_ptr(),
+                                                     mask.data_ptr(), status.data_ptr(), _stream()))
+    return padded, mask
+
+
+def scatter_segments(batch: PackedBatch, wave_padded, boarders_padded, max_segment_frames: int, with_mask: bool = True,
+                     check: bool = True):
+    """``batched_segments [B, S, max_segment_frames]`` (+ ``segments_waveforms_mask``) from the padded
+    ``input_values [B, N_max]`` float32 and the padded boarders (ref:src/aat/training/collate.py:321-335)."""
+    import torch
+
+    if wave_padded.dtype != torch.float32 or wave_padded.dim() != 2 or not wave_padded.is_contiguous():
+        raise TypeError("wave_padded must be a contiguous float32 [B, N_max] CUDA tensor")
+    B, s_max = boarders_padded.shape
+    out = torch.empty((B, s_max, max_segment_frames), dtype=torch.float32, device=wave_padded.device)
+    mask = torch.empty_like(out) if with_mask else None
+    status = torch.empty(B, dtype=torch.int32, device=wave_padded.device)
+    _cabi.check(_cabi.lib().aat_scatter_segments(
+        batch.ctx.handle, wave_padded.data_ptr(), int(wave_padded.shape[1]), B, boarders_padded.data_ptr(), s_max,
+        int(max_segment_frames), out.data_ptr(), mask.data_ptr() if with_mask else None, status.data_ptr(), _stream()))
+    if check:
+        _raise_on_status(status, "scatter_segments")
+    return (out, mask) if with_mask else out
+
+
+def scatter_mel_segments(batch: PackedBatch, boarders_padded, max_segment_frames: int, mel=None, check: bool = True):
+    """``batched_segments_melspectrograms [B, S, n_mels, 1 + max_segment_frames // hop]`` from the batch's packed
+    log-mel (ref:src/aat/training/collate.py:309-312, 337-342)."""
+    import torch
+
+    mel = batch.mel if mel is None else mel
+    hop = int(batch.tokenizer.hop_length)
+    max_items = 1 + int(max_segment_frames) // hop
+    B, s_max = boarders_padded.shape
+    out = torch.empty((B, s_max, batch.n_mels, max_items), dtype=torch.float32, device=mel.device)
+    status = torch.empty(B, dtype=torch.int32, device=mel.device)
+    _cabi.check(_cabi.lib().aat_scatter_mel_segments(batch.ctx.handle, batch.handle, mel.data_ptr(),
+                                                     boarders_padded.data_ptr(), s_max, max_items, out.data_ptr(),
+                                                     status.data_ptr(), _stream()))
+    if check:
+        _raise_on_status(status, "scatter_mel_segments")
+    return out

@@ -109,6 +109,12 @@ struct aat_plan {
     // scratch written by the boundaries kernel for its fused frame-CSR epilogue
     int64_t *d_seg_local = nullptr;     // [total_seg_slots]
     int64_t *d_utt_frames = nullptr;    // [B]
+    // waveform normalisation (aat_normalize): 4096-sample chunks
+    int32_t norm_chunks = 0;
+    int32_t *d_chunk_utt = nullptr;     // [norm_chunks]
+    int32_t *d_chunk_first = nullptr;   // [B+1]
+    double *d_norm_partial = nullptr;   // [norm_chunks, 3] (n, mean, M2)
+    double *d_norm_stats = nullptr;     // [B, 2] (mean, population variance)
 };
 
 namespace aat {
@@ -129,6 +135,15 @@ int launch_mean_pool(aat_ctx *ctx, const void *emb, int emb_dtype, int64_t n_row
                      cudaStream_t stream);
 int launch_colsum_accumulate(double *acc, const double *colsum, int32_t dim, cudaStream_t stream);
 int launch_colsum_finalize(const double *acc, int32_t dim, float *mean, cudaStream_t stream);
+int launch_normalize(aat_ctx *ctx, const aat_plan *plan, const void *wave, int in_dtype, int mode, void *out,
+                     int out_dtype, double *stats, cudaStream_t stream);
+int launch_pad_boarders(const aat_plan *plan, const int64_t *seg_len, const int32_t *seg_count, int64_t s_max,
+                        int64_t *boarders, int64_t *mask, int32_t *status, cudaStream_t stream);
+int launch_scatter_segments(const float *wave, int64_t n_max, int32_t n_utts, const int64_t *boarders, int64_t s_max,
+                            int64_t max_frames, float *out, float *mask, int32_t *status, cudaStream_t stream);
+int launch_scatter_mel_segments(aat_ctx *ctx, const aat_plan *plan, const float *mel, const int64_t *boarders,
+                                int64_t s_max, int64_t max_items, float *out, int32_t *status, cudaStream_t stream);
+constexpr int kNormChunk = 4096;
 int logmel_tables_init(aat_ctx *ctx);
 int pool_scratch_init(aat_ctx *ctx);
 void pool_scratch_free(aat_ctx *ctx);

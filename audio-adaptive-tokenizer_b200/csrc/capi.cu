@@ -282,7 +282,7 @@ int aat_plan_create(aat_ctx *ctx, int32_t n_utts, const int64_t *n_samples_host,
     plan->h_wave_off.assign(n_utts + 1, 0);
     plan->h_frame_off.assign(n_utts + 1, 0);
     plan->h_seg_slot_off.assign(n_utts + 1, 0);
-    std::vector<int32_t> tile_first(n_utts + 1, 0), tile_utt;
+    std::vector<int32_t> tile_first(n_utts + 1, 0), tile_utt, chunk_first(n_utts + 1, 0), chunk_utt;
     for (int b = 0; b < n_utts; ++b) {
         const int64_t n = n_samples_host[b];
         if (n < 1) {
@@ -303,6 +303,9 @@ int aat_plan_create(aat_ctx *ctx, int32_t n_utts, const int64_t *n_samples_host,
         }
         tile_first[b + 1] = tile_first[b] + (int32_t)tiles;
         tile_utt.insert(tile_utt.end(), (size_t)tiles, b);
+        const int64_t chunks = (n + kNormChunk - 1) / kNormChunk;
+        chunk_first[b + 1] = chunk_first[b] + (int32_t)chunks;
+        chunk_utt.insert(chunk_utt.end(), (size_t)chunks, b);
     }
     plan->total_samples = plan->h_wave_off[n_utts];
     plan->total_frames = plan->h_frame_off[n_utts];
@@ -314,9 +317,17 @@ int aat_plan_create(aat_ctx *ctx, int32_t n_utts, const int64_t *n_samples_host,
         (rc = upload(&plan->d_frame_off, plan->h_frame_off.data(), (size_t)n_utts + 1)) ||
         (rc = upload(&plan->d_seg_slot_off, plan->h_seg_slot_off.data(), (size_t)n_utts + 1)) ||
         (rc = upload(&plan->d_tile_utt, tile_utt.data(), tile_utt.size())) ||
-        (rc = upload(&plan->d_tile_first, tile_first.data(), tile_first.size()))) {
+        (rc = upload(&plan->d_tile_first, tile_first.data(), tile_first.size())) ||
+        (rc = upload(&plan->d_chunk_utt, chunk_utt.data(), chunk_utt.size())) ||
+        (rc = upload(&plan->d_chunk_first, chunk_first.data(), chunk_first.size()))) {
         aat_plan_destroy(plan);
         return rc;
+    }
+    plan->norm_chunks = (int32_t)chunk_utt.size();
+    if (cudaMalloc(&plan->d_norm_partial, sizeof(double) * 3 * (size_t)(plan->norm_chunks ? plan->norm_chunks : 1)) != cudaSuccess ||
+        cudaMalloc(&plan->d_norm_stats, sizeof(double) * 2 * (size_t)(n_utts ? n_utts : 1)) != cudaSuccess) {
+        aat_plan_destroy(plan);
+        AAT_REQUIRE(false, AAT_ERR_CUDA, "aat_plan_create: out of device memory");
     }
     if (cudaMalloc(&plan->d_seg_local, sizeof(int64_t) * (size_t)(plan->total_seg_slots ? plan->total_seg_slots : 1)) != cudaSuccess ||
         cudaMalloc(&plan->d_utt_frames, sizeof(int64_t) * (size_t)(n_utts ? n_utts : 1)) != cudaSuccess) {
@@ -339,6 +350,10 @@ int aat_plan_destroy(aat_plan *plan)
     cudaFree(plan->d_tile_first);
     cudaFree(plan->d_seg_local);
     cudaFree(plan->d_utt_frames);
+    cudaFree(plan->d_chunk_utt);
+    cudaFree(plan->d_chunk_first);
+    cudaFree(plan->d_norm_partial);
+    cudaFree(plan->d_norm_stats);
     delete plan;
     return AAT_OK;
 }
@@ -421,6 +436,48 @@ int aat_colsum_finalize(aat_ctx *ctx, const double *acc_dev, int32_t dim, float 
 {
     AAT_REQUIRE(ctx && acc_dev && mean_dev && dim > 0, AAT_ERR_INVALID, "aat_colsum_finalize: bad argument");
     return launch_colsum_finalize(acc_dev, dim, mean_dev, static_cast<cudaStream_t>(stream));
+}
+
+int aat_normalize(aat_ctx *ctx, const aat_plan *plan, const void *wave_dev, int in_dtype, int mode, void *out_dev,
+                  int out_dtype, double *stats_dev, void *stream)
+{
+    AAT_REQUIRE(ctx && plan && wave_dev && (out_dev || stats_dev), AAT_ERR_INVALID, "aat_normalize: NULL argument");
+    AAT_REQUIRE(plan->ctx == ctx, AAT_ERR_INVALID, "aat_normalize: plan belongs to another context");
+    return launch_normalize(ctx, plan, wave_dev, in_dtype, mode, out_dev, out_dtype, stats_dev,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int aat_pad_segment_boarders(aat_ctx *ctx, const aat_plan *plan, const int64_t *seg_len_dev,
+                             const int32_t *seg_count_dev, int64_t s_max, int64_t *boarders_dev, int64_t *mask_dev,
+                             int32_t *status_dev, void *stream)
+{
+    AAT_REQUIRE(ctx && plan && seg_len_dev && seg_count_dev && boarders_dev && mask_dev && status_dev, AAT_ERR_INVALID,
+                "aat_pad_segment_boarders: NULL argument");
+    AAT_REQUIRE(s_max >= 0, AAT_ERR_INVALID, "aat_pad_segment_boarders: negative s_max");
+    return launch_pad_boarders(plan, seg_len_dev, seg_count_dev, s_max, boarders_dev, mask_dev, status_dev,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int aat_scatter_segments(aat_ctx *ctx, const float *wave_padded_dev, int64_t n_max, int32_t n_utts,
+                         const int64_t *boarders_dev, int64_t s_max, int64_t max_frames, float *out_dev,
+                         float *mask_dev, int32_t *status_dev, void *stream)
+{
+    AAT_REQUIRE(ctx && wave_padded_dev && boarders_dev && out_dev && status_dev, AAT_ERR_INVALID,
+                "aat_scatter_segments: NULL argument");
+    AAT_REQUIRE(n_max >= 0 && n_utts >= 0 && s_max >= 0 && max_frames >= 0, AAT_ERR_INVALID,
+                "aat_scatter_segments: negative size");
+    return launch_scatter_segments(wave_padded_dev, n_max, n_utts, boarders_dev, s_max, max_frames, out_dev, mask_dev,
+                                   status_dev, static_cast<cudaStream_t>(stream));
+}
+
+int aat_scatter_mel_segments(aat_ctx *ctx, const aat_plan *plan, const float *mel_dev, const int64_t *boarders_dev,
+                             int64_t s_max, int64_t max_items, float *out_dev, int32_t *status_dev, void *stream)
+{
+    AAT_REQUIRE(ctx && plan && mel_dev && boarders_dev && out_dev && status_dev, AAT_ERR_INVALID,
+                "aat_scatter_mel_segments: NULL argument");
+    AAT_REQUIRE(s_max >= 0 && max_items >= 0, AAT_ERR_INVALID, "aat_scatter_mel_segments: negative size");
+    return launch_scatter_mel_segments(ctx, plan, mel_dev, boarders_dev, s_max, max_items, out_dev, status_dev,
+                                       static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------------------------------------ host API

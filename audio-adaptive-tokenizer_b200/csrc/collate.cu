@@ -1,0 +1,302 @@
+// Callers on either side of the hot path — HBM-bound byte movers.
+//
+// N2  aat_normalize: the per-utterance normalisations that feed the path
+//       z-score   (x - mean) / (std + 1e-6)        ref:scripts/audio_tokenization_melspec.py:40,
+//                                                   ref:src/aat/training/collate.py:135,138,152
+//       wav2vec2  (x - mean) / sqrt(var + 1e-7)    ref:src/aat/training/collate.py:301 ->
+//                                                   TF:models/wav2vec2/feature_extraction_wav2vec2.py:78-95
+//     Statistics in float64: every 4096-sample chunk yields (n, mean, M2) with a two-pass reduction inside
+//     the CTA; an utterance's chunks are merged in order with Chan's formula (robust against a DC offset,
+//     deterministic, one pass over HBM); a second kernel applies the affine map.
+// N1  the collator's ragged -> padded layout (ref:src/aat/training/collate.py:242-253, 291-346), which the
+//     reference builds with a double Python loop ("todo vectorize", :248):
+//       aat_pad_segment_boarders   cumulative segment ends -> [B, S_max] int64, zero padded, + mask
+//       aat_scatter_segments       waveform slices  -> [B, S_max, max_frames] float32 + mask
+//       aat_scatter_mel_segments   log-mel slices   -> [B, S_max, n_mels, max_items] float32
+//     One CTA per (utterance, segment) row; 128-bit stores; zero fill of the padding in the same pass.
+#include "aat_internal.cuh"
+
+namespace aat {
+
+namespace {
+
+constexpr int kStatThreads = 256;
+constexpr int kStatPer = 16;                         // samples per thread
+constexpr int kStatChunk = kStatThreads * kStatPer;  // 4096 samples per CTA
+
+__device__ __forceinline__ double block_sum(double v, double *s_red)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kStatThreads / 32; ++w) t += s_red[w]; // fixed order: deterministic
+    return t;
+}
+
+// grid = total chunks (chunk_utt / chunk_first tables as for the mel tiles); partial[chunk] = (n, mean, M2)
+template <typename WaveT>
+__global__ void __launch_bounds__(kStatThreads)
+wave_chunk_stats_kernel(const WaveT *wave, const int64_t *n_samples, const int64_t *wave_off, const int32_t *chunk_utt,
+                        const int32_t *chunk_first, double *partial)
+{
+    __shared__ double s_red[kStatThreads / 32];
+    const int utt = chunk_utt[blockIdx.x];
+    const int64_t c = blockIdx.x - chunk_first[utt];
+    const int64_t n = n_samples[utt];
+    const int64_t j0 = c * kStatChunk;
+    const int64_t len = (n - j0 < kStatChunk) ? n - j0 : kStatChunk;
+    const WaveT *src = wave + wave_off[utt] + j0;
+    double v[kStatPer];
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < kStatPer; ++k) {
+        const int i = threadIdx.x + k * kStatThreads;
+        v[k] = (i < len) ? (double)src[i] : 0.0;
+        s += v[k];
+    }
+    const double mean = block_sum(s, s_red) / (double)len;
+    double q = 0.0;
+#pragma unroll
+    for (int k = 0; k < kStatPer; ++k) {
+        const int i = threadIdx.x + k * kStatThreads;
+        const double d = v[k] - mean;
+        q += (i < len) ? d * d : 0.0;
+    }
+    const double m2 = block_sum(q, s_red);
+    if (threadIdx.x == 0) {
+        partial[3 * (size_t)blockIdx.x + 0] = (double)len;
+        partial[3 * (size_t)blockIdx.x + 1] = mean;
+        partial[3 * (size_t)blockIdx.x + 2] = m2;
+    }
+}
+
+// one thread per utterance merges its chunk statistics in order (Chan et al.): stats[2b] = mean, [2b+1] = population variance
+__global__ void wave_merge_stats_kernel(int n_utts, const int32_t *chunk_first, const double *partial, double *stats)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_utts) return;
+    double n = 0.0, mean = 0.0, m2 = 0.0;
+    for (int c = chunk_first[b]; c < chunk_first[b + 1]; ++c) {
+        const double nb = partial[3 * (size_t)c], mb = partial[3 * (size_t)c + 1], qb = partial[3 * (size_t)c + 2];
+        const double tot = n + nb, delta = mb - mean;
+        mean += delta * (nb / tot);
+        m2 += qb + delta * delta * (n * nb / tot);
+        n = tot;
+    }
+    stats[2 * b] = mean;
+    stats[2 * b + 1] = (n > 0.0) ? m2 / n : 0.0;
+}
+
+template <typename InT, typename OutT>
+__global__ void __launch_bounds__(kStatThreads)
+wave_apply_norm_kernel(const InT *wave, OutT *out, const int64_t *n_samples, const int64_t *wave_off,
+                       const int32_t *chunk_utt, const int32_t *chunk_first, const double *stats, int mode)
+{
+    const int utt = chunk_utt[blockIdx.x];
+    const int64_t c = blockIdx.x - chunk_first[utt];
+    const int64_t n = n_samples[utt];
+    const int64_t j0 = c * kStatChunk;
+    const int64_t len = (n - j0 < kStatChunk) ? n - j0 : kStatChunk;
+    const double mean = stats[2 * utt], var = stats[2 * utt + 1];
+    const InT *src = wave + wave_off[utt] + j0;
+    OutT *dst = out + wave_off[utt] + j0;
+    if (mode == 0) { // z-score, float64 arithmetic as numpy does for float64 input
+        const double denom = sqrt(var) + 1e-6;
+        for (int i = threadIdx.x; i < len; i += kStatThreads) dst[i] = (OutT)(((double)src[i] - mean) / denom);
+    } else { // wav2vec2 feature extractor: float32 arithmetic on the float32-rounded statistics
+        const float mf = (float)mean;
+        const float denom = sqrtf(__fadd_rn((float)var, 1e-7f));
+        for (int i = threadIdx.x; i < len; i += kStatThreads)
+            dst[i] = (OutT)__fdiv_rn(__fsub_rn((float)src[i], mf), denom);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- N1
+__global__ void pad_boarders_kernel(int n_utts, int64_t s_max, const int64_t *seg_slot_off, const int64_t *seg_len,
+                                    const int32_t *seg_count, int64_t *boarders, int64_t *mask, int32_t *status)
+{
+    // one warp per utterance: inclusive scan of the lengths (ref:src/aat/training/collate.py:158 `.cumsum()`)
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= n_utts) return;
+    const int cnt = seg_count[b];
+    const int64_t *len = seg_len + seg_slot_off[b];
+    int64_t *brow = boarders + (size_t)b * s_max, *mrow = mask + (size_t)b * s_max;
+    if (lane == 0 && cnt > s_max) status[b] = AAT_ERR_CAPACITY;
+    int64_t base = 0;
+    for (int64_t i0 = 0; i0 < s_max; i0 += 32) {
+        const int64_t i = i0 + lane;
+        const int64_t v = (i < cnt) ? len[i] : 0;
+        int64_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int64_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (i < s_max) {
+            brow[i] = (i < cnt) ? base + incl : 0;
+            mrow[i] = (i < cnt) ? 1 : 0;
+        }
+        base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+// grid = B * s_max rows.  Row (b, s): out[b, s, :len] = wave[b, prev:boarder], rest 0; mask likewise.
+__global__ void __launch_bounds__(256)
+scatter_segments_kernel(const float *wave, int64_t n_max, const int64_t *boarders, int64_t s_max, int64_t max_frames,
+                        float *out, float *mask, int32_t *status)
+{
+    const int64_t row = blockIdx.x;
+    const int64_t b = row / s_max, s = row - b * s_max;
+    const int64_t *brow = boarders + b * s_max;
+    const int64_t end = brow[s];
+    float *o = out + (size_t)row * max_frames;
+    float *m = mask ? mask + (size_t)row * max_frames : nullptr;
+    int64_t len = 0, begin = 0;
+    if (s == 0 || end != 0) { // `if segment_i > 0 and segment_boarder == 0: continue` (collate.py:326-327)
+        begin = (s == 0) ? 0 : brow[s - 1];
+        len = end - begin;
+        // the reference asserts prev < boarder and fails on a shape mismatch when the slice is longer than the
+        // tile or runs past the padded waveform; report instead of raising
+        if (len <= 0 || len > max_frames || end > n_max) {
+            if (threadIdx.x == 0) atomicMin(status + b, (int32_t)AAT_ERR_INVALID);
+            if (len < 0) len = 0;
+            if (len > max_frames) len = max_frames;
+            if (begin + len > n_max) len = (n_max > begin) ? n_max - begin : 0;
+        }
+    }
+    const float *src = wave + (size_t)b * n_max + begin;
+    if ((max_frames & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+        (m == nullptr || (reinterpret_cast<uintptr_t>(mask) & 15) == 0)) {
+        // rows are 16-byte aligned: 128-bit stores (the ragged source is read with scalar, coalesced loads)
+        for (int64_t i = 4 * (int64_t)threadIdx.x; i < max_frames; i += 4 * (int64_t)blockDim.x) {
+            float4 v, k;
+            v.x = (i + 0 < len) ? src[i + 0] : 0.0f, k.x = (i + 0 < len) ? 1.0f : 0.0f;
+            v.y = (i + 1 < len) ? src[i + 1] : 0.0f, k.y = (i + 1 < len) ? 1.0f : 0.0f;
+            v.z = (i + 2 < len) ? src[i + 2] : 0.0f, k.z = (i + 2 < len) ? 1.0f : 0.0f;
+            v.w = (i + 3 < len) ? src[i + 3] : 0.0f, k.w = (i + 3 < len) ? 1.0f : 0.0f;
+            *reinterpret_cast<float4 *>(o + i) = v;
+            if (m) *reinterpret_cast<float4 *>(m + i) = k;
+        }
+    } else {
+        for (int64_t i = threadIdx.x; i < max_frames; i += blockDim.x) {
+            const bool in = i < len;
+            o[i] = in ? src[i] : 0.0f;
+            if (m) m[i] = in ? 1.0f : 0.0f;
+        }
+    }
+}
+
+// grid = B * s_max rows; out[b, s, mel, :cols] = mel_b[mel, prev/hop : boarder/hop], rest 0
+__global__ void __launch_bounds__(256)
+scatter_mel_segments_kernel(const float *mel, const int64_t *frame_off, const int64_t *n_samples, int hop, int n_mels,
+                            const int64_t *boarders, int64_t s_max, int64_t max_items, float *out, int32_t *status)
+{
+    const int64_t row = blockIdx.x;
+    const int64_t b = row / s_max, s = row - b * s_max;
+    const int64_t *brow = boarders + b * s_max;
+    const int64_t end = brow[s];
+    const int64_t T = 1 + n_samples[b] / hop;
+    float *o = out + (size_t)row * n_mels * max_items;
+    int64_t c0 = 0, cols = 0;
+    if (s == 0 || end != 0) {
+        const int64_t begin = (s == 0) ? 0 : brow[s - 1];
+        c0 = begin / hop;
+        int64_t c1 = end / hop;
+        if (c1 > T) c1 = T; // numpy slicing clamps at the array end
+        if (c0 > T) c0 = T;
+        cols = c1 - c0;
+        if (cols > max_items) { // the reference fails on the shape mismatch
+            if (threadIdx.x == 0) atomicMin(status + b, (int32_t)AAT_ERR_INVALID);
+            cols = max_items;
+        }
+        if (cols < 0) cols = 0;
+    }
+    const float *src = mel + (size_t)n_mels * frame_off[b] + c0;
+    const int64_t total = (int64_t)n_mels * max_items;
+    for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
+        const int64_t r = i / max_items, c = i - r * max_items;
+        o[i] = (c < cols) ? src[(size_t)r * T + c] : 0.0f;
+    }
+}
+
+} // namespace
+
+int launch_normalize(aat_ctx *ctx, const aat_plan *plan, const void *wave, int in_dtype, int mode, void *out,
+                     int out_dtype, double *stats, cudaStream_t stream)
+{
+    (void)ctx;
+    AAT_REQUIRE(in_dtype == AAT_F32 || in_dtype == AAT_F64, AAT_ERR_UNSUPPORTED, "aat_normalize: input dtype must be F32 or F64");
+    AAT_REQUIRE(out_dtype == AAT_F32 || out_dtype == AAT_F64, AAT_ERR_UNSUPPORTED, "aat_normalize: output dtype must be F32 or F64");
+    AAT_REQUIRE(mode == 0 || mode == 1, AAT_ERR_INVALID, "aat_normalize: unknown mode %d", mode);
+    if (plan->norm_chunks == 0) return AAT_OK;
+    double *st = stats ? stats : plan->d_norm_stats;
+    if (in_dtype == AAT_F32)
+        wave_chunk_stats_kernel<float><<<plan->norm_chunks, kStatThreads, 0, stream>>>(
+            static_cast<const float *>(wave), plan->d_n_samples, plan->d_wave_off, plan->d_chunk_utt, plan->d_chunk_first,
+            plan->d_norm_partial);
+    else
+        wave_chunk_stats_kernel<double><<<plan->norm_chunks, kStatThreads, 0, stream>>>(
+            static_cast<const double *>(wave), plan->d_n_samples, plan->d_wave_off, plan->d_chunk_utt, plan->d_chunk_first,
+            plan->d_norm_partial);
+    AAT_LAUNCH_CHECK();
+    wave_merge_stats_kernel<<<(plan->n_utts + 127) / 128, 128, 0, stream>>>(plan->n_utts, plan->d_chunk_first,
+                                                                            plan->d_norm_partial, st);
+    AAT_LAUNCH_CHECK();
+    if (out == nullptr) return AAT_OK; // statistics only
+#define AAT_APPLY(IN, OUT)                                                                                         \
+    wave_apply_norm_kernel<IN, OUT><<<plan->norm_chunks, kStatThreads, 0, stream>>>(                                \
+        static_cast<const IN *>(wave), static_cast<OUT *>(out), plan->d_n_samples, plan->d_wave_off, plan->d_chunk_utt, \
+        plan->d_chunk_first, st, mode)
+    if (in_dtype == AAT_F32 && out_dtype == AAT_F32) AAT_APPLY(float, float);
+    else if (in_dtype == AAT_F32) AAT_APPLY(float, double);
+    else if (out_dtype == AAT_F32) AAT_APPLY(double, float);
+    else AAT_APPLY(double, double);
+#undef AAT_APPLY
+    AAT_LAUNCH_CHECK();
+    return AAT_OK;
+}
+
+int launch_pad_boarders(const aat_plan *plan, const int64_t *seg_len, const int32_t *seg_count, int64_t s_max,
+                        int64_t *boarders, int64_t *mask, int32_t *status, cudaStream_t stream)
+{
+    if (plan->n_utts == 0 || s_max == 0) return AAT_OK;
+    AAT_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)plan->n_utts, stream));
+    const int warps = 4;
+    pad_boarders_kernel<<<(plan->n_utts + warps - 1) / warps, warps * 32, 0, stream>>>(
+        plan->n_utts, s_max, plan->d_seg_slot_off, seg_len, seg_count, boarders, mask, status);
+    AAT_LAUNCH_CHECK();
+    return AAT_OK;
+}
+
+int launch_scatter_segments(const float *wave, int64_t n_max, int32_t n_utts, const int64_t *boarders, int64_t s_max,
+                            int64_t max_frames, float *out, float *mask, int32_t *status, cudaStream_t stream)
+{
+    if (n_utts == 0 || s_max == 0 || max_frames == 0) return AAT_OK;
+    AAT_REQUIRE((int64_t)n_utts * s_max < (int64_t)INT32_MAX, AAT_ERR_UNSUPPORTED, "aat_scatter_segments: too many rows");
+    AAT_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)n_utts, stream));
+    scatter_segments_kernel<<<(unsigned)(n_utts * s_max), 256, 0, stream>>>(wave, n_max, boarders, s_max, max_frames, out,
+                                                                          mask, status);
+    AAT_LAUNCH_CHECK();
+    return AAT_OK;
+}
+
+int launch_scatter_mel_segments(aat_ctx *ctx, const aat_plan *plan, const float *mel, const int64_t *boarders,
+                                int64_t s_max, int64_t max_items, float *out, int32_t *status, cudaStream_t stream)
+{
+    if (plan->n_utts == 0 || s_max == 0 || max_items == 0) return AAT_OK;
+    AAT_REQUIRE((int64_t)plan->n_utts * s_max < (int64_t)INT32_MAX, AAT_ERR_UNSUPPORTED, "aat_scatter_mel_segments: too many rows");
+    AAT_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)plan->n_utts, stream));
+    scatter_mel_segments_kernel<<<(unsigned)(plan->n_utts * s_max), 256, 0, stream>>>(
+        mel, plan->d_frame_off, plan->d_n_samples, ctx->cfg.hop_length, ctx->cfg.num_mel_filters, boarders, s_max,
+        max_items, out, status);
+    AAT_LAUNCH_CHECK();
+    return AAT_OK;
+}
+
+} // namespace aat

@@ -61,7 +61,9 @@ def make_waves(name, rank):
 
 # ------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """`nvidia-smi -lms` in the background; samples are time-stamped so that only those taken inside the
+    timed region are summarised (the process is started early because it needs ~0.3 s to produce a line)."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
@@ -74,22 +76,34 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
+        import datetime
+
         for line in self.proc.stdout:
             parts = [p.strip() for p in line.split(",")]
-            if len(parts) >= 7:
-                self.samples.append(parts)
+            if len(parts) >= 8:
+                try:
+                    ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except ValueError:
+                    ts = time.time()
+                self.samples.append((ts, parts[1:]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is not None:
             self.proc.terminate()
+        inside = [p for ts, p in self.samples if t0 is None or (t0 <= ts <= t1)]
+        scope = "timed region"
+        if not inside:  # region shorter than the sampling period: fall back to the samples nearest to it
+            mid = 0.5 * ((t0 or 0) + (t1 or 0))
+            inside = [p for _, p in sorted(self.samples, key=lambda s: abs(s[0] - mid))[:3]]
+            scope = "nearest samples (region shorter than the sampling period)"
         sm, reasons, sm_max = [], set(), None
-        for p in self.samples:
+        for p in inside:
             try:
                 sm.append(float(p[0]))
                 sm_max = float(p[1])
@@ -99,7 +113,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": sm_max, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "scope": scope}
 
 
 # ------------------------------------------------------------------------------------------- CPU baseline
@@ -254,17 +268,22 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(args.warmup):
         step(i)
     barrier()
+    t_spin = time.time()
+    while not sampler.samples and time.time() - t_spin < 2.0:  # keep the GPU busy until nvidia-smi is up
+        step(0)
+        torch.cuda.synchronize()
 
     # ---- timed region: K steps + the one collective
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     _cabi.profile_enable(batch.ctx.handle, ("pool",))
     launches0 = _cabi.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    wall0 = time.time()
     ev0.record()
     for i in range(args.steps):
         step(i)
@@ -272,11 +291,12 @@ def run_b200(args):
     mean_vec = dm.result()
     ev1.record()
     barrier()
+    wall1 = time.time()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = _cabi.launch_count() - launches0
     prof = _cabi.profile_summary(batch.ctx.handle)
     _cabi.profile_enable(batch.ctx.handle, ())
-    clocks = sampler.stop()
+    clocks = sampler.stop(wall0, wall1)
     assert bool(torch.isfinite(mean_vec).all())
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -420,7 +440,7 @@ def main():
         args.warmup = 1 if args.warmup is None else args.warmup
         run_reference(args)
     else:
-        args.steps = 200 if args.steps is None else args.steps
+        args.steps = 2000 if args.steps is None else args.steps
         args.warmup = max(3, 10 if args.warmup is None else args.warmup)
         run_b200(args)
 

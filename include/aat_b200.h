@@ -197,6 +197,45 @@ int aat_colsum_accumulate(aat_ctx *ctx, double *acc_dev, const double *colsum_de
 /* mean_dev[d] = float32(acc_dev[d] / acc_dev[dim]) — after the SUM allreduce of acc_dev over ranks. */
 int aat_colsum_finalize(aat_ctx *ctx, const double *acc_dev, int32_t dim, float *mean_dev, void *stream);
 
+/* ------------------------------------------------------------------ callers either side of the path
+ * (SURVEY.md section 8f rows N1, N2).  Device entry points, asynchronous on `stream`. */
+
+typedef enum aat_norm_mode {
+    AAT_NORM_ZSCORE = 0, /* (x - mean) / (std + 1e-6), float64: ref:scripts/audio_tokenization_melspec.py:40,
+                            ref:src/aat/training/collate.py:135,138,152 */
+    AAT_NORM_W2V2 = 1    /* (x - mean) / sqrt(var + 1e-7), float32: ref:src/aat/training/collate.py:301 ->
+                            Wav2Vec2FeatureExtractor.zero_mean_unit_var_norm */
+} aat_norm_mode;
+
+/* Per-utterance waveform normalisation on the packed layout.  Statistics are accumulated in float64.
+ * out_dev   : packed like the input, AAT_F32 or AAT_F64; NULL = statistics only
+ * stats_dev : optional float64 [2 * n_utts]: (mean, population variance) per utterance */
+int aat_normalize(aat_ctx *ctx, const aat_plan *plan, const void *wave_dev, int in_dtype, int mode, void *out_dev,
+                  int out_dtype, double *stats_dev, void *stream);
+
+/* `_make_padded_segments_boarders` (ref:src/aat/training/collate.py:242-253) on the output of aat_boundaries:
+ * boarders_dev [n_utts, s_max] = cumulative segment ends (the collator's `frames_boarders`, :158), zero padded;
+ * mask_dev [n_utts, s_max] = 1 for real segments.  status_dev [n_utts] gets AAT_ERR_CAPACITY when an utterance
+ * has more than s_max segments. */
+int aat_pad_segment_boarders(aat_ctx *ctx, const aat_plan *plan, const int64_t *seg_len_dev,
+                             const int32_t *seg_count_dev, int64_t s_max, int64_t *boarders_dev, int64_t *mask_dev,
+                             int32_t *status_dev, void *stream);
+
+/* The collator's waveform scatter (ref:src/aat/training/collate.py:321-335):
+ * out_dev [n_utts, s_max, max_frames] = wave_padded_dev[b, prev:boarder] left aligned, zero elsewhere;
+ * mask_dev (optional) likewise with ones.  wave_padded_dev is [n_utts, n_max] float32 (the feature extractor's
+ * padded `input_values`).  status_dev [n_utts] gets AAT_ERR_INVALID where the reference would raise
+ * (non-increasing boarders, a segment longer than max_frames or running past n_max). */
+int aat_scatter_segments(aat_ctx *ctx, const float *wave_padded_dev, int64_t n_max, int32_t n_utts,
+                         const int64_t *boarders_dev, int64_t s_max, int64_t max_frames, float *out_dev,
+                         float *mask_dev, int32_t *status_dev, void *stream);
+
+/* The collator's log-mel scatter (ref:src/aat/training/collate.py:337-342):
+ * out_dev [n_utts, s_max, n_mels, max_items] = mel_b[:, prev // hop : boarder // hop], zero elsewhere;
+ * mel_dev is the packed log-mel of the plan. */
+int aat_scatter_mel_segments(aat_ctx *ctx, const aat_plan *plan, const float *mel_dev, const int64_t *boarders_dev,
+                             int64_t s_max, int64_t max_items, float *out_dev, int32_t *status_dev, void *stream);
+
 /* ------------------------------------------------------------------ host-buffer entry points
  * Same operations for callers that hold numpy arrays, exactly like the reference's methods:
  * the library stages host<->device copies in its own scratch and synchronises. */

@@ -1,0 +1,67 @@
+"""ORACLE (test infrastructure, not product code) — port of the collator's ragged -> padded layout and of
+the waveform normalisations either side of the hot path.
+
+PARITY UNPINNED for these rows: `aat.training.collate` does not import in the build container
+(`from transformers.trainer import ALL_LAYERNORM_LAYERS` fails on transformers 5.5.0, and `__call__` needs
+HF Hub processors), so no golden vector could be produced by the live reference.  The loops below are a
+statement-by-statement restatement of the cited lines; the tests compare the CUDA path with them.
+
+  ref:src/aat/training/collate.py:242-253   _make_padded_segments_boarders
+  ref:src/aat/training/collate.py:309-346   batched_segments / segments_waveforms_mask / melspectrogram tiles
+  ref:src/aat/training/collate.py:135,138,152, ref:scripts/audio_tokenization_melspec.py:40   z-score
+  TF:models/wav2vec2/feature_extraction_wav2vec2.py:78-95   zero_mean_unit_var_norm (no attention mask branch)
+
+Nothing under ``audio-adaptive-tokenizer_b200/`` may import this module.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def make_padded_segments_boarders(segments_boarders, batch_size):
+    max_len = max(len(x) for x in segments_boarders)
+    padded = torch.zeros([batch_size, max_len], dtype=torch.long)
+    mask = torch.zeros_like(padded)
+    for i, sb in enumerate(segments_boarders):
+        padded[i, : len(sb)] = torch.tensor(sb, dtype=torch.long)
+        mask[i, : len(sb)] = 1
+    return padded, mask
+
+
+def scatter_segments(audio_input_values, segments_boarders_padded, max_segment_waveform_frames, items_melspecs=None,
+                     hop_length=160, num_mel_filters=64):
+    """Returns (batched_segments, segments_waveforms_mask, batched_segments_melspectrograms)."""
+    batch_size, segments_count = segments_boarders_padded.shape
+    max_melspec_items = int(1 + np.floor(max_segment_waveform_frames / hop_length))
+    mel_tiles = None
+    if items_melspecs is not None:
+        mel_tiles = torch.zeros([batch_size, segments_count, num_mel_filters, max_melspec_items])
+    batched_segments = torch.zeros([batch_size, segments_count, max_segment_waveform_frames])
+    segments_waveforms_mask = torch.zeros([batch_size, segments_count, max_segment_waveform_frames])
+    for batch_i in range(batch_size):
+        prev = 0
+        for segment_i in range(segments_count):
+            boarder = int(segments_boarders_padded[batch_i, segment_i])
+            if segment_i > 0 and boarder == 0:
+                continue
+            assert prev < boarder
+            length = boarder - prev
+            current = audio_input_values[batch_i, prev:boarder]
+            batched_segments[batch_i, segment_i, :length] = current
+            segments_waveforms_mask[batch_i, segment_i, :length] = 1
+            if mel_tiles is not None:
+                a, b = prev // hop_length, boarder // hop_length
+                seg = items_melspecs[batch_i][:, a:b]
+                mel_tiles[batch_i, segment_i, :, : seg.shape[1]] = torch.from_numpy(np.ascontiguousarray(seg))
+            prev = boarder
+    return batched_segments, segments_waveforms_mask, mel_tiles
+
+
+def znorm(x: np.ndarray) -> np.ndarray:
+    return (x - x.mean()) / (x.std() + 1e-6)
+
+
+def w2v2_norm(x: np.ndarray) -> np.ndarray:
+    x = np.asarray(x, dtype=np.float32)
+    return (x - x.mean()) / np.sqrt(x.var() + 1e-7)

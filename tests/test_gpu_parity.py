@@ -466,3 +466,82 @@ def test_config2_full_size_properties(tok):
     assert torch.allclose(lhs, rhs, rtol=1e-6, atol=1e-3)
     want = ref_port.mean_pool_csr(e1[: seg_off[40]].cpu(), seg_off[:41]).numpy()[0]
     assert_pooled_close(p1[:40].cpu().numpy(), want)
+
+
+# ----------------------------------------------------------------------------------------- N1 / N2
+def test_waveform_normalisations(tok):
+    import torch
+
+    from aat_b200 import collate, synth
+    from oracle import collate_port
+
+    rng = np.random.default_rng(17)
+    lengths = [256000, 4095, 4096, 4097, 100, 70001]
+    waves = [synth.bursty_speech(n, 600 + i).astype(np.float64) + (0.0 if i % 2 else 3.5) for i, n in enumerate(lengths)]
+    batch = tok.plan(lengths)
+    packed = batch.pack([torch.from_numpy(w) for w in waves])
+    out, stats = collate.normalize_waveforms(batch, packed, "zscore", return_stats=True)
+    out32 = collate.normalize_waveforms(batch, packed.float(), "w2v2")
+    torch.cuda.synchronize()
+    assert out.dtype == torch.float64 and out32.dtype == torch.float32
+    for b, w in enumerate(waves):
+        o0, o1 = int(batch.wave_off[b]), int(batch.wave_off[b + 1])
+        want = collate_port.znorm(w)
+        np.testing.assert_allclose(out[o0:o1].cpu().numpy(), want, rtol=1e-12, atol=1e-12)
+        assert abs(float(stats[b, 0]) - w.mean()) <= 1e-13 * max(1.0, abs(w.mean()))
+        assert abs(float(stats[b, 1]) - w.var()) <= 1e-12 * w.var()
+        want32 = collate_port.w2v2_norm(w.astype(np.float32))
+        np.testing.assert_allclose(out32[o0:o1].cpu().numpy(), want32, rtol=2e-6, atol=2e-6)
+
+
+def test_znorm_then_logmel_matches_reference_golden(tok, golden):
+    """Device z-score -> K1+K2 reproduces the reference's mel of the numpy-normalised waveform."""
+    import torch
+
+    from aat_b200 import collate, synth
+
+    raw = synth.bursty_speech(256000, synth.seed_for(2, 2)).astype(np.float64)
+    batch = tok.plan([raw.size])
+    normed = collate.normalize_waveforms(batch, torch.from_numpy(raw).cuda(), "zscore")
+    batch.logmel(normed)
+    batch.boundaries()
+    torch.cuda.synchronize()
+    assert_mel_close(batch.mel_of(0).cpu().numpy(), golden.get("c2_16s_znorm", "mel"), min_exact=0.999)
+    assert batch.segments_of(0)[1].tolist() == golden.get("c2_16s_znorm", "lengths").tolist()
+
+
+def test_padded_layout_matches_collator_port(tok):
+    import torch
+
+    from aat_b200 import collate, synth
+    from oracle import collate_port
+
+    lengths = [64000, 40000, 96000, 2080]
+    waves = [synth.bursty_speech(n, 700 + i) for i, n in enumerate(lengths)]
+    batch = tok.plan(lengths)
+    batch.logmel(batch.pack([torch.from_numpy(w) for w in waves]))
+    batch.boundaries()
+    torch.cuda.synchronize()
+    seg_lengths = [batch.segments_of(b)[1] for b in range(len(lengths))]
+    boarders = [np.cumsum(l) for l in seg_lengths]
+    want_pad, want_mask = collate_port.make_padded_segments_boarders(boarders, len(lengths))
+    got_pad, got_mask = collate.pad_segment_boarders(batch)
+    assert torch.equal(got_pad.cpu(), want_pad) and torch.equal(got_mask.cpu(), want_mask)
+
+    # the feature extractor's padded input_values: [B, N_max] float32, long enough for the zero-padded tails
+    n_max = max(int(b[-1]) for b in boarders)
+    padded_wave = np.zeros((len(lengths), n_max), dtype=np.float32)
+    for b, w in enumerate(waves):
+        padded_wave[b, : w.size] = collate_port.w2v2_norm(w)
+    max_frames = tok.max_segment_frames
+    mels = [batch.mel_of(b).cpu().numpy() for b in range(len(lengths))]
+    want_seg, want_segmask, want_mel = collate_port.scatter_segments(torch.from_numpy(padded_wave), want_pad, max_frames,
+                                                                     items_melspecs=mels)
+    got_seg, got_segmask = collate.scatter_segments(batch, torch.from_numpy(padded_wave).cuda(), got_pad, max_frames)
+    got_mel = collate.scatter_mel_segments(batch, got_pad, max_frames)
+    torch.cuda.synchronize()
+    assert torch.equal(got_seg.cpu(), want_seg) and torch.equal(got_segmask.cpu(), want_segmask)
+    assert torch.equal(got_mel.cpu(), want_mel)
+    # a tile that is too small is what makes the reference raise
+    with pytest.raises(Exception):
+        collate.scatter_segments(batch, torch.from_numpy(padded_wave).cuda(), got_pad, 1000)
