@@ -218,10 +218,13 @@ scatter_mel_segments_kernel(const float *mel, const int64_t *frame_off, const in
         if (cols < 0) cols = 0;
     }
     const float *src = mel + (size_t)n_mels * frame_off[b] + c0;
-    const int64_t total = (int64_t)n_mels * max_items;
-    for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
-        const int64_t r = i / max_items, c = i - r * max_items;
-        o[i] = (c < cols) ? src[(size_t)r * T + c] : 0.0f;
+    // a warp per mel row, lanes along time: coalesced reads of the source row and of the tile row, no divisions
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int items = (int)max_items, ncols = (int)cols;
+    for (int r = warp; r < n_mels; r += n_warps) {
+        const float *srow = src + (size_t)r * T;
+        float *orow = o + (size_t)r * items;
+        for (int c = lane; c < items; c += 32) orow[c] = (c < ncols) ? srow[c] : 0.0f;
     }
 }
 

@@ -1,0 +1,47 @@
+"""CPU checks of the collator port (oracle for SURVEY §8f rows N1/N2): the restated loops agree with an
+independent vectorised formulation, and the GPU-facing ABI declares the matching entry points."""
+import numpy as np
+import torch
+
+from oracle import collate_port
+
+
+def test_padded_boarders_and_scatter_against_vectorised_numpy():
+    rng = np.random.default_rng(0)
+    B, max_frames, hop, n_mels = 5, 24000, 160, 64
+    seg_lengths = [rng.integers(2000, 24000, size=int(rng.integers(1, 9))) for _ in range(B)]
+    boarders = [np.cumsum(l) for l in seg_lengths]
+    padded, mask = collate_port.make_padded_segments_boarders(boarders, B)
+    s_max = max(len(b) for b in boarders)
+    assert padded.shape == (B, s_max) and padded.dtype == torch.long
+    for b in range(B):
+        assert padded[b, : len(boarders[b])].tolist() == boarders[b].tolist()
+        assert padded[b, len(boarders[b]):].sum() == 0 and mask[b].sum() == len(boarders[b])
+    n_max = max(int(b[-1]) for b in boarders)
+    wave = torch.from_numpy(rng.standard_normal((B, n_max)).astype(np.float32))
+    mels = [rng.standard_normal((n_mels, 1 + n_max // hop)).astype(np.float32) for _ in range(B)]
+    seg, segmask, tiles = collate_port.scatter_segments(wave, padded, max_frames, items_melspecs=mels)
+    assert seg.shape == (B, s_max, max_frames) and tiles.shape == (B, s_max, n_mels, 1 + max_frames // hop)
+    for b in range(B):
+        starts = np.concatenate([[0], boarders[b][:-1]])
+        for s, (a, e) in enumerate(zip(starts, boarders[b])):
+            assert torch.equal(seg[b, s, : e - a], wave[b, a:e]) and seg[b, s, e - a:].abs().sum() == 0
+            assert segmask[b, s].sum() == e - a
+            cols = e // hop - a // hop
+            assert np.array_equal(tiles[b, s, :, :cols].numpy(), mels[b][:, a // hop: e // hop])
+        assert seg[b, len(boarders[b]):].abs().sum() == 0
+    # a segment longer than the tile makes the reference (and the port) fail
+    try:
+        collate_port.scatter_segments(wave, padded, 1000)
+        raise AssertionError("expected a shape mismatch")
+    except RuntimeError:
+        pass
+
+
+def test_normalisation_ports():
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(50000) * 0.3 + 2.0
+    z = collate_port.znorm(x)
+    assert z.dtype == np.float64 and abs(z.mean()) < 1e-12 and abs(z.std() - 1.0) < 1e-5
+    w = collate_port.w2v2_norm(x)
+    assert w.dtype == np.float32 and abs(float(w.mean())) < 1e-4 and abs(float(w.std()) - 1.0) < 1e-3
