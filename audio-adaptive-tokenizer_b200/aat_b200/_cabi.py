@@ -76,7 +76,7 @@ SIGNATURES = {
     "aat_process_boarders": (ctypes.c_int, [c_void, c_i64, c_void, c_i64, c_void, c_void, c_i64, c_void, c_void, c_void]),
     "aat_segment_frame_csr": (ctypes.c_int, [c_void] * 8),
     "aat_segment_mean_pool": (ctypes.c_int, [c_void, c_void, ctypes.c_int, c_i64, c_i32, c_void, c_i64, c_void, c_void,
-                                             c_void, c_void]),
+                                             c_void, ctypes.c_int, c_void]),
     "aat_colsum_accumulate": (ctypes.c_int, [c_void, c_void, c_void, c_i32, c_void]),
     "aat_colsum_finalize": (ctypes.c_int, [c_void, c_void, c_i32, c_void, c_void]),
     "aat_normalize": (ctypes.c_int, [c_void, c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, ctypes.c_int, c_void, c_void]),

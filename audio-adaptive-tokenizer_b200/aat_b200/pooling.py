@@ -30,7 +30,7 @@ def _torch_dtype_code(dtype) -> int:
     return code
 
 
-def _pool_device(ctx: Context, emb, seg_off, n_seg: int, n_seg_dev, out, colsum, stream):
+def _pool_device(ctx: Context, emb, seg_off, n_seg: int, n_seg_dev, out, colsum, stream, accumulate: bool = False):
     """Raw K4 launch on CUDA tensors (no allocation, no sync)."""
     if emb.dim() != 2 or not emb.is_contiguous():
         raise ValueError("emb must be a contiguous [T, D] tensor")
@@ -39,7 +39,7 @@ def _pool_device(ctx: Context, emb, seg_off, n_seg: int, n_seg_dev, out, colsum,
     _cabi.check(_cabi.lib().aat_segment_mean_pool(
         ctx.handle, emb.data_ptr(), _torch_dtype_code(emb.dtype), int(emb.shape[0]), int(emb.shape[1]),
         seg_off.data_ptr(), int(n_seg), n_seg_dev.data_ptr() if n_seg_dev is not None else None, out.data_ptr(),
-        colsum.data_ptr() if colsum is not None else None, stream))
+        colsum.data_ptr() if colsum is not None else None, 1 if accumulate else 0, stream))
     return out
 
 
@@ -122,6 +122,11 @@ class DatasetMean:
     def colsum_buffer(self):
         """Pass this as ``colsum=`` to the pool call, then call :meth:`accumulate`."""
         return self.batch
+
+    def running_buffer(self):
+        """Pass this as ``colsum=`` with ``accumulate=True``: the pool call adds the batch's sums straight into
+        the running totals (no separate accumulate kernel)."""
+        return self.acc
 
     def accumulate(self):
         import torch

@@ -358,11 +358,13 @@ class PackedBatch:
             self.n_seg.data_ptr(), self.utt_seg_off.data_ptr(), self._stream()))
         return self.seg_off, self.n_seg
 
-    def pool(self, emb, out, colsum=None):
-        """K4 with the device-resident CSR of :meth:`frame_csr`.  ``out`` is [capacity, D] float32."""
+    def pool(self, emb, out, colsum=None, accumulate: bool = False):
+        """K4 with the device-resident CSR of :meth:`frame_csr`.  ``out`` is [capacity, D] float32; ``colsum``
+        ([D+1] float64) receives the column sums of the pooled vectors, added to its content when ``accumulate``."""
         from .pooling import _pool_device
 
-        return _pool_device(self.ctx, emb, self.seg_off, int(out.shape[0]), self.n_seg, out, colsum, self._stream())
+        return _pool_device(self.ctx, emb, self.seg_off, int(out.shape[0]), self.n_seg, out, colsum, self._stream(),
+                            accumulate)
 
     # ---- host views (synchronising; for tests and the numpy-facing callers)
     def mel_of(self, b: int):

@@ -38,6 +38,11 @@ extern std::atomic<int64_t> g_launch_count;
         }                               \
     } while (0)
 
+// Every kernel of the library asks for the same (maximum) shared-memory carve-out, so the SMs are not
+// drained and reconfigured between the kernels of a step (they differ widely in shared-memory footprint).
+#define AAT_MAX_SMEM_CARVEOUT(kernel) \
+    AAT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
+
 #define AAT_LAUNCH_CHECK()                         \
     do {                                           \
         aat::g_launch_count.fetch_add(1);          \
@@ -132,7 +137,7 @@ int launch_segment_frame_csr(aat_ctx *ctx, const aat_plan *plan, const int64_t *
                              int64_t *seg_off, int64_t *n_seg, int64_t *utt_seg_off, cudaStream_t stream);
 int launch_mean_pool(aat_ctx *ctx, const void *emb, int emb_dtype, int64_t n_rows, int32_t dim,
                      const int64_t *seg_off, int64_t n_seg, const int64_t *n_seg_dev, float *out, double *colsum,
-                     cudaStream_t stream);
+                     bool colsum_accumulate, cudaStream_t stream);
 int launch_colsum_accumulate(double *acc, const double *colsum, int32_t dim, cudaStream_t stream);
 int launch_colsum_finalize(const double *acc, int32_t dim, float *mean, cudaStream_t stream);
 int launch_normalize(aat_ctx *ctx, const aat_plan *plan, const void *wave, int in_dtype, int mode, void *out,

@@ -591,6 +591,7 @@ int launch_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel, cons
     p.utt_frames = plan->d_utt_frames;
     const size_t smem = sizeof(float) * (size_t)(2 * kChunk + kRing) + sizeof(int) * (size_t)(2 * kChunk);
     AAT_CUDA_CHECK(cudaFuncSetAttribute(boundaries_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AAT_MAX_SMEM_CARVEOUT(boundaries_kernel);
     {
         ProfileScope prof(ctx, AAT_K_BOUNDARIES, stream);
         boundaries_kernel<<<plan->n_utts, kThreads, smem, stream>>>(p);

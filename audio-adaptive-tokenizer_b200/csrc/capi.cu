@@ -419,11 +419,11 @@ int aat_segment_frame_csr(aat_ctx *ctx, const aat_plan *plan, const int64_t *seg
 
 int aat_segment_mean_pool(aat_ctx *ctx, const void *emb_dev, int emb_dtype, int64_t n_rows, int32_t dim,
                           const int64_t *seg_off_dev, int64_t n_seg, const int64_t *n_seg_dev, float *out_dev,
-                          double *colsum_dev, void *stream)
+                          double *colsum_dev, int colsum_accumulate, void *stream)
 {
     AAT_REQUIRE(ctx, AAT_ERR_INVALID, "aat_segment_mean_pool: NULL context");
     return launch_mean_pool(ctx, emb_dev, emb_dtype, n_rows, dim, seg_off_dev, n_seg, n_seg_dev, out_dev, colsum_dev,
-                            static_cast<cudaStream_t>(stream));
+                            colsum_accumulate != 0, static_cast<cudaStream_t>(stream));
 }
 
 int aat_colsum_accumulate(aat_ctx *ctx, double *acc_dev, const double *colsum_dev, int32_t dim, void *stream)
@@ -686,7 +686,8 @@ int aat_host_mean_pool(aat_ctx *ctx, const void *emb_host, int emb_dtype, int64_
     cudaStream_t st = ctx->host_stream;
     if (emb_bytes) AAT_CUDA_CHECK(cudaMemcpyAsync(d_emb, emb_host, emb_bytes, cudaMemcpyHostToDevice, st));
     AAT_CUDA_CHECK(cudaMemcpyAsync(d_off, seg_off_host, off_bytes, cudaMemcpyHostToDevice, st));
-    rc = launch_mean_pool(ctx, d_emb, emb_dtype, n_rows, dim, d_off, n_seg, nullptr, d_out, colsum_host ? d_cs : nullptr, st);
+    rc = launch_mean_pool(ctx, d_emb, emb_dtype, n_rows, dim, d_off, n_seg, nullptr, d_out, colsum_host ? d_cs : nullptr,
+                          false, st);
     if (rc) return rc;
     if (out_bytes) AAT_CUDA_CHECK(cudaMemcpyAsync(out_host, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
     if (colsum_host) AAT_CUDA_CHECK(cudaMemcpyAsync(colsum_host, d_cs, cs_bytes, cudaMemcpyDeviceToHost, st));

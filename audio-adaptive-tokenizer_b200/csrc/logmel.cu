@@ -439,6 +439,7 @@ int launch_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave, int wave
     const size_t smem = smem_layout(p.stage_pad, wave_bytes, p.n_mels, p.nnz).total;
     auto kernel = wave_dtype == AAT_F32 ? logmel_kernel<float> : logmel_kernel<double>;
     AAT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AAT_MAX_SMEM_CARVEOUT(kernel);
     int per_sm = 0;
     AAT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
     AAT_REQUIRE(per_sm >= 1, AAT_ERR_UNSUPPORTED, "aat_logmel: kernel does not fit on an SM (%zu bytes of shared memory)", smem);

@@ -472,38 +472,42 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
     }
 }
 
-// colsum_out[d] = sum over the pool CTAs of their per-CTA column sums; colsum_out[dim] = S.
-// Block = 32 columns x 8 slices of the CTA axis (coalesced 256-byte rows); the slice partials are then
-// added in slice order, so the result does not depend on scheduling.
-constexpr int kReduceSlices = 8;
+// colsum_out[d] (+)= sum over the pool CTAs of their per-CTA column sums; colsum_out[dim] (+)= S.
+// Block = 32 columns x 32 slices of the CTA axis (coalesced 256-byte rows).  Every thread issues all of its
+// (<= 16) loads before it adds anything, so the kernel costs one memory latency, not one per row; the slice
+// partials are then added in slice order, so the result does not depend on scheduling.
+constexpr int kReduceSlices = 32;
+constexpr int kReducePer = 16; // rows per thread: supports up to 512 pool CTAs
 __global__ void __launch_bounds__(32 * kReduceSlices)
-colsum_reduce_kernel(const double *partial, int n_ctas, int dim, int64_t n_seg, const int64_t *n_seg_dev, double *out)
+colsum_reduce_kernel(const double *partial, int n_ctas, int dim, int64_t n_seg, const int64_t *n_seg_dev, double *out,
+                     bool accumulate)
 {
     __shared__ double s_part[kReduceSlices][33];
     const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const int d = blockIdx.x * 32 + lane;
     const int per = (n_ctas + kReduceSlices - 1) / kReduceSlices;
-    const int c0 = slice * per, c1 = min(n_ctas, c0 + per);
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    if (d < dim) {
-        int c = c0;
-        for (; c + 4 <= c1; c += 4) {
-            s0 += partial[(size_t)c * dim + d];
-            s1 += partial[(size_t)(c + 1) * dim + d];
-            s2 += partial[(size_t)(c + 2) * dim + d];
-            s3 += partial[(size_t)(c + 3) * dim + d];
-        }
-        for (; c < c1; ++c) s0 += partial[(size_t)c * dim + d];
+    const int c0 = slice * per;
+    double v[kReducePer];
+#pragma unroll
+    for (int k = 0; k < kReducePer; ++k) {
+        const int c = c0 + k;
+        v[k] = (k < per && c < n_ctas && d < dim) ? partial[(size_t)c * dim + d] : 0.0;
     }
-    s_part[slice][lane] = (s0 + s1) + (s2 + s3);
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < kReducePer; ++k) s += v[k];
+    s_part[slice][lane] = s;
     __syncthreads();
     if (slice == 0 && d < dim) {
-        double s = 0.0;
+        double t = 0.0;
 #pragma unroll
-        for (int k = 0; k < kReduceSlices; ++k) s += s_part[k][lane];
-        out[d] = s;
+        for (int k = 0; k < kReduceSlices; ++k) t += s_part[k][lane];
+        out[d] = accumulate ? out[d] + t : t;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) out[dim] = (double)(n_seg_dev ? min(*n_seg_dev, n_seg) : n_seg);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const double count = (double)(n_seg_dev ? min(*n_seg_dev, n_seg) : n_seg);
+        out[dim] = accumulate ? out[dim] + count : count;
+    }
 }
 
 __global__ void colsum_accumulate_kernel(double *acc, const double *colsum, int n)
@@ -524,6 +528,7 @@ int launch_typed(aat_ctx *ctx, PoolParams &p, size_t smem, bool colsum, cudaStre
     const int threads = p.n_consumers + 32;
     auto kernel = colsum ? pool_kernel<EmbT, kSlabs, true> : pool_kernel<EmbT, kSlabs, false>;
     AAT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AAT_MAX_SMEM_CARVEOUT(kernel);
     // persistent grid: the cross-CTA carry needs every CTA resident at once, so size it from the
     // occupancy the driver reports for this very instantiation
     int per_sm = 0;
@@ -560,6 +565,7 @@ int pool_scratch_init(aat_ctx *ctx)
 {
     PoolScratch &ps = ctx->pool;
     ps.max_ctas = ctx->num_sms * kMaxCtasPerSm;
+    if (ps.max_ctas > 512) ps.max_ctas = 512; // colsum_reduce_kernel covers 32 slices x 16 rows
     ps.max_dim = 4096;
     AAT_CUDA_CHECK(cudaMalloc(&ps.head, sizeof(float) * (size_t)ps.max_ctas * ps.max_dim));
     AAT_CUDA_CHECK(cudaMalloc(&ps.head_flag, sizeof(int) * (size_t)ps.max_ctas));
@@ -579,7 +585,7 @@ void pool_scratch_free(aat_ctx *ctx)
 
 int launch_mean_pool(aat_ctx *ctx, const void *emb, int emb_dtype, int64_t n_rows, int32_t dim,
                      const int64_t *seg_off, int64_t n_seg, const int64_t *n_seg_dev, float *out, double *colsum,
-                     cudaStream_t stream)
+                     bool colsum_accumulate, cudaStream_t stream)
 {
     int esize;
     switch (emb_dtype) {
@@ -599,7 +605,8 @@ int launch_mean_pool(aat_ctx *ctx, const void *emb, int emb_dtype, int64_t n_row
     AAT_REQUIRE((reinterpret_cast<uintptr_t>(emb) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                 AAT_ERR_INVALID, "aat_segment_mean_pool: emb_dev and out_dev must be 16-byte aligned");
     if (n_seg == 0) {
-        if (colsum) AAT_CUDA_CHECK(cudaMemsetAsync(colsum, 0, sizeof(double) * (size_t)(dim + 1), stream));
+        if (colsum && !colsum_accumulate)
+            AAT_CUDA_CHECK(cudaMemsetAsync(colsum, 0, sizeof(double) * (size_t)(dim + 1), stream));
         return AAT_OK;
     }
     AAT_REQUIRE(emb != nullptr || n_rows == 0, AAT_ERR_INVALID, "aat_segment_mean_pool: emb_dev is NULL");
@@ -639,8 +646,9 @@ int launch_mean_pool(aat_ctx *ctx, const void *emb, int emb_dtype, int64_t n_row
         rc = launch_slabs<__nv_bfloat16>(ctx, p, slabs, smem, want_colsum, stream, &grid);
     if (rc != AAT_OK) return rc;
     if (want_colsum) {
+        AAT_MAX_SMEM_CARVEOUT(colsum_reduce_kernel);
         colsum_reduce_kernel<<<(dim + 31) / 32, 32 * kReduceSlices, 0, stream>>>(ctx->pool.colsum, grid, dim, n_seg,
-                                                                                 n_seg_dev, colsum);
+                                                                                 n_seg_dev, colsum, colsum_accumulate);
         AAT_LAUNCH_CHECK();
     }
     return AAT_OK;
@@ -648,6 +656,7 @@ int launch_mean_pool(aat_ctx *ctx, const void *emb, int emb_dtype, int64_t n_row
 
 int launch_colsum_accumulate(double *acc, const double *colsum, int32_t dim, cudaStream_t stream)
 {
+    AAT_MAX_SMEM_CARVEOUT(colsum_accumulate_kernel);
     colsum_accumulate_kernel<<<(dim + 1 + 127) / 128, 128, 0, stream>>>(acc, colsum, dim + 1);
     AAT_LAUNCH_CHECK();
     return AAT_OK;

@@ -186,11 +186,13 @@ int aat_segment_frame_csr(aat_ctx *ctx, const aat_plan *plan, const int64_t *seg
  * out_dev   : float32 [S, dim]; an empty segment yields NaN, as torch's mean does
  * n_seg     : S when n_seg_dev is NULL; otherwise an upper bound and S is read from n_seg_dev[0]
  * colsum_dev: optional float64 [dim+1]: column sums over the S pooled vectors and, last, S itself
- *             (input of the dataset-level mean allreduce); overwritten, not accumulated
+ *             (input of the dataset-level mean allreduce)
+ * colsum_accumulate : 0 = colsum_dev is overwritten; 1 = this batch's sums are ADDED to colsum_dev
+ *             (running totals over batches without a separate kernel)
  * One pass over emb; dim * sizeof(element) must be a multiple of 16 and emb_dev 16-byte aligned. */
 int aat_segment_mean_pool(aat_ctx *ctx, const void *emb_dev, int emb_dtype, int64_t n_rows, int32_t dim,
                           const int64_t *seg_off_dev, int64_t n_seg, const int64_t *n_seg_dev, float *out_dev,
-                          double *colsum_dev, void *stream);
+                          double *colsum_dev, int colsum_accumulate, void *stream);
 
 /* acc_dev[0..dim] += colsum_dev[0..dim] (float64), for accumulating over batches before the allreduce. */
 int aat_colsum_accumulate(aat_ctx *ctx, double *acc_dev, const double *colsum_dev, int32_t dim, void *stream);

@@ -333,6 +333,20 @@ def test_pool_colsum_and_dataset_mean(c_oracle):
     assert dm.count == cat.shape[0]
     want = cat.mean(dim=0).float().numpy()
     np.testing.assert_allclose(dm.result().cpu().numpy(), want, rtol=1e-6, atol=1e-7)
+    # running totals straight from the pool call (accumulate=True) give the same answer
+    from aat_b200.pooling import _pool_device
+    import ctypes
+
+    dm2 = DatasetMean(768)
+    rng = np.random.default_rng(31)
+    for b in range(3):
+        emb = torch.from_numpy(rng.standard_normal((4000 + 500 * b, 768), dtype=np.float32)).cuda()
+        off = torch.from_numpy(_random_offsets(rng, emb.shape[0], 6, 74)).cuda()
+        out = torch.empty(off.numel() - 1, 768, device="cuda")
+        _pool_device(dm2.ctx, emb, off, off.numel() - 1, None, out, dm2.running_buffer(),
+                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), accumulate=True)
+    assert dm2.count == dm.count
+    np.testing.assert_allclose(dm2.result().cpu().numpy(), want, rtol=1e-6, atol=1e-7)
 
 
 # ----------------------------------------------------------------------------------------- batched path
