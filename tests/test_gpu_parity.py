@@ -559,3 +559,44 @@ def test_padded_layout_matches_collator_port(tok):
     # a tile that is too small is what makes the reference raise
     with pytest.raises(Exception):
         collate.scatter_segments(batch, torch.from_numpy(padded_wave).cuda(), got_pad, 1000)
+
+
+# ----------------------------------------------------------------------------------------- non-default constructor arguments
+@pytest.mark.parametrize("kwargs", [
+    dict(hop_length=200, num_mel_filters=80),
+    dict(hop_length=100, num_mel_filters=40, running_mean_points=5, max_amplitude_for_minima=12),
+    dict(hop_length=160, num_mel_filters=128, running_mean_points=30, min_segment_duration_milliseconds=50,
+         max_segment_duration_milliseconds=400),
+    dict(hop_length=400, num_mel_filters=23, running_mean_points=3, max_amplitude_for_minima=16.5),
+    dict(sampling_rate=8000, hop_length=80, num_mel_filters=32),
+])
+def test_non_default_configurations_match_oracle(kwargs):
+    """hop, mel count, running-mean width, gate and durations are free parameters of the reference's
+    constructor (ref:src/aat/tokenizer.py:15-24); n_fft stays 400."""
+    from aat_b200 import AdaptiveAudioAmplitudeTokenizer, AudioWaveform, synth
+    from oracle import ref_port
+
+    import warnings
+
+    tok = AdaptiveAudioAmplitudeTokenizer(**kwargs)
+    with warnings.catch_warnings():  # sampling_rate=8000 leaves the filters above 4 kHz empty: transformers warns
+        warnings.simplefilter("ignore")
+        ref = ref_port.RefTokenizer(**kwargs)
+    assert np.array_equal(tok.mel_filters, ref.mel_filters)
+    for seed, n in ((1, 96000), (2, 31999), (3, 4000)):
+        wave = synth.bursty_speech(n, 4000 + seed)
+        mel = tok.get_melspec(wave)
+        want_mel = ref.get_melspec(wave)
+        assert_mel_close(mel, want_mel, min_exact=0.999)
+        assert np.array_equal(tok.find_amplitude_minimas(want_mel), ref.find_amplitude_minimas(want_mel))
+        want_lengths, want_boarders, _ = ref.segment_lengths(wave, melspec=want_mel)
+        assert tok.segment_lengths(wave, melspec=want_mel).tolist() == want_lengths
+        boarders, _ = tok.pretokenize(wave)
+        assert boarders == ref.pretokenize(wave)[0]
+
+
+def test_unsupported_fft_length_raises_not_implemented():
+    from aat_b200 import AdaptiveAudioAmplitudeTokenizer
+
+    with pytest.raises(NotImplementedError):
+        AdaptiveAudioAmplitudeTokenizer(n_fft=512).get_melspec(np.zeros(4000))
