@@ -84,6 +84,7 @@ SIGNATURES = {
     "aat_scatter_segments": (ctypes.c_int, [c_void, c_void, c_i64, c_i32, c_void, c_i64, c_i64, c_void, c_void, c_void,
                                             c_void]),
     "aat_scatter_mel_segments": (ctypes.c_int, [c_void, c_void, c_void, c_void, c_i64, c_i64, c_void, c_void, c_void]),
+    "aat_masked_mean_pool": (ctypes.c_int, [c_void, c_void, ctypes.c_int, c_i64, c_i64, c_i32, c_void, c_void, c_void, c_void]),
     "aat_host_logmel": (ctypes.c_int, [c_void, c_void, ctypes.c_int, c_i64, c_void]),
     "aat_host_find_minimas": (ctypes.c_int, [c_void, c_void, c_i64, c_void, c_void]),
     "aat_host_process_boarders": (ctypes.c_int, [c_void, c_i64, c_void, c_i64, c_void, c_void, c_i64, c_void, c_void]),

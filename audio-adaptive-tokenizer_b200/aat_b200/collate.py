@@ -106,3 +106,41 @@ def scatter_mel_segments(batch: PackedBatch, boarders_padded, max_segment_frames
     if check:
         _raise_on_status(status, "scatter_mel_segments")
     return out
+
+
+def masked_mean_pool(audio_embeds, audio_embeds_attention_mask):
+    """Mean over the valid frames of ``audio_embeds [R, L, D]`` under ``audio_embeds_attention_mask [R, L]`` —
+    the ``SegmentProjectionEnum.mean`` pooling that ``AslmModel.audio_embeddings_projection`` leaves as
+    ``NotImplementedError`` (ref:src/aslm/modeling_aslm.py:258-259).  Returns ``(pooled [R, D] float32,
+    row_mask [R] int64)``; rows without a valid frame are zero and masked out, like the CLS branch (:249-254)."""
+    import torch
+
+    from .context import default_context
+    from .pooling import _torch_dtype_code
+
+    if audio_embeds.dim() != 3 or not audio_embeds.is_cuda:
+        raise TypeError("audio_embeds must be a CUDA tensor [R, L, D]")
+    emb = audio_embeds.contiguous()
+    R, L, D = emb.shape
+    mask = audio_embeds_attention_mask.to(device=emb.device, dtype=torch.int64).contiguous()
+    if mask.shape != (R, L):
+        raise ValueError("mask must have shape [R, L]")
+    out = torch.empty((R, D), dtype=torch.float32, device=emb.device)
+    row_mask = torch.empty(R, dtype=torch.int64, device=emb.device)
+    ctx = default_context(emb.device.index)
+    with torch.cuda.device(emb.device):
+        _cabi.check(_cabi.lib().aat_masked_mean_pool(ctx.handle, emb.data_ptr(), _torch_dtype_code(emb.dtype), R, L, D,
+                                                     mask.data_ptr(), out.data_ptr(), row_mask.data_ptr(), _stream()))
+    return out, row_mask
+
+
+def uniform_segment_lengths(n_samples: int, frames_per_segment: int):
+    """Uniform segmentation of the collator (ref:src/aat/training/collate.py:141-149): equal segments plus the
+    remainder; returns the lengths (host integers — there is no arithmetic to accelerate)."""
+    import numpy as np
+
+    num = n_samples // frames_per_segment
+    lengths = [frames_per_segment] * num
+    if n_samples % frames_per_segment > 0:
+        lengths.append(n_samples - sum(lengths))
+    return np.asarray(lengths, dtype=np.int64)

@@ -148,6 +148,8 @@ int launch_scatter_segments(const float *wave, int64_t n_max, int32_t n_utts, co
                             int64_t max_frames, float *out, float *mask, int32_t *status, cudaStream_t stream);
 int launch_scatter_mel_segments(aat_ctx *ctx, const aat_plan *plan, const float *mel, const int64_t *boarders,
                                 int64_t s_max, int64_t max_items, float *out, int32_t *status, cudaStream_t stream);
+int launch_masked_mean_pool(const void *emb, int emb_dtype, int64_t n_rows, int64_t seq_len, int32_t dim,
+                            const int64_t *mask, float *out, int64_t *row_mask, cudaStream_t stream);
 constexpr int kNormChunk = 4096;
 int logmel_tables_init(aat_ctx *ctx);
 int pool_scratch_init(aat_ctx *ctx);

@@ -480,6 +480,15 @@ int aat_scatter_mel_segments(aat_ctx *ctx, const aat_plan *plan, const float *me
                                        static_cast<cudaStream_t>(stream));
 }
 
+int aat_masked_mean_pool(aat_ctx *ctx, const void *emb_dev, int emb_dtype, int64_t n_rows, int64_t seq_len, int32_t dim,
+                         const int64_t *mask_dev, float *out_dev, int64_t *row_mask_dev, void *stream)
+{
+    AAT_REQUIRE(ctx && (emb_dev || n_rows == 0) && mask_dev && out_dev, AAT_ERR_INVALID, "aat_masked_mean_pool: NULL argument");
+    AAT_REQUIRE(n_rows >= 0 && seq_len >= 0 && dim > 0, AAT_ERR_INVALID, "aat_masked_mean_pool: negative size");
+    return launch_masked_mean_pool(emb_dev, emb_dtype, n_rows, seq_len, dim, mask_dev, out_dev, row_mask_dev,
+                                   static_cast<cudaStream_t>(stream));
+}
+
 // ------------------------------------------------------------------------------------------------ host API
 // One utterance, host buffers in / host buffers out: H2D -> kernels -> D2H on the context's own stream.
 

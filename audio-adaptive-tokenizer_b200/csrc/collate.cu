@@ -14,6 +14,9 @@
 //       aat_scatter_segments       waveform slices  -> [B, S_max, max_frames] float32 + mask
 //       aat_scatter_mel_segments   log-mel slices   -> [B, S_max, n_mels, max_items] float32
 //     One CTA per (utterance, segment) row; 128-bit stores; zero fill of the padding in the same pass.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "aat_internal.cuh"
 
 namespace aat {
@@ -228,7 +231,133 @@ scatter_mel_segments_kernel(const float *mel, const int64_t *frame_off, const in
     }
 }
 
+// ---------------------------------------------------------------------------------------------- N4
+// Masked mean over the valid frames of every row of the padded layout [R, L, D] (R = batch * segments):
+// the `SegmentProjectionEnum.mean` branch the reference leaves as NotImplementedError
+// (ref:src/aslm/modeling_aslm.py:258-259), under the frame mask of encode_audio (:195-218).
+// One CTA per row; a thread owns one 16-byte column slab; only frames whose mask is set are read, four
+// loads in flight per thread.  Rows without a valid frame give zeros and row_mask = 0.
+template <typename T>
+struct Vec16;
+template <>
+struct Vec16<float> {
+    static constexpr int kCols = 4;
+    __device__ static void add(const void *p, float (&a)[4])
+    {
+        const float4 x = __ldg(reinterpret_cast<const float4 *>(p));
+        a[0] += x.x, a[1] += x.y, a[2] += x.z, a[3] += x.w;
+    }
+};
+template <>
+struct Vec16<__half> {
+    static constexpr int kCols = 8;
+    __device__ static void add(const void *p, float (&a)[8])
+    {
+        const uint4 x = __ldg(reinterpret_cast<const uint4 *>(p));
+        const __half2 *h = reinterpret_cast<const __half2 *>(&x);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(h[i]);
+            a[2 * i] += f.x, a[2 * i + 1] += f.y;
+        }
+    }
+};
+template <>
+struct Vec16<__nv_bfloat16> {
+    static constexpr int kCols = 8;
+    __device__ static void add(const void *p, float (&a)[8])
+    {
+        const uint4 x = __ldg(reinterpret_cast<const uint4 *>(p));
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            a[2 * i] += __uint_as_float(w[i] << 16);
+            a[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+masked_mean_pool_kernel(const unsigned char *emb, const int64_t *mask, int64_t seq_len, int dim, int slabs_per_row,
+                        float *out, int64_t *row_mask)
+{
+    using V = Vec16<T>;
+    constexpr int kCols = V::kCols;
+    extern __shared__ int s_valid[]; // indices of the valid frames of this row
+    __shared__ int s_count;
+    const int64_t r = blockIdx.x;
+    const int64_t *mrow = mask + r * seq_len;
+    if (threadIdx.x == 0) { // seq_len is short (<= 74 frames at the reference's settings): a serial compaction is fine
+        int c = 0;
+        for (int64_t t = 0; t < seq_len; ++t)
+            if (mrow[t] != 0) s_valid[c++] = (int)t;
+        s_count = c;
+        if (row_mask) row_mask[r] = c > 0;
+    }
+    __syncthreads();
+    const int count = s_count;
+    const size_t row_bytes = (size_t)dim * sizeof(T);
+    const unsigned char *base = emb + (size_t)r * seq_len * row_bytes;
+    for (int slab = threadIdx.x; slab < slabs_per_row; slab += blockDim.x) {
+        float acc[4][kCols];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < kCols; ++k) acc[u][k] = 0.0f;
+        const unsigned char *col = base + (size_t)slab * 16;
+        int i = 0;
+        for (; i + 4 <= count; i += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) V::add(col + (size_t)s_valid[i + u] * row_bytes, acc[u]);
+        }
+        for (; i < count; ++i) V::add(col + (size_t)s_valid[i] * row_bytes, acc[0]);
+        float *o = out + (size_t)r * dim + (size_t)slab * kCols;
+        const float n = (float)count;
+#pragma unroll
+        for (int k = 0; k < kCols; k += 4) {
+            float4 v;
+            v.x = count ? __fdiv_rn((acc[0][k] + acc[1][k]) + (acc[2][k] + acc[3][k]), n) : 0.0f;
+            v.y = count ? __fdiv_rn((acc[0][k + 1] + acc[1][k + 1]) + (acc[2][k + 1] + acc[3][k + 1]), n) : 0.0f;
+            v.z = count ? __fdiv_rn((acc[0][k + 2] + acc[1][k + 2]) + (acc[2][k + 2] + acc[3][k + 2]), n) : 0.0f;
+            v.w = count ? __fdiv_rn((acc[0][k + 3] + acc[1][k + 3]) + (acc[2][k + 3] + acc[3][k + 3]), n) : 0.0f;
+            *reinterpret_cast<float4 *>(o + k) = v;
+        }
+    }
+}
+
 } // namespace
+
+int launch_masked_mean_pool(const void *emb, int emb_dtype, int64_t n_rows, int64_t seq_len, int32_t dim,
+                            const int64_t *mask, float *out, int64_t *row_mask, cudaStream_t stream)
+{
+    int esize;
+    switch (emb_dtype) {
+    case AAT_F32: esize = 4; break;
+    case AAT_F16:
+    case AAT_BF16: esize = 2; break;
+    default: AAT_REQUIRE(false, AAT_ERR_UNSUPPORTED, "aat_masked_mean_pool: embedding dtype must be F32, F16 or BF16");
+    }
+    const int64_t row_bytes = (int64_t)dim * esize;
+    AAT_REQUIRE(row_bytes % 16 == 0, AAT_ERR_UNSUPPORTED, "aat_masked_mean_pool: dim * sizeof(element) must be a multiple of 16");
+    AAT_REQUIRE((reinterpret_cast<uintptr_t>(emb) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, AAT_ERR_INVALID,
+                "aat_masked_mean_pool: emb_dev and out_dev must be 16-byte aligned");
+    AAT_REQUIRE(n_rows < (int64_t)INT32_MAX && seq_len < (1 << 20), AAT_ERR_UNSUPPORTED, "aat_masked_mean_pool: shape too large");
+    if (n_rows == 0 || dim == 0) return AAT_OK;
+    const int slabs = (int)(row_bytes / 16);
+    int threads = ((slabs + 31) / 32) * 32;
+    if (threads > 256) threads = 256;
+    const size_t smem = sizeof(int) * (size_t)(seq_len ? seq_len : 1);
+    const unsigned char *e = static_cast<const unsigned char *>(emb);
+    if (emb_dtype == AAT_F32)
+        masked_mean_pool_kernel<float><<<(unsigned)n_rows, threads, smem, stream>>>(e, mask, seq_len, dim, slabs, out, row_mask);
+    else if (emb_dtype == AAT_F16)
+        masked_mean_pool_kernel<__half><<<(unsigned)n_rows, threads, smem, stream>>>(e, mask, seq_len, dim, slabs, out, row_mask);
+    else
+        masked_mean_pool_kernel<__nv_bfloat16><<<(unsigned)n_rows, threads, smem, stream>>>(e, mask, seq_len, dim, slabs, out, row_mask);
+    AAT_LAUNCH_CHECK();
+    return AAT_OK;
+}
 
 int launch_normalize(aat_ctx *ctx, const aat_plan *plan, const void *wave, int in_dtype, int mode, void *out,
                      int out_dtype, double *stats, cudaStream_t stream)

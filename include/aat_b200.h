@@ -238,6 +238,15 @@ int aat_scatter_segments(aat_ctx *ctx, const float *wave_padded_dev, int64_t n_m
 int aat_scatter_mel_segments(aat_ctx *ctx, const aat_plan *plan, const float *mel_dev, const int64_t *boarders_dev,
                              int64_t s_max, int64_t max_items, float *out_dev, int32_t *status_dev, void *stream);
 
+/* Masked mean over the valid frames of the padded layout: the
+ * `SegmentProjectionEnum.mean` branch that the reference leaves as NotImplementedError
+ * (ref:src/aslm/modeling_aslm.py:258-259), under the frame mask built by encode_audio (:195-218).
+ * emb_dev [n_rows, seq_len, dim] (F32/F16/BF16), mask_dev [n_rows, seq_len] int64 (non-zero = valid)
+ * -> out_dev [n_rows, dim] float32 = sum of the valid frames / their count (zeros when none is valid);
+ * row_mask_dev (optional) [n_rows] int64 = 1 where the row has a valid frame (the segment-level mask). */
+int aat_masked_mean_pool(aat_ctx *ctx, const void *emb_dev, int emb_dtype, int64_t n_rows, int64_t seq_len, int32_t dim,
+                         const int64_t *mask_dev, float *out_dev, int64_t *row_mask_dev, void *stream);
+
 /* ------------------------------------------------------------------ host-buffer entry points
  * Same operations for callers that hold numpy arrays, exactly like the reference's methods:
  * the library stages host<->device copies in its own scratch and synchronises. */

@@ -65,3 +65,13 @@ def znorm(x: np.ndarray) -> np.ndarray:
 def w2v2_norm(x: np.ndarray) -> np.ndarray:
     x = np.asarray(x, dtype=np.float32)
     return (x - x.mean()) / np.sqrt(x.var() + 1e-7)
+
+
+def masked_mean_pool(audio_embeds, audio_embeds_attention_mask):
+    """Definition used for row N4 (the reference raises NotImplementedError at ref:src/aslm/modeling_aslm.py:258-259):
+    masked mean over the frame axis, zeros where no frame is valid; row mask as in the CLS branch (:249-254)."""
+    m = audio_embeds_attention_mask.to(torch.float64).unsqueeze(-1)
+    s = (audio_embeds.to(torch.float64) * m).sum(dim=1)
+    n = m.sum(dim=1)
+    out = torch.where(n > 0, s / n.clamp(min=1), torch.zeros_like(s))
+    return out, (audio_embeds_attention_mask != 0).any(dim=-1).long()

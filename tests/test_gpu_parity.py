@@ -600,3 +600,26 @@ def test_unsupported_fft_length_raises_not_implemented():
 
     with pytest.raises(NotImplementedError):
         AdaptiveAudioAmplitudeTokenizer(n_fft=512).get_melspec(np.zeros(4000))
+
+
+def test_masked_mean_pool_in_padded_layout():
+    """mean over valid frames of [B*S, L, D] under the feature mask."""
+    import torch
+
+    from aat_b200 import collate
+    from oracle import collate_port
+
+    g = torch.Generator().manual_seed(3)
+    for dtype, D, tol in ((torch.float32, 768, 1e-6), (torch.float32, 1024, 1e-6), (torch.float16, 768, 2e-3),
+                          (torch.bfloat16, 512, 2e-2)):
+        R, L = 97, 74
+        x = torch.randn(R, L, D, generator=g).to(dtype)
+        lengths = torch.randint(0, L + 1, (R,), generator=g)
+        mask = (torch.arange(L)[None, :] < lengths[:, None]).long()
+        mask[5] = 0                       # a fully padded segment
+        mask[7, ::3] = 0                  # a non-prefix mask
+        want, want_rows = collate_port.masked_mean_pool(x, mask)
+        got, rows = collate.masked_mean_pool(x.cuda(), mask.cuda())
+        assert torch.equal(rows.cpu(), want_rows)
+        assert torch.allclose(got.cpu().double(), want, rtol=tol, atol=tol)
+        assert float(got[5].abs().max()) == 0.0
