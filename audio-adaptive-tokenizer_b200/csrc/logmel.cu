@@ -338,12 +338,18 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
             const int Ti = (int)T;
             auto band = [&](int m) {
                 const int j0 = s_mrow[m];
-                const int n = s_mrow[m + 1] - j0;
+                int n = s_mrow[m + 1] - j0;
                 const double *ww = s_mw + j0;
                 const double *pp = pw + s_mbin[m];
-                double acc = 0.0;
+                double a0 = 0.0, a1 = 0.0;
 #pragma unroll 1
-                for (int t = 0; t < n; ++t) acc = fma(ww[t], pp[t], acc);
+                while (n >= 2) { // two independent chains, pointers walk: ~5 instructions per tap
+                    a0 = fma(ww[0], pp[0], a0);
+                    a1 = fma(ww[1], pp[1], a1);
+                    ww += 2, pp += 2, n -= 2;
+                }
+                if (n) a0 = fma(ww[0], pp[0], a0);
+                const double acc = a0 + a1;
                 return (acc < 1e-10) ? 1e-10 : acc; // np.maximum(mel_floor, .): NaN propagates
             };
 #pragma unroll
