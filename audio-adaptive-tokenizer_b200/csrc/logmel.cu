@@ -117,11 +117,17 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 //   log10(x) = e * log10(2) + (-log10(inv_c[i])) + log1p(r) / ln(10)
 // The table stores inv_c[i] = double(1 / c_i) and -log10 of that ROUNDED value, so the identity is
 // exact and the only errors are the final roundings (~1e-16 relative), far below float32 resolution.
+__device__ __forceinline__ bool log10_needs_slow_path(double x)
+{
+    const int hi = (int)(__double_as_longlong(x) >> 32);
+    return (unsigned)(hi - 0x00100000) >= 0x7fe00000u; // zero, subnormal, inf, nan, negative
+}
+
+// Branch-free: valid for positive normal x; callers patch the rare special values with log10_needs_slow_path.
 __device__ __forceinline__ double fast_log10(double x, const double2 *__restrict__ table)
 {
     const long long bits = __double_as_longlong(x);
     const int hi = (int)(bits >> 32);
-    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log10(x); // zero, subnormal, inf, nan, negative
     const int e = (hi >> 20) - 1023;
     const int idx = (hi >> 14) & (kLogTable - 1);
     const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
@@ -328,6 +334,7 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
         // Two filters are evaluated together so that two independent dependency chains are in flight.
         constexpr int kGroups = kThreads / kFrames; // 10
         constexpr int kMaxPerThread = (kMaxMels + kGroups - 1) / kGroups;
+        constexpr int kBatch = 7; // filters whose logs are evaluated together (7 x 10 groups covers 64..70 filters)
         float outs[kMaxPerThread];
         {
             const int f = tid & (kFrames - 1);
@@ -353,19 +360,28 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
                 return (acc < 1e-10) ? 1e-10 : acc; // np.maximum(mel_floor, .): NaN propagates
             };
 #pragma unroll
-            for (int i = 0; i < kMaxPerThread; i += 2) {
-                const int m0 = q + i * kGroups, m1 = m0 + kGroups;
-                if (m0 < p.n_mels) {
-                    const bool two = m1 < p.n_mels;
-                    const double a0 = band(m0);
-                    const double a1 = two ? band(m1) : 1.0;
-                    const float o0 = (float)fast_log10(a0, s_logt);
-                    const float o1 = (float)fast_log10(a1, s_logt);
-                    outs[i] = o0;
-                    if (i + 1 < kMaxPerThread) outs[i + 1] = o1;
-                    if (live) {
-                        dst[(unsigned)(m0 * Ti)] = o0;
-                        if (two) dst[(unsigned)(m1 * Ti)] = o1;
+            for (int i0 = 0; i0 < kMaxPerThread; i0 += kBatch) {
+                if (q + i0 * kGroups < p.n_mels) {
+                    // gather the sums of this batch of filters, then take all their logs as one unrolled,
+                    // branch-free block: up to seven independent Horner chains in flight per thread
+                    double acc[kBatch];
+#pragma unroll
+                    for (int k = 0; k < kBatch; ++k) {
+                        const int m = q + (i0 + k) * kGroups;
+                        acc[k] = (i0 + k < kMaxPerThread && m < p.n_mels) ? band(m) : 1.0;
+                    }
+                    double lg[kBatch];
+#pragma unroll
+                    for (int k = 0; k < kBatch; ++k) lg[k] = fast_log10(acc[k], s_logt);
+#pragma unroll
+                    for (int k = 0; k < kBatch; ++k) {
+                        const int m = q + (i0 + k) * kGroups;
+                        if (i0 + k < kMaxPerThread && m < p.n_mels) {
+                            if (log10_needs_slow_path(acc[k])) lg[k] = log10(acc[k]); // NaN / inf inputs only
+                            const float o = (float)lg[k];
+                            outs[i0 + k] = o;
+                            if (live) dst[(unsigned)(m * Ti)] = o;
+                        }
                     }
                 }
             }
