@@ -5,6 +5,8 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <mutex>
+#include <utility>
 #include <cstdarg>
 #include <cstdio>
 #include <vector>
@@ -94,6 +96,10 @@ struct aat_ctx {
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
     cudaStream_t host_stream = nullptr;
+    // aat_host_* entry points: serialised (they share the staging buffers; ctypes callers release the GIL) and
+    // backed by a small most-recently-used cache of single-utterance plans keyed by the sample count
+    std::mutex host_mutex;
+    std::vector<std::pair<int64_t, aat_plan *>> host_plans;
     aat::Profiler prof{};
 };
 

@@ -220,6 +220,8 @@ int aat_destroy(aat_ctx *ctx)
     if (ctx->dev_scratch) cudaFree(ctx->dev_scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->host_stream) cudaStreamDestroy(ctx->host_stream);
+    for (auto &kv : ctx->host_plans) aat_plan_destroy(kv.second);
+    ctx->host_plans.clear();
     for (cudaEvent_t e : ctx->prof.start) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->prof.stop) cudaEventDestroy(e);
     delete ctx;
@@ -492,6 +494,30 @@ int aat_masked_mean_pool(aat_ctx *ctx, const void *emb_dev, int emb_dtype, int64
 // ------------------------------------------------------------------------------------------------ host API
 // One utterance, host buffers in / host buffers out: H2D -> kernels -> D2H on the context's own stream.
 
+// Single-utterance plan for `n_samples`, from the context's cache (most recently used first, 8 entries).
+static int host_plan_for(aat_ctx *ctx, int64_t n_samples, aat_plan **out)
+{
+    auto &cache = ctx->host_plans;
+    for (size_t i = 0; i < cache.size(); ++i)
+        if (cache[i].first == n_samples) {
+            auto hit = cache[i];
+            cache.erase(cache.begin() + (long)i);
+            cache.insert(cache.begin(), hit);
+            *out = hit.second;
+            return AAT_OK;
+        }
+    aat_plan *plan = nullptr;
+    int rc = aat_plan_create(ctx, 1, &n_samples, &plan);
+    if (rc) return rc;
+    cache.insert(cache.begin(), std::make_pair(n_samples, plan));
+    if (cache.size() > 8) {
+        aat_plan_destroy(cache.back().second);
+        cache.pop_back();
+    }
+    *out = plan;
+    return AAT_OK;
+}
+
 static int host_pipeline(aat_ctx *ctx, const void *wave_host, int wave_dtype, int64_t n_samples,
                          const float *mel_in_host, bool want_boundaries, float *mel_out_host, int64_t *minima_host,
                          int64_t *n_minima_host, int64_t *seg_start_host, int64_t *seg_len_host, int64_t capacity,
@@ -499,8 +525,9 @@ static int host_pipeline(aat_ctx *ctx, const void *wave_host, int wave_dtype, in
 {
     DeviceGuard guard(ctx->device);
     AAT_REQUIRE(guard.ok, AAT_ERR_CUDA, "cudaSetDevice(%d) failed", ctx->device);
+    std::lock_guard<std::mutex> lock(ctx->host_mutex);
     aat_plan *plan = nullptr;
-    int rc = aat_plan_create(ctx, 1, &n_samples, &plan);
+    int rc = host_plan_for(ctx, n_samples, &plan);
     if (rc) return rc;
     const int M = ctx->cfg.num_mel_filters;
     const int64_t T = plan->total_frames;
@@ -513,10 +540,7 @@ static int host_pipeline(aat_ctx *ctx, const void *wave_host, int wave_dtype, in
                        align256(sizeof(int64_t) * T) + 3 * 256;
     size_t pin_bytes = dev_bytes;
     rc = ensure_scratch(ctx, dev_bytes, pin_bytes);
-    if (rc) {
-        aat_plan_destroy(plan);
-        return rc;
-    }
+    if (rc) return rc;
     Arena d(ctx->dev_scratch), h(ctx->pinned);
     unsigned char *d_wave = d.take<unsigned char>(need_wave ? wsize * n_samples : 0);
     float *d_mel = d.take<float>((size_t)M * T);
@@ -538,10 +562,7 @@ static int host_pipeline(aat_ctx *ctx, const void *wave_host, int wave_dtype, in
     int32_t *h_status = h.take<int32_t>(1);
     cudaStream_t st = ctx->host_stream;
 
-    auto fail = [&](int code) {
-        aat_plan_destroy(plan);
-        return code;
-    };
+    auto fail = [&](int code) { return code; }; // the plan stays in the context's cache
 #define AAT_TRY_CUDA(expr)                                                                            \
     do {                                                                                              \
         cudaError_t e__ = (expr);                                                                     \
@@ -594,7 +615,6 @@ static int host_pipeline(aat_ctx *ctx, const void *wave_host, int wave_dtype, in
         if (minima_host) memcpy(minima_host, h_minima, sizeof(int64_t) * (*h_min_count));
         if (n_minima_host) *n_minima_host = *h_min_count;
     }
-    aat_plan_destroy(plan);
     return AAT_OK;
 }
 
@@ -629,6 +649,7 @@ int aat_host_process_boarders(aat_ctx *ctx, int64_t n_samples, const int64_t *bo
     AAT_REQUIRE(n_samples >= 0 && n_boarders >= 0 && capacity >= 0, AAT_ERR_INVALID,
                 "aat_host_process_boarders: negative size");
     DeviceGuard guard(ctx->device);
+    std::lock_guard<std::mutex> lock(ctx->host_mutex);
     size_t bytes = align256(sizeof(int64_t) * n_boarders) + 2 * align256(sizeof(int64_t) * capacity) + 2 * 256;
     int rc = ensure_scratch(ctx, bytes, bytes);
     if (rc) return rc;
@@ -681,6 +702,7 @@ int aat_host_mean_pool(aat_ctx *ctx, const void *emb_host, int emb_dtype, int64_
     AAT_REQUIRE(emb_dtype == AAT_F32 || emb_dtype == AAT_F16 || emb_dtype == AAT_BF16, AAT_ERR_UNSUPPORTED,
                 "aat_host_mean_pool: embedding dtype must be F32, F16 or BF16");
     DeviceGuard guard(ctx->device);
+    std::lock_guard<std::mutex> lock(ctx->host_mutex);
     const size_t emb_bytes = esize * (size_t)n_rows * dim, out_bytes = sizeof(float) * (size_t)n_seg * dim;
     const size_t off_bytes = sizeof(int64_t) * ((size_t)n_seg + 1), cs_bytes = sizeof(double) * ((size_t)dim + 1);
     // embeddings are copied straight from the caller's buffer (registering/pinning is the caller's choice)
