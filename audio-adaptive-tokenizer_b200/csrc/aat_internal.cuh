@@ -51,15 +51,38 @@ extern std::atomic<int64_t> g_launch_count;
         AAT_CUDA_CHECK(cudaGetLastError());        \
     } while (0)
 
-// Banded form of the dense (bins, mels) float64 filter bank: filter m covers the consecutive bins
-// [bin[m], bin[m] + row_start[m+1] - row_start[m]) with weights weight[row_start[m] ...].
-struct MelTable {
+// The dense (bins, mels) float64 filter bank as a balanced schedule of short bands for the log-mel kernel.
+// Every filter covers a run of consecutive bins; runs longer than kMelPartMax are cut into parts.  Parts are
+// sorted by length and dealt out to kMelGroups thread groups, two per group and round ("slot"); all parts of
+// a slot are zero-padded to the slot's (even) length, so the tap loops have CTA-uniform trip counts.
+constexpr int kMelPartMax = 10; // taps per part
+constexpr int kMelGroups = 10;  // thread groups of the mel phase (160 threads / 16 frames)
+constexpr int kMelMaxParts = 215; // rows of the partial-sum buffer (+1 spare row) that fit next to the power spectra
+struct MelSchedule {
     int n_mels = 0;
-    int nnz = 0;              // total band length
-    int *row_start = nullptr; // device [n_mels + 1]
-    int *bin = nullptr;       // device [n_mels] first bin of each filter
-    double *weight = nullptr; // device [nnz]
+    int nnz = 0;         // total band length of the filters
+    int n_parts = 0;
+    int n_slots = 0;     // rounds of 2 * kMelGroups parts
+    int n_weights = 0;   // padded weights (doubles, even)
+    int *slot_len = nullptr;       // device [n_slots]: even, 2..kMelPartMax
+    uint32_t *slot_desc = nullptr; // device [n_slots * 2 * kMelGroups]: (weight pair offset << 16) | (sum row << 8) | first bin
+    double *weight = nullptr;      // device [n_weights]
+    uint32_t *filter_parts = nullptr; // device [n_mels]: 0, or (further parts << 8) | their first sum row (the first part is row m)
 };
+
+// One tile (kMelFramesPerTile consecutive frames of one utterance) of the log-mel kernel.
+struct alignas(16) MelTile {
+    int64_t src;      // element index (in the packed waveform) of the first staged sample; < wave_off for the first tile
+    int64_t n;        // samples of the utterance
+    int64_t wave_off; // first sample of the utterance
+    int64_t mel_off;  // element index of mel[0][first frame of the tile] in the packed log-mel
+    int64_t amp_off;  // index of the tile's first frame in the per-frame arrays
+    int32_t T;        // frames of the utterance (row stride of its mel block)
+    int32_t valid;    // frames of this tile that exist (1..kMelFramesPerTile); 0 marks "no tile"
+    int32_t interior; // the whole staged range lies inside the utterance (no reflection needed)
+    int32_t pad_;
+};
+static_assert(sizeof(MelTile) == 64, "MelTile is copied as four 16-byte pieces");
 
 // Scratch for the pool kernel's cross-CTA partial sums.
 struct PoolScratch {
@@ -85,10 +108,10 @@ struct aat_ctx {
     int num_sms = 0;
     aat_config cfg{};
     double *window_half = nullptr; // device [400], 0.5 * window (exact scaling, folds the /2 of the two-frame split)
-    double2 *twiddle = nullptr;    // device [20 * 20], W_400^(k1 * n2) at [k1 * 20 + n2]
+    double2 *twiddle = nullptr;    // device [19 * 20], W_400^(k1 * n2) at [(k1 - 1) * 20 + n2], k1 = 1..19
     unsigned *ticket = nullptr;    // device [1], "last CTA done" counter of the boundaries kernel (self-resetting)
     double2 *log_table = nullptr;  // device [128], (1/c_i, -log10(1/c_i)) for the log-mel kernel's log10
-    aat::MelTable mel{};
+    aat::MelSchedule mel{};
     aat::PoolScratch pool{};
     // staging for aat_host_* entry points (grown on demand, never inside stream capture)
     void *dev_scratch = nullptr;
@@ -115,8 +138,7 @@ struct aat_plan {
     int64_t *d_wave_off = nullptr;      // [B+1]
     int64_t *d_frame_off = nullptr;     // [B+1]
     int64_t *d_seg_slot_off = nullptr;  // [B+1]
-    int32_t *d_tile_utt = nullptr;      // [mel_tiles] utterance of each tile
-    int32_t *d_tile_first = nullptr;    // [B+1] first tile index of each utterance
+    aat::MelTile *d_mel_tile = nullptr; // [mel_tiles] tile descriptors of the log-mel kernel
     // scratch written by the boundaries kernel for its fused frame-CSR epilogue
     int64_t *d_seg_local = nullptr;     // [total_seg_slots]
     int64_t *d_utt_frames = nullptr;    // [B]

@@ -1,5 +1,6 @@
 // C ABI of libaat_b200.so (include/aat_b200.h): context and plan management, argument checking,
 // and the aat_host_* entry points that stage host buffers through pinned memory.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -91,6 +92,90 @@ struct Arena {
     }
 };
 
+// dense (bins, mels) -> banded rows -> balanced schedule (see MelSchedule).  Filter m covers bins
+// [first_m, last_m] (its first and last non-zero weight; interior zeros are kept so the run stays contiguous).
+int build_mel_schedule(aat_ctx *ctx, const double *filters)
+{
+    const int M = ctx->cfg.num_mel_filters;
+    struct Part {
+        int first_bin, len, row;
+        const double *col; // filters + m: weight of bin k at col[k * M]
+    };
+    // sum rows: row m holds the first part of filter m, the further parts of wide filters follow from row M on
+    std::vector<Part> parts, extra;
+    std::vector<uint32_t> filter_parts(M, 0);
+    int nnz = 0;
+    for (int m = 0; m < M; ++m) {
+        int lo = -1, hi = -1;
+        for (int k = 0; k < kBins; ++k)
+            if (filters[(size_t)k * M + m] != 0.0) {
+                if (lo < 0) lo = k;
+                hi = k;
+            }
+        if (lo < 0) {
+            // empty filter (band above Nyquist): one zero tap, so that row m is written and 0 * NaN stays NaN as in
+            // the reference's dense product
+            parts.push_back(Part{0, 1, m, nullptr});
+            continue;
+        }
+        nnz += hi - lo + 1;
+        const int first_extra = M + (int)extra.size();
+        int n_extra = 0;
+        for (int b = lo; b <= hi; b += kMelPartMax) {
+            const int len = (hi - b + 1 < kMelPartMax) ? hi - b + 1 : kMelPartMax;
+            if (b == lo)
+                parts.push_back(Part{b, len, m, filters + m});
+            else
+                extra.push_back(Part{b, len, first_extra + n_extra++, filters + m});
+        }
+        AAT_REQUIRE(M + (int)extra.size() <= kMelMaxParts, AAT_ERR_UNSUPPORTED,
+                    "aat_create: the mel filter bank is too dense for the log-mel kernel (more than %d bands of %d bins)",
+                    kMelMaxParts, kMelPartMax);
+        filter_parts[m] = n_extra ? (((uint32_t)n_extra << 8) | (uint32_t)first_extra) : 0u;
+    }
+    parts.insert(parts.end(), extra.begin(), extra.end());
+    const int n_parts = (int)parts.size();
+    std::vector<int> order(n_parts);
+    for (int i = 0; i < n_parts; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return parts[a].len > parts[b].len; });
+    constexpr int kPerSlot = 2 * kMelGroups;
+    const int n_slots = (n_parts + kPerSlot - 1) / kPerSlot;
+    std::vector<int> slot_len(n_slots ? n_slots : 1, 2);
+    std::vector<uint32_t> slot_desc((size_t)(n_slots ? n_slots : 1) * kPerSlot, 0);
+    std::vector<double> weights;
+    for (int s = 0; s < n_slots; ++s) {
+        const int L = (parts[order[s * kPerSlot]].len + 1) & ~1; // longest part of the slot, rounded up to even
+        slot_len[s] = L;
+        for (int e = 0; e < kPerSlot; ++e) {
+            const int i = s * kPerSlot + e;
+            const size_t at = weights.size();
+            weights.resize(at + L, 0.0);
+            int start = 0, row = n_parts; // dummy entry: zero weights, sums go to the spare row
+            if (i < n_parts) {
+                const Part &pt = parts[order[i]];
+                start = (pt.first_bin + L <= kBins) ? pt.first_bin : kBins - L;
+                row = pt.row;
+                for (int t = 0; t < pt.len && pt.col; ++t)
+                    weights[at + (pt.first_bin - start) + t] = pt.col[(size_t)(pt.first_bin + t) * M];
+            }
+            AAT_REQUIRE(at / 2 < 65536, AAT_ERR_UNSUPPORTED, "aat_create: mel schedule too large");
+            slot_desc[(size_t)s * kPerSlot + e] = ((uint32_t)(at / 2) << 16) | ((uint32_t)row << 8) | (uint32_t)start;
+        }
+    }
+    MelSchedule &ms = ctx->mel;
+    ms.n_mels = M;
+    ms.nnz = nnz;
+    ms.n_parts = n_parts;
+    ms.n_slots = n_slots;
+    ms.n_weights = (int)weights.size();
+    int rc;
+    if ((rc = upload(&ms.slot_len, slot_len.data(), slot_len.size()))) return rc;
+    if ((rc = upload(&ms.slot_desc, slot_desc.data(), slot_desc.size()))) return rc;
+    if ((rc = upload(&ms.weight, weights.data(), weights.size()))) return rc;
+    if ((rc = upload(&ms.filter_parts, filter_parts.data(), filter_parts.size()))) return rc;
+    return AAT_OK;
+}
+
 size_t dtype_size(int dt)
 {
     switch (dt) {
@@ -160,41 +245,19 @@ int aat_create(int device, const aat_config *cfg, const double *window_host, con
     int rc = upload(&ctx->window_half, win.data(), win.size());
     if (rc) return rc;
 
-    // W_400^(k1 * n2), evaluated in long double and rounded once
-    std::vector<double2> tw(400);
+    // W_400^(k1 * n2) for k1 = 1..19 (row k1 = 0 is all ones and never read), long double, rounded once
+    std::vector<double2> tw(19 * 20);
     const long double two_pi = 6.283185307179586476925286766559005768L;
-    for (int k1 = 0; k1 < 20; ++k1)
+    for (int k1 = 1; k1 < 20; ++k1)
         for (int n2 = 0; n2 < 20; ++n2) {
             const int e = (k1 * n2) % kNfft;
             const long double a = two_pi * (long double)e / (long double)kNfft;
-            tw[k1 * 20 + n2] = make_double2((double)cosl(a), (double)-sinl(a));
+            tw[(k1 - 1) * 20 + n2] = make_double2((double)cosl(a), (double)-sinl(a));
         }
     rc = upload(&ctx->twiddle, tw.data(), tw.size());
     if (rc) return rc;
 
-    // dense (bins, mels) -> banded rows: filter m covers bins [first_m, last_m] (its first and last non-zero
-    // weight; interior zeros, if any, are kept so the row stays contiguous), weights stored densely
-    const int M = cfg->num_mel_filters;
-    std::vector<int> row_start(M + 1, 0), first_bin(M, 0);
-    std::vector<double> weights;
-    for (int m = 0; m < M; ++m) {
-        int lo = -1, hi = -1;
-        for (int k = 0; k < kBins; ++k)
-            if (mel_filters_host[(size_t)k * M + m] != 0.0) {
-                if (lo < 0) lo = k;
-                hi = k;
-            }
-        if (lo >= 0) {
-            first_bin[m] = lo;
-            for (int k = lo; k <= hi; ++k) weights.push_back(mel_filters_host[(size_t)k * M + m]);
-        }
-        row_start[m + 1] = (int)weights.size();
-    }
-    ctx->mel.n_mels = M;
-    ctx->mel.nnz = (int)weights.size();
-    if ((rc = upload(&ctx->mel.row_start, row_start.data(), row_start.size()))) return rc;
-    if ((rc = upload(&ctx->mel.bin, first_bin.data(), first_bin.size()))) return rc;
-    if ((rc = upload(&ctx->mel.weight, weights.data(), weights.size()))) return rc;
+    if ((rc = build_mel_schedule(ctx, mel_filters_host))) return rc;
 
     AAT_CUDA_CHECK(cudaMalloc(&ctx->ticket, sizeof(unsigned)));
     AAT_CUDA_CHECK(cudaMemset(ctx->ticket, 0, sizeof(unsigned)));
@@ -213,9 +276,10 @@ int aat_destroy(aat_ctx *ctx)
     cudaFree(ctx->twiddle);
     cudaFree(ctx->log_table);
     cudaFree(ctx->ticket);
-    cudaFree(ctx->mel.row_start);
-    cudaFree(ctx->mel.bin);
+    cudaFree(ctx->mel.slot_len);
+    cudaFree(ctx->mel.slot_desc);
     cudaFree(ctx->mel.weight);
+    cudaFree(ctx->mel.filter_parts);
     pool_scratch_free(ctx);
     if (ctx->dev_scratch) cudaFree(ctx->dev_scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -284,7 +348,10 @@ int aat_plan_create(aat_ctx *ctx, int32_t n_utts, const int64_t *n_samples_host,
     plan->h_wave_off.assign(n_utts + 1, 0);
     plan->h_frame_off.assign(n_utts + 1, 0);
     plan->h_seg_slot_off.assign(n_utts + 1, 0);
-    std::vector<int32_t> tile_first(n_utts + 1, 0), tile_utt, chunk_first(n_utts + 1, 0), chunk_utt;
+    std::vector<int32_t> chunk_first(n_utts + 1, 0), chunk_utt;
+    std::vector<MelTile> tiles_desc;
+    const int hop = ctx->cfg.hop_length, n_mels = ctx->cfg.num_mel_filters;
+    const int64_t stage_pad = (((int64_t)(kMelFramesPerTile - 1) * hop + kNfft) + 3) & ~int64_t(3);
     for (int b = 0; b < n_utts; ++b) {
         const int64_t n = n_samples_host[b];
         if (n < 1) {
@@ -299,12 +366,23 @@ int aat_plan_create(aat_ctx *ctx, int32_t n_utts, const int64_t *n_samples_host,
         plan->h_seg_slot_off[b + 1] = plan->h_seg_slot_off[b] + seg_capacity(ctx->cfg, n);
         if (T > plan->max_frames) plan->max_frames = T;
         const int64_t tiles = (T + kMelFramesPerTile - 1) / kMelFramesPerTile;
-        if ((int64_t)tile_utt.size() + tiles > (int64_t)INT32_MAX) {
+        if ((int64_t)tiles_desc.size() + tiles > (int64_t)INT32_MAX || T > (int64_t)INT32_MAX) {
             delete plan;
             AAT_REQUIRE(false, AAT_ERR_UNSUPPORTED, "aat_plan_create: batch too large (mel tiles exceed 2^31)");
         }
-        tile_first[b + 1] = tile_first[b] + (int32_t)tiles;
-        tile_utt.insert(tile_utt.end(), (size_t)tiles, b);
+        for (int64_t t = 0; t < tiles; ++t) {
+            const int64_t f0 = t * kMelFramesPerTile, g0 = f0 * hop - kNfft / 2;
+            MelTile d{};
+            d.src = plan->h_wave_off[b] + g0;
+            d.n = n;
+            d.wave_off = plan->h_wave_off[b];
+            d.mel_off = (int64_t)n_mels * plan->h_frame_off[b] + f0;
+            d.amp_off = plan->h_frame_off[b] + f0;
+            d.T = (int32_t)T;
+            d.valid = (int32_t)(T - f0 < kMelFramesPerTile ? T - f0 : kMelFramesPerTile);
+            d.interior = (g0 >= 0 && g0 + stage_pad <= n) ? 1 : 0;
+            tiles_desc.push_back(d);
+        }
         const int64_t chunks = (n + kNormChunk - 1) / kNormChunk;
         chunk_first[b + 1] = chunk_first[b] + (int32_t)chunks;
         chunk_utt.insert(chunk_utt.end(), (size_t)chunks, b);
@@ -312,14 +390,13 @@ int aat_plan_create(aat_ctx *ctx, int32_t n_utts, const int64_t *n_samples_host,
     plan->total_samples = plan->h_wave_off[n_utts];
     plan->total_frames = plan->h_frame_off[n_utts];
     plan->total_seg_slots = plan->h_seg_slot_off[n_utts];
-    plan->mel_tiles = (int32_t)tile_utt.size();
+    plan->mel_tiles = (int32_t)tiles_desc.size();
     int rc;
     if ((rc = upload(&plan->d_n_samples, plan->h_n_samples.data(), (size_t)n_utts)) ||
         (rc = upload(&plan->d_wave_off, plan->h_wave_off.data(), (size_t)n_utts + 1)) ||
         (rc = upload(&plan->d_frame_off, plan->h_frame_off.data(), (size_t)n_utts + 1)) ||
         (rc = upload(&plan->d_seg_slot_off, plan->h_seg_slot_off.data(), (size_t)n_utts + 1)) ||
-        (rc = upload(&plan->d_tile_utt, tile_utt.data(), tile_utt.size())) ||
-        (rc = upload(&plan->d_tile_first, tile_first.data(), tile_first.size())) ||
+        (rc = upload(&plan->d_mel_tile, tiles_desc.data(), tiles_desc.size())) ||
         (rc = upload(&plan->d_chunk_utt, chunk_utt.data(), chunk_utt.size())) ||
         (rc = upload(&plan->d_chunk_first, chunk_first.data(), chunk_first.size()))) {
         aat_plan_destroy(plan);
@@ -348,8 +425,7 @@ int aat_plan_destroy(aat_plan *plan)
     cudaFree(plan->d_wave_off);
     cudaFree(plan->d_frame_off);
     cudaFree(plan->d_seg_slot_off);
-    cudaFree(plan->d_tile_utt);
-    cudaFree(plan->d_tile_first);
+    cudaFree(plan->d_mel_tile);
     cudaFree(plan->d_seg_local);
     cudaFree(plan->d_utt_frames);
     cudaFree(plan->d_chunk_utt);

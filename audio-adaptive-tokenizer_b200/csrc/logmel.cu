@@ -21,11 +21,12 @@
 //     (ref:src/aat/tokenizer.py:67), so the boundary kernel does not have to re-read the mel.
 //
 // Execution shape: persistent CTAs (grid = resident CTAs, three per SM), each looping over tiles of 16
-// consecutive frames of one utterance (8 frame pairs x 20 threads = 160 threads).  The raw samples of
-// the NEXT tile are fetched with cp.async (LDGSTS, no registers) as soon as pass 1 has consumed the
-// current ones, so the global-load latency that dominated the first version of this kernel (ncu: 37 %
-// of stall samples on the load->convert dependency, profiles/) hides behind pass 2, the split and the
-// mel projection; the filter-bank and log tables are loaded into shared memory once per CTA.
+// consecutive frames of one utterance (8 frame pairs x 20 threads = 160 threads).  Everything a tile needs to
+// know (source offset, output offsets, edge flags) is one 64-byte host-built descriptor; descriptors run two
+// tiles ahead and the raw samples one tile ahead, both by cp.async (LDGSTS, no registers), so no thread ever
+// waits on a global load inside the loop.  The mel projection runs from a host-built balanced schedule of
+// short bands (MelSchedule): CTA-uniform, fully unrolled tap loops with four independent FMA chains per
+// thread, partial sums through shared memory, then a branch-free batch of table-driven log10.
 #include "aat_internal.cuh"
 
 namespace aat {
@@ -40,6 +41,24 @@ constexpr int kPairStride = 20 * kRow;       // 420 double2; 420 % 8 == 4 keeps 
 constexpr int kPowStride = kBins;            // 201 doubles (odd)
 constexpr int kLogTable = 64;                // entries of the log10 table (|r| < 2^-7, degree-8 series)
 
+// FP64 literals cost two UMOVs per use as immediates (and the compiler folds __constant__ initialisers back
+// into immediates); as kernel parameters they are constant-bank operands of DFMA/DADD, i.e. free.
+struct LogmelConsts {
+    double c1, c2, s1, s2; // cos(2 pi/5), cos(4 pi/5), sin(2 pi/5), sin(4 pi/5)
+    double k[8];           // log1p(r)/ln(10) = r (k[0] + r (k[1] + ...)), k[i] = (-1)^i / ((i + 1) ln 10)
+    double log10_2;
+    double int_magic;      // 2^52 + 2^31
+};
+static const LogmelConsts kLogmelConsts = {
+    0.30901699437494742410229341718282,  -0.80901699437494742410229341718282,
+    0.95105651629515357211643933337938,  0.58778525229247312916870595463907,
+    {0.43429448190325182765112891891661, -0.21714724095162591382556445945830, 0.14476482730108394255037630630554,
+     -0.10857362047581295691278222972915, 0.08685889638065036553022578378332, -0.07238241365054197127518815315277,
+     0.06204206884332168966444698841666, -0.05428681023790647845639111486458},
+    0.30102999566398119521373889472449,
+    4503601774854144.0,
+};
+
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ double2 cmul(double2 a, double2 b)
@@ -49,7 +68,7 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b)
 
 // 20-point forward DFT in registers, Good-Thomas 4 x 5:
 //   n = (5 n1 + 4 n2) mod 20,  k = (5 k1 + 16 k2) mod 20,  X[k] = sum x[n] W4^(n1 k1) W5^(n2 k2)
-__device__ __forceinline__ void dft20(double2 (&v)[20])
+__device__ __forceinline__ void dft20(double2 (&v)[20], const LogmelConsts &K)
 {
     // five radix-4 butterflies over n1 (stride 5), in place: slot (5 k1 + 4 n2) % 20
 #pragma unroll
@@ -63,10 +82,7 @@ __device__ __forceinline__ void dft20(double2 (&v)[20])
         v[i3] = make_double2(d0.x - d1.y, d0.y + d1.x); // d0 + i d1
     }
     // four radix-5 butterflies over n2 (stride 4), result k2 lands in slot (5 k1 + 16 k2) % 20
-    constexpr double c1 = 0.30901699437494742410229341718282;  // cos(2 pi / 5)
-    constexpr double c2 = -0.80901699437494742410229341718282; // cos(4 pi / 5)
-    constexpr double s1 = 0.95105651629515357211643933337938;  // sin(2 pi / 5)
-    constexpr double s2 = 0.58778525229247312916870595463907;  // sin(4 pi / 5)
+    const double c1 = K.c1, c2 = K.c2, s1 = K.s1, s2 = K.s2;
 #pragma unroll
     for (int k1 = 0; k1 < 4; ++k1) {
         const int b = 5 * k1;
@@ -124,7 +140,7 @@ __device__ __forceinline__ bool log10_needs_slow_path(double x)
 }
 
 // Branch-free: valid for positive normal x; callers patch the rare special values with log10_needs_slow_path.
-__device__ __forceinline__ double fast_log10(double x, const double2 *__restrict__ table)
+__device__ __forceinline__ double fast_log10(double x, const double2 *__restrict__ table, const LogmelConsts &K)
 {
     const long long bits = __double_as_longlong(x);
     const int hi = (int)(bits >> 32);
@@ -133,55 +149,54 @@ __device__ __forceinline__ double fast_log10(double x, const double2 *__restrict
     const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
     const double2 t = table[idx];
     const double r = fma(m, t.x, -1.0);
-    // log1p(r)/ln(10) = r * (c1 + r * (c2 + ...)), c_k = (-1)^(k+1) / (k ln 10)
-    constexpr double k1 = 0.43429448190325182765112891891661;  //  1/ln10
-    constexpr double k2 = -0.21714724095162591382556445945830; // -1/(2 ln10)
-    constexpr double k3 = 0.14476482730108394255037630630554;  //  1/(3 ln10)
-    constexpr double k4 = -0.10857362047581295691278222972915; // -1/(4 ln10)
-    constexpr double k5 = 0.08685889638065036553022578378332;  //  1/(5 ln10)
-    constexpr double k6 = -0.07238241365054197127518815315277; // -1/(6 ln10)
-    constexpr double k7 = 0.06204206884332168966444698841666;  //  1/(7 ln10)
-    constexpr double k8 = -0.05428681023790647845639111486458; // -1/(8 ln10)
-    double q = k8;
-    q = fma(q, r, k7);
-    q = fma(q, r, k6);
-    q = fma(q, r, k5);
-    q = fma(q, r, k4);
-    q = fma(q, r, k3);
-    q = fma(q, r, k2);
-    q = fma(q, r, k1);
-    constexpr double log10_2 = 0.30102999566398119521373889472449;
-    return fma((double)e, log10_2, fma(q, r, t.y));
+    double q = K.k[7];
+    q = fma(q, r, K.k[6]);
+    q = fma(q, r, K.k[5]);
+    q = fma(q, r, K.k[4]);
+    q = fma(q, r, K.k[3]);
+    q = fma(q, r, K.k[2]);
+    q = fma(q, r, K.k[1]);
+    q = fma(q, r, K.k[0]);
+    // double(e) without I2F: 2^52 + 2^31 + e is exact in the low word of a double
+    const double ed = __hiloint2double(0x43300000, e ^ (int)0x80000000) - K.int_magic;
+    return fma(ed, K.log10_2, fma(q, r, t.y));
 }
+
+// zero, subnormal, inf, nan, negative: the library routine, kept out of line (it is ~250 instructions and
+// would otherwise be inlined at every call site of the unrolled log batch)
+__device__ __noinline__ double slow_log10(double x) { return log10(x); }
 
 struct LogmelParams {
     const void *wave;
     float *mel;
     float *amp;
-    const int64_t *n_samples;
-    const int64_t *wave_off;
-    const int64_t *frame_off;
-    const int32_t *tile_utt;
-    const int32_t *tile_first;
+    const MelTile *tiles;
     const double *window_half;
     const double2 *twiddle;
     const double2 *log_table;
-    const int *mel_row_start;
-    const int *mel_bin;
+    const int *slot_len;
+    const uint32_t *slot_desc;
     const double *mel_weight;
+    const uint32_t *filter_parts;
     int n_tiles;
     int hop;
     int n_mels;
-    int nnz;
+    int n_parts;
+    int n_slots;
+    int n_weights;
     int stage_len; // (kFrames - 1) * hop + 400
     int stage_pad; // stage_len rounded up to 16 bytes worth of samples
+    LogmelConsts K;
 };
+
+constexpr int kTwiddles = 19 * 20;
+constexpr int kTileRing = 3; // descriptors: current tile, the tile whose samples are being fetched, the one after
 
 struct SmemLayout {
-    size_t raw, win, tw, logt, mw, mbin, mrow, ex, mel, total;
+    size_t ex, sum, raw, tw, logt, mw, sdesc, slen, fparts, tiles, mel, total;
 };
 
-__host__ __device__ inline SmemLayout smem_layout(int stage_pad, int wave_bytes, int n_mels, int nnz)
+__host__ __device__ inline SmemLayout smem_layout(int stage_pad, int wave_bytes, int n_mels, int n_slots, int n_weights)
 {
     SmemLayout L{};
     size_t o = 0;
@@ -190,79 +205,135 @@ __host__ __device__ inline SmemLayout smem_layout(int stage_pad, int wave_bytes,
         o += (bytes + 15) & ~size_t(15);
         return at;
     };
-    L.ex = take(sizeof(double2) * kPairs * kPairStride); // exchange matrix; later the power spectra (16 x 201 doubles)
+    // exchange matrix of the two FFT passes; afterwards the power spectra (16 x 201 doubles) and, behind them,
+    // the partial band sums ((n_parts + 1) x 16 doubles; kMelMaxParts is sized so that they fit)
+    L.ex = take(sizeof(double2) * kPairs * kPairStride);
+    L.sum = L.ex + sizeof(double) * kFrames * kPowStride;
     L.raw = take((size_t)stage_pad * wave_bytes);
-    L.win = 0; // the window is read through the read-only L1 path (20 coalesced loads at the top of pass 1)
-    L.tw = take(sizeof(double2) * 400);
+    L.tw = take(sizeof(double2) * kTwiddles);
     L.logt = take(sizeof(double2) * kLogTable);
-    L.mw = take(sizeof(double) * nnz);
-    L.mbin = take(sizeof(int) * n_mels);
-    L.mrow = take(sizeof(int) * (n_mels + 1));
+    L.mw = take(sizeof(double) * n_weights);
+    L.sdesc = take(sizeof(uint32_t) * n_slots * 2 * kMelGroups);
+    L.slen = take(sizeof(int) * n_slots);
+    L.fparts = take(sizeof(uint32_t) * n_mels);
+    L.tiles = take(sizeof(MelTile) * kTileRing);
     L.mel = L.ex; // float32 mel tile for the amplitude epilogue: overlays the power spectra once they are dead
     L.total = o;
     return L;
+}
+static_assert(sizeof(double) * (kFrames * kPowStride + (kMelMaxParts + 1) * kFrames) <= sizeof(double2) * kPairs * kPairStride,
+              "power spectra + partial band sums must fit in the exchange matrix");
+static_assert(sizeof(float) * kFrames * (kMaxMels + 1) <= sizeof(double) * kFrames * kPowStride,
+              "the float32 mel tile overlays the power spectra only");
+
+// Two bands of kTapPairs * 2 taps each, four independent FMA chains (explicit _rn: no contraction of the
+// final additions, so the sums do not depend on the compiler's mood).
+template <int kTapPairs>
+__device__ __forceinline__ void band_pair(const double2 *__restrict__ wa, const double *__restrict__ pa,
+                                          const double2 *__restrict__ wb, const double *__restrict__ pb, double &ra,
+                                          double &rb)
+{
+    double2 w = wa[0], u = wb[0];
+    double a0 = __dmul_rn(w.x, pa[0]), a1 = __dmul_rn(w.y, pa[1]);
+    double b0 = __dmul_rn(u.x, pb[0]), b1 = __dmul_rn(u.y, pb[1]);
+#pragma unroll
+    for (int i = 1; i < kTapPairs; ++i) {
+        w = wa[i], u = wb[i];
+        a0 = fma(w.x, pa[2 * i], a0);
+        a1 = fma(w.y, pa[2 * i + 1], a1);
+        b0 = fma(u.x, pb[2 * i], b0);
+        b1 = fma(u.y, pb[2 * i + 1], b1);
+    }
+    ra = __dadd_rn(a0, a1);
+    rb = __dadd_rn(b0, b1);
+}
+
+// First / last tiles of an utterance (and unaligned ones): element-wise copies with np.pad(mode="reflect")
+// index arithmetic (TF:audio_utils.py:769-771).  Rare, so out of line: the 64-bit modulo is bulky.
+template <typename WaveT>
+__device__ __noinline__ void fetch_edge_tile(WaveT *dst, const WaveT *utt, int64_t g0, int64_t n, int stage_len, int tid)
+{
+#pragma unroll 1
+    for (int i = tid; i < stage_len; i += kThreads) cp_async<(int)sizeof(WaveT)>(dst + i, utt + reflect_index(g0 + i, n));
 }
 
 template <typename WaveT>
 __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const SmemLayout L = smem_layout(p.stage_pad, (int)sizeof(WaveT), p.n_mels, p.nnz);
+    const SmemLayout L = smem_layout(p.stage_pad, (int)sizeof(WaveT), p.n_mels, p.n_slots, p.n_weights);
     double2 *s_ex = reinterpret_cast<double2 *>(smem_raw + L.ex);
     double *s_pow = reinterpret_cast<double *>(smem_raw + L.ex);
+    double *s_sum = reinterpret_cast<double *>(smem_raw + L.sum);
     WaveT *s_rawbuf = reinterpret_cast<WaveT *>(smem_raw + L.raw);
     const double *__restrict__ g_win = p.window_half;
     double2 *s_tw = reinterpret_cast<double2 *>(smem_raw + L.tw);
     double2 *s_logt = reinterpret_cast<double2 *>(smem_raw + L.logt);
     double *s_mw = reinterpret_cast<double *>(smem_raw + L.mw);
-    int *s_mbin = reinterpret_cast<int *>(smem_raw + L.mbin);
-    int *s_mrow = reinterpret_cast<int *>(smem_raw + L.mrow);
+    uint32_t *s_sdesc = reinterpret_cast<uint32_t *>(smem_raw + L.sdesc);
+    int *s_slen = reinterpret_cast<int *>(smem_raw + L.slen);
+    uint32_t *s_fparts = reinterpret_cast<uint32_t *>(smem_raw + L.fparts);
+    MelTile *s_tiles = reinterpret_cast<MelTile *>(smem_raw + L.tiles);
     float *s_mel = reinterpret_cast<float *>(smem_raw + L.mel);
 
     const int tid = threadIdx.x;
     constexpr int kVec = 16 / (int)sizeof(WaveT); // samples per 16-byte copy
+    const bool wave_aligned = (reinterpret_cast<uintptr_t>(p.wave) & 15) == 0;
 
+    // Descriptor of tile `tile_id` -> ring slot (asynchronous; four threads move 16 bytes each).  Past the end
+    // the slot is marked "no tile".  Joins the cp.async group of the sample fetch that follows it.
+    auto fetch_desc = [&](int tile_id, int slot) {
+        if (tid < 4) {
+            if (tile_id < p.n_tiles)
+                cp_async<16>(reinterpret_cast<unsigned char *>(s_tiles + slot) + 16 * tid,
+                             reinterpret_cast<const unsigned char *>(p.tiles + tile_id) + 16 * tid);
+            else if (tid == 3)
+                s_tiles[slot].valid = 0;
+        }
+    };
     // Asynchronous fetch of one tile's raw samples (reflect padding resolved per element,
     // TF:audio_utils.py:769-771); interior, 16-byte aligned tiles move 16 bytes per copy.
-    auto prefetch = [&](int tile_id) {
-        if (tile_id < p.n_tiles) {
-            const int utt = p.tile_utt[tile_id];
-            const int64_t n = p.n_samples[utt];
-            const int64_t woff = p.wave_off[utt];
-            const int64_t g0 = (int64_t)(tile_id - p.tile_first[utt]) * kFrames * p.hop - kNfft / 2;
-            const WaveT *wave = reinterpret_cast<const WaveT *>(p.wave) + woff;
-            WaveT *dst = s_rawbuf;
-            const bool interior = g0 >= 0 && g0 + p.stage_pad <= n;
-            const bool aligned = ((woff + g0) % kVec) == 0 && (reinterpret_cast<uintptr_t>(p.wave) & 15) == 0;
-            if (interior && aligned) {
-                for (int i = tid * kVec; i < p.stage_pad; i += kThreads * kVec) cp_async<16>(dst + i, wave + g0 + i);
+    auto fetch_samples = [&](const MelTile &d) {
+        if (d.valid > 0) {
+            const WaveT *wave = reinterpret_cast<const WaveT *>(p.wave);
+            const int64_t src = d.src;
+            if (d.interior && wave_aligned && (src & (kVec - 1)) == 0) {
+                const WaveT *from = wave + src;
+                for (int i = tid * kVec; i < p.stage_pad; i += kThreads * kVec) cp_async<16>(s_rawbuf + i, from + i);
             } else {
-                for (int i = tid; i < p.stage_len; i += kThreads)
-                    cp_async<(int)sizeof(WaveT)>(dst + i, wave + reflect_index(g0 + i, n));
+                fetch_edge_tile<WaveT>(s_rawbuf, wave + d.wave_off, src - d.wave_off, d.n, p.stage_len, tid);
             }
         }
         cp_async_commit();
     };
 
-    prefetch(blockIdx.x);
-    for (int i = tid; i < 400; i += kThreads) s_tw[i] = p.twiddle[i];
+    // ---- prologue: descriptors of the first two tiles, samples of the first, the per-CTA tables ----
+    fetch_desc(blockIdx.x, 0);
+    fetch_desc(blockIdx.x + gridDim.x, 1);
+    cp_async_commit();
+    for (int i = tid; i < kTwiddles; i += kThreads) s_tw[i] = p.twiddle[i];
     for (int i = tid; i < kLogTable; i += kThreads) s_logt[i] = p.log_table[i];
-    for (int i = tid; i < p.nnz; i += kThreads) s_mw[i] = p.mel_weight[i];
-    for (int i = tid; i < p.n_mels; i += kThreads) s_mbin[i] = p.mel_bin[i];
-    for (int i = tid; i <= p.n_mels; i += kThreads) s_mrow[i] = p.mel_row_start[i];
+    for (int i = tid; i < p.n_weights; i += kThreads) s_mw[i] = p.mel_weight[i];
+    for (int i = tid; i < p.n_slots * 2 * kMelGroups; i += kThreads) s_sdesc[i] = p.slot_desc[i];
+    for (int i = tid; i < p.n_slots; i += kThreads) s_slen[i] = p.slot_len[i];
+    for (int i = tid; i < p.n_mels; i += kThreads) s_fparts[i] = p.filter_parts[i];
+    cp_async_wait<0>();
+    __syncthreads();
+    fetch_samples(s_tiles[0]);
 
     const int pair = tid / 20;
     const int lane20 = tid - pair * 20;
     double2 *ex = s_ex + pair * kPairStride;
     const int mel_stride = p.n_mels + 1;
+    const int f = tid & (kFrames - 1); // mel / log phases: frame of the tile
+    const int q = tid / kFrames;       // ... and thread group (filters q, q + 10, ...)
 
+    int slot = 0; // ring slot of the current tile
     for (int tile_id = blockIdx.x; tile_id < p.n_tiles; tile_id += gridDim.x) {
-        const int utt = p.tile_utt[tile_id];
-        const int64_t T = 1 + p.n_samples[utt] / p.hop;
-        const int64_t f0 = (int64_t)(tile_id - p.tile_first[utt]) * kFrames;
-        const int64_t fbase = p.frame_off[utt];
+        const int slot_next = slot + 1 == kTileRing ? 0 : slot + 1;
+        const int slot_after = slot_next + 1 == kTileRing ? 0 : slot_next + 1;
 
-        cp_async_wait<0>(); // this tile's samples have arrived
+        cp_async_wait<0>(); // this tile's samples and the next tile's descriptor have arrived
         __syncthreads();    // ... for every thread; also fences the previous tile's shared-memory reuse
 
         // ---- pass 1: thread n2 transforms x[20 n1 + n2] over n1, applies W_400^(n2 k1) ----
@@ -275,13 +346,15 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
                 const double w = __ldg(g_win + 20 * n1 + lane20);
                 v[n1] = make_double2((double)wa[20 * n1] * w, (double)wb[20 * n1] * w);
             }
-            dft20(v);
+            dft20(v, p.K);
             ex[lane20] = v[0];
 #pragma unroll
-            for (int k1 = 1; k1 < 20; ++k1) ex[k1 * kRow + lane20] = cmul(v[k1], s_tw[k1 * 20 + lane20]);
+            for (int k1 = 1; k1 < 20; ++k1) ex[k1 * kRow + lane20] = cmul(v[k1], s_tw[(k1 - 1) * 20 + lane20]);
         }
         __syncthreads();
-        prefetch(tile_id + gridDim.x); // the raw buffer is free again: the next tile lands during the rest of this one
+        // the raw buffer is free again: the next tile lands during the rest of this one
+        fetch_desc(tile_id + 2 * (int)gridDim.x, slot_after);
+        fetch_samples(s_tiles[slot_next]);
 
         // ---- pass 2 + split: thread k1 transforms row k1 over n2 and keeps Z[k1 + 20 k2] in registers ----
         // It owns the bins k = k1 + 20 j (j = 0..9, and j = 10 for k1 = 0).  The mirror Z[400 - k] of those bins
@@ -294,7 +367,7 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
             double2 *row = ex + lane20 * kRow;
 #pragma unroll
             for (int n2 = 0; n2 < 20; ++n2) v[n2] = row[n2];
-            dft20(v);
+            dft20(v, p.K);
 #pragma unroll
             for (int k2 = 10; k2 < 20; ++k2) row[k2] = v[k2]; // a thread reads and rewrites only its own row
             __syncthreads();
@@ -328,59 +401,72 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
         }
         __syncthreads();
 
-        // ---- mel projection (banded rows), floor, log10, float32 store ----
-        // thread (f, q): frame f = tid % 16, filters q, q + 10, ...  Half-warps share a filter, so the
-        // weights are broadcast reads and the 16 frames hit 16 different banks (row stride 201 doubles).
-        // Two filters are evaluated together so that two independent dependency chains are in flight.
-        constexpr int kGroups = kThreads / kFrames; // 10
-        constexpr int kMaxPerThread = (kMaxMels + kGroups - 1) / kGroups;
-        constexpr int kBatch = 7; // filters whose logs are evaluated together (7 x 10 groups covers 64..70 filters)
-        float outs[kMaxPerThread];
+        // ---- mel projection: thread (f, q) runs the bands the schedule deals to group q, two per slot ----
+        // A half-warp is 16 frames of one band: the weights are broadcast reads and the power values hit 16
+        // different banks (row stride 201 doubles).  Slot lengths are CTA-uniform, so the switch does not diverge.
         {
-            const int f = tid & (kFrames - 1);
-            const int q = tid / kFrames;
             const double *pw = s_pow + f * kPowStride;
-            float *dst = p.mel + (size_t)p.n_mels * fbase + f0 + f;
-            const bool live = f0 + f < T;
-            const int Ti = (int)T;
-            auto band = [&](int m) {
-                const int j0 = s_mrow[m];
-                int n = s_mrow[m + 1] - j0;
-                const double *ww = s_mw + j0;
-                const double *pp = pw + s_mbin[m];
-                double a0 = 0.0, a1 = 0.0;
-#pragma unroll 1
-                while (n >= 2) { // two independent chains, pointers walk: ~5 instructions per tap
-                    a0 = fma(ww[0], pp[0], a0);
-                    a1 = fma(ww[1], pp[1], a1);
-                    ww += 2, pp += 2, n -= 2;
+            const double2 *w2 = reinterpret_cast<const double2 *>(s_mw);
+            for (int s = 0; s < p.n_slots; ++s) {
+                const uint32_t da = s_sdesc[s * 2 * kMelGroups + q], db = s_sdesc[s * 2 * kMelGroups + kMelGroups + q];
+                const double2 *wa = w2 + (da >> 16), *wb = w2 + (db >> 16);
+                const double *pa = pw + (da & 0xffu), *pb = pw + (db & 0xffu);
+                double ra, rb;
+                switch (s_slen[s]) {
+                case 2: band_pair<1>(wa, pa, wb, pb, ra, rb); break;
+                case 4: band_pair<2>(wa, pa, wb, pb, ra, rb); break;
+                case 6: band_pair<3>(wa, pa, wb, pb, ra, rb); break;
+                case 8: band_pair<4>(wa, pa, wb, pb, ra, rb); break;
+                default: band_pair<kMelPartMax / 2>(wa, pa, wb, pb, ra, rb); break;
                 }
-                if (n) a0 = fma(ww[0], pp[0], a0);
-                const double acc = a0 + a1;
+                s_sum[((da >> 8) & 0xffu) * kFrames + f] = ra;
+                s_sum[((db >> 8) & 0xffu) * kFrames + f] = rb;
+            }
+        }
+        __syncthreads();
+
+        // ---- filter sums -> floor -> log10 -> float32: thread (f, q) finishes filters q, q + 10, ... ----
+        const MelTile &cur = s_tiles[slot];
+        {
+            constexpr int kMaxPerThread = (kMaxMels + kMelGroups - 1) / kMelGroups;
+            constexpr int kBatch = 7; // filters whose logs are evaluated together (7 x 10 groups covers 64..70 filters)
+            float *dst = p.mel + cur.mel_off + f;
+            const bool live = f < cur.valid;
+            const size_t T = (size_t)cur.T;
+            float *smel = s_mel + f * mel_stride;
+            const double *sums = s_sum + f;
+            auto filter_sum = [&](int m) {
+                double acc = sums[m * kFrames]; // row m: the filter's first (usually only) band
+                const uint32_t fp = s_fparts[m];
+                if (fp) { // wide filter: add its further bands in bin order
+                    const double *row = sums + (fp & 0xffu) * kFrames;
+#pragma unroll 1
+                    for (int n = (int)(fp >> 8); n > 0; --n, row += kFrames) acc = __dadd_rn(acc, *row);
+                }
                 return (acc < 1e-10) ? 1e-10 : acc; // np.maximum(mel_floor, .): NaN propagates
             };
 #pragma unroll
             for (int i0 = 0; i0 < kMaxPerThread; i0 += kBatch) {
-                if (q + i0 * kGroups < p.n_mels) {
+                if (q + i0 * kMelGroups < p.n_mels) {
                     // gather the sums of this batch of filters, then take all their logs as one unrolled,
                     // branch-free block: up to seven independent Horner chains in flight per thread
                     double acc[kBatch];
 #pragma unroll
                     for (int k = 0; k < kBatch; ++k) {
-                        const int m = q + (i0 + k) * kGroups;
-                        acc[k] = (i0 + k < kMaxPerThread && m < p.n_mels) ? band(m) : 1.0;
+                        const int m = q + (i0 + k) * kMelGroups;
+                        acc[k] = (i0 + k < kMaxPerThread && m < p.n_mels) ? filter_sum(m) : 1.0;
                     }
                     double lg[kBatch];
 #pragma unroll
-                    for (int k = 0; k < kBatch; ++k) lg[k] = fast_log10(acc[k], s_logt);
+                    for (int k = 0; k < kBatch; ++k) lg[k] = fast_log10(acc[k], s_logt, p.K);
 #pragma unroll
                     for (int k = 0; k < kBatch; ++k) {
-                        const int m = q + (i0 + k) * kGroups;
+                        const int m = q + (i0 + k) * kMelGroups;
                         if (i0 + k < kMaxPerThread && m < p.n_mels) {
-                            if (log10_needs_slow_path(acc[k])) lg[k] = log10(acc[k]); // NaN / inf inputs only
+                            if (log10_needs_slow_path(acc[k])) lg[k] = slow_log10(acc[k]); // NaN / inf inputs only
                             const float o = (float)lg[k];
-                            outs[i0 + k] = o;
-                            if (live) dst[(unsigned)(m * Ti)] = o;
+                            smel[m] = o; // the power spectra are dead: the float32 tile overlays them
+                            if (live) dst[(size_t)m * T] = o;
                         }
                     }
                 }
@@ -389,26 +475,17 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
 
         // ---- fused amplitude curve: numpy's mean(axis=0) adds the rows in order in float32 ----
         if (p.amp != nullptr) {
-            __syncthreads(); // the power spectra are dead: stage the float32 tile over them
-            {
-                const int f = tid & (kFrames - 1);
-                const int q = tid / kFrames;
-#pragma unroll
-                for (int i = 0; i < kMaxPerThread; ++i) {
-                    const int m = q + i * kGroups;
-                    if (m < p.n_mels) s_mel[f * mel_stride + m] = outs[i];
-                }
-            }
             __syncthreads();
-            if (tid < kFrames && f0 + tid < T) {
+            if (tid < kFrames && tid < cur.valid) {
                 const float *col = s_mel + tid * mel_stride;
                 float acc = col[0];
                 for (int m = 1; m < p.n_mels; ++m) acc = __fadd_rn(acc, col[m]);
                 const float mean = __fdiv_rn(acc, (float)p.n_mels);
-                p.amp[fbase + f0 + tid] = __fmul_rn(-10.0f, mean);
+                p.amp[cur.amp_off + tid] = __fmul_rn(-10.0f, mean);
             }
         }
         // the next iteration's first __syncthreads orders these reads before the next overwrite
+        slot = slot_next;
     }
     cp_async_wait<0>();
 }
@@ -439,26 +516,26 @@ int launch_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave, int wave
     p.wave = wave;
     p.mel = mel;
     p.amp = amp;
-    p.n_samples = plan->d_n_samples;
-    p.wave_off = plan->d_wave_off;
-    p.frame_off = plan->d_frame_off;
-    p.tile_utt = plan->d_tile_utt;
-    p.tile_first = plan->d_tile_first;
+    p.tiles = plan->d_mel_tile;
     p.window_half = ctx->window_half;
     p.twiddle = ctx->twiddle;
     p.log_table = ctx->log_table;
-    p.mel_row_start = ctx->mel.row_start;
-    p.mel_bin = ctx->mel.bin;
+    p.slot_len = ctx->mel.slot_len;
+    p.slot_desc = ctx->mel.slot_desc;
     p.mel_weight = ctx->mel.weight;
+    p.filter_parts = ctx->mel.filter_parts;
     p.n_tiles = plan->mel_tiles;
     p.hop = ctx->cfg.hop_length;
     p.n_mels = ctx->mel.n_mels;
-    p.nnz = ctx->mel.nnz;
+    p.n_parts = ctx->mel.n_parts;
+    p.n_slots = ctx->mel.n_slots;
+    p.n_weights = ctx->mel.n_weights;
+    p.K = kLogmelConsts;
     p.stage_len = (kFrames - 1) * p.hop + kNfft;
     const int wave_bytes = wave_dtype == AAT_F32 ? 4 : 8;
     const int vec = 16 / wave_bytes;
     p.stage_pad = (p.stage_len + vec - 1) / vec * vec;
-    const size_t smem = smem_layout(p.stage_pad, wave_bytes, p.n_mels, p.nnz).total;
+    const size_t smem = smem_layout(p.stage_pad, wave_bytes, p.n_mels, p.n_slots, p.n_weights).total;
     auto kernel = wave_dtype == AAT_F32 ? logmel_kernel<float> : logmel_kernel<double>;
     AAT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AAT_MAX_SMEM_CARVEOUT(kernel);

@@ -33,6 +33,26 @@ namespace aat {
 
 namespace {
 
+// -DAAT_POOL_TRACE (profiles/pool_timeline.py builds a separate library with it): every CTA records the global
+// timer at six points of its life; never compiled into the product library.
+#ifdef AAT_POOL_TRACE
+__device__ unsigned long long g_pool_trace[1024 * 8];
+__device__ __forceinline__ unsigned long long trace_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define POOL_TRACE(slot)                                                     \
+    do {                                                                     \
+        if (threadIdx.x == 0) g_pool_trace[blockIdx.x * 8 + (slot)] = trace_now(); \
+    } while (0)
+#else
+#define POOL_TRACE(slot) \
+    do {                 \
+    } while (0)
+#endif
+
 constexpr int kStages = 4;
 constexpr int kStageBytes = 24 * 1024; // 8 rows of 768 fp32, 6 rows of 1024 fp32
 constexpr int kMaxConsumers = 256;
@@ -201,6 +221,7 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
     __shared__ int s_votes[kMaxConsumers / 32];
     __shared__ int64_t s_off[kOffCache];
 
+    POOL_TRACE(0); // CTA entry
     const int tid = threadIdx.x;
     const int n_consumers = p.n_consumers;
     const int64_t G = gridDim.x;
@@ -317,6 +338,7 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
             }
         };
         load_segment();
+        POOL_TRACE(1); // first segment located
         auto reduce_acc = [&](int j, int k) { return (acc[j][0][k] + acc[j][1][k]) + (acc[j][2][k] + acc[j][3][k]); };
         auto clear_acc = [&]() {
 #pragma unroll
@@ -412,6 +434,9 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
         for (int64_t ch = 0; ch < n_chunks; ++ch) {
             const int s = (int)(ch % kStages);
             mbar_wait(&s_full[s], (uint32_t)((ch / kStages) & 1));
+#ifdef AAT_POOL_TRACE
+            if (ch == 0) POOL_TRACE(2); // first stage landed
+#endif
             const unsigned char *stage = smem_raw + s * stage_stride;
             const int64_t chunk_end = (row + p.rows_per_stage < r1) ? row + p.rows_per_stage : r1;
             int rr = 0; // row within the stage
@@ -458,7 +483,9 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&s_empty[s]);
         }
+        POOL_TRACE(3); // last stage consumed
         flush(r1); // the segment still open at the end of this CTA's rows
+        POOL_TRACE(4); // carry collected
     }
 
     if (kColsum) {
@@ -470,6 +497,14 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
                 for (int k = 0; k < kCols; ++k) p.colsum[(size_t)c * p.dim + (size_t)slab * kCols + k] = csum[kColsum ? j : 0][k];
         }
     }
+#ifdef AAT_POOL_TRACE
+    POOL_TRACE(5); // exit
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_pool_trace[blockIdx.x * 8 + 6] = smid;
+    }
+#endif
 }
 
 // colsum_out[d] (+)= sum over the pool CTAs of their per-CTA column sums; colsum_out[dim] (+)= S.
@@ -653,6 +688,13 @@ int launch_mean_pool(aat_ctx *ctx, const void *emb, int emb_dtype, int64_t n_row
     }
     return AAT_OK;
 }
+
+#ifdef AAT_POOL_TRACE
+extern "C" __attribute__((visibility("default"))) int aat_debug_pool_trace(unsigned long long *out_host, int n_ctas)
+{
+    return (int)cudaMemcpyFromSymbol(out_host, g_pool_trace, sizeof(unsigned long long) * 8 * (size_t)n_ctas);
+}
+#endif
 
 int launch_colsum_accumulate(double *acc, const double *colsum, int32_t dim, cudaStream_t stream)
 {
