@@ -105,6 +105,22 @@ __device__ __forceinline__ void consumer_barrier(int n_consumers)
 {
     asm volatile("bar.sync 1, %0;" ::"r"(n_consumers) : "memory");
 }
+// barrier over the consumer threads that also ANDs a predicate across them
+__device__ __forceinline__ bool consumer_barrier_and(int n_consumers, bool pred)
+{
+    uint32_t r;
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.u32 q, %2, 0;\n"
+        "bar.red.and.pred p, 1, %1, q;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(r)
+        : "r"(n_consumers), "r"((uint32_t)pred)
+        : "memory");
+    return r != 0;
+}
 __device__ __forceinline__ int ld_acquire(const int *p)
 {
     int v;
@@ -210,6 +226,32 @@ __device__ int64_t coop_upper_bound(const int64_t *off, int64_t count, int64_t k
     return lo;
 }
 
+// First window of segment offsets a CTA looks at: centred on the segment index that a uniform segment length
+// would give for row r0.  When the source is 16-byte aligned the producer fetches it with ONE bulk copy issued
+// ahead of the embedding stream — a plain load issued a microsecond later queues behind ~28 MB of bulk traffic
+// from all CTAs and takes 3.5-6 us (profiles/r1_pool_timeline.txt).
+struct OffWindow {
+    int64_t first;
+    int count;
+    bool bulk;
+};
+__device__ __forceinline__ OffWindow first_window(const int64_t *seg_off, int64_t r0, int64_t n_rows, int64_t S_total)
+{
+    OffWindow w;
+    const int64_t guess = (int64_t)((double)r0 / (double)n_rows * (double)S_total);
+    int64_t w0 = guess - kOffCache / 2;
+    const int64_t w_max = S_total + 1 - kOffCache;
+    if (w0 > w_max) w0 = w_max;
+    if (w0 < 0) w0 = 0;
+    if ((reinterpret_cast<uintptr_t>(seg_off + w0) & 15) != 0 && w0 > 0) --w0;
+    const int64_t avail = S_total + 1 - w0;
+    w.first = w0;
+    w.count = (int)(avail < kOffCache ? avail : kOffCache);
+    w.bulk = (reinterpret_cast<uintptr_t>(seg_off + w0) & 15) == 0 && w.count >= 2;
+    if (w.bulk) w.count &= ~1; // whole 16-byte units
+    return w;
+}
+
 template <typename EmbT, int kSlabs, bool kColsum>
 __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolParams p)
 {
@@ -218,10 +260,13 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_full[kStages];
     __shared__ __align__(8) uint64_t s_empty[kStages];
+    __shared__ __align__(8) uint64_t s_offbar;
     __shared__ int s_votes[kMaxConsumers / 32];
-    __shared__ int64_t s_off[kOffCache];
+    __shared__ __align__(16) int64_t s_off[kOffCache];
 
     POOL_TRACE(0); // CTA entry
+    // issued before anything else: the only global load the first bulk copies depend on
+    const int64_t S_total = p.n_seg_dev ? min(*p.n_seg_dev, p.n_seg) : p.n_seg;
     const int tid = threadIdx.x;
     const int n_consumers = p.n_consumers;
     const int64_t G = gridDim.x;
@@ -236,6 +281,7 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
             mbar_init(&s_full[s], 1);
             mbar_init(&s_empty[s], n_consumers / 32);
         }
+        mbar_init(&s_offbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -243,9 +289,13 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
     if (tid >= n_consumers) {
         // ============================== producer warp ==============================
         const int lane = tid - n_consumers;
-        if (lane == 0) {
-            const int64_t S_prod = p.n_seg_dev ? min(*p.n_seg_dev, p.n_seg) : p.n_seg;
-            for (int64_t ch = 0; ch < (S_prod > 0 ? n_chunks : 0); ++ch) {
+        if (lane == 0 && r0 < r1 && S_total > 0) {
+            const OffWindow w = first_window(p.seg_off, r0, p.n_rows, S_total);
+            if (w.bulk) {
+                mbar_expect_tx(&s_offbar, (uint32_t)(w.count * sizeof(int64_t)));
+                bulk_g2s(s_off, p.seg_off + w.first, (uint32_t)(w.count * sizeof(int64_t)), &s_offbar);
+            }
+            for (int64_t ch = 0; ch < n_chunks; ++ch) {
                 const int s = (int)(ch % kStages);
                 const int64_t use = ch / kStages;
                 if (use > 0) mbar_wait(&s_empty[s], (uint32_t)((use - 1) & 1));
@@ -255,10 +305,9 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
                 mbar_expect_tx(&s_full[s], bytes);
                 bulk_g2s(smem_raw + s * stage_stride, p.emb + (size_t)row * p.row_bytes, bytes, &s_full[s]);
             }
-        } else {
+        } else if (lane != 0) {
             // idle lanes: empty segments never meet a row, so they are written here (torch: mean of
             // an empty slice is NaN).  Grid-stride over all segments, 31 lanes per CTA.
-            const int64_t S_total = p.n_seg_dev ? min(*p.n_seg_dev, p.n_seg) : p.n_seg;
             const float nan = __int_as_float(0x7fc00000);
             for (int64_t s = c * 31 + (lane - 1); s < S_total; s += G * 31) {
                 if (p.seg_off[s] == p.seg_off[s + 1]) {
@@ -271,7 +320,6 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
     }
 
     // ================================ consumers ================================
-    const int64_t S_total = p.n_seg_dev ? min(*p.n_seg_dev, p.n_seg) : p.n_seg;
     float acc[kSlabs][4][kCols];
     double csum[kColsum ? kSlabs : 1][kCols];
 #pragma unroll
@@ -304,12 +352,15 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
         };
         int64_t idx;
         {
-            int64_t guess = (int64_t)((double)r0 / (double)p.n_rows * (double)S_total);
-            int64_t w0 = guess - kOffCache / 2;
-            const int64_t w_max = S_total + 1 - kOffCache;
-            if (w0 > w_max) w0 = w_max;
-            if (w0 < 0) w0 = 0;
-            fill_cache(w0);
+            const OffWindow w = first_window(p.seg_off, r0, p.n_rows, S_total);
+            if (w.bulk) {
+                mbar_wait(&s_offbar, 0); // the producer's bulk copy of the window has landed
+                cache_base = w.first;
+                cache_n = w.count;
+            } else {
+                fill_cache(w.first);
+            }
+            const int64_t w0 = w.first;
             const bool lower_ok = w0 == 0 || s_off[0] <= r0;
             const bool upper_ok = w0 + cache_n == S_total + 1 || s_off[cache_n - 1] > r0;
             if (lower_ok && upper_ok) {
@@ -364,6 +415,23 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
             }
         };
 
+        // Early look at the next CTA's piece: if this CTA turns out to own a segment that runs on into CTA c + 1
+        // only, the final flush finds flag and partial sums already in registers instead of paying two dependent
+        // global round trips (~2 us under load, on every CTA's critical path) after its last row.
+        constexpr bool kEarlyCarry = kSlabs == 1;
+        int carry_flag = 0;
+        float carry[kCols];
+        auto prefetch_carry = [&]() {
+            if (kEarlyCarry && tid >= p.slabs_per_row) carry_flag = 1; // no slab: neutral in the vote
+            if (kEarlyCarry && c + 1 < G && tid < p.slabs_per_row) {
+                carry_flag = ld_acquire(p.head_flag + c + 1);
+                if (carry_flag) {
+#pragma unroll
+                    for (int k = 0; k < kCols; ++k) carry[k] = __ldcg(p.head + (size_t)(c + 1) * p.dim + tid * kCols + k);
+                }
+            }
+        };
+
         // flush the accumulators for the segment that ends (or is cut) at `row_end`.
         // Ownership rule for a segment cut by CTA boundaries: the CTA that holds its FIRST row owns it.
         // Every other CTA publishes its piece as soon as it has it and never waits before publishing;
@@ -401,29 +469,39 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
                     int64_t ce = p.n_rows > 0 ? (last_row < p.n_rows ? (last_row * G) / p.n_rows : G - 1) : G - 1;
                     while (ce + 1 < G && cta_row_begin(ce + 1, p.n_rows, G) <= last_row) ++ce;
                     while (ce > c && cta_row_begin(ce, p.n_rows, G) > last_row) --ce;
-                    if (tid == 0) {
-                        for (int64_t m = c + 1; m <= ce; ++m) {
-                            if (cta_row_begin(m, p.n_rows, G) == cta_row_begin(m + 1, p.n_rows, G)) continue;
-                            while (ld_acquire(p.head_flag + m) == 0) {}
-                            p.head_flag[m] = 0; // single consumer resets: safe for CUDA-graph replays
-                        }
-                    }
-                    consumer_barrier(n_consumers);
-#pragma unroll
-                    for (int j = 0; j < kSlabs; ++j) {
-                        const int slab = tid + j * n_consumers;
+                    // the threads polled the flag at slightly different times: take the early path only if all saw it
+                    const bool early = kEarlyCarry && ce == c + 1 && consumer_barrier_and(n_consumers, carry_flag != 0);
+                    if (early) {
+                        if (tid == 0) p.head_flag[c + 1] = 0; // single consumer resets: safe for CUDA-graph replays
                         float sum[kCols];
-                        if (slab < p.slabs_per_row) {
 #pragma unroll
-                            for (int k = 0; k < kCols; ++k) sum[k] = reduce_acc(j, k);
+                        for (int k = 0; k < kCols; ++k) sum[k] = reduce_acc(0, k) + carry[k];
+                        write_pooled(0, sum, nrows);
+                    } else {
+                        if (tid == 0) {
                             for (int64_t m = c + 1; m <= ce; ++m) {
                                 if (cta_row_begin(m, p.n_rows, G) == cta_row_begin(m + 1, p.n_rows, G)) continue;
-#pragma unroll
-                                for (int k = 0; k < kCols; ++k)
-                                    sum[k] += __ldcg(p.head + (size_t)m * p.dim + slab * kCols + k);
+                                while (ld_acquire(p.head_flag + m) == 0) {}
+                                p.head_flag[m] = 0; // single consumer resets: safe for CUDA-graph replays
                             }
                         }
-                        write_pooled(j, sum, nrows);
+                        consumer_barrier(n_consumers);
+#pragma unroll
+                        for (int j = 0; j < kSlabs; ++j) {
+                            const int slab = tid + j * n_consumers;
+                            float sum[kCols];
+                            if (slab < p.slabs_per_row) {
+#pragma unroll
+                                for (int k = 0; k < kCols; ++k) sum[k] = reduce_acc(j, k);
+                                for (int64_t m = c + 1; m <= ce; ++m) {
+                                    if (cta_row_begin(m, p.n_rows, G) == cta_row_begin(m + 1, p.n_rows, G)) continue;
+#pragma unroll
+                                    for (int k = 0; k < kCols; ++k)
+                                        sum[k] += __ldcg(p.head + (size_t)m * p.dim + slab * kCols + k);
+                                }
+                            }
+                            write_pooled(j, sum, nrows);
+                        }
                     }
                 }
             }
@@ -431,8 +509,10 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
         };
 
         int64_t row = r0;
+        const int64_t ch_carry = n_chunks >= 2 ? n_chunks - 2 : 0;
         for (int64_t ch = 0; ch < n_chunks; ++ch) {
             const int s = (int)(ch % kStages);
+            if (ch == ch_carry) prefetch_carry();
             mbar_wait(&s_full[s], (uint32_t)((ch / kStages) & 1));
 #ifdef AAT_POOL_TRACE
             if (ch == 0) POOL_TRACE(2); // first stage landed

@@ -34,17 +34,22 @@ def main():
     d_off = torch.from_numpy(off).to(dev)
     embs = [torch.randn(n_rows, dim, device=dev) for _ in range(4)]
     out = torch.empty(S, dim, device=dev)
+    out_cap = torch.empty(4 * S, dim, device=dev)
+    d_off_cap = torch.zeros(4 * S + 1, dtype=torch.int64, device=dev)
+    d_off_cap[:S + 1] = d_off
     colsum = torch.zeros(dim + 1, dtype=torch.float64, device=dev)
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    for variant, cs in (("without colsum", None), ("with colsum", colsum)):
+    n_seg_dev = torch.tensor([S], dtype=torch.int64, device=dev)
+    for variant, cs, nsd, cap in (("without colsum", None, None, S), ("with colsum", colsum, None, S),
+                                  ("with colsum, S read from the device (bench.py's call)", colsum, n_seg_dev, 4 * S)):
         for i in range(8):
-            _pool_device(ctx, embs[i % 4], d_off, S, None, out, cs, stream)
+            _pool_device(ctx, embs[i % 4], d_off_cap if nsd is not None else d_off, cap, nsd, out_cap if nsd is not None else out, cs, stream)
         torch.cuda.synchronize()
         runs = []
         for i in range(20):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            _pool_device(ctx, embs[i % 4], d_off, S, None, out, cs, stream)
+            _pool_device(ctx, embs[i % 4], d_off_cap if nsd is not None else d_off, cap, nsd, out_cap if nsd is not None else out, cs, stream)
             e1.record()
             torch.cuda.synchronize()
             G = 296
@@ -59,6 +64,9 @@ def main():
             t0 = t[:, 0].min()
             rel.append((t[:, :6] - t0) / 1e3)
         rel = np.stack(rel)  # [runs, G, 6]
+        dump = os.environ.get("AAT_TIMELINE_DUMP")
+        if dump:
+            np.savez(f"{dump}_{len(variant)}.npz", rel=rel, sm=runs[-1][1][:, 6])
         names = ["CTA entry", "first segment located", "first stage landed", "last stage consumed", "carry collected", "exit"]
         print(f"# pool {n_rows} x {dim}, {S} segments, {variant}: CUDA-event duration median {ev:.2f} us; 15 runs, 296 CTAs")
         print(f"{'stamp (us after the first CTA entry)':40s} {'min':>8s} {'median':>8s} {'p95':>8s} {'max':>8s}")
@@ -74,6 +82,26 @@ def main():
               f"bytes / (max exit) = {nb / np.median(rel[:, :, 5].max(1)) / 1e3:.0f} GB/s")
         sm = runs[-1][1][:, 6]
         print(f"# distinct SMs used: {len(set(sm.tolist()))}")
+        # is the spread a property of the SM (both CTAs of an SM agree, stable across runs) or of the rows (CTA index)?
+        done = rel[:, :, 3]                      # [runs, G] last stage consumed
+        by_cta = done.mean(0)
+        print(f"# spread of 'last stage consumed': std over CTAs of the run-mean = {by_cta.std():.2f} us; "
+              f"mean over CTAs of the run-std = {done.std(0).mean():.2f} us (small => systematic per CTA)")
+        per_sm = {}
+        for c in range(G):
+            per_sm.setdefault(int(sm[c]), []).append(by_cta[c])
+        pairs = np.array([v for v in per_sm.values() if len(v) == 2])
+        if len(pairs):
+            print(f"# the two CTAs of an SM: mean |difference| = {np.abs(pairs[:, 0] - pairs[:, 1]).mean():.2f} us; "
+                  f"correlation = {np.corrcoef(pairs[:, 0], pairs[:, 1])[0, 1]:.2f}")
+        order = np.argsort(by_cta)
+        print("# slowest 12 CTAs (index, smid, us):", [(int(c), int(sm[c]), round(float(by_cta[c]), 1)) for c in order[-12:]])
+        print("# fastest 12 CTAs (index, smid, us):", [(int(c), int(sm[c]), round(float(by_cta[c]), 1)) for c in order[:12]])
+        q = [by_cta[i * G // 8:(i + 1) * G // 8].mean() for i in range(8)]
+        print("# mean by octile of the CTA index (position in the row range):", [round(float(x), 1) for x in q])
+        smo = np.argsort(sm)
+        q = [by_cta[smo][i * G // 8:(i + 1) * G // 8].mean() for i in range(8)]
+        print("# mean by octile of the SM id:", [round(float(x), 1) for x in q])
         print()
 
 
