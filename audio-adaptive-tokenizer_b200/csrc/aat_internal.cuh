@@ -67,7 +67,7 @@ struct MelSchedule {
     int *slot_len = nullptr;       // device [n_slots]: even, 2..kMelPartMax
     uint32_t *slot_desc = nullptr; // device [n_slots * 2 * kMelGroups]: (weight pair offset << 16) | (sum row << 8) | first bin
     double *weight = nullptr;      // device [n_weights]
-    uint32_t *filter_parts = nullptr; // device [n_mels]: 0, or (further parts << 8) | their first sum row (the first part is row m)
+    uint16_t *filter_parts = nullptr; // device [n_mels]: 0, or (further parts << 8) | their first sum row (the first part is row m)
 };
 
 // One tile (kMelFramesPerTile consecutive frames of one utterance) of the log-mel kernel.
@@ -110,7 +110,7 @@ struct aat_ctx {
     double *window_half = nullptr; // device [400], 0.5 * window (exact scaling, folds the /2 of the two-frame split)
     double2 *twiddle = nullptr;    // device [19 * 20], W_400^(k1 * n2) at [(k1 - 1) * 20 + n2], k1 = 1..19
     unsigned *ticket = nullptr;    // device [1], "last CTA done" counter of the boundaries kernel (self-resetting)
-    double2 *log_table = nullptr;  // device [128], (1/c_i, -log10(1/c_i)) for the log-mel kernel's log10
+    double2 *log_table = nullptr;  // device [32], (1/c_i, -log10(1/c_i)) for the log-mel kernel's log10
     aat::MelSchedule mel{};
     aat::PoolScratch pool{};
     // staging for aat_host_* entry points (grown on demand, never inside stream capture)

@@ -103,7 +103,7 @@ int build_mel_schedule(aat_ctx *ctx, const double *filters)
     };
     // sum rows: row m holds the first part of filter m, the further parts of wide filters follow from row M on
     std::vector<Part> parts, extra;
-    std::vector<uint32_t> filter_parts(M, 0);
+    std::vector<uint16_t> filter_parts(M, 0);
     int nnz = 0;
     for (int m = 0; m < M; ++m) {
         int lo = -1, hi = -1;
@@ -131,7 +131,7 @@ int build_mel_schedule(aat_ctx *ctx, const double *filters)
         AAT_REQUIRE(M + (int)extra.size() <= kMelMaxParts, AAT_ERR_UNSUPPORTED,
                     "aat_create: the mel filter bank is too dense for the log-mel kernel (more than %d bands of %d bins)",
                     kMelMaxParts, kMelPartMax);
-        filter_parts[m] = n_extra ? (((uint32_t)n_extra << 8) | (uint32_t)first_extra) : 0u;
+        filter_parts[m] = n_extra ? (uint16_t)((n_extra << 8) | first_extra) : (uint16_t)0;
     }
     parts.insert(parts.end(), extra.begin(), extra.end());
     const int n_parts = (int)parts.size();

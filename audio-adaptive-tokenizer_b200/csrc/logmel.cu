@@ -39,7 +39,7 @@ constexpr int kThreads = kPairs * 20;        // 160
 constexpr int kRow = 21;                     // padded row (double2 units): 21 is odd -> conflict-free columns
 constexpr int kPairStride = 20 * kRow;       // 420 double2; 420 % 8 == 4 keeps neighbouring pairs on distinct banks
 constexpr int kPowStride = kBins;            // 201 doubles (odd)
-constexpr int kLogTable = 64;                // entries of the log10 table (|r| < 2^-7, degree-8 series)
+constexpr int kLogTable = 32;                // entries of the log10 table (|r| < 2^-6, degree-8 series: |error| < 3e-18)
 
 // FP64 literals cost two UMOVs per use as immediates (and the compiler folds __constant__ initialisers back
 // into immediates); as kernel parameters they are constant-bank operands of DFMA/DADD, i.e. free.
@@ -129,7 +129,7 @@ template <int kPending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
 // log10 of a positive finite double to full double accuracy, table driven:
-//   x = 2^e * m, m in [1, 2); i = top 6 mantissa bits; r = m * inv_c[i] - 1 (|r| < 2^-7, one FMA);
+//   x = 2^e * m, m in [1, 2); i = top 5 mantissa bits; r = m * inv_c[i] - 1 (|r| < 2^-6, one FMA);
 //   log10(x) = e * log10(2) + (-log10(inv_c[i])) + log1p(r) / ln(10)
 // The table stores inv_c[i] = double(1 / c_i) and -log10 of that ROUNDED value, so the identity is
 // exact and the only errors are the final roundings (~1e-16 relative), far below float32 resolution.
@@ -145,7 +145,7 @@ __device__ __forceinline__ double fast_log10(double x, const double2 *__restrict
     const long long bits = __double_as_longlong(x);
     const int hi = (int)(bits >> 32);
     const int e = (hi >> 20) - 1023;
-    const int idx = (hi >> 14) & (kLogTable - 1);
+    const int idx = (hi >> 15) & (kLogTable - 1);
     const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
     const double2 t = table[idx];
     const double r = fma(m, t.x, -1.0);
@@ -177,7 +177,7 @@ struct LogmelParams {
     const int *slot_len;
     const uint32_t *slot_desc;
     const double *mel_weight;
-    const uint32_t *filter_parts;
+    const uint16_t *filter_parts;
     int n_tiles;
     int hop;
     int n_mels;
@@ -192,11 +192,19 @@ struct LogmelParams {
 constexpr int kTwiddles = 19 * 20;
 constexpr int kTileRing = 3; // descriptors: current tile, the tile whose samples are being fetched, the one after
 
+// Raw-sample staging for hop 160: frame pairs start 320 samples apart, a multiple of the 32 banks, so the lanes of
+// a warp that belong to the next pair would collide with the first pair's (2-way conflict on all 40 sample loads of
+// pass 1).  A gap after every 320 samples shifts each pair by 20 banks: then bank = thread index, conflict-free.
+constexpr int kRawBlock = 320;
+template <typename WaveT>
+__host__ __device__ constexpr int raw_gap() { return sizeof(WaveT) == 4 ? 20 : 4; } // (20 - 320) mod 32 words / mod 16 double words
+__host__ __device__ inline int raw_elems(int stage_pad, int gap) { return stage_pad + gap * ((stage_pad - 1) / kRawBlock); }
+
 struct SmemLayout {
     size_t ex, sum, raw, tw, logt, mw, sdesc, slen, fparts, tiles, mel, total;
 };
 
-__host__ __device__ inline SmemLayout smem_layout(int stage_pad, int wave_bytes, int n_mels, int n_slots, int n_weights)
+__host__ __device__ inline SmemLayout smem_layout(int raw_elems, int wave_bytes, int n_mels, int n_slots, int n_weights)
 {
     SmemLayout L{};
     size_t o = 0;
@@ -209,13 +217,13 @@ __host__ __device__ inline SmemLayout smem_layout(int stage_pad, int wave_bytes,
     // the partial band sums ((n_parts + 1) x 16 doubles; kMelMaxParts is sized so that they fit)
     L.ex = take(sizeof(double2) * kPairs * kPairStride);
     L.sum = L.ex + sizeof(double) * kFrames * kPowStride;
-    L.raw = take((size_t)stage_pad * wave_bytes);
+    L.raw = take((size_t)raw_elems * wave_bytes);
     L.tw = take(sizeof(double2) * kTwiddles);
     L.logt = take(sizeof(double2) * kLogTable);
     L.mw = take(sizeof(double) * n_weights);
     L.sdesc = take(sizeof(uint32_t) * n_slots * 2 * kMelGroups);
     L.slen = take(sizeof(int) * n_slots);
-    L.fparts = take(sizeof(uint32_t) * n_mels);
+    L.fparts = take(sizeof(uint16_t) * n_mels);
     L.tiles = take(sizeof(MelTile) * kTileRing);
     L.mel = L.ex; // float32 mel tile for the amplitude epilogue: overlays the power spectra once they are dead
     L.total = o;
@@ -251,17 +259,20 @@ __device__ __forceinline__ void band_pair(const double2 *__restrict__ wa, const 
 // First / last tiles of an utterance (and unaligned ones): element-wise copies with np.pad(mode="reflect")
 // index arithmetic (TF:audio_utils.py:769-771).  Rare, so out of line: the 64-bit modulo is bulky.
 template <typename WaveT>
-__device__ __noinline__ void fetch_edge_tile(WaveT *dst, const WaveT *utt, int64_t g0, int64_t n, int stage_len, int tid)
+__device__ __noinline__ void fetch_edge_tile(WaveT *dst, const WaveT *utt, int64_t g0, int64_t n, int stage_len, int gap,
+                                             int tid)
 {
 #pragma unroll 1
-    for (int i = tid; i < stage_len; i += kThreads) cp_async<(int)sizeof(WaveT)>(dst + i, utt + reflect_index(g0 + i, n));
+    for (int i = tid; i < stage_len; i += kThreads)
+        cp_async<(int)sizeof(WaveT)>(dst + i + gap * (i / kRawBlock), utt + reflect_index(g0 + i, n));
 }
 
-template <typename WaveT>
+template <typename WaveT, bool kHop160>
 __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const SmemLayout L = smem_layout(p.stage_pad, (int)sizeof(WaveT), p.n_mels, p.n_slots, p.n_weights);
+    constexpr int kGap = kHop160 ? raw_gap<WaveT>() : 0;
+    const SmemLayout L = smem_layout(raw_elems(p.stage_pad, kGap), (int)sizeof(WaveT), p.n_mels, p.n_slots, p.n_weights);
     double2 *s_ex = reinterpret_cast<double2 *>(smem_raw + L.ex);
     double *s_pow = reinterpret_cast<double *>(smem_raw + L.ex);
     double *s_sum = reinterpret_cast<double *>(smem_raw + L.sum);
@@ -272,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
     double *s_mw = reinterpret_cast<double *>(smem_raw + L.mw);
     uint32_t *s_sdesc = reinterpret_cast<uint32_t *>(smem_raw + L.sdesc);
     int *s_slen = reinterpret_cast<int *>(smem_raw + L.slen);
-    uint32_t *s_fparts = reinterpret_cast<uint32_t *>(smem_raw + L.fparts);
+    uint16_t *s_fparts = reinterpret_cast<uint16_t *>(smem_raw + L.fparts);
     MelTile *s_tiles = reinterpret_cast<MelTile *>(smem_raw + L.tiles);
     float *s_mel = reinterpret_cast<float *>(smem_raw + L.mel);
 
@@ -299,9 +310,10 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
             const int64_t src = d.src;
             if (d.interior && wave_aligned && (src & (kVec - 1)) == 0) {
                 const WaveT *from = wave + src;
-                for (int i = tid * kVec; i < p.stage_pad; i += kThreads * kVec) cp_async<16>(s_rawbuf + i, from + i);
+                for (int i = tid * kVec; i < p.stage_pad; i += kThreads * kVec)
+                    cp_async<16>(s_rawbuf + i + kGap * (i / kRawBlock), from + i);
             } else {
-                fetch_edge_tile<WaveT>(s_rawbuf, wave + d.wave_off, src - d.wave_off, d.n, p.stage_len, tid);
+                fetch_edge_tile<WaveT>(s_rawbuf, wave + d.wave_off, src - d.wave_off, d.n, p.stage_len, kGap, tid);
             }
         }
         cp_async_commit();
@@ -327,6 +339,7 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
     const int mel_stride = p.n_mels + 1;
     const int f = tid & (kFrames - 1); // mel / log phases: frame of the tile
     const int q = tid / kFrames;       // ... and thread group (filters q, q + 10, ...)
+    const int n_mine = q < p.n_mels ? (p.n_mels - q + kMelGroups - 1) / kMelGroups : 0; // filters of this thread
 
     int slot = 0; // ring slot of the current tile
     for (int tile_id = blockIdx.x; tile_id < p.n_tiles; tile_id += gridDim.x) {
@@ -339,12 +352,16 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
         // ---- pass 1: thread n2 transforms x[20 n1 + n2] over n1, applies W_400^(n2 k1) ----
         {
             double2 v[20];
-            const WaveT *wa = s_rawbuf + (2 * pair) * p.hop + lane20;
-            const WaveT *wb = wa + p.hop;
+            const WaveT *wa = s_rawbuf + pair * (kHop160 ? kRawBlock + kGap : 2 * p.hop) + lane20;
+            const int hop = kHop160 ? 160 : p.hop;
 #pragma unroll
             for (int n1 = 0; n1 < 20; ++n1) {
                 const double w = __ldg(g_win + 20 * n1 + lane20);
-                v[n1] = make_double2((double)wa[20 * n1] * w, (double)wb[20 * n1] * w);
+                // frame a: samples 20 n1 + lane20 of the pair's block; frame b: one hop later.  With the gapped layout
+                // the offsets that cross into the next 320-sample block are known at compile time.
+                const int ia = 20 * n1 + (kHop160 && 20 * n1 >= kRawBlock ? kGap : 0);
+                const int ib = hop + 20 * n1 + (kHop160 && 160 + 20 * n1 >= kRawBlock ? kGap : 0);
+                v[n1] = make_double2((double)wa[ia] * w, (double)wa[ib] * w);
             }
             dft20(v, p.K);
             ex[lane20] = v[0];
@@ -447,23 +464,29 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
             };
 #pragma unroll
             for (int i0 = 0; i0 < kMaxPerThread; i0 += kBatch) {
-                if (q + i0 * kMelGroups < p.n_mels) {
+                if (i0 < n_mine) {
                     // gather the sums of this batch of filters, then take all their logs as one unrolled,
                     // branch-free block: up to seven independent Horner chains in flight per thread
                     double acc[kBatch];
 #pragma unroll
-                    for (int k = 0; k < kBatch; ++k) {
-                        const int m = q + (i0 + k) * kMelGroups;
-                        acc[k] = (i0 + k < kMaxPerThread && m < p.n_mels) ? filter_sum(m) : 1.0;
-                    }
+                    for (int k = 0; k < kBatch; ++k)
+                        acc[k] = (i0 + k < kMaxPerThread && i0 + k < n_mine) ? filter_sum(q + (i0 + k) * kMelGroups) : 1.0;
                     double lg[kBatch];
+                    unsigned worst = 0; // after the floor a value is >= 1e-10, +inf or NaN: one test for the whole batch
 #pragma unroll
-                    for (int k = 0; k < kBatch; ++k) lg[k] = fast_log10(acc[k], s_logt, p.K);
+                    for (int k = 0; k < kBatch; ++k) {
+                        lg[k] = fast_log10(acc[k], s_logt, p.K);
+                        worst = max(worst, (unsigned)__double2hiint(acc[k]));
+                    }
+                    if (worst >= 0x7ff00000u) {
+#pragma unroll
+                        for (int k = 0; k < kBatch; ++k) // unrolled: a runtime index would push acc/lg into local memory
+                            if (log10_needs_slow_path(acc[k])) lg[k] = slow_log10(acc[k]); // NaN / inf inputs only
+                    }
 #pragma unroll
                     for (int k = 0; k < kBatch; ++k) {
                         const int m = q + (i0 + k) * kMelGroups;
-                        if (i0 + k < kMaxPerThread && m < p.n_mels) {
-                            if (log10_needs_slow_path(acc[k])) lg[k] = slow_log10(acc[k]); // NaN / inf inputs only
+                        if (i0 + k < kMaxPerThread && i0 + k < n_mine) {
                             const float o = (float)lg[k];
                             smel[m] = o; // the power spectra are dead: the float32 tile overlays them
                             if (live) dst[(size_t)m * T] = o;
@@ -535,8 +558,11 @@ int launch_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave, int wave
     const int wave_bytes = wave_dtype == AAT_F32 ? 4 : 8;
     const int vec = 16 / wave_bytes;
     p.stage_pad = (p.stage_len + vec - 1) / vec * vec;
-    const size_t smem = smem_layout(p.stage_pad, wave_bytes, p.n_mels, p.n_slots, p.n_weights).total;
-    auto kernel = wave_dtype == AAT_F32 ? logmel_kernel<float> : logmel_kernel<double>;
+    const bool hop160 = p.hop == 160;
+    const int gap = hop160 ? (wave_dtype == AAT_F32 ? raw_gap<float>() : raw_gap<double>()) : 0;
+    const size_t smem = smem_layout(raw_elems(p.stage_pad, gap), wave_bytes, p.n_mels, p.n_slots, p.n_weights).total;
+    auto kernel = wave_dtype == AAT_F32 ? (hop160 ? logmel_kernel<float, true> : logmel_kernel<float, false>)
+                                        : (hop160 ? logmel_kernel<double, true> : logmel_kernel<double, false>);
     AAT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AAT_MAX_SMEM_CARVEOUT(kernel);
     int per_sm = 0;
