@@ -64,6 +64,7 @@ SIGNATURES = {
     "aat_destroy": (ctypes.c_int, [c_void]),
     "aat_profile_enable": (ctypes.c_int, [c_void, ctypes.c_uint32]),
     "aat_profile_summary": (ctypes.c_int, [c_void, c_void, c_void]),
+    "aat_profile_sample_every": (ctypes.c_int, [c_void, c_i32]),
     "aat_get_config": (ctypes.c_int, [c_void, ctypes.POINTER(AatConfig)]),
     "aat_plan_create": (ctypes.c_int, [c_void, c_i32, c_void, ctypes.POINTER(c_void)]),
     "aat_plan_destroy": (ctypes.c_int, [c_void]),
@@ -136,7 +137,9 @@ def check(status: int) -> None:
 KERNEL_NAMES = ("logmel", "boundaries", "frame_csr", "pool")
 
 
-def profile_enable(ctx_handle, names=KERNEL_NAMES) -> None:
+def profile_enable(ctx_handle, names=KERNEL_NAMES, every: int = 1) -> None:
+    """Record CUDA-event pairs around the named kernels (every ``every``-th launch of each)."""
+    check(lib().aat_profile_sample_every(ctx_handle, every))
     mask = 0
     for n in names:
         mask |= 1 << KERNEL_NAMES.index(n)

@@ -99,6 +99,8 @@ struct Profiler {
     std::vector<cudaEvent_t> start, stop;
     std::vector<int> kernel;
     size_t used = 0;
+    int every = 1;                 // record every n-th launch of a kernel
+    int64_t seen[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // launches of each kernel id since the last enable
 };
 
 } // namespace aat
@@ -185,6 +187,34 @@ void pool_scratch_free(aat_ctx *ctx);
 
 constexpr int kMelFramesPerTile = 16; // frames one CTA of the log-mel kernel produces
 
+// Programmatic dependent launch (PDL) between the kernels of a step.  A kernel launched through launch_pdl may
+// start while its predecessor in the stream is still running; it must call pdl_wait() before it touches
+// anything the predecessor writes (and before it writes anything the predecessor reads), and calls
+// pdl_launch_dependents() afterwards so that its own successor may be scheduled early in turn.  Because
+// every kernel waits before it triggers, completion is transitive along the chain.  Both instructions are
+// no-ops when the kernel was launched normally, and a normal launch after one of these kernels is fully ordered.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // RAII helper: records an event pair around one launch when profiling is enabled for `id`.
 struct ProfileScope {
     aat_ctx *ctx;
@@ -193,7 +223,7 @@ struct ProfileScope {
     ProfileScope(aat_ctx *c, int id, cudaStream_t s) : ctx(c), stream(s)
     {
         Profiler &p = c->prof;
-        if ((p.mask >> id) & 1u) {
+        if (((p.mask >> id) & 1u) && (p.seen[id]++ % p.every) == 0) {
             if (p.used < p.start.size()) {
                 slot = (long)p.used++;
                 p.kernel[slot] = id;

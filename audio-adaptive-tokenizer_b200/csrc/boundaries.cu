@@ -293,9 +293,27 @@ constexpr int kWorkers = 192;        // warps 1..6
 constexpr int kEmitThread = 224;     // warp 7, lane 0
 constexpr int kRing = 8192;          // cumsum ring (power of two) >= running_mean_points + 2 + 3 * kChunk
 
+// -DAAT_POOL_TRACE (the trace build of profiles/): global-timer stamps of CTA 0..63, thread 0
+#ifdef AAT_POOL_TRACE
+__device__ unsigned long long g_bnd_trace[256 * 32];
+#define BND_TRACE(slot)                                                                        \
+    do {                                                                                       \
+        if (threadIdx.x == 0 && blockIdx.x < 256 && (slot) < 32) {                             \
+            unsigned long long t__;                                                            \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                            \
+            g_bnd_trace[blockIdx.x * 32 + (slot)] = t__;                                       \
+        }                                                                                      \
+    } while (0)
+#else
+#define BND_TRACE(slot) \
+    do {                \
+    } while (0)
+#endif
+
 __device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(kWorkers) : "memory"); }
 
-__global__ void __launch_bounds__(kThreads) boundaries_kernel(const BoundaryParams p)
+template <int kChunk>
+__global__ void __launch_bounds__(kThreads) boundaries_kernel_t(const BoundaryParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *s_amp = reinterpret_cast<float *>(smem_raw);          // [2][kChunk]
@@ -304,8 +322,11 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel(const BoundaryPara
     __shared__ int s_wcount[kWorkers / 32];
     __shared__ int s_found[2];
 
+    BND_TRACE(0);
     const int tid = threadIdx.x;
     const int utt = blockIdx.x;
+    pdl_wait(); // the log-mel kernel's mel / amp; also orders this kernel's writes after the previous readers
+    pdl_launch_dependents();
     const int64_t n = p.n_samples[utt];
     const int64_t T = 1 + n / p.hop;
     const int64_t fbase = p.frame_off[utt];
@@ -350,6 +371,7 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel(const BoundaryPara
     int64_t n_minima = 0;                                                // workers and emit thread keep their own copy
     float run = 0.0f;                                                    // scan thread's carry
 
+    BND_TRACE(1); // prologue done
     for (int64_t it = 0; it < n_chunks + 3; ++it) {
         if (tid == 0) {
             // ---------------- scan: chunk it - 1 ----------------
@@ -488,6 +510,7 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel(const BoundaryPara
             }
         }
         __syncthreads();
+        BND_TRACE(2 + (int)it); // end of pipeline iteration `it`
     }
 
     if (tid == kEmitThread) {
@@ -513,6 +536,7 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel(const BoundaryPara
     if (p.seg_off != nullptr) {
         __shared__ int s_last;
         __syncthreads();
+        BND_TRACE(28); // segments written
         if (tid == kEmitThread) {
             __threadfence(); // this CTA's segment writes (all by this thread) are visible before the ticket
             s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
@@ -526,8 +550,18 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel(const BoundaryPara
                              p.utt_seg_off, s_seg, s_frm);
             if (tid == 0) *p.ticket = 0; // ready for the next launch (graph replays included)
         }
+        BND_TRACE(29); // ticket taken (and, in the last CTA, the CSR rebased)
     }
 }
+
+#ifdef AAT_POOL_TRACE
+} // namespace
+extern "C" __attribute__((visibility("default"))) int aat_debug_bnd_trace(unsigned long long *out_host, int n_ctas)
+{
+    return (int)cudaMemcpyFromSymbol(out_host, g_bnd_trace, sizeof(unsigned long long) * 32 * (size_t)n_ctas);
+}
+namespace {
+#endif
 
 __global__ void process_boarders_kernel(int64_t n_samples, const int64_t *boarders, int64_t n_boarders,
                                         int64_t min_frames, int64_t max_frames, int64_t *seg_start, int64_t *seg_len,
@@ -583,18 +617,22 @@ int launch_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel, cons
     p.n_utts = plan->n_utts;
     p.ticket = ctx->ticket;
     const size_t csr_smem = sizeof(int64_t) * 2 * (size_t)(plan->n_utts + 1);
-    const bool fuse_csr = seg_off != nullptr && csr_smem <= sizeof(float) * (size_t)(2 * kChunk + kRing);
+    // Stage size: 128-frame stages were measured slower (31 us vs 27 us at 64 x 16 s) and 256 equal: the kernel is
+    // bound by the merge/split thread and the CSR epilogue, not by the pipeline fill (profiles/r1_bnd_timeline.txt).
+    constexpr int chunk = kChunk;
+    const bool fuse_csr = seg_off != nullptr && csr_smem <= sizeof(float) * (size_t)(2 * chunk + kRing);
     p.seg_off = fuse_csr ? seg_off : nullptr;
     p.n_seg = n_seg;
     p.utt_seg_off = utt_seg_off;
     p.seg_local = plan->d_seg_local;
     p.utt_frames = plan->d_utt_frames;
-    const size_t smem = sizeof(float) * (size_t)(2 * kChunk + kRing) + sizeof(int) * (size_t)(2 * kChunk);
-    AAT_CUDA_CHECK(cudaFuncSetAttribute(boundaries_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AAT_MAX_SMEM_CARVEOUT(boundaries_kernel);
+    const size_t smem = sizeof(float) * (size_t)(2 * chunk + kRing) + sizeof(int) * (size_t)(2 * chunk);
+    auto kernel = boundaries_kernel_t<kChunk>;
+    AAT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AAT_MAX_SMEM_CARVEOUT(kernel);
     {
         ProfileScope prof(ctx, AAT_K_BOUNDARIES, stream);
-        boundaries_kernel<<<plan->n_utts, kThreads, smem, stream>>>(p);
+        AAT_CUDA_CHECK(launch_pdl(kernel, dim3(plan->n_utts), dim3(kThreads), smem, stream, p));
         AAT_LAUNCH_CHECK();
     }
     if (seg_off != nullptr && !fuse_csr) // batch too large for the fused epilogue's scratch: separate kernel

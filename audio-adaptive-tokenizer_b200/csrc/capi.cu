@@ -309,6 +309,14 @@ int aat_profile_enable(aat_ctx *ctx, uint32_t kernel_mask)
     }
     p.mask = kernel_mask;
     p.used = 0;
+    for (int64_t &n : p.seen) n = 0;
+    return AAT_OK;
+}
+
+int aat_profile_sample_every(aat_ctx *ctx, int32_t every)
+{
+    AAT_REQUIRE(ctx && every >= 1, AAT_ERR_INVALID, "aat_profile_sample_every: NULL context or every < 1");
+    ctx->prof.every = every;
     return AAT_OK;
 }
 

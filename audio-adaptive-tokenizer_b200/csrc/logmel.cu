@@ -331,6 +331,9 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
     for (int i = tid; i < p.n_mels; i += kThreads) s_fparts[i] = p.filter_parts[i];
     cp_async_wait<0>();
     __syncthreads();
+    // everything above reads tables that no kernel writes; the samples may come from the previous kernel
+    pdl_wait();
+    pdl_launch_dependents();
     fetch_samples(s_tiles[0]);
 
     const int pair = tid / 20;
@@ -571,7 +574,7 @@ int launch_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave, int wave
     int grid = ctx->num_sms * per_sm;
     if (grid > plan->mel_tiles) grid = plan->mel_tiles;
     ProfileScope prof(ctx, AAT_K_LOGMEL, stream);
-    kernel<<<grid, kThreads, smem, stream>>>(p);
+    AAT_CUDA_CHECK(launch_pdl(kernel, dim3(grid), dim3(kThreads), smem, stream, p));
     AAT_LAUNCH_CHECK();
     return AAT_OK;
 }

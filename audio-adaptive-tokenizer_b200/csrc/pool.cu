@@ -265,8 +265,6 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
     __shared__ __align__(16) int64_t s_off[kOffCache];
 
     POOL_TRACE(0); // CTA entry
-    // issued before anything else: the only global load the first bulk copies depend on
-    const int64_t S_total = p.n_seg_dev ? min(*p.n_seg_dev, p.n_seg) : p.n_seg;
     const int tid = threadIdx.x;
     const int n_consumers = p.n_consumers;
     const int64_t G = gridDim.x;
@@ -286,24 +284,40 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
     }
     __syncthreads();
 
+    auto issue_stage = [&](int64_t ch) {
+        const int s = (int)(ch % kStages);
+        const int64_t row = r0 + ch * p.rows_per_stage;
+        const int64_t rows = (r1 - row < p.rows_per_stage) ? r1 - row : p.rows_per_stage;
+        const uint32_t bytes = (uint32_t)(rows * p.row_bytes);
+        mbar_expect_tx(&s_full[s], bytes);
+        bulk_g2s(smem_raw + s * stage_stride, p.emb + (size_t)row * p.row_bytes, bytes, &s_full[s]);
+    };
+    // The embedding rows are not written by the kernel in front of this one (the boundary scan), so the first stage
+    // is requested before the dependency wait: under programmatic dependent launch it lands while that kernel is
+    // still running.  Segment offsets and counts are its outputs and are only touched after the wait.
+    const bool producer = tid == n_consumers;
+    if (producer && r0 < r1) issue_stage(0);
+    pdl_wait();
+    pdl_launch_dependents();
+    const int64_t S_total = p.n_seg_dev ? min(*p.n_seg_dev, p.n_seg) : p.n_seg;
+
     if (tid >= n_consumers) {
         // ============================== producer warp ==============================
         const int lane = tid - n_consumers;
-        if (lane == 0 && r0 < r1 && S_total > 0) {
+        if (lane == 0 && r0 < r1 && S_total <= 0) {
+            mbar_wait(&s_full[0], 0); // nothing to pool: let the speculative first stage land before the CTA exits
+        } else if (lane == 0 && r0 < r1) {
+            // the offsets window goes ahead of the bulk of the stream: a plain load issued later would queue behind
+            // ~28 MB of bulk traffic from all CTAs and take 3.5-6 us (profiles/r1_pool_timeline_before.txt)
             const OffWindow w = first_window(p.seg_off, r0, p.n_rows, S_total);
             if (w.bulk) {
                 mbar_expect_tx(&s_offbar, (uint32_t)(w.count * sizeof(int64_t)));
                 bulk_g2s(s_off, p.seg_off + w.first, (uint32_t)(w.count * sizeof(int64_t)), &s_offbar);
             }
-            for (int64_t ch = 0; ch < n_chunks; ++ch) {
-                const int s = (int)(ch % kStages);
+            for (int64_t ch = 1; ch < n_chunks; ++ch) {
                 const int64_t use = ch / kStages;
-                if (use > 0) mbar_wait(&s_empty[s], (uint32_t)((use - 1) & 1));
-                const int64_t row = r0 + ch * p.rows_per_stage;
-                const int64_t rows = (r1 - row < p.rows_per_stage) ? r1 - row : p.rows_per_stage;
-                const uint32_t bytes = (uint32_t)(rows * p.row_bytes);
-                mbar_expect_tx(&s_full[s], bytes);
-                bulk_g2s(smem_raw + s * stage_stride, p.emb + (size_t)row * p.row_bytes, bytes, &s_full[s]);
+                if (use > 0) mbar_wait(&s_empty[(int)(ch % kStages)], (uint32_t)((use - 1) & 1));
+                issue_stage(ch);
             }
         } else if (lane != 0) {
             // idle lanes: empty segments never meet a row, so they are written here (torch: mean of
@@ -598,6 +612,8 @@ colsum_reduce_kernel(const double *partial, int n_ctas, int dim, int64_t n_seg, 
                      bool accumulate)
 {
     __shared__ double s_part[kReduceSlices][33];
+    pdl_wait(); // the pool kernel's per-CTA sums
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const int d = blockIdx.x * 32 + lane;
     const int per = (n_ctas + kReduceSlices - 1) / kReduceSlices;
@@ -659,7 +675,7 @@ int launch_typed(aat_ctx *ctx, PoolParams &p, size_t smem, bool colsum, cudaStre
     if (by_rows < grid) grid = by_rows < 1 ? 1 : (int)by_rows;
     *grid_out = grid;
     ProfileScope prof(ctx, AAT_K_POOL, stream); // the streaming kernel alone (not the colsum reduce)
-    kernel<<<grid, threads, smem, stream>>>(p);
+    AAT_CUDA_CHECK(launch_pdl(kernel, dim3(grid), dim3(threads), smem, stream, p));
     AAT_LAUNCH_CHECK();
     return AAT_OK;
 }
@@ -762,8 +778,9 @@ int launch_mean_pool(aat_ctx *ctx, const void *emb, int emb_dtype, int64_t n_row
     if (rc != AAT_OK) return rc;
     if (want_colsum) {
         AAT_MAX_SMEM_CARVEOUT(colsum_reduce_kernel);
-        colsum_reduce_kernel<<<(dim + 31) / 32, 32 * kReduceSlices, 0, stream>>>(ctx->pool.colsum, grid, dim, n_seg,
-                                                                                 n_seg_dev, colsum, colsum_accumulate);
+        AAT_CUDA_CHECK(launch_pdl(colsum_reduce_kernel, dim3((dim + 31) / 32), dim3(32 * kReduceSlices), 0, stream,
+                                  (const double *)ctx->pool.colsum, grid, (int)dim, n_seg, n_seg_dev, colsum,
+                                  colsum_accumulate));
         AAT_LAUNCH_CHECK();
     }
     return AAT_OK;

@@ -102,6 +102,11 @@ int aat_profile_enable(aat_ctx *ctx, uint32_t kernel_mask);
 /* Synchronises the recorded events and returns, per kernel id, the number of recorded launches and
  * the sum of their durations in milliseconds (arrays of AAT_K_COUNT entries). */
 int aat_profile_summary(aat_ctx *ctx, int64_t *launches, double *total_ms);
+/* Record only every `every`-th launch of each enabled kernel (default 1 = all).  An event between two kernels
+ * forces the second to start after the first has drained, so sampling keeps most launches of a timed loop free to
+ * overlap (programmatic dependent launch) while the sampled ones are timed in isolation.  Takes effect at the next
+ * aat_profile_enable. */
+int aat_profile_sample_every(aat_ctx *ctx, int32_t every);
 
 /* ------------------------------------------------------------------ context
  * Replaces AdaptiveAudioAmplitudeTokenizer.__init__ (ref:src/aat/tokenizer.py:15-53).
