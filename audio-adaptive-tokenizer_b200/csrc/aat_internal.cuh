@@ -141,6 +141,8 @@ struct aat_plan {
     int64_t *d_frame_off = nullptr;     // [B+1]
     int64_t *d_seg_slot_off = nullptr;  // [B+1]
     aat::MelTile *d_mel_tile = nullptr; // [mel_tiles] tile descriptors of the log-mel kernel
+    int32_t *d_mel_sched = nullptr;     // [2] the log-mel kernel's tile counter and exit counter (self-resetting:
+                                        // one log-mel launch per plan may be in flight at a time)
     // scratch written by the boundaries kernel for its fused frame-CSR epilogue
     int64_t *d_seg_local = nullptr;     // [total_seg_slots]
     int64_t *d_utt_frames = nullptr;    // [B]

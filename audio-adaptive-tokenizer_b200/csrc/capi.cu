@@ -416,6 +416,11 @@ int aat_plan_create(aat_ctx *ctx, int32_t n_utts, const int64_t *n_samples_host,
         aat_plan_destroy(plan);
         AAT_REQUIRE(false, AAT_ERR_CUDA, "aat_plan_create: out of device memory");
     }
+    if (cudaMalloc(&plan->d_mel_sched, sizeof(int32_t) * 2) != cudaSuccess ||
+        cudaMemset(plan->d_mel_sched, 0, sizeof(int32_t) * 2) != cudaSuccess) {
+        aat_plan_destroy(plan);
+        AAT_REQUIRE(false, AAT_ERR_CUDA, "aat_plan_create: out of device memory");
+    }
     if (cudaMalloc(&plan->d_seg_local, sizeof(int64_t) * (size_t)(plan->total_seg_slots ? plan->total_seg_slots : 1)) != cudaSuccess ||
         cudaMalloc(&plan->d_utt_frames, sizeof(int64_t) * (size_t)(n_utts ? n_utts : 1)) != cudaSuccess) {
         aat_plan_destroy(plan);
@@ -434,6 +439,7 @@ int aat_plan_destroy(aat_plan *plan)
     cudaFree(plan->d_frame_off);
     cudaFree(plan->d_seg_slot_off);
     cudaFree(plan->d_mel_tile);
+    cudaFree(plan->d_mel_sched);
     cudaFree(plan->d_seg_local);
     cudaFree(plan->d_utt_frames);
     cudaFree(plan->d_chunk_utt);

@@ -186,6 +186,7 @@ struct LogmelParams {
     int n_weights;
     int stage_len; // (kFrames - 1) * hop + 400
     int stage_pad; // stage_len rounded up to 16 bytes worth of samples
+    int *sched;    // [2] dynamic tile counter, exit counter (both left at zero by the last CTA to exit)
     LogmelConsts K;
 };
 
@@ -201,7 +202,7 @@ __host__ __device__ constexpr int raw_gap() { return sizeof(WaveT) == 4 ? 20 : 4
 __host__ __device__ inline int raw_elems(int stage_pad, int gap) { return stage_pad + gap * ((stage_pad - 1) / kRawBlock); }
 
 struct SmemLayout {
-    size_t ex, sum, raw, tw, logt, mw, sdesc, slen, fparts, tiles, mel, total;
+    size_t ex, sum, raw, tw, logt, mw, sdesc, slen, fparts, tiles, next, mel, total;
 };
 
 __host__ __device__ inline SmemLayout smem_layout(int raw_elems, int wave_bytes, int n_mels, int n_slots, int n_weights)
@@ -225,6 +226,7 @@ __host__ __device__ inline SmemLayout smem_layout(int raw_elems, int wave_bytes,
     L.slen = take(sizeof(int) * n_slots);
     L.fparts = take(sizeof(uint16_t) * n_mels);
     L.tiles = take(sizeof(MelTile) * kTileRing);
+    L.next = take(sizeof(int)); // the tile id thread 0 grabbed during the current tile
     L.mel = L.ex; // float32 mel tile for the amplitude epilogue: overlays the power spectra once they are dead
     L.total = o;
     return L;
@@ -285,6 +287,7 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
     int *s_slen = reinterpret_cast<int *>(smem_raw + L.slen);
     uint16_t *s_fparts = reinterpret_cast<uint16_t *>(smem_raw + L.fparts);
     MelTile *s_tiles = reinterpret_cast<MelTile *>(smem_raw + L.tiles);
+    int *s_next = reinterpret_cast<int *>(smem_raw + L.next);
     float *s_mel = reinterpret_cast<float *>(smem_raw + L.mel);
 
     const int tid = threadIdx.x;
@@ -344,13 +347,23 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
     const int q = tid / kFrames;       // ... and thread group (filters q, q + 10, ...)
     const int n_mine = q < p.n_mels ? (p.n_mels - q + kMelGroups - 1) / kMelGroups : 0; // filters of this thread
 
+    // Tile schedule: the first three tiles of a CTA are static (blockIdx + k * grid); every later one is grabbed from a
+    // global counter three tiles ahead of its use (descriptor two ahead, samples one ahead), so the tile-count
+    // remainder (6404 tiles over 444 CTAs = 14.4 each) and slow CTAs even out instead of setting the kernel's tail.
+    // Thread 0 issues the atomic right after a tile's first barrier and parks the result in shared memory before
+    // the second one: its latency hides behind pass 1.
+    const int G = (int)gridDim.x;
+    int tile_id = blockIdx.x, next_id = tile_id + G, after_id = next_id + G;
+
     int slot = 0; // ring slot of the current tile
-    for (int tile_id = blockIdx.x; tile_id < p.n_tiles; tile_id += gridDim.x) {
+    while (tile_id < p.n_tiles) {
         const int slot_next = slot + 1 == kTileRing ? 0 : slot + 1;
         const int slot_after = slot_next + 1 == kTileRing ? 0 : slot_next + 1;
 
         cp_async_wait<0>(); // this tile's samples and the next tile's descriptor have arrived
         __syncthreads();    // ... for every thread; also fences the previous tile's shared-memory reuse
+        int grabbed = 0;
+        if (tid == 0) grabbed = atomicAdd(p.sched, 1);
 
         // ---- pass 1: thread n2 transforms x[20 n1 + n2] over n1, applies W_400^(n2 k1) ----
         {
@@ -371,9 +384,11 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
 #pragma unroll
             for (int k1 = 1; k1 < 20; ++k1) ex[k1 * kRow + lane20] = cmul(v[k1], s_tw[(k1 - 1) * 20 + lane20]);
         }
+        if (tid == 0) *s_next = 3 * G + grabbed;
         __syncthreads();
+        const int grabbed_id = *s_next; // this CTA's tile after `after_id`
         // the raw buffer is free again: the next tile lands during the rest of this one
-        fetch_desc(tile_id + 2 * (int)gridDim.x, slot_after);
+        fetch_desc(after_id, slot_after);
         fetch_samples(s_tiles[slot_next]);
 
         // ---- pass 2 + split: thread k1 transforms row k1 over n2 and keeps Z[k1 + 20 k2] in registers ----
@@ -512,8 +527,14 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
         }
         // the next iteration's first __syncthreads orders these reads before the next overwrite
         slot = slot_next;
+        tile_id = next_id, next_id = after_id, after_id = grabbed_id;
     }
     cp_async_wait<0>();
+    // the last CTA to leave resets the tile scheduler for the next launch (graph replays included)
+    if (tid == 0 && atomicAdd(p.sched + 1, 1) == G - 1) {
+        p.sched[0] = 0;
+        p.sched[1] = 0;
+    }
 }
 
 } // namespace
@@ -557,6 +578,7 @@ int launch_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave, int wave
     p.n_slots = ctx->mel.n_slots;
     p.n_weights = ctx->mel.n_weights;
     p.K = kLogmelConsts;
+    p.sched = plan->d_mel_sched;
     p.stage_len = (kFrames - 1) * p.hop + kNfft;
     const int wave_bytes = wave_dtype == AAT_F32 ? 4 : 8;
     const int vec = 16 / wave_bytes;

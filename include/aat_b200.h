@@ -140,7 +140,8 @@ int aat_plan_offsets(const aat_plan *plan, int64_t *wave_off_host, int64_t *fram
  * wave_dev   : packed samples, AAT_F32 or AAT_F64
  * mel_dev    : packed (n_mels, T_b) float32 blocks (see layout above)
  * amp_dev    : optional (may be NULL) float32 per frame: -10 * mean over mels of the float32
- *              log-mel, accumulated in the order numpy uses (ref:src/aat/tokenizer.py:67) */
+ *              log-mel, accumulated in the order numpy uses (ref:src/aat/tokenizer.py:67)
+ * One launch per plan may be in flight at a time (the plan owns the kernel's tile counter). */
 int aat_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave_dev, int wave_dtype, float *mel_dev,
                float *amp_dev, void *stream);
 
