@@ -51,23 +51,19 @@ extern std::atomic<int64_t> g_launch_count;
         AAT_CUDA_CHECK(cudaGetLastError());        \
     } while (0)
 
-// The dense (bins, mels) float64 filter bank as a balanced schedule of short bands for the log-mel kernel.
-// Every filter covers a run of consecutive bins; runs longer than kMelPartMax are cut into parts.  Parts are
-// sorted by length and dealt out to kMelGroups thread groups, two per group and round ("slot"); all parts of
-// a slot are zero-padded to the slot's (even) length, so the tap loops have CTA-uniform trip counts.
-constexpr int kMelPartMax = 10; // taps per part
-constexpr int kMelGroups = 10;  // thread groups of the mel phase (160 threads / 16 frames)
-constexpr int kMelMaxParts = 215; // rows of the partial-sum buffer (+1 spare row) that fit next to the power spectra
+// The dense (bins, mels) float64 filter bank in the banded form the log-mel kernel walks.  Every filter covers a
+// run of consecutive bins.  In the kernel thread (frame f, group q) evaluates the filters q, q + kMelGroups, ... of
+// its frame and keeps the sums in registers until their log10 is taken; the two groups that share a warp (q even and
+// q + 1) own neighbouring filters, whose runs are zero-padded to a common even length so that the fully unrolled
+// tap loops have warp-uniform trip counts.
+constexpr int kMelGroups = 10;    // thread groups of the mel phase (160 threads / 16 frames)
+constexpr int kMelMaxWeights = 1536; // padded weights that fit the kernel's shared-memory budget at two CTAs per SM
 struct MelSchedule {
     int n_mels = 0;
-    int nnz = 0;         // total band length of the filters
-    int n_parts = 0;
-    int n_slots = 0;     // rounds of 2 * kMelGroups parts
-    int n_weights = 0;   // padded weights (doubles, even)
-    int *slot_len = nullptr;       // device [n_slots]: even, 2..kMelPartMax
-    uint32_t *slot_desc = nullptr; // device [n_slots * 2 * kMelGroups]: (weight pair offset << 16) | (sum row << 8) | first bin
-    double *weight = nullptr;      // device [n_weights]
-    uint16_t *filter_parts = nullptr; // device [n_mels]: 0, or (further parts << 8) | their first sum row (the first part is row m)
+    int nnz = 0;        // total band length of the filters
+    int n_weights = 0;  // padded weights (doubles, even per filter)
+    uint32_t *filter_desc = nullptr; // device [n_mels]: (weight pair offset << 16) | (tap pairs << 8) | first bin
+    double *weight = nullptr;        // device [n_weights]
 };
 
 // One tile (kMelFramesPerTile consecutive frames of one utterance) of the log-mel kernel.

@@ -92,87 +92,51 @@ struct Arena {
     }
 };
 
-// dense (bins, mels) -> banded rows -> balanced schedule (see MelSchedule).  Filter m covers bins
-// [first_m, last_m] (its first and last non-zero weight; interior zeros are kept so the run stays contiguous).
+// dense (bins, mels) -> banded rows (see MelSchedule).  Filter m covers bins [first_m, last_m] (its first and last
+// non-zero weight; interior zeros are kept so the run stays contiguous).
 int build_mel_schedule(aat_ctx *ctx, const double *filters)
 {
     const int M = ctx->cfg.num_mel_filters;
-    struct Part {
-        int first_bin, len, row;
-        const double *col; // filters + m: weight of bin k at col[k * M]
-    };
-    // sum rows: row m holds the first part of filter m, the further parts of wide filters follow from row M on
-    std::vector<Part> parts, extra;
-    std::vector<uint16_t> filter_parts(M, 0);
+    std::vector<int> lo(M, -1), hi(M, -1);
     int nnz = 0;
     for (int m = 0; m < M; ++m) {
-        int lo = -1, hi = -1;
         for (int k = 0; k < kBins; ++k)
             if (filters[(size_t)k * M + m] != 0.0) {
-                if (lo < 0) lo = k;
-                hi = k;
+                if (lo[m] < 0) lo[m] = k;
+                hi[m] = k;
             }
-        if (lo < 0) {
-            // empty filter (band above Nyquist): one zero tap, so that row m is written and 0 * NaN stays NaN as in
-            // the reference's dense product
-            parts.push_back(Part{0, 1, m, nullptr});
-            continue;
-        }
-        nnz += hi - lo + 1;
-        const int first_extra = M + (int)extra.size();
-        int n_extra = 0;
-        for (int b = lo; b <= hi; b += kMelPartMax) {
-            const int len = (hi - b + 1 < kMelPartMax) ? hi - b + 1 : kMelPartMax;
-            if (b == lo)
-                parts.push_back(Part{b, len, m, filters + m});
-            else
-                extra.push_back(Part{b, len, first_extra + n_extra++, filters + m});
-        }
-        AAT_REQUIRE(M + (int)extra.size() <= kMelMaxParts, AAT_ERR_UNSUPPORTED,
-                    "aat_create: the mel filter bank is too dense for the log-mel kernel (more than %d bands of %d bins)",
-                    kMelMaxParts, kMelPartMax);
-        filter_parts[m] = n_extra ? (uint16_t)((n_extra << 8) | first_extra) : (uint16_t)0;
+        if (lo[m] >= 0) nnz += hi[m] - lo[m] + 1;
     }
-    parts.insert(parts.end(), extra.begin(), extra.end());
-    const int n_parts = (int)parts.size();
-    std::vector<int> order(n_parts);
-    for (int i = 0; i < n_parts; ++i) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return parts[a].len > parts[b].len; });
-    constexpr int kPerSlot = 2 * kMelGroups;
-    const int n_slots = (n_parts + kPerSlot - 1) / kPerSlot;
-    std::vector<int> slot_len(n_slots ? n_slots : 1, 2);
-    std::vector<uint32_t> slot_desc((size_t)(n_slots ? n_slots : 1) * kPerSlot, 0);
+    // an empty filter (band above Nyquist) is one zero tap at bin 0: 0 * NaN stays NaN as in the reference's dense product
+    auto len_of = [&](int m) { return lo[m] < 0 ? 1 : hi[m] - lo[m] + 1; };
+    std::vector<uint32_t> desc(M, 0);
     std::vector<double> weights;
-    for (int s = 0; s < n_slots; ++s) {
-        const int L = (parts[order[s * kPerSlot]].len + 1) & ~1; // longest part of the slot, rounded up to even
-        slot_len[s] = L;
-        for (int e = 0; e < kPerSlot; ++e) {
-            const int i = s * kPerSlot + e;
-            const size_t at = weights.size();
-            weights.resize(at + L, 0.0);
-            int start = 0, row = n_parts; // dummy entry: zero weights, sums go to the spare row
-            if (i < n_parts) {
-                const Part &pt = parts[order[i]];
-                start = (pt.first_bin + L <= kBins) ? pt.first_bin : kBins - L;
-                row = pt.row;
-                for (int t = 0; t < pt.len && pt.col; ++t)
-                    weights[at + (pt.first_bin - start) + t] = pt.col[(size_t)(pt.first_bin + t) * M];
-            }
-            AAT_REQUIRE(at / 2 < 65536, AAT_ERR_UNSUPPORTED, "aat_create: mel schedule too large");
-            slot_desc[(size_t)s * kPerSlot + e] = ((uint32_t)(at / 2) << 16) | ((uint32_t)row << 8) | (uint32_t)start;
-        }
+    for (int m = 0; m < M; ++m) {
+        // the filter evaluated by the other half of the warp: groups q (even) and q + 1 sit in one warp
+        const int q = m % kMelGroups;
+        const int partner = (q % 2 == 0) ? m + 1 : m - 1;
+        int L = len_of(m);
+        if (partner >= 0 && partner < M && partner / kMelGroups == m / kMelGroups && len_of(partner) > L) L = len_of(partner);
+        L = (L + 1) & ~1;
+        const int first = lo[m] < 0 ? 0 : lo[m];
+        const int start = (first + L <= kBins) ? first : kBins - L;
+        AAT_REQUIRE(start >= 0, AAT_ERR_UNSUPPORTED, "aat_create: mel filter %d is wider than the spectrum", m);
+        const size_t at = weights.size();
+        weights.resize(at + L, 0.0);
+        if (lo[m] >= 0)
+            for (int k = lo[m]; k <= hi[m]; ++k) weights[at + (k - start)] = filters[(size_t)k * M + m];
+        AAT_REQUIRE(weights.size() <= (size_t)kMelMaxWeights, AAT_ERR_UNSUPPORTED,
+                    "aat_create: the mel filter bank is too dense for the log-mel kernel (more than %d banded weights)",
+                    kMelMaxWeights);
+        desc[m] = ((uint32_t)(at / 2) << 16) | ((uint32_t)(L / 2) << 8) | (uint32_t)start;
     }
     MelSchedule &ms = ctx->mel;
     ms.n_mels = M;
     ms.nnz = nnz;
-    ms.n_parts = n_parts;
-    ms.n_slots = n_slots;
     ms.n_weights = (int)weights.size();
     int rc;
-    if ((rc = upload(&ms.slot_len, slot_len.data(), slot_len.size()))) return rc;
-    if ((rc = upload(&ms.slot_desc, slot_desc.data(), slot_desc.size()))) return rc;
+    if ((rc = upload(&ms.filter_desc, desc.data(), desc.size()))) return rc;
     if ((rc = upload(&ms.weight, weights.data(), weights.size()))) return rc;
-    if ((rc = upload(&ms.filter_parts, filter_parts.data(), filter_parts.size()))) return rc;
     return AAT_OK;
 }
 
@@ -276,10 +240,8 @@ int aat_destroy(aat_ctx *ctx)
     cudaFree(ctx->twiddle);
     cudaFree(ctx->log_table);
     cudaFree(ctx->ticket);
-    cudaFree(ctx->mel.slot_len);
-    cudaFree(ctx->mel.slot_desc);
+    cudaFree(ctx->mel.filter_desc);
     cudaFree(ctx->mel.weight);
-    cudaFree(ctx->mel.filter_parts);
     pool_scratch_free(ctx);
     if (ctx->dev_scratch) cudaFree(ctx->dev_scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

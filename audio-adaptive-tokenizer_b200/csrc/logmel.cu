@@ -174,15 +174,11 @@ struct LogmelParams {
     const double *window_half;
     const double2 *twiddle;
     const double2 *log_table;
-    const int *slot_len;
-    const uint32_t *slot_desc;
+    const uint32_t *filter_desc;
     const double *mel_weight;
-    const uint16_t *filter_parts;
     int n_tiles;
     int hop;
     int n_mels;
-    int n_parts;
-    int n_slots;
     int n_weights;
     int stage_len; // (kFrames - 1) * hop + 400
     int stage_pad; // stage_len rounded up to 16 bytes worth of samples
@@ -202,10 +198,10 @@ __host__ __device__ constexpr int raw_gap() { return sizeof(WaveT) == 4 ? 20 : 4
 __host__ __device__ inline int raw_elems(int stage_pad, int gap) { return stage_pad + gap * ((stage_pad - 1) / kRawBlock); }
 
 struct SmemLayout {
-    size_t ex, sum, raw, tw, logt, mw, sdesc, slen, fparts, tiles, next, mel, total;
+    size_t ex, raw, tw, logt, mw, fdesc, tiles, next, mel, total;
 };
 
-__host__ __device__ inline SmemLayout smem_layout(int raw_elems, int wave_bytes, int n_mels, int n_slots, int n_weights)
+__host__ __device__ inline SmemLayout smem_layout(int raw_elems, int wave_bytes, int n_mels, int n_weights)
 {
     SmemLayout L{};
     size_t o = 0;
@@ -214,48 +210,81 @@ __host__ __device__ inline SmemLayout smem_layout(int raw_elems, int wave_bytes,
         o += (bytes + 15) & ~size_t(15);
         return at;
     };
-    // exchange matrix of the two FFT passes; afterwards the power spectra (16 x 201 doubles) and, behind them,
-    // the partial band sums ((n_parts + 1) x 16 doubles; kMelMaxParts is sized so that they fit)
+    // exchange matrix of the two FFT passes; afterwards the power spectra (16 x 201 doubles) and, behind them, the
+    // float32 mel tile of the amplitude epilogue
     L.ex = take(sizeof(double2) * kPairs * kPairStride);
-    L.sum = L.ex + sizeof(double) * kFrames * kPowStride;
+    L.mel = L.ex + sizeof(double) * kFrames * kPowStride;
     L.raw = take((size_t)raw_elems * wave_bytes);
     L.tw = take(sizeof(double2) * kTwiddles);
     L.logt = take(sizeof(double2) * kLogTable);
     L.mw = take(sizeof(double) * n_weights);
-    L.sdesc = take(sizeof(uint32_t) * n_slots * 2 * kMelGroups);
-    L.slen = take(sizeof(int) * n_slots);
-    L.fparts = take(sizeof(uint16_t) * n_mels);
+    L.fdesc = take(sizeof(uint32_t) * n_mels);
     L.tiles = take(sizeof(MelTile) * kTileRing);
     L.next = take(sizeof(int)); // the tile id thread 0 grabbed during the current tile
-    L.mel = L.ex; // float32 mel tile for the amplitude epilogue: overlays the power spectra once they are dead
     L.total = o;
     return L;
 }
-static_assert(sizeof(double) * (kFrames * kPowStride + (kMelMaxParts + 1) * kFrames) <= sizeof(double2) * kPairs * kPairStride,
-              "power spectra + partial band sums must fit in the exchange matrix");
-static_assert(sizeof(float) * kFrames * (kMaxMels + 1) <= sizeof(double) * kFrames * kPowStride,
-              "the float32 mel tile overlays the power spectra only");
+static_assert(sizeof(double) * kFrames * kPowStride + sizeof(float) * kFrames * (kMaxMels + 1) <=
+                  sizeof(double2) * kPairs * kPairStride,
+              "power spectra + float32 mel tile must fit in the exchange matrix");
 
-// Two bands of kTapPairs * 2 taps each, four independent FMA chains (explicit _rn: no contraction of the
-// final additions, so the sums do not depend on the compiler's mood).
+// One band of kTapPairs * 2 taps: four independent FMA chains (explicit _rn: no contraction of the final additions,
+// so the sum does not depend on the compiler's mood).
 template <int kTapPairs>
-__device__ __forceinline__ void band_pair(const double2 *__restrict__ wa, const double *__restrict__ pa,
-                                          const double2 *__restrict__ wb, const double *__restrict__ pb, double &ra,
-                                          double &rb)
+__device__ __forceinline__ double band(const double2 *__restrict__ w2, const double *__restrict__ pw)
 {
-    double2 w = wa[0], u = wb[0];
-    double a0 = __dmul_rn(w.x, pa[0]), a1 = __dmul_rn(w.y, pa[1]);
-    double b0 = __dmul_rn(u.x, pb[0]), b1 = __dmul_rn(u.y, pb[1]);
+    double2 w = w2[0];
+    double a0 = __dmul_rn(w.x, pw[0]), a1 = __dmul_rn(w.y, pw[1]);
+    if (kTapPairs == 1) return __dadd_rn(a0, a1);
+    w = w2[1];
+    double a2 = __dmul_rn(w.x, pw[2]), a3 = __dmul_rn(w.y, pw[3]);
 #pragma unroll
-    for (int i = 1; i < kTapPairs; ++i) {
-        w = wa[i], u = wb[i];
-        a0 = fma(w.x, pa[2 * i], a0);
-        a1 = fma(w.y, pa[2 * i + 1], a1);
-        b0 = fma(u.x, pb[2 * i], b0);
-        b1 = fma(u.y, pb[2 * i + 1], b1);
+    for (int i = 2; i < kTapPairs; ++i) {
+        w = w2[i];
+        if (i & 1) {
+            a2 = fma(w.x, pw[2 * i], a2);
+            a3 = fma(w.y, pw[2 * i + 1], a3);
+        } else {
+            a0 = fma(w.x, pw[2 * i], a0);
+            a1 = fma(w.y, pw[2 * i + 1], a1);
+        }
     }
-    ra = __dadd_rn(a0, a1);
-    rb = __dadd_rn(b0, b1);
+    return __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
+}
+
+// Runtime tap count (warp-uniform by construction of the schedule) -> the unrolled instance.  Out of line: it is
+// called from every slot of the unrolled log batch, and ten unrolled bodies per call site would not fit the
+// instruction cache.
+__device__ __noinline__ double band_sum(int tap_pairs, const double2 *__restrict__ w2, const double *__restrict__ pw)
+{
+    switch (tap_pairs) {
+    case 1: return band<1>(w2, pw);
+    case 2: return band<2>(w2, pw);
+    case 3: return band<3>(w2, pw);
+    case 4: return band<4>(w2, pw);
+    case 5: return band<5>(w2, pw);
+    case 6: return band<6>(w2, pw);
+    case 7: return band<7>(w2, pw);
+    case 8: return band<8>(w2, pw);
+    case 9: return band<9>(w2, pw);
+    case 10: return band<10>(w2, pw);
+    default: break;
+    }
+    // wider filters (coarse banks): same four chains, rolled
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (int i = 0; i + 1 < tap_pairs; i += 2) {
+        const double2 w = w2[i], u = w2[i + 1];
+        a0 = fma(w.x, pw[2 * i], a0);
+        a1 = fma(w.y, pw[2 * i + 1], a1);
+        a2 = fma(u.x, pw[2 * i + 2], a2);
+        a3 = fma(u.y, pw[2 * i + 3], a3);
+    }
+    if (tap_pairs & 1) {
+        const double2 w = w2[tap_pairs - 1];
+        a0 = fma(w.x, pw[2 * tap_pairs - 2], a0);
+        a1 = fma(w.y, pw[2 * tap_pairs - 1], a1);
+    }
+    return __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
 }
 
 // First / last tiles of an utterance (and unaligned ones): element-wise copies with np.pad(mode="reflect")
@@ -274,18 +303,15 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int kGap = kHop160 ? raw_gap<WaveT>() : 0;
-    const SmemLayout L = smem_layout(raw_elems(p.stage_pad, kGap), (int)sizeof(WaveT), p.n_mels, p.n_slots, p.n_weights);
+    const SmemLayout L = smem_layout(raw_elems(p.stage_pad, kGap), (int)sizeof(WaveT), p.n_mels, p.n_weights);
     double2 *s_ex = reinterpret_cast<double2 *>(smem_raw + L.ex);
     double *s_pow = reinterpret_cast<double *>(smem_raw + L.ex);
-    double *s_sum = reinterpret_cast<double *>(smem_raw + L.sum);
     WaveT *s_rawbuf = reinterpret_cast<WaveT *>(smem_raw + L.raw);
     const double *__restrict__ g_win = p.window_half;
     double2 *s_tw = reinterpret_cast<double2 *>(smem_raw + L.tw);
     double2 *s_logt = reinterpret_cast<double2 *>(smem_raw + L.logt);
     double *s_mw = reinterpret_cast<double *>(smem_raw + L.mw);
-    uint32_t *s_sdesc = reinterpret_cast<uint32_t *>(smem_raw + L.sdesc);
-    int *s_slen = reinterpret_cast<int *>(smem_raw + L.slen);
-    uint16_t *s_fparts = reinterpret_cast<uint16_t *>(smem_raw + L.fparts);
+    uint32_t *s_fdesc = reinterpret_cast<uint32_t *>(smem_raw + L.fdesc);
     MelTile *s_tiles = reinterpret_cast<MelTile *>(smem_raw + L.tiles);
     int *s_next = reinterpret_cast<int *>(smem_raw + L.next);
     float *s_mel = reinterpret_cast<float *>(smem_raw + L.mel);
@@ -329,9 +355,7 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
     for (int i = tid; i < kTwiddles; i += kThreads) s_tw[i] = p.twiddle[i];
     for (int i = tid; i < kLogTable; i += kThreads) s_logt[i] = p.log_table[i];
     for (int i = tid; i < p.n_weights; i += kThreads) s_mw[i] = p.mel_weight[i];
-    for (int i = tid; i < p.n_slots * 2 * kMelGroups; i += kThreads) s_sdesc[i] = p.slot_desc[i];
-    for (int i = tid; i < p.n_slots; i += kThreads) s_slen[i] = p.slot_len[i];
-    for (int i = tid; i < p.n_mels; i += kThreads) s_fparts[i] = p.filter_parts[i];
+    for (int i = tid; i < p.n_mels; i += kThreads) s_fdesc[i] = p.filter_desc[i];
     cp_async_wait<0>();
     __syncthreads();
     // everything above reads tables that no kernel writes; the samples may come from the previous kernel
@@ -436,48 +460,24 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
         }
         __syncthreads();
 
-        // ---- mel projection: thread (f, q) runs the bands the schedule deals to group q, two per slot ----
-        // A half-warp is 16 frames of one band: the weights are broadcast reads and the power values hit 16
-        // different banks (row stride 201 doubles).  Slot lengths are CTA-uniform, so the switch does not diverge.
-        {
-            const double *pw = s_pow + f * kPowStride;
-            const double2 *w2 = reinterpret_cast<const double2 *>(s_mw);
-            for (int s = 0; s < p.n_slots; ++s) {
-                const uint32_t da = s_sdesc[s * 2 * kMelGroups + q], db = s_sdesc[s * 2 * kMelGroups + kMelGroups + q];
-                const double2 *wa = w2 + (da >> 16), *wb = w2 + (db >> 16);
-                const double *pa = pw + (da & 0xffu), *pb = pw + (db & 0xffu);
-                double ra, rb;
-                switch (s_slen[s]) {
-                case 2: band_pair<1>(wa, pa, wb, pb, ra, rb); break;
-                case 4: band_pair<2>(wa, pa, wb, pb, ra, rb); break;
-                case 6: band_pair<3>(wa, pa, wb, pb, ra, rb); break;
-                case 8: band_pair<4>(wa, pa, wb, pb, ra, rb); break;
-                default: band_pair<kMelPartMax / 2>(wa, pa, wb, pb, ra, rb); break;
-                }
-                s_sum[((da >> 8) & 0xffu) * kFrames + f] = ra;
-                s_sum[((db >> 8) & 0xffu) * kFrames + f] = rb;
-            }
-        }
-        __syncthreads();
-
-        // ---- filter sums -> floor -> log10 -> float32: thread (f, q) finishes filters q, q + 10, ... ----
+        // ---- mel projection, floor, log10, float32: thread (f, q) finishes filters q, q + 10, ... of frame f ----
+        // A half-warp is 16 frames of one filter: the weights are broadcast reads and the power values hit 16
+        // different banks (row stride 201 doubles).  The two half-warps of a warp own neighbouring filters padded to one
+        // length, so the switch on the tap count does not diverge.  The sums stay in registers: no second pass, no
+        // barrier between projection and log.
         const MelTile &cur = s_tiles[slot];
         {
             constexpr int kMaxPerThread = (kMaxMels + kMelGroups - 1) / kMelGroups;
             constexpr int kBatch = 7; // filters whose logs are evaluated together (7 x 10 groups covers 64..70 filters)
+            const double *pw = s_pow + f * kPowStride;
+            const double2 *w2 = reinterpret_cast<const double2 *>(s_mw);
             float *dst = p.mel + cur.mel_off + f;
             const bool live = f < cur.valid;
             const size_t T = (size_t)cur.T;
             float *smel = s_mel + f * mel_stride;
-            const double *sums = s_sum + f;
             auto filter_sum = [&](int m) {
-                double acc = sums[m * kFrames]; // row m: the filter's first (usually only) band
-                const uint32_t fp = s_fparts[m];
-                if (fp) { // wide filter: add its further bands in bin order
-                    const double *row = sums + (fp & 0xffu) * kFrames;
-#pragma unroll 1
-                    for (int n = (int)(fp >> 8); n > 0; --n, row += kFrames) acc = __dadd_rn(acc, *row);
-                }
+                const uint32_t d = s_fdesc[m];
+                const double acc = band_sum((int)((d >> 8) & 0xffu), w2 + (d >> 16), pw + (d & 0xffu));
                 return (acc < 1e-10) ? 1e-10 : acc; // np.maximum(mel_floor, .): NaN propagates
             };
 #pragma unroll
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
                         const int m = q + (i0 + k) * kMelGroups;
                         if (i0 + k < kMaxPerThread && i0 + k < n_mine) {
                             const float o = (float)lg[k];
-                            smel[m] = o; // the power spectra are dead: the float32 tile overlays them
+                            smel[m] = o; // float32 tile of the amplitude epilogue (behind the power spectra)
                             if (live) dst[(size_t)m * T] = o;
                         }
                     }
@@ -567,15 +567,11 @@ int launch_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave, int wave
     p.window_half = ctx->window_half;
     p.twiddle = ctx->twiddle;
     p.log_table = ctx->log_table;
-    p.slot_len = ctx->mel.slot_len;
-    p.slot_desc = ctx->mel.slot_desc;
+    p.filter_desc = ctx->mel.filter_desc;
     p.mel_weight = ctx->mel.weight;
-    p.filter_parts = ctx->mel.filter_parts;
     p.n_tiles = plan->mel_tiles;
     p.hop = ctx->cfg.hop_length;
     p.n_mels = ctx->mel.n_mels;
-    p.n_parts = ctx->mel.n_parts;
-    p.n_slots = ctx->mel.n_slots;
     p.n_weights = ctx->mel.n_weights;
     p.K = kLogmelConsts;
     p.sched = plan->d_mel_sched;
@@ -585,7 +581,7 @@ int launch_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave, int wave
     p.stage_pad = (p.stage_len + vec - 1) / vec * vec;
     const bool hop160 = p.hop == 160;
     const int gap = hop160 ? (wave_dtype == AAT_F32 ? raw_gap<float>() : raw_gap<double>()) : 0;
-    const size_t smem = smem_layout(raw_elems(p.stage_pad, gap), wave_bytes, p.n_mels, p.n_slots, p.n_weights).total;
+    const size_t smem = smem_layout(raw_elems(p.stage_pad, gap), wave_bytes, p.n_mels, p.n_weights).total;
     auto kernel = wave_dtype == AAT_F32 ? (hop160 ? logmel_kernel<float, true> : logmel_kernel<float, false>)
                                         : (hop160 ? logmel_kernel<double, true> : logmel_kernel<double, false>);
     AAT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
