@@ -141,7 +141,7 @@ struct aat_plan {
                                         // one log-mel launch per plan may be in flight at a time)
     // scratch written by the boundaries kernel for its fused frame-CSR epilogue
     int64_t *d_seg_local = nullptr;     // [total_seg_slots]
-    int64_t *d_utt_frames = nullptr;    // [B]
+    int64_t *d_utt_frames = nullptr;    // [B] look-back words of the boundary kernel's CSR epilogue (zero between launches)
     // waveform normalisation (aat_normalize): 4096-sample chunks
     int32_t norm_chunks = 0;
     int32_t *d_chunk_utt = nullptr;     // [norm_chunks]

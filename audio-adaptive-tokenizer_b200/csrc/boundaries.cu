@@ -107,6 +107,15 @@ __device__ __forceinline__ void finish_segments(I n_samples, I min_frames, int64
 }
 
 
+constexpr unsigned long long kTotalsReady = 1ull << 63;
+// polling load: relaxed but a real memory operation every time (never hoisted, never served from L1)
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ int64_t ld_cg(const int64_t *p) { return __ldcg(reinterpret_cast<const long long *>(p)); }
 
 // Segment lengths -> packed CSR of HuBERT frame offsets (per-segment encode convention), by ONE CTA.
@@ -193,71 +202,6 @@ __device__ void build_frame_csr(int n_utts, const int64_t *seg_slot_off, const i
     }
 }
 
-// Fused form used by the boundaries kernel's last CTA: every utterance's CTA has already written its frame
-// total and the local (within-utterance) frame offset of each segment, so what is left is one scan over the
-// utterances and a rebase — two rounds of independent loads instead of a per-utterance dependency chain.
-__device__ void rebase_frame_csr(int n_utts, const int64_t *seg_slot_off, const int64_t *seg_local,
-                                 const int64_t *utt_frames, const int32_t *seg_count, int64_t *seg_off,
-                                 int64_t *n_seg_out, int64_t *utt_seg_off_out, int64_t *s_seg, int64_t *s_frm)
-{
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_threads = blockDim.x, n_warps = n_threads >> 5;
-    __shared__ int64_t s_wsum[2][32];
-    for (int b = tid; b < n_utts; b += n_threads) {
-        s_seg[b + 1] = __ldcg(seg_count + b);
-        s_frm[b + 1] = ld_cg(utt_frames + b);
-    }
-    if (tid == 0) s_seg[0] = 0, s_frm[0] = 0;
-    __syncthreads();
-    const int per = (n_utts + n_threads - 1) / n_threads;
-    const int b0 = 1 + tid * per, b1 = min(n_utts + 1, b0 + per);
-    int64_t a = 0, f = 0;
-    for (int b = b0; b < b1; ++b) a += s_seg[b], f += s_frm[b];
-    int64_t ia = a, jf = f;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int64_t va = __shfl_up_sync(0xffffffffu, ia, d), vf = __shfl_up_sync(0xffffffffu, jf, d);
-        if (lane >= d) ia += va, jf += vf;
-    }
-    if (lane == 31) s_wsum[0][warp] = ia, s_wsum[1][warp] = jf;
-    __syncthreads();
-    if (warp == 0) {
-        int64_t wa = lane < n_warps ? s_wsum[0][lane] : 0, wf = lane < n_warps ? s_wsum[1][lane] : 0;
-        int64_t xa = wa, xf = wf;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int64_t va = __shfl_up_sync(0xffffffffu, xa, d), vf = __shfl_up_sync(0xffffffffu, xf, d);
-            if (lane >= d) xa += va, xf += vf;
-        }
-        s_wsum[0][lane] = xa - wa, s_wsum[1][lane] = xf - wf;
-    }
-    __syncthreads();
-    {
-        int64_t ra = s_wsum[0][warp] + ia - a, rf = s_wsum[1][warp] + jf - f;
-        for (int b = b0; b < b1; ++b) {
-            ra += s_seg[b], rf += s_frm[b];
-            s_seg[b] = ra, s_frm[b] = rf;
-        }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        *n_seg_out = s_seg[n_utts];
-        seg_off[s_seg[n_utts]] = s_frm[n_utts];
-    }
-    if (utt_seg_off_out)
-        for (int b = tid; b <= n_utts; b += n_threads) utt_seg_off_out[b] = s_seg[b];
-    // rebase: half-warps take utterances round-robin; loads of successive utterances are independent
-    const int half = tid >> 4, hl = tid & 15, n_halves = n_threads >> 4;
-#pragma unroll 4
-    for (int b = half; b < n_utts; b += n_halves) {
-        const int cnt = (int)(s_seg[b + 1] - s_seg[b]);
-        const int64_t *src = seg_local + seg_slot_off[b];
-        int64_t *dst = seg_off + s_seg[b];
-        const int64_t base = s_frm[b];
-        for (int i = hl; i < cnt; i += 16) dst[i] = base + ld_cg(src + i);
-    }
-}
-
 struct BoundaryParams {
     const float *mel;
     const float *amp;
@@ -275,7 +219,7 @@ struct BoundaryParams {
     int64_t *n_seg;
     int64_t *utt_seg_off;
     int64_t *seg_local;   // [total_seg_slots] plan scratch: within-utterance frame offsets
-    int64_t *utt_frames;  // [n_utts] plan scratch: frames per utterance
+    unsigned long long *utt_totals; // [n_utts] plan scratch, zero between launches: ready | frames << 32 | segments
     unsigned *ticket;
     int n_utts;
     int64_t min_frames, max_frames;
@@ -321,6 +265,7 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel_t(const BoundaryPa
     int *s_min = reinterpret_cast<int *>(s_cs + kRing);           // [2][kChunk] minima (global frame index) per chunk
     __shared__ int s_wcount[kWorkers / 32];
     __shared__ int s_found[2];
+    __shared__ int64_t s_total[2]; // this utterance's segment count and frame total (emit thread -> epilogue)
 
     BND_TRACE(0);
     const int tid = threadIdx.x;
@@ -529,28 +474,63 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel_t(const BoundaryPa
         p.seg_count[utt] = (int32_t)(count < capacity ? count : capacity);
         if (p.minima_count) p.minima_count[utt] = (int32_t)n_minima;
         p.status[utt] = status;
-        if (p.seg_off) p.utt_frames[utt] = frames;
+        if (p.seg_off) {
+            s_total[0] = count < capacity ? count : capacity, s_total[1] = frames;
+            // one 64-bit store: ready bit | frames | segment count.  The word carries everything the later utterances'
+            // look-back needs, so neither side needs release/acquire ordering (no membar, no L1 invalidation).
+            __stcg(p.utt_totals + utt, kTotalsReady | ((unsigned long long)frames << 32) |
+                                           (unsigned long long)(uint32_t)s_total[0]);
+        }
     }
 
-    // ---- fused epilogue: the last CTA to finish turns all segment lengths into the packed frame CSR ----
+    // ---- fused epilogue: the packed frame CSR by decoupled look-back ----
+    // Every utterance's CTA publishes (segments, frames) in one word, sums the words of the utterances before it
+    // (they are resident or done: CTAs are dispatched in index order, and nobody waits before publishing) and
+    // writes its own slice of seg_off.  No CTA does serial work for the others: the epilogue costs one round trip
+    // after the slowest utterance instead of a rebase pass by the last CTA (6 us at 64 utterances,
+    // profiles/r1_bnd_timeline.txt).  The last CTA through the ticket clears the words for the next launch.
     if (p.seg_off != nullptr) {
+        __shared__ int64_t s_wsum[2][kThreads / 32];
         __shared__ int s_last;
-        __syncthreads();
-        BND_TRACE(28); // segments written
-        if (tid == kEmitThread) {
-            __threadfence(); // this CTA's segment writes (all by this thread) are visible before the ticket
-            s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
+        int64_t cnt = 0, frm = 0;
+        for (int b = tid; b < utt; b += kThreads) {
+            unsigned long long v;
+            do {
+                v = ld_relaxed_u64(p.utt_totals + b);
+            } while (!(v & kTotalsReady));
+            cnt += (int64_t)(v & 0xffffffffull);
+            frm += (int64_t)((v >> 32) & 0x7fffffffull);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+            frm += __shfl_xor_sync(0xffffffffu, frm, d);
+        }
+        if ((tid & 31) == 0) s_wsum[0][tid >> 5] = cnt, s_wsum[1][tid >> 5] = frm;
+        __syncthreads(); // also: the emit thread's s_total and its seg_local stores are visible to the CTA
+        BND_TRACE(28); // look-back done
+        int64_t base_seg = 0, base_frm = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) base_seg += s_wsum[0][w], base_frm += s_wsum[1][w];
+        const int64_t my_cnt = s_total[0], my_frm = s_total[1];
+        const int64_t *local = p.seg_local + slot0;
+        int64_t *dst = p.seg_off + base_seg;
+        for (int64_t i = tid; i < my_cnt; i += kThreads) dst[i] = base_frm + __ldcg(reinterpret_cast<const long long *>(local + i));
+        if (tid == 0) {
+            if (p.utt_seg_off) p.utt_seg_off[utt] = base_seg;
+            if (utt == p.n_utts - 1) {
+                if (p.utt_seg_off) p.utt_seg_off[p.n_utts] = base_seg + my_cnt;
+                *p.n_seg = base_seg + my_cnt;
+                p.seg_off[base_seg + my_cnt] = base_frm + my_frm;
+            }
+            s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1); // after this CTA's look-back
         }
         __syncthreads();
-        if (s_last) {
-            __threadfence();
-            int64_t *s_seg = reinterpret_cast<int64_t *>(smem_raw); // the pipeline buffers are free now
-            int64_t *s_frm = s_seg + p.n_utts + 1;
-            rebase_frame_csr(p.n_utts, p.seg_slot_off, p.seg_local, p.utt_frames, p.seg_count, p.seg_off, p.n_seg,
-                             p.utt_seg_off, s_seg, s_frm);
-            if (tid == 0) *p.ticket = 0; // ready for the next launch (graph replays included)
+        if (s_last) { // everybody has read every word: clear them for the next launch (graph replays included)
+            for (int b = tid; b < p.n_utts; b += kThreads) p.utt_totals[b] = 0ull;
+            if (tid == 0) *p.ticket = 0;
         }
-        BND_TRACE(29); // ticket taken (and, in the last CTA, the CSR rebased)
+        BND_TRACE(29);
     }
 }
 
@@ -616,16 +596,15 @@ int launch_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel, cons
     p.max_amp = ctx->cfg.max_amplitude_for_minima;
     p.n_utts = plan->n_utts;
     p.ticket = ctx->ticket;
-    const size_t csr_smem = sizeof(int64_t) * 2 * (size_t)(plan->n_utts + 1);
     // Stage size: 128-frame stages were measured slower (31 us vs 27 us at 64 x 16 s) and 256 equal: the kernel is
-    // bound by the merge/split thread and the CSR epilogue, not by the pipeline fill (profiles/r1_bnd_timeline.txt).
+    // bound by the merge/split thread, not by the pipeline fill (profiles/r1_bnd_timeline.txt).
     constexpr int chunk = kChunk;
-    const bool fuse_csr = seg_off != nullptr && csr_smem <= sizeof(float) * (size_t)(2 * chunk + kRing);
+    const bool fuse_csr = seg_off != nullptr; // look-back epilogue: no scratch beyond one word per utterance
     p.seg_off = fuse_csr ? seg_off : nullptr;
     p.n_seg = n_seg;
     p.utt_seg_off = utt_seg_off;
     p.seg_local = plan->d_seg_local;
-    p.utt_frames = plan->d_utt_frames;
+    p.utt_totals = reinterpret_cast<unsigned long long *>(plan->d_utt_frames);
     const size_t smem = sizeof(float) * (size_t)(2 * chunk + kRing) + sizeof(int) * (size_t)(2 * chunk);
     auto kernel = boundaries_kernel_t<kChunk>;
     AAT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -384,7 +384,8 @@ int aat_plan_create(aat_ctx *ctx, int32_t n_utts, const int64_t *n_samples_host,
         AAT_REQUIRE(false, AAT_ERR_CUDA, "aat_plan_create: out of device memory");
     }
     if (cudaMalloc(&plan->d_seg_local, sizeof(int64_t) * (size_t)(plan->total_seg_slots ? plan->total_seg_slots : 1)) != cudaSuccess ||
-        cudaMalloc(&plan->d_utt_frames, sizeof(int64_t) * (size_t)(n_utts ? n_utts : 1)) != cudaSuccess) {
+        cudaMalloc(&plan->d_utt_frames, sizeof(int64_t) * (size_t)(n_utts ? n_utts : 1)) != cudaSuccess ||
+        cudaMemset(plan->d_utt_frames, 0, sizeof(int64_t) * (size_t)(n_utts ? n_utts : 1)) != cudaSuccess) {
         aat_plan_destroy(plan);
         AAT_REQUIRE(false, AAT_ERR_CUDA, "aat_plan_create: out of device memory");
     }
