@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaat_b200.so")
+LIB_PATH = os.environ.get("AAT_B200_LIB") or os.path.join(_HERE, "libaat_b200.so")  # override: profiles/ experiments
 CSRC_DIR = os.path.join(os.path.dirname(_HERE), "csrc")
 
 AAT_OK = 0

@@ -58,6 +58,12 @@ constexpr int kStageBytes = 24 * 1024; // 8 rows of 768 fp32, 6 rows of 1024 fp3
 constexpr int kMaxConsumers = 256;
 constexpr int kMaxSlabs = 4; // 16-byte column slabs per consumer thread -> dim*e <= 16 KB
 constexpr int kMaxCtasPerSm = 2;
+// stages requested before the dependency wait (<= kStages); measured at config 2: 1 -> 0.1907 ms/step, 2 -> 0.1899,
+// 4 -> 0.1895, and the event-timed kernel alone is no slower (gpurun b18)
+#ifndef AAT_POOL_PRE_STAGES
+#define AAT_POOL_PRE_STAGES 4
+#endif
+constexpr int kPreStages = AAT_POOL_PRE_STAGES;
 constexpr int kOffCache = 256; // segment offsets of the CTA's neighbourhood kept in shared memory
 
 // ---------------------------------------------------------------- PTX helpers (mbarrier + bulk copy)
@@ -292,11 +298,13 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
         mbar_expect_tx(&s_full[s], bytes);
         bulk_g2s(smem_raw + s * stage_stride, p.emb + (size_t)row * p.row_bytes, bytes, &s_full[s]);
     };
-    // The embedding rows are not written by the kernel in front of this one (the boundary scan), so the first stage
+    // The embedding rows are not written by the kernel in front of this one (the boundary scan), so the whole ring
     // is requested before the dependency wait: under programmatic dependent launch it lands while that kernel is
     // still running.  Segment offsets and counts are its outputs and are only touched after the wait.
     const bool producer = tid == n_consumers;
-    if (producer && r0 < r1) issue_stage(0);
+    const int64_t n_pre = n_chunks < kPreStages ? n_chunks : kPreStages;
+    if (producer)
+        for (int64_t ch = 0; ch < n_pre; ++ch) issue_stage(ch);
     pdl_wait();
     pdl_launch_dependents();
     const int64_t S_total = p.n_seg_dev ? min(*p.n_seg_dev, p.n_seg) : p.n_seg;
@@ -305,7 +313,7 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
         // ============================== producer warp ==============================
         const int lane = tid - n_consumers;
         if (lane == 0 && r0 < r1 && S_total <= 0) {
-            mbar_wait(&s_full[0], 0); // nothing to pool: let the speculative first stage land before the CTA exits
+            for (int64_t ch = 0; ch < n_pre; ++ch) mbar_wait(&s_full[ch], 0); // nothing to pool: let the speculative stages land
         } else if (lane == 0 && r0 < r1) {
             // the offsets window goes ahead of the bulk of the stream: a plain load issued later would queue behind
             // ~28 MB of bulk traffic from all CTAs and take 3.5-6 us (profiles/r1_pool_timeline_before.txt)
@@ -314,7 +322,7 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
                 mbar_expect_tx(&s_offbar, (uint32_t)(w.count * sizeof(int64_t)));
                 bulk_g2s(s_off, p.seg_off + w.first, (uint32_t)(w.count * sizeof(int64_t)), &s_offbar);
             }
-            for (int64_t ch = 1; ch < n_chunks; ++ch) {
+            for (int64_t ch = n_pre; ch < n_chunks; ++ch) {
                 const int64_t use = ch / kStages;
                 if (use > 0) mbar_wait(&s_empty[(int)(ch % kStages)], (uint32_t)((use - 1) & 1));
                 issue_stage(ch);
