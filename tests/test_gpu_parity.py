@@ -433,6 +433,98 @@ def test_pipeline_replays_in_a_cuda_graph(tok):
         assert torch.equal(out[:n_seg], want) and torch.equal(batch.seg_len, want_len)
 
 
+def test_back_to_back_steps_match_synchronised_steps(tok):
+    """The kernels of a step overlap each other's tails (programmatic dependent launch), the log-mel kernel takes its
+    tiles from a self-resetting counter and the boundary kernel builds the CSR by look-back over self-clearing words:
+    a loop of steps enqueued without any synchronisation, on rotating inputs, must give exactly what the same steps
+    give when every kernel is followed by a device synchronisation."""
+    import torch
+
+    from aat_b200 import synth
+    from aat_b200.pooling import DatasetMean
+
+    lengths = [48000, 160000, 3000, 96000, 256000, 20000, 131072, 64000]
+    sets = []
+    for k in range(3):
+        waves = [synth.bursty_speech(n, 4000 + 17 * k + i) for i, n in enumerate(lengths)]
+        sets.append(torch.from_numpy(np.concatenate(waves)).cuda())
+    batch = tok.plan(lengths)
+    dim = 256
+    # reference pass: one kernel at a time
+    want = []
+    embs = []
+    for k, wave in enumerate(sets):
+        batch.logmel(wave)
+        torch.cuda.synchronize()
+        batch.boundaries()
+        torch.cuda.synchronize()
+        n_seg = int(batch.n_seg.item())
+        n_rows = int(batch.seg_off[n_seg].item())
+        g = torch.Generator(device="cuda").manual_seed(k)
+        emb = torch.randn(n_rows + 64, dim, device="cuda", generator=g)  # a few rows after the last segment
+        embs.append(emb)
+        out = torch.zeros(batch.total_seg_slots, dim, device="cuda")
+        cs = torch.zeros(dim + 1, dtype=torch.float64, device="cuda")
+        batch.pool(emb, out, colsum=cs)
+        torch.cuda.synchronize()
+        want.append((batch.mel.clone(), batch.seg_len.clone(), batch.seg_count.clone(), batch.seg_off[: n_seg + 1].clone(),
+                     out[:n_seg].clone(), cs.clone(), n_seg))
+    # free-running loop: 12 steps back to back, results copied out on the same stream
+    got = []
+    outs = [torch.zeros(batch.total_seg_slots, dim, device="cuda") for _ in range(12)]
+    css = [torch.zeros(dim + 1, dtype=torch.float64, device="cuda") for _ in range(12)]
+    for it in range(12):
+        k = it % 3
+        batch.logmel(sets[k])
+        batch.boundaries()
+        batch.pool(embs[k], outs[it], colsum=css[it])
+        got.append((batch.mel.clone(), batch.seg_len.clone(), batch.seg_count.clone(), batch.seg_off.clone(), batch.n_seg.clone()))
+    torch.cuda.synchronize()
+    for it in range(12):
+        mel, seg_len, seg_count, seg_off, out, cs, n_seg = want[it % 3]
+        g_mel, g_len, g_count, g_off, g_nseg = got[it]
+        assert int(g_nseg.item()) == n_seg, it
+        assert torch.equal(g_mel, mel) and torch.equal(g_count, seg_count), it
+        assert torch.equal(g_off[: n_seg + 1], seg_off), it
+        for b in range(len(lengths)):
+            o, c = int(batch.seg_slot_off[b]), int(seg_count[b].item())
+            assert torch.equal(g_len[o: o + c], seg_len[o: o + c]), (it, b)
+        assert torch.equal(outs[it][:n_seg], out), it
+        assert torch.equal(css[it], cs), it
+    # nothing but the library's kernels on the stream: reduce(i) -> logmel(i + 1) overlap as well
+    acc = torch.zeros(dim + 1, dtype=torch.float64, device="cuda")
+    out = torch.zeros(batch.total_seg_slots, dim, device="cuda")
+    for it in range(9):
+        k = it % 3
+        batch.logmel(sets[k])
+        batch.boundaries()
+        batch.pool(embs[k], out, colsum=acc, accumulate=True)
+    torch.cuda.synchronize()
+    mel, seg_len, seg_count, seg_off, ref_out, cs, n_seg = want[2]
+    assert int(batch.n_seg.item()) == n_seg and torch.equal(batch.mel, mel)
+    assert torch.equal(batch.seg_off[: n_seg + 1], seg_off) and torch.equal(out[:n_seg], ref_out)
+    total = 3.0 * (want[0][5] + want[1][5] + want[2][5])
+    assert torch.allclose(acc, total, rtol=1e-12, atol=0.0)
+
+
+def test_profile_sampling_records_every_nth_launch(tok):
+    import torch
+
+    from aat_b200 import _cabi, synth
+
+    lengths = [32000] * 4
+    batch = tok.plan(lengths)
+    wave = batch.pack([torch.from_numpy(synth.bursty_speech(n, 60 + i)) for i, n in enumerate(lengths)])
+    _cabi.profile_enable(batch.ctx.handle, ("logmel", "boundaries"), every=4)
+    for _ in range(10):
+        batch.logmel(wave), batch.boundaries()
+    torch.cuda.synchronize()
+    prof = _cabi.profile_summary(batch.ctx.handle)
+    _cabi.profile_enable(batch.ctx.handle, ())
+    assert prof["logmel"][0] == 3 and prof["boundaries"][0] == 3 and prof["pool"][0] == 0
+    assert prof["logmel"][1] > 0.0
+
+
 # ----------------------------------------------------------------------------------------- full-size properties
 def test_config2_full_size_properties(tok):
     """BASELINE config 2 (64 x 16 s, D = 768): size-independent properties on the whole batch plus
