@@ -66,6 +66,21 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b)
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
+// double(float(x)) without the two conversions: they run on the 16-lane XU path (8.3 + 5.9 issue cycles per scheduler,
+// 23 + 19 cycles of latency, profiles/r1_ubench_fp64.txt) while the FP64 pipe has room.  Veltkamp's splitting with
+// C = 2^29 + 1 returns x rounded to nearest on 24 significant bits (three dependent FP64 operations).  It differs from
+// the conversion pair only for exact ties (2^-29 of the values, where it may round away from even) and outside
+// float32's normal range (|x| < 1.2e-38: the squared magnitude is then below the mel floor by 60 orders of magnitude).
+__device__ __forceinline__ double round_to_float(double x)
+{
+#ifdef AAT_LOGMEL_F2F
+    return (double)(float)x;
+#else
+    const double g = __dmul_rn(x, 536870913.0);
+    return __dadd_rn(g, __dsub_rn(x, g));
+#endif
+}
+
 // 20-point forward DFT in registers, Good-Thomas 4 x 5:
 //   n = (5 n1 + 4 n2) mod 20,  k = (5 k1 + 16 k2) mod 20,  X[k] = sum x[n] W4^(n1 k1) W5^(n2 k2)
 __device__ __forceinline__ void dft20(double2 (&v)[20], const LogmelConsts &K)
@@ -442,10 +457,10 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
                     else
                         y = mir[19 - j];
                     // X_a = (z + conj y), X_b = (z - conj y) / i   (the 1/2 lives in the window table)
-                    const float ar = (float)(z.x + y.x), ai = (float)(z.y - y.y);
-                    const float br = (float)(z.y + y.y), bi = (float)(y.x - z.x);
-                    pa[j] = (double)ar * (double)ar + (double)ai * (double)ai;
-                    pb[j] = (double)br * (double)br + (double)bi * (double)bi;
+                    const double ar = round_to_float(z.x + y.x), ai = round_to_float(z.y - y.y);
+                    const double br = round_to_float(z.y + y.y), bi = round_to_float(y.x - z.x);
+                    pa[j] = ar * ar + ai * ai;
+                    pb[j] = br * br + bi * bi;
                 }
             }
             __syncthreads(); // every thread has read its mirror values: overlay the matrix with the power spectra
