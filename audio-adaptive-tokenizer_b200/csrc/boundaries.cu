@@ -248,9 +248,20 @@ __device__ unsigned long long g_bnd_trace[256 * 32];
             g_bnd_trace[blockIdx.x * 32 + (slot)] = t__;                                       \
         }                                                                                      \
     } while (0)
+#define BND_TRACE_ANY(slot)                                                                    \
+    do {                                                                                       \
+        if (blockIdx.x < 256 && (slot) < 32) {                                                 \
+            unsigned long long t__;                                                            \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                            \
+            g_bnd_trace[blockIdx.x * 32 + (slot)] = t__;                                       \
+        }                                                                                      \
+    } while (0)
 #else
 #define BND_TRACE(slot) \
     do {                \
+    } while (0)
+#define BND_TRACE_ANY(slot) \
+    do {                    \
     } while (0)
 #endif
 
@@ -440,6 +451,7 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel_t(const BoundaryPa
             // ---------------- emit: chunk it - 3 ----------------
             const int64_t c = it - 3;
             if (c >= 0 && c < n_chunks) {
+                BND_TRACE_ANY(10 + 2 * (int)c); // merge/split thread: start of chunk c
                 const int found = s_found[c & 1];
                 const int *mq = s_min + (c & 1) * kChunk;
                 if (narrow) {
@@ -452,6 +464,7 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel_t(const BoundaryPa
                                               capacity, st64);
                 }
                 n_minima += found;
+                BND_TRACE_ANY(11 + 2 * (int)c); // ... end of chunk c
             }
         }
         __syncthreads();

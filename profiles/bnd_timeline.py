@@ -49,6 +49,13 @@ def main():
         if rel[0, 0, 2 + it] <= 0:
             break
         row(f"end of pipeline iteration {it}", 2 + it)
+    for c in range(8):
+        if rel[0, 0, 10 + 2 * c] <= 0:
+            break
+        v = rel[:, :, 11 + 2 * c] - rel[:, :, 10 + 2 * c]
+        st = rel[:, :, 10 + 2 * c]
+        print(f"merge/split thread, chunk {c}: starts {np.median(np.median(st, 1)):6.2f} us, takes "
+              f"{np.median(v.min(1)):5.2f} / {np.median(np.median(v, 1)):5.2f} / {np.median(v.max(1)):5.2f} us (min / median / max over CTAs)")
     row("segments written", 28)
     row("ticket / CSR rebase done", 29)
 
