@@ -202,6 +202,128 @@ __device__ void build_frame_csr(int n_utts, const int64_t *seg_slot_off, const i
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Two-phase form of the merge/split loop used by the boundary kernel.  The decisions are sequential in `prev`
+// (ref:src/aat/tokenizer.py:154-175), but writing a segment — three 64-bit stores with their address arithmetic, the
+// HuBERT frame count, the running frame offset — is not: done by the deciding thread it cost ~40 dependent
+// instructions per boarder (2.1 us per 512-frame chunk, the bottleneck stage of the pipeline,
+// profiles/r1_bnd_timeline_lookback.txt).  Now lane 0 of the emit warp only appends (start, length) pairs to a
+// shared-memory queue, and the whole warp writes the queue out: coalesced stores, frame offsets by a warp scan.
+constexpr int kSegQueue = 128; // (start, length) pairs per flush
+
+template <typename I>
+struct MergeSplit {
+    I prev = 0;       // last accepted boarder
+    // np.split of one over-long gap, resumable across queue flushes (pieces j = 0 .. n_cuts)
+    bool splitting = false;
+    I len = 0, k = 0, last_cut = 0, lo = 0, j = 0, n_cuts = 0, pending = 0;
+};
+
+// Appends segments to q[n ...] until the queue is full or the boarders [i, found) are used up; returns the new n.
+// next(i) yields boarder i in samples.
+template <typename I, typename Next>
+__device__ __forceinline__ int fill_segment_queue(MergeSplit<I> &ms, int &i, const int found, Next next, const I min_frames,
+                                                  const I max_frames, longlong2 *q)
+{
+    int n = 0;
+    // fast path: boarders that are merged or accepted whole — no data-dependent branch (a lone warp pays ~20 cycles
+    // for every taken one): the pair is stored unconditionally and the queue length advances only when it is accepted
+    if (!ms.splitting) {
+        I prev = ms.prev;
+        bool long_gap = false;
+        auto step = [&](const I b) { // false: over-long gap, the resumable loop below cuts it up
+            const I len = b - prev;
+            if (len > max_frames) return false;
+            const bool accept = len >= min_frames;
+            q[n] = make_longlong2((long long)prev, (long long)len);
+            n += accept ? 1 : 0;
+            prev = accept ? b : prev;
+            ++i;
+            return true;
+        };
+        // four boarders per trip: their loads are independent of the decisions and issue together
+        while (i + 4 <= found && n + 4 <= kSegQueue) {
+            const I b0 = next(i), b1 = next(i + 1), b2 = next(i + 2), b3 = next(i + 3);
+            if (!(step(b0) && step(b1) && step(b2) && step(b3))) {
+                long_gap = true;
+                break;
+            }
+        }
+        while (!long_gap && i < found && n < kSegQueue)
+            if (!step(next(i))) break;
+        ms.prev = prev;
+    }
+    while (n < kSegQueue) {
+        if (ms.splitting) { // np.split: a[lo:c] with Python slice clamping, then the remainder
+            if (ms.j < ms.n_cuts) {
+                const I c = (ms.j == ms.k - 1) ? ms.last_cut : (I)((ms.j + 1) * max_frames);
+                const I a0 = ms.lo < ms.len ? ms.lo : ms.len;
+                const I a1 = c < ms.len ? c : ms.len;
+                q[n++] = make_longlong2((long long)(ms.prev + a0), (long long)(a1 > a0 ? (I)(a1 - a0) : (I)0));
+                ms.lo = c;
+                ++ms.j;
+            } else {
+                const I a0 = ms.lo < ms.len ? ms.lo : ms.len;
+                q[n++] = make_longlong2((long long)(ms.prev + a0), (long long)(ms.len - a0));
+                ms.prev = ms.pending;
+                ms.splitting = false;
+            }
+            continue;
+        }
+        if (i == found) break;
+        const I b = next(i++);
+        const I len = b - ms.prev;
+        if (len < min_frames) continue; // merge forward: prev stays
+        if (len > max_frames) {
+            ms.len = len;
+            ms.k = len / max_frames;
+            const I gap = len - ms.k * max_frames;
+            ms.n_cuts = ms.k;
+            ms.last_cut = ms.k * max_frames;
+            if (gap == 0)
+                ms.n_cuts = ms.k - 1; // drop last empty segment
+            else if (gap < min_frames)
+                ms.last_cut = len - min_frames; // may fall below the previous cut when min > max
+            ms.lo = 0, ms.j = 0, ms.pending = b;
+            ms.splitting = true;
+            continue;
+        }
+        q[n++] = make_longlong2((long long)ms.prev, (long long)len);
+        ms.prev = b;
+    }
+    return n;
+}
+
+// The whole warp writes q[0, n) behind the `count` segments already out; count / frames / status are warp-uniform.
+__device__ __forceinline__ void flush_segment_queue(const longlong2 *q, const int n, const int lane, int64_t *seg_start,
+                                                    int64_t *seg_len, int64_t *local, const int64_t capacity, int64_t &count,
+                                                    int64_t &frames, int32_t &status)
+{
+    for (int base = 0; base < n; base += 32) {
+        const int idx = base + lane;
+        const int64_t slot = count + idx;
+        const bool live = idx < n && slot < capacity;
+        longlong2 e = make_longlong2(0, 0);
+        if (idx < n) e = q[idx];
+        const int64_t fr = live ? hubert_frames((int64_t)e.y) : 0;
+        int64_t incl = fr;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int64_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (live) {
+            seg_start[slot] = e.x;
+            seg_len[slot] = e.y;
+            if (local) local[slot] = frames + incl - fr;
+        }
+        frames += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    count += n;
+    if (count > capacity) status = AAT_ERR_CAPACITY;
+}
+
 struct BoundaryParams {
     const float *mel;
     const float *amp;
@@ -274,6 +396,8 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel_t(const BoundaryPa
     float *s_amp = reinterpret_cast<float *>(smem_raw);          // [2][kChunk]
     float *s_cs = s_amp + 2 * kChunk;                             // [kRing]: cs index g lives at s_cs[g & (kRing - 1)]
     int *s_min = reinterpret_cast<int *>(s_cs + kRing);           // [2][kChunk] minima (global frame index) per chunk
+    longlong2 *s_queue = reinterpret_cast<longlong2 *>(s_min + 2 * kChunk); // [kSegQueue] segments waiting to be written
+    __shared__ int s_qctl[2]; // queue length, "chunk done" of the emit warp's current round
     __shared__ int s_wcount[kWorkers / 32];
     __shared__ int s_found[2];
     __shared__ int64_t s_total[2]; // this utterance's segment count and frame total (emit thread -> epilogue)
@@ -322,8 +446,33 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel_t(const BoundaryPa
     int64_t *local_ptr = p.seg_off ? p.seg_local + slot0 : nullptr;
     const int64_t kLim = 0x3fffffffLL;
     const bool narrow = n < kLim && p.min_frames < kLim && p.max_frames < kLim && capacity < kLim;
-    SegStateT<int32_t> st32{0, 0, 0, 0, local_ptr};
-    SegStateT<int64_t> st64{0, 0, 0, 0, local_ptr};
+    MergeSplit<int32_t> ms32;
+    MergeSplit<int64_t> ms64;
+    int64_t seg_written = 0, seg_frames = 0; // emit warp: segments out so far and their HuBERT frames (warp-uniform)
+    int32_t seg_status = 0;
+    const int emit_lane = tid - kEmitThread; // 0..31 in the emit warp
+    // One round of the emit warp: lane 0 decides (queue), the warp writes; repeated until the boarders are used up.
+    auto emit_round = [&](const int found, auto next32, auto next64) {
+        int i = 0;
+        for (;;) {
+            if (emit_lane == 0) {
+                int nq;
+                if (narrow)
+                    nq = fill_segment_queue<int32_t>(ms32, i, found, next32, (int32_t)p.min_frames, (int32_t)p.max_frames, s_queue);
+                else
+                    nq = fill_segment_queue<int64_t>(ms64, i, found, next64, p.min_frames, p.max_frames, s_queue);
+                s_qctl[0] = nq;
+                s_qctl[1] = (i == found) && !(narrow ? ms32.splitting : ms64.splitting);
+            }
+            __syncwarp();
+            const int nq = s_qctl[0];
+            const int done = s_qctl[1];
+            flush_segment_queue(s_queue, nq, emit_lane, seg_start, seg_len, local_ptr, capacity, seg_written, seg_frames,
+                                seg_status);
+            __syncwarp();
+            if (done) break;
+        }
+    };
     int64_t n_minima = 0;                                                // workers and emit thread keep their own copy
     float run = 0.0f;                                                    // scan thread's carry
 
@@ -447,43 +596,43 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel_t(const BoundaryPa
                 }
                 if (amp_in) prefetch(it + 1);
             }
-        } else if (tid == kEmitThread) {
-            // ---------------- emit: chunk it - 3 ----------------
+        } else if (tid >= kEmitThread) {
+            // ---------------- emit: chunk it - 3 (warp 7) ----------------
             const int64_t c = it - 3;
             if (c >= 0 && c < n_chunks) {
-                BND_TRACE_ANY(10 + 2 * (int)c); // merge/split thread: start of chunk c
+                if (emit_lane == 0) BND_TRACE_ANY(10 + 2 * (int)c); // merge/split: start of chunk c
                 const int found = s_found[c & 1];
                 const int *mq = s_min + (c & 1) * kChunk;
-                if (narrow) {
-                    const int32_t mn = (int32_t)p.min_frames, mx = (int32_t)p.max_frames, cap = (int32_t)capacity;
-                    for (int i = 0; i < found; ++i)
-                        push_boarder<int32_t>(mq[i] * p.hop, mn, mx, seg_start, seg_len, cap, st32);
-                } else {
-                    for (int i = 0; i < found; ++i)
-                        push_boarder<int64_t>((int64_t)mq[i] * p.hop, p.min_frames, p.max_frames, seg_start, seg_len,
-                                              capacity, st64);
-                }
+                emit_round(found, [&](int i) { return (int32_t)(mq[i] * p.hop); },
+                           [&](int i) { return (int64_t)mq[i] * p.hop; });
                 n_minima += found;
-                BND_TRACE_ANY(11 + 2 * (int)c); // ... end of chunk c
+                if (emit_lane == 0) BND_TRACE_ANY(11 + 2 * (int)c); // ... end of chunk c
             }
         }
         __syncthreads();
         BND_TRACE(2 + (int)it); // end of pipeline iteration `it`
     }
 
-    if (tid == kEmitThread) {
-        int64_t count, frames;
-        int32_t status;
-        if (narrow) {
-            const int32_t mn = (int32_t)p.min_frames, mx = (int32_t)p.max_frames, cap = (int32_t)capacity;
-            push_boarder<int32_t>((int32_t)n, mn, mx, seg_start, seg_len, cap, st32); // ref:src/aat/tokenizer.py:137
-            finish_segments<int32_t>((int32_t)n, mn, seg_start, seg_len, cap, st32);
-            count = st32.count, frames = st32.frames, status = st32.status;
-        } else {
-            push_boarder<int64_t>(n, p.min_frames, p.max_frames, seg_start, seg_len, capacity, st64);
-            finish_segments<int64_t>(n, p.min_frames, seg_start, seg_len, capacity, st64);
-            count = st64.count, frames = st64.frames, status = st64.status;
+    if (tid >= kEmitThread) {
+        // the end of the waveform is the last boarder (ref:src/aat/tokenizer.py:137), then the zero-padded tail of
+        // min_segment_frames samples (ref:src/aat/tokenizer.py:177-181)
+        if (emit_lane == 0) BND_TRACE_ANY(20);
+        emit_round(1, [&](int) { return (int32_t)n; }, [&](int) { return n; });
+        if (emit_lane == 0) BND_TRACE_ANY(21);
+        // only lane 0 ran the merge/split decisions: the last accepted boarder lives in its registers
+        const int64_t prev = __shfl_sync(0xffffffffu, narrow ? (int64_t)ms32.prev : ms64.prev, 0);
+        if (prev != n) {
+            if (seg_status == 0) seg_status = (n - prev > p.min_frames) ? AAT_ERR_TAIL : 1;
+            if (emit_lane == 0) s_queue[0] = make_longlong2((long long)prev, (long long)p.min_frames);
+            __syncwarp();
+            flush_segment_queue(s_queue, 1, emit_lane, seg_start, seg_len, local_ptr, capacity, seg_written, seg_frames,
+                                seg_status);
         }
+    }
+    if (tid == kEmitThread) {
+        BND_TRACE_ANY(22);
+        const int64_t count = seg_written, frames = seg_frames;
+        const int32_t status = seg_status;
         p.seg_count[utt] = (int32_t)(count < capacity ? count : capacity);
         if (p.minima_count) p.minima_count[utt] = (int32_t)n_minima;
         p.status[utt] = status;
@@ -502,15 +651,16 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel_t(const BoundaryPa
     // writes its own slice of seg_off.  No CTA does serial work for the others: the epilogue costs one round trip
     // after the slowest utterance instead of a rebase pass by the last CTA (6 us at 64 utterances,
     // profiles/r1_bnd_timeline.txt).  The last CTA through the ticket clears the words for the next launch.
+    if (tid == kEmitThread) BND_TRACE_ANY(23);
     if (p.seg_off != nullptr) {
         __shared__ int64_t s_wsum[2][kThreads / 32];
         __shared__ int s_last;
         int64_t cnt = 0, frm = 0;
         for (int b = tid; b < utt; b += kThreads) {
             unsigned long long v;
-            do {
-                v = ld_relaxed_u64(p.utt_totals + b);
-            } while (!(v & kTotalsReady));
+            // back off between polls: thousands of threads spinning on the same few L2 lines delay the very stores they
+            // are waiting for (the last word took 3.8 us to be seen without it)
+            while (!((v = ld_relaxed_u64(p.utt_totals + b)) & kTotalsReady)) __nanosleep(100);
             cnt += (int64_t)(v & 0xffffffffull);
             frm += (int64_t)((v >> 32) & 0x7fffffffull);
         }
@@ -618,7 +768,8 @@ int launch_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel, cons
     p.utt_seg_off = utt_seg_off;
     p.seg_local = plan->d_seg_local;
     p.utt_totals = reinterpret_cast<unsigned long long *>(plan->d_utt_frames);
-    const size_t smem = sizeof(float) * (size_t)(2 * chunk + kRing) + sizeof(int) * (size_t)(2 * chunk);
+    const size_t smem = sizeof(float) * (size_t)(2 * chunk + kRing) + sizeof(int) * (size_t)(2 * chunk) +
+                        sizeof(longlong2) * (size_t)kSegQueue;
     auto kernel = boundaries_kernel_t<kChunk>;
     AAT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AAT_MAX_SMEM_CARVEOUT(kernel);

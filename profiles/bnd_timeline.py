@@ -56,8 +56,12 @@ def main():
         st = rel[:, :, 10 + 2 * c]
         print(f"merge/split thread, chunk {c}: starts {np.median(np.median(st, 1)):6.2f} us, takes "
               f"{np.median(v.min(1)):5.2f} / {np.median(np.median(v, 1)):5.2f} / {np.median(v.max(1)):5.2f} us (min / median / max over CTAs)")
-    row("segments written", 28)
-    row("ticket / CSR rebase done", 29)
+    row("emit warp: pipeline left", 20)
+    row("emit warp: last boarder done", 21)
+    row("emit warp: tail segment done", 22)
+    row("emit warp: totals published", 23)
+    row("look-back done", 28)
+    row("CSR slice written, ticket taken", 29)
 
 
 if __name__ == "__main__":
