@@ -482,6 +482,7 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel_t(const BoundaryPa
             // ---------------- scan: chunk it - 1 ----------------
             const int64_t c = it - 1;
             if (c >= 0 && c < n_chunks) {
+                if (c == 1) BND_TRACE_ANY(24); // scan of chunk 1 starts
                 const int64_t j0 = c * kChunk;
                 const int len = (int)(((j0 + kChunk < T) ? j0 + kChunk : T) - j0);
                 const float *src_s = s_amp + (c & 1) * kChunk;
@@ -510,6 +511,7 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel_t(const BoundaryPa
                     run = __fadd_rn(run, src_s[i]);
                     dst_s[i] = run;
                 }
+                if (c == 1) BND_TRACE_ANY(25); // ... ends
             }
         } else if (tid >= 32 && tid < 32 + kWorkers) {
             const int w = tid - 32;
@@ -517,6 +519,7 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel_t(const BoundaryPa
             {
                 const int64_t c = it - 2;
                 if (c >= 0 && c < n_chunks) {
+                    if (c == 1 && w == 0) BND_TRACE_ANY(26); // test of chunk 1 starts
                     const int64_t lo = (c == 0) ? 1 : cand_hi(c - 1);
                     const int64_t hi = cand_hi(c);
                     const int64_t range = hi > lo ? hi - lo : 0;
@@ -566,6 +569,7 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel_t(const BoundaryPa
                     if (w == 0) s_found[c & 1] = total;
                     n_minima += total;
                     worker_barrier(); // s_wcount is reused next iteration
+                    if (c == 1 && w == 0) BND_TRACE_ANY(27); // ... ends
                 }
             }
             // ---------------- load: chunk it ----------------
@@ -595,6 +599,7 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel_t(const BoundaryPa
                     }
                 }
                 if (amp_in) prefetch(it + 1);
+                if (it == 3 && w == 0) BND_TRACE_ANY(9); // workers done with iteration 3 (test chunk 1, load chunk 3)
             }
         } else if (tid >= kEmitThread) {
             // ---------------- emit: chunk it - 3 (warp 7) ----------------

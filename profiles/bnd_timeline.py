@@ -56,6 +56,10 @@ def main():
         st = rel[:, :, 10 + 2 * c]
         print(f"merge/split thread, chunk {c}: starts {np.median(np.median(st, 1)):6.2f} us, takes "
               f"{np.median(v.min(1)):5.2f} / {np.median(np.median(v, 1)):5.2f} / {np.median(v.max(1)):5.2f} us (min / median / max over CTAs)")
+    for name, a, b in (("scan thread, chunk 1 (512 frames)", 24, 25), ("worker warps, test of chunk 1", 26, 27),
+                       ("worker warps, test of chunk 1 + load of chunk 3", 26, 9)):
+        v = rel[:, :, b] - rel[:, :, a]
+        print(f"{name}: {np.median(v.min(1)):5.2f} / {np.median(np.median(v, 1)):5.2f} / {np.median(v.max(1)):5.2f} us (min / median / max over CTAs)")
     row("emit warp: pipeline left", 20)
     row("emit warp: last boarder done", 21)
     row("emit warp: tail segment done", 22)
