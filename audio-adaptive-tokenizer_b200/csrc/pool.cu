@@ -53,17 +53,19 @@ __device__ __forceinline__ unsigned long long trace_now()
     } while (0)
 #endif
 
-constexpr int kStages = 4;
-constexpr int kStageBytes = 24 * 1024; // 8 rows of 768 fp32, 6 rows of 1024 fp32
+#ifndef AAT_POOL_STAGES
+#define AAT_POOL_STAGES 4
+#define AAT_POOL_STAGE_KB 24
+#define AAT_POOL_CTAS 2
+#endif
+constexpr int kStages = AAT_POOL_STAGES;
+constexpr int kStageBytes = AAT_POOL_STAGE_KB * 1024; // 24 KB: 8 rows of 768 fp32, 6 rows of 1024 fp32
 constexpr int kMaxConsumers = 256;
 constexpr int kMaxSlabs = 4; // 16-byte column slabs per consumer thread -> dim*e <= 16 KB
-constexpr int kMaxCtasPerSm = 2;
+constexpr int kMaxCtasPerSm = AAT_POOL_CTAS;
 // stages requested before the dependency wait (<= kStages); measured at config 2: 1 -> 0.1907 ms/step, 2 -> 0.1899,
 // 4 -> 0.1895, and the event-timed kernel alone is no slower (gpurun b18)
-#ifndef AAT_POOL_PRE_STAGES
-#define AAT_POOL_PRE_STAGES 4
-#endif
-constexpr int kPreStages = AAT_POOL_PRE_STAGES;
+constexpr int kPreStages = kStages;
 constexpr int kOffCache = 256; // segment offsets of the CTA's neighbourhood kept in shared memory
 
 // ---------------------------------------------------------------- PTX helpers (mbarrier + bulk copy)

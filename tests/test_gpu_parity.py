@@ -687,6 +687,31 @@ def test_non_default_configurations_match_oracle(kwargs):
         assert boarders == ref.pretokenize(wave)[0]
 
 
+@pytest.mark.parametrize("kwargs, n, kind", [
+    (dict(min_segment_duration_milliseconds=10, max_segment_duration_milliseconds=20), 960000, "speech"),
+    (dict(min_segment_duration_milliseconds=10, max_segment_duration_milliseconds=50), 1920000, "silence"),
+    (dict(min_segment_duration_milliseconds=30, max_segment_duration_milliseconds=35), 480000, "speech"),
+    (dict(min_segment_duration_milliseconds=40, max_segment_duration_milliseconds=25), 320000, "speech"),  # min > max
+])
+def test_many_segments_per_chunk_and_long_splits(kwargs, n, kind):
+    """The boundary kernel queues segments in shared memory (128 per flush) and cuts over-long gaps with a resumable
+    np.split: short durations make one 512-frame chunk overflow the queue several times, and a silent stretch makes
+    ONE boarder produce thousands of pieces across many flushes."""
+    from aat_b200 import AdaptiveAudioAmplitudeTokenizer, synth
+    from oracle import ref_port
+
+    tok = AdaptiveAudioAmplitudeTokenizer(**kwargs)
+    ref = ref_port.RefTokenizer(**kwargs)
+    wave = synth.bursty_speech(n, 77) if kind == "speech" else np.zeros(n, dtype=np.float32)
+    if kind == "silence":
+        wave[:16000] = synth.bursty_speech(16000, 78)  # a second of sound, then nothing
+    want_mel = ref.get_melspec(wave)
+    want_lengths, _, _ = ref.segment_lengths(wave, melspec=want_mel)
+    got = tok.segment_lengths(wave, melspec=want_mel).tolist()
+    assert len(want_lengths) > 800
+    assert got == want_lengths
+
+
 def test_unsupported_fft_length_raises_not_implemented():
     from aat_b200 import AdaptiveAudioAmplitudeTokenizer
 
