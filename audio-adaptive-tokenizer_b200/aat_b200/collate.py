@@ -144,3 +144,44 @@ def uniform_segment_lengths(n_samples: int, frames_per_segment: int):
     if n_samples % frames_per_segment > 0:
         lengths.append(n_samples - sum(lengths))
     return np.asarray(lengths, dtype=np.int64)
+
+
+def crop_to_words(frames_boarders_raw, word_start, word_end, word_start_idx: int, n_words: int, sampling_rate: int,
+                  hop_length: int, running_mean_points: int, n_samples: int, n_mel_frames: int,
+                  melspec_overlapping: int = 5):
+    """The collator's n-word cropping (ref:src/aat/training/collate.py:169-212) as a pure function of the segment
+    lengths: which segments, waveform samples and mel frames survive when ``n_words`` consecutive words starting at
+    ``word_start_idx`` (the reference draws it with ``random.randint(0, len(words) - n_words)``, :176) are kept.
+
+    frames_boarders_raw : segment lengths in samples (their sum must be ``n_samples``, the reference asserts it, :172)
+    word_start, word_end: per-word times in seconds (``item['word_start']`` / ``item['word_end']``)
+
+    Returns ``(frames_boarders, (wave_lo, wave_hi), (mel_lo, mel_hi), (word_lo, word_hi))``: the boarders of the kept
+    segments rebased to the first kept segment (leading zero cut off, :197-199), the half-open waveform slice widened
+    by ``melspec_overlapping`` hops each side (:203-206), the mel slice widened by the running-mean window on the left
+    (:208-211), and the word range.  Host integers only — there is nothing here for a GPU to accelerate; the outputs
+    are what ``scatter_segments`` / ``scatter_mel_segments`` are then fed with."""
+    import numpy as np
+
+    raw = np.asarray(frames_boarders_raw, dtype=np.int64)
+    if int(raw.sum()) != int(n_samples):
+        raise AssertionError("segment lengths must add up to the waveform length (ref:src/aat/training/collate.py:172)")
+    boarders = raw.cumsum()
+    word_end_idx = word_start_idx + n_words
+    start_frame = int(word_start[word_start_idx] * sampling_rate)
+    end_frame = int(word_end[word_end_idx - 1] * sampling_rate)
+    with_zero = np.insert(boarders, 0, [0])
+    first = max(int(np.searchsorted(with_zero, start_frame)) - 1, 0)
+    last = int(np.searchsorted(with_zero, end_frame, side="right"))
+    if not last < len(with_zero):
+        raise AssertionError("the last word ends after the last segment (ref:src/aat/training/collate.py:186)")
+    seg_lo, seg_hi = int(with_zero[first]), int(with_zero[last])
+    if not (seg_lo <= start_frame and seg_hi >= end_frame):
+        raise AssertionError("the kept segments do not cover the kept words (ref:src/aat/training/collate.py:189-192)")
+    kept = with_zero[first: last + 1] - seg_lo
+    overlap = melspec_overlapping * hop_length
+    wave_lo = max(0, seg_lo - overlap)
+    wave_hi = min(seg_hi + overlap, int(n_samples))
+    mel_lo = max(0, wave_lo // hop_length - running_mean_points - melspec_overlapping)
+    mel_hi = min(wave_hi // hop_length + melspec_overlapping, int(n_mel_frames))
+    return kept[1:], (wave_lo, wave_hi), (mel_lo, mel_hi), (word_start_idx, word_end_idx)

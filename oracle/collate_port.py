@@ -75,3 +75,43 @@ def masked_mean_pool(audio_embeds, audio_embeds_attention_mask):
     n = m.sum(dim=1)
     out = torch.where(n > 0, s / n.clamp(min=1), torch.zeros_like(s))
     return out, (audio_embeds_attention_mask != 0).any(dim=-1).long()
+
+
+def crop_to_words(waveform, melspec, frames_boarders_raw, words, word_start, word_end, word_start_idx, n_words, sampling_rate,
+                  hop_length, running_mean_points):
+    """ref:src/aat/training/collate.py:169-212, statement by statement, with the random draw (:176) passed in as
+    ``word_start_idx``.  Returns (words, waveform, melspec, frames_boarders) as the collator leaves them."""
+    frames_boarders_raw = np.asarray(frames_boarders_raw)
+    frames_boarders = frames_boarders_raw.cumsum()
+    waveform_num_frames = waveform.shape[-1]
+    assert frames_boarders_raw.sum() == waveform_num_frames
+    waveform_end_frame = waveform.shape[-1]
+    word_end_idx = word_start_idx + n_words
+    words = words[word_start_idx:word_end_idx]
+    waveform_start_frame = int(word_start[word_start_idx] * sampling_rate)
+    waveform_end_frame = int(word_end[word_end_idx - 1] * sampling_rate)
+    frames_boarders_with_zero = np.insert(frames_boarders, 0, [0])
+    waveform_start_segment_idx = np.searchsorted(frames_boarders_with_zero, waveform_start_frame)
+    waveform_start_segment_idx -= 1
+    waveform_start_segment_idx = max(waveform_start_segment_idx, 0)
+    assert waveform_start_segment_idx >= 0
+    waveform_end_segment_idx = np.searchsorted(frames_boarders_with_zero, waveform_end_frame, side='right')
+    assert waveform_end_segment_idx < len(frames_boarders_with_zero)
+    start_segment_waveform_num = frames_boarders_with_zero[waveform_start_segment_idx]
+    assert start_segment_waveform_num <= waveform_start_frame
+    end_segment_waveform_num = frames_boarders_with_zero[waveform_end_segment_idx]
+    assert end_segment_waveform_num >= waveform_end_frame
+    frames_boarders = frames_boarders_with_zero[waveform_start_segment_idx:(waveform_end_segment_idx + 1)]
+    frames_boarders = frames_boarders - start_segment_waveform_num
+    assert frames_boarders[0] == 0
+    frames_boarders = frames_boarders[1:]
+    melspec_overlapping = 5
+    waveform_frames_overlapping = melspec_overlapping * hop_length
+    start_segment_waveform_num = max(0, start_segment_waveform_num - waveform_frames_overlapping)
+    end_segment_waveform_num = min(end_segment_waveform_num + waveform_frames_overlapping, waveform.shape[-1])
+    waveform = waveform[start_segment_waveform_num:end_segment_waveform_num]
+    start_segment_melspec, end_segment_melspec = start_segment_waveform_num // hop_length, end_segment_waveform_num // hop_length
+    start_segment_melspec = max(0, start_segment_melspec - running_mean_points - melspec_overlapping)
+    end_segment_melspec = min(end_segment_melspec + melspec_overlapping, melspec.shape[-1])
+    melspec = melspec[:, start_segment_melspec:end_segment_melspec]
+    return words, waveform, melspec, frames_boarders

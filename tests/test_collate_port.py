@@ -45,3 +45,43 @@ def test_normalisation_ports():
     assert z.dtype == np.float64 and abs(z.mean()) < 1e-12 and abs(z.std() - 1.0) < 1e-5
     w = collate_port.w2v2_norm(x)
     assert w.dtype == np.float32 and abs(float(w.mean())) < 1e-4 and abs(float(w.std()) - 1.0) < 1e-3
+
+
+def test_crop_to_words_matches_the_collator_port():
+    """the n-word cropping of ref:src/aat/training/collate.py:169-212 (host index arithmetic)."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "audio-adaptive-tokenizer_b200"))
+    from aat_b200 import collate
+
+    rng = np.random.default_rng(5)
+    sr, hop, npts = 16000, 160, 12
+    checked = 0
+    for trial in range(200):
+        lengths = rng.integers(2000, 24001, size=int(rng.integers(3, 40)))
+        n = int(lengths.sum())
+        T = 1 + n // hop
+        wave = rng.standard_normal(n).astype(np.float32)
+        mel = rng.standard_normal((8, T)).astype(np.float32)
+        n_all = int(rng.integers(4, 30))
+        cuts = np.sort(rng.uniform(0.0, n / sr, size=2 * n_all))
+        word_start, word_end = cuts[0::2], cuts[1::2]
+        words = [f"w{i}" for i in range(n_all)]
+        n_words = int(rng.integers(1, n_all))
+        idx = int(rng.integers(0, n_all - n_words + 1))
+        try:
+            want = collate_port.crop_to_words(wave, mel, lengths, words, word_start, word_end, idx, n_words, sr, hop, npts)
+        except AssertionError:
+            with np.testing.assert_raises(AssertionError):
+                collate.crop_to_words(lengths, word_start, word_end, idx, n_words, sr, hop, npts, n, T)
+            continue
+        boarders, (w0, w1), (m0, m1), (a, b) = collate.crop_to_words(lengths, word_start, word_end, idx, n_words, sr, hop,
+                                                                    npts, n, T)
+        assert words[a:b] == want[0]
+        assert np.array_equal(wave[w0:w1], want[1]) and np.array_equal(mel[:, m0:m1], want[2])
+        assert np.array_equal(boarders, want[3])
+        checked += 1
+    assert checked > 150
+    with np.testing.assert_raises(AssertionError):
+        collate.crop_to_words([1000, 2000], [0.0], [0.1], 0, 1, sr, hop, npts, 2999, 19)
