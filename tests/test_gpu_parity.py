@@ -255,6 +255,12 @@ def test_pool_ragged_against_oracle(c_oracle, dim):
     off = off[: int(np.argmax(off == n_rows)) + 1].astype(np.int64)
     got = mean_pool_segments(torch.from_numpy(emb).cuda(), off).cpu().numpy()[0]
     assert_pooled_close(got, c_oracle.mean_pool_f64(emb, off))
+    # Zipf-heavy: mostly minimal segments, a few very long ones (SURVEY §8d, config 3 ragged stress)
+    lens = np.minimum(6 * rng.zipf(1.6, size=n_rows), n_rows // 3)
+    off = np.minimum(np.concatenate([[0], np.cumsum(lens)]), n_rows)
+    off = off[: int(np.argmax(off == n_rows)) + 1].astype(np.int64)
+    got = mean_pool_segments(torch.from_numpy(emb).cuda(), off).cpu().numpy()[0]
+    assert_pooled_close(got, c_oracle.mean_pool_f64(emb, off))
 
 
 def test_pool_empty_segments_gaps_and_degenerate_shapes(c_oracle):
