@@ -107,7 +107,6 @@ struct aat_ctx {
     aat_config cfg{};
     double *window_half = nullptr; // device [400], 0.5 * window (exact scaling, folds the /2 of the two-frame split)
     double2 *twiddle = nullptr;    // device [19 * 20], W_400^(k1 * n2) at [(k1 - 1) * 20 + n2], k1 = 1..19
-    unsigned *ticket = nullptr;    // device [1], "last CTA done" counter of the boundaries kernel (self-resetting)
     double2 *log_table = nullptr;  // device [32], (1/c_i, -log10(1/c_i)) for the log-mel kernel's log10
     aat::MelSchedule mel{};
     aat::PoolScratch pool{};
@@ -137,8 +136,8 @@ struct aat_plan {
     int64_t *d_frame_off = nullptr;     // [B+1]
     int64_t *d_seg_slot_off = nullptr;  // [B+1]
     aat::MelTile *d_mel_tile = nullptr; // [mel_tiles] tile descriptors of the log-mel kernel
-    int32_t *d_mel_sched = nullptr;     // [2] the log-mel kernel's tile counter and exit counter (self-resetting:
-                                        // one log-mel launch per plan may be in flight at a time)
+    int32_t *d_mel_sched = nullptr;     // [4] self-resetting counters: the log-mel kernel's tile and exit counters, the
+                                        // boundary kernel's completion ticket (one launch per plan in flight at a time)
     // scratch written by the boundaries kernel for its fused frame-CSR epilogue
     int64_t *d_seg_local = nullptr;     // [total_seg_slots]
     int64_t *d_utt_frames = nullptr;    // [B] look-back words of the boundary kernel's CSR epilogue (zero between launches)

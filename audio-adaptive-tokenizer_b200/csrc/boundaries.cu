@@ -336,7 +336,7 @@ struct BoundaryParams {
     int64_t *minima;
     int32_t *minima_count;
     int32_t *status;
-    // optional fused frame CSR (built by the last CTA to finish)
+    // optional fused frame CSR (every CTA writes its utterance's slice after a look-back)
     int64_t *seg_off;
     int64_t *n_seg;
     int64_t *utt_seg_off;
@@ -763,7 +763,7 @@ int launch_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel, cons
     p.npts = ctx->cfg.running_mean_points;
     p.max_amp = ctx->cfg.max_amplitude_for_minima;
     p.n_utts = plan->n_utts;
-    p.ticket = ctx->ticket;
+    p.ticket = reinterpret_cast<unsigned *>(plan->d_mel_sched + 2); // per plan, so plans on different streams are independent
     // Stage size: 128-frame stages were measured slower (31 us vs 27 us at 64 x 16 s) and 256 equal: the kernel is
     // bound by the merge/split thread, not by the pipeline fill (profiles/r1_bnd_timeline.txt).
     constexpr int chunk = kChunk;

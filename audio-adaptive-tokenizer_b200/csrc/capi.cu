@@ -223,8 +223,6 @@ int aat_create(int device, const aat_config *cfg, const double *window_host, con
 
     if ((rc = build_mel_schedule(ctx, mel_filters_host))) return rc;
 
-    AAT_CUDA_CHECK(cudaMalloc(&ctx->ticket, sizeof(unsigned)));
-    AAT_CUDA_CHECK(cudaMemset(ctx->ticket, 0, sizeof(unsigned)));
     if ((rc = logmel_tables_init(ctx))) return rc;
     if ((rc = pool_scratch_init(ctx))) return rc;
     AAT_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking));
@@ -239,7 +237,6 @@ int aat_destroy(aat_ctx *ctx)
     cudaFree(ctx->window_half);
     cudaFree(ctx->twiddle);
     cudaFree(ctx->log_table);
-    cudaFree(ctx->ticket);
     cudaFree(ctx->mel.filter_desc);
     cudaFree(ctx->mel.weight);
     pool_scratch_free(ctx);
@@ -378,8 +375,8 @@ int aat_plan_create(aat_ctx *ctx, int32_t n_utts, const int64_t *n_samples_host,
         aat_plan_destroy(plan);
         AAT_REQUIRE(false, AAT_ERR_CUDA, "aat_plan_create: out of device memory");
     }
-    if (cudaMalloc(&plan->d_mel_sched, sizeof(int32_t) * 2) != cudaSuccess ||
-        cudaMemset(plan->d_mel_sched, 0, sizeof(int32_t) * 2) != cudaSuccess) {
+    if (cudaMalloc(&plan->d_mel_sched, sizeof(int32_t) * 4) != cudaSuccess ||
+        cudaMemset(plan->d_mel_sched, 0, sizeof(int32_t) * 4) != cudaSuccess) {
         aat_plan_destroy(plan);
         AAT_REQUIRE(false, AAT_ERR_CUDA, "aat_plan_create: out of device memory");
     }

@@ -161,9 +161,10 @@ int aat_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave_dev, int wav
  * status_dev     : int32 [n_utts]; negative = aat_status (AAT_ERR_CAPACITY / AAT_ERR_TAIL) for that utterance,
  *                  otherwise bit 0 is set when the last segment is the zero-padded tail
  *                  (ref:src/aat/tokenizer.py:177-181)
- * seg_off_dev, n_seg_dev, utt_seg_off_dev : optional (NULL = skip); when given, the kernel's last CTA also
- *                  emits the packed frame CSR, exactly what aat_segment_frame_csr would write
- * One launch per context may be in flight at a time (the context owns the kernel's completion counter). */
+ * seg_off_dev, n_seg_dev, utt_seg_off_dev : optional (NULL = skip); when given, the kernel also emits the packed
+ *                  frame CSR (every utterance's CTA writes its own slice after a look-back over the utterances
+ *                  before it), exactly what aat_segment_frame_csr would write
+ * One launch per plan may be in flight at a time (the plan owns the completion ticket and the look-back words). */
 int aat_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel_dev, const float *amp_dev,
                    int64_t *seg_start_dev, int64_t *seg_len_dev, int32_t *seg_count_dev, int64_t *minima_dev,
                    int32_t *minima_count_dev, int32_t *status_dev, int64_t *seg_off_dev, int64_t *n_seg_dev,

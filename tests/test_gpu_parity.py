@@ -513,6 +513,38 @@ def test_back_to_back_steps_match_synchronised_steps(tok):
     assert torch.allclose(acc, total, rtol=1e-12, atol=0.0)
 
 
+def test_two_plans_on_two_streams_are_independent(tok):
+    """Tile counter, completion ticket and look-back words belong to the plan: two plans driven concurrently from two
+    streams give what they give alone."""
+    import torch
+
+    from aat_b200 import synth
+
+    specs = [[64000] * 24, [160000, 31999, 256000, 8000, 96000, 48000, 20000, 131072]]
+    plans, waves, want = [], [], []
+    for k, lengths in enumerate(specs):
+        batch = tok.plan(lengths)
+        wave = batch.pack([torch.from_numpy(synth.bursty_speech(n, 8800 + 50 * k + i)) for i, n in enumerate(lengths)])
+        batch.logmel(wave), batch.boundaries()
+        torch.cuda.synchronize()
+        n_seg = int(batch.n_seg.item())
+        want.append((batch.mel.clone(), batch.seg_count.clone(), batch.seg_off[: n_seg + 1].clone(), n_seg))
+        plans.append(batch), waves.append(wave)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for rep in range(20):
+        for k in (0, 1):
+            with torch.cuda.stream(streams[k]):
+                plans[k].logmel(waves[k])
+                plans[k].boundaries()
+    torch.cuda.synchronize()
+    for k in (0, 1):
+        mel, count, off, n_seg = want[k]
+        assert int(plans[k].n_seg.item()) == n_seg
+        assert torch.equal(plans[k].mel, mel) and torch.equal(plans[k].seg_count, count)
+        assert torch.equal(plans[k].seg_off[: n_seg + 1], off)
+
+
 def test_profile_sampling_records_every_nth_launch(tok):
     import torch
 
