@@ -6,7 +6,7 @@
 
 constexpr int kIters = 4096;
 
-enum Op { DFMA, DADD, DMUL, F2D, D2F, I2D, D2F2D, FFMA };
+enum Op { DFMA, DADD, DMUL, F2D, D2F, I2D, D2F2D, FFMA, FADD32 };
 
 template <int OP>
 __device__ __forceinline__ double step(double x, double a, double b)
@@ -18,6 +18,10 @@ __device__ __forceinline__ double step(double x, double a, double b)
     if (OP == D2F) return __hiloint2double(__float_as_int((float)x), 0x12345678);                                               // F2F.F32.F64
     if (OP == I2D) return (double)(int)(__double_as_longlong(x) >> 40);                                                        // I2F.F64.S32
     if (OP == D2F2D) return (double)(float)x;
+    if (OP == FADD32) { // float chain carried in the low word: one FADD per step
+        const float f = __fadd_rn(__int_as_float(__double2loint(x)), (float)b);
+        return __hiloint2double(__double2hiint(x), __float_as_int(f));
+    }
     return x;
 }
 
@@ -72,6 +76,7 @@ int main()
     run<D2F>("F2F.F32.F64 (+mov)", out, cyc);
     run<I2D>("I2F.F64.S32 (+shift)", out, cyc);
     run<D2F2D>("double(float(x)) round trip", out, cyc);
+    run<FADD32>("FADD (float32, _rn)", out, cyc);
     cudaError_t e = cudaDeviceSynchronize();
     printf("status: %s\n", cudaGetErrorString(e));
     return e != cudaSuccess;
