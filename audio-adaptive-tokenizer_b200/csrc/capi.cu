@@ -174,31 +174,9 @@ int64_t aat_num_mel_frames(const aat_config *cfg, int64_t n_samples)
     return 1 + n_samples / cfg->hop_length;
 }
 
-int aat_create(int device, const aat_config *cfg, const double *window_host, const double *mel_filters_host,
-               aat_ctx **out)
+static int init_context(aat_ctx *ctx, const double *window_host, const double *mel_filters_host)
 {
-    AAT_REQUIRE(cfg && window_host && mel_filters_host && out, AAT_ERR_INVALID, "aat_create: NULL argument");
-    AAT_REQUIRE(cfg->n_fft == kNfft, AAT_ERR_UNSUPPORTED,
-                "aat_create: n_fft=%d is not implemented (the FFT kernel is specialised for n_fft=400)", cfg->n_fft);
-    AAT_REQUIRE(cfg->hop_length >= 1 && cfg->hop_length <= kNfft, AAT_ERR_UNSUPPORTED,
-                "aat_create: hop_length=%d outside 1..%d", cfg->hop_length, kNfft);
-    AAT_REQUIRE(cfg->num_mel_filters >= 1 && cfg->num_mel_filters <= kMaxMels, AAT_ERR_UNSUPPORTED,
-                "aat_create: num_mel_filters=%d outside 1..%d", cfg->num_mel_filters, kMaxMels);
-    AAT_REQUIRE(cfg->running_mean_points >= 1 && cfg->running_mean_points <= kMaxRunningMean, AAT_ERR_UNSUPPORTED,
-                "aat_create: running_mean_points=%d outside 1..%d", cfg->running_mean_points, kMaxRunningMean);
-    AAT_REQUIRE(cfg->max_segment_frames > 0, AAT_ERR_INVALID,
-                "aat_create: max_segment_frames must be positive (the reference divides by it)");
-    AAT_REQUIRE(cfg->min_segment_frames >= 0, AAT_ERR_INVALID, "aat_create: min_segment_frames must be >= 0");
-    int n_dev = 0;
-    AAT_CUDA_CHECK(cudaGetDeviceCount(&n_dev));
-    AAT_REQUIRE(device >= 0 && device < n_dev, AAT_ERR_CUDA, "aat_create: no CUDA device %d (%d visible)", device, n_dev);
-    DeviceGuard guard(device);
-    AAT_REQUIRE(guard.ok, AAT_ERR_CUDA, "aat_create: cudaSetDevice(%d) failed", device);
-
-    aat_ctx *ctx = new (std::nothrow) aat_ctx();
-    AAT_REQUIRE(ctx, AAT_ERR_INVALID, "aat_create: out of host memory");
-    ctx->device = device;
-    ctx->cfg = *cfg;
+    const int device = ctx->device;
     cudaDeviceProp prop{};
     AAT_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     ctx->num_sms = prop.multiProcessorCount;
@@ -226,6 +204,39 @@ int aat_create(int device, const aat_config *cfg, const double *window_host, con
     if ((rc = logmel_tables_init(ctx))) return rc;
     if ((rc = pool_scratch_init(ctx))) return rc;
     AAT_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking));
+    return AAT_OK;
+}
+
+int aat_create(int device, const aat_config *cfg, const double *window_host, const double *mel_filters_host,
+               aat_ctx **out)
+{
+    AAT_REQUIRE(cfg && window_host && mel_filters_host && out, AAT_ERR_INVALID, "aat_create: NULL argument");
+    AAT_REQUIRE(cfg->n_fft == kNfft, AAT_ERR_UNSUPPORTED,
+                "aat_create: n_fft=%d is not implemented (the FFT kernel is specialised for n_fft=400)", cfg->n_fft);
+    AAT_REQUIRE(cfg->hop_length >= 1 && cfg->hop_length <= kNfft, AAT_ERR_UNSUPPORTED,
+                "aat_create: hop_length=%d outside 1..%d", cfg->hop_length, kNfft);
+    AAT_REQUIRE(cfg->num_mel_filters >= 1 && cfg->num_mel_filters <= kMaxMels, AAT_ERR_UNSUPPORTED,
+                "aat_create: num_mel_filters=%d outside 1..%d", cfg->num_mel_filters, kMaxMels);
+    AAT_REQUIRE(cfg->running_mean_points >= 1 && cfg->running_mean_points <= kMaxRunningMean, AAT_ERR_UNSUPPORTED,
+                "aat_create: running_mean_points=%d outside 1..%d", cfg->running_mean_points, kMaxRunningMean);
+    AAT_REQUIRE(cfg->max_segment_frames > 0, AAT_ERR_INVALID,
+                "aat_create: max_segment_frames must be positive (the reference divides by it)");
+    AAT_REQUIRE(cfg->min_segment_frames >= 0, AAT_ERR_INVALID, "aat_create: min_segment_frames must be >= 0");
+    int n_dev = 0;
+    AAT_CUDA_CHECK(cudaGetDeviceCount(&n_dev));
+    AAT_REQUIRE(device >= 0 && device < n_dev, AAT_ERR_CUDA, "aat_create: no CUDA device %d (%d visible)", device, n_dev);
+    DeviceGuard guard(device);
+    AAT_REQUIRE(guard.ok, AAT_ERR_CUDA, "aat_create: cudaSetDevice(%d) failed", device);
+
+    aat_ctx *ctx = new (std::nothrow) aat_ctx();
+    AAT_REQUIRE(ctx, AAT_ERR_INVALID, "aat_create: out of host memory");
+    ctx->device = device;
+    ctx->cfg = *cfg;
+    const int rc = init_context(ctx, window_host, mel_filters_host);
+    if (rc != AAT_OK) { // aat_destroy copes with a partially built context and keeps the error message
+        aat_destroy(ctx);
+        return rc;
+    }
     *out = ctx;
     return AAT_OK;
 }
