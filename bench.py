@@ -14,6 +14,13 @@ One JSON line on stdout (rank 0).  `value` = whole-job audio-hours/s with inputs
 timed region; `roofline` = the pool kernel's algorithmic bytes / its CUDA-event duration measured in
 the timed region, against MEASURED_PEAKS.json; `cpu_baseline` = the oracle port of the reference's
 CPU path on a bounded sample.  `--impl reference` times that CPU path alone with all host cores.
+
+The kernels of a step are chained by programmatic dependent launch (each one's prologue overlaps its
+predecessor's tail).  A CUDA event in front of a kernel switches that overlap off for that launch, so the pool
+kernel is event-timed on every `--pool-sample-every`-th launch of the timed region only (default 8): the
+sampled launches give the kernel's duration in isolation (what the roofline needs), the others run the way a
+user's loop runs them (what `value` measures).  `kernel_us` comes from an extra, untimed pass with events
+around every kernel.
 """
 from __future__ import annotations
 
