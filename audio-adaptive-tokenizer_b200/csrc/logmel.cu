@@ -213,7 +213,7 @@ __host__ __device__ constexpr int raw_gap() { return sizeof(WaveT) == 4 ? 20 : 4
 __host__ __device__ inline int raw_elems(int stage_pad, int gap) { return stage_pad + gap * ((stage_pad - 1) / kRawBlock); }
 
 struct SmemLayout {
-    size_t ex, raw, tw, logt, mw, fdesc, tiles, next, mel, total;
+    size_t ex, raw, tw, logt, mw, fdesc, tiles, next, mel, acc, total;
 };
 
 __host__ __device__ inline SmemLayout smem_layout(int raw_elems, int wave_bytes, int n_mels, int n_weights)
@@ -229,6 +229,7 @@ __host__ __device__ inline SmemLayout smem_layout(int raw_elems, int wave_bytes,
     // float32 mel tile of the amplitude epilogue
     L.ex = take(sizeof(double2) * kPairs * kPairStride);
     L.mel = L.ex + sizeof(double) * kFrames * kPowStride;
+    L.acc = (L.mel + sizeof(float) * kFrames * (kMaxMels + 1) + 15) & ~size_t(15); // per-thread filter sums [13][160]
     L.raw = take((size_t)raw_elems * wave_bytes);
     L.tw = take(sizeof(double2) * kTwiddles);
     L.logt = take(sizeof(double2) * kLogTable);
@@ -239,9 +240,10 @@ __host__ __device__ inline SmemLayout smem_layout(int raw_elems, int wave_bytes,
     L.total = o;
     return L;
 }
-static_assert(sizeof(double) * kFrames * kPowStride + sizeof(float) * kFrames * (kMaxMels + 1) <=
+static_assert(sizeof(double) * kFrames * kPowStride + sizeof(float) * kFrames * (kMaxMels + 1) + 16 +
+                      sizeof(double) * ((kMaxMels + kMelGroups - 1) / kMelGroups) * kThreads <=
                   sizeof(double2) * kPairs * kPairStride,
-              "power spectra + float32 mel tile must fit in the exchange matrix");
+              "power spectra + float32 mel tile + staged filter sums must fit in the exchange matrix");
 
 // One band of kTapPairs * 2 taps: four independent FMA chains (explicit _rn: no contraction of the final additions,
 // so the sum does not depend on the compiler's mood).
@@ -267,10 +269,10 @@ __device__ __forceinline__ double band(const double2 *__restrict__ w2, const dou
     return __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
 }
 
-// Runtime tap count (warp-uniform by construction of the schedule) -> the unrolled instance.  Out of line: it is
-// called from every slot of the unrolled log batch, and ten unrolled bodies per call site would not fit the
-// instruction cache.
-__device__ __noinline__ double band_sum(int tap_pairs, const double2 *__restrict__ w2, const double *__restrict__ pw)
+// Runtime tap count (warp-uniform by construction of the schedule) -> the unrolled instance.  One call site (a rolled
+// loop over the thread's filters): ten unrolled bodies per slot of the unrolled log batch would not fit the instruction
+// cache, and an out-of-line function costs ~25 instructions of argument / live-register shuffling per call.
+__device__ __forceinline__ double band_sum(int tap_pairs, const double2 *__restrict__ w2, const double *__restrict__ pw)
 {
     switch (tap_pairs) {
     case 1: return band<1>(w2, pw);
@@ -330,6 +332,7 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
     MelTile *s_tiles = reinterpret_cast<MelTile *>(smem_raw + L.tiles);
     int *s_next = reinterpret_cast<int *>(smem_raw + L.next);
     float *s_mel = reinterpret_cast<float *>(smem_raw + L.mel);
+    double *s_acc = reinterpret_cast<double *>(smem_raw + L.acc);
 
     const int tid = threadIdx.x;
     constexpr int kVec = 16 / (int)sizeof(WaveT); // samples per 16-byte copy
@@ -490,11 +493,15 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
             const bool live = f < cur.valid;
             const size_t T = (size_t)cur.T;
             float *smel = s_mel + f * mel_stride;
-            auto filter_sum = [&](int m) {
-                const uint32_t d = s_fdesc[m];
+            // projection: a rolled loop (one copy of the unrolled tap bodies); the floored sums wait in the thread's own
+            // shared-memory slots for the unrolled log batch below
+            double *my_acc = s_acc + tid;
+#pragma unroll 1
+            for (int i = 0; i < n_mine; ++i) {
+                const uint32_t d = s_fdesc[q + i * kMelGroups];
                 const double acc = band_sum((int)((d >> 8) & 0xffu), w2 + (d >> 16), pw + (d & 0xffu));
-                return (acc < 1e-10) ? 1e-10 : acc; // np.maximum(mel_floor, .): NaN propagates
-            };
+                my_acc[i * kThreads] = (acc < 1e-10) ? 1e-10 : acc; // np.maximum(mel_floor, .): NaN propagates
+            }
 #pragma unroll
             for (int i0 = 0; i0 < kMaxPerThread; i0 += kBatch) {
                 if (i0 < n_mine) {
@@ -503,7 +510,7 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
                     double acc[kBatch];
 #pragma unroll
                     for (int k = 0; k < kBatch; ++k)
-                        acc[k] = (i0 + k < kMaxPerThread && i0 + k < n_mine) ? filter_sum(q + (i0 + k) * kMelGroups) : 1.0;
+                        acc[k] = (i0 + k < kMaxPerThread && i0 + k < n_mine) ? my_acc[(i0 + k) * kThreads] : 1.0;
                     double lg[kBatch];
                     unsigned worst = 0; // after the floor a value is >= 1e-10, +inf or NaN: one test for the whole batch
 #pragma unroll
