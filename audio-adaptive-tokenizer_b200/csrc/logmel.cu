@@ -496,9 +496,11 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
             // projection: a rolled loop (one copy of the unrolled tap bodies); the floored sums wait in the thread's own
             // shared-memory slots for the unrolled log batch below
             double *my_acc = s_acc + tid;
+            uint32_t d_next = n_mine > 0 ? s_fdesc[q] : 0u; // descriptors run one filter ahead of the taps
 #pragma unroll 1
             for (int i = 0; i < n_mine; ++i) {
-                const uint32_t d = s_fdesc[q + i * kMelGroups];
+                const uint32_t d = d_next;
+                if (i + 1 < n_mine) d_next = s_fdesc[q + (i + 1) * kMelGroups];
                 const double acc = band_sum((int)((d >> 8) & 0xffu), w2 + (d >> 16), pw + (d & 0xffu));
                 my_acc[i * kThreads] = (acc < 1e-10) ? 1e-10 : acc; // np.maximum(mel_floor, .): NaN propagates
             }
