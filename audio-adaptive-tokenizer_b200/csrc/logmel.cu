@@ -451,20 +451,23 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
             double pa[11], pb[11];
             const double2 *mir = ex + ((lane20 == 0) ? 0 : 20 - lane20) * kRow;
 #pragma unroll
-            for (int j = 0; j < 11; ++j) {
-                if (j < 10 || lane20 == 0) {
-                    const double2 z = v[j];
-                    double2 y;
-                    if (lane20 == 0)
-                        y = (j == 0) ? z : ((j == 10) ? z : mir[20 - j]); // Z[0] and Z[200] mirror themselves
-                    else
-                        y = mir[19 - j];
-                    // X_a = (z + conj y), X_b = (z - conj y) / i   (the 1/2 lives in the window table)
-                    const double ar = round_to_float(z.x + y.x), ai = round_to_float(z.y - y.y);
-                    const double br = round_to_float(z.y + y.y), bi = round_to_float(y.x - z.x);
-                    pa[j] = ar * ar + ai * ai;
-                    pb[j] = br * br + bi * bi;
-                }
+            for (int j = 0; j < 10; ++j) {
+                const double2 z = v[j];
+                double2 y;
+                if (lane20 == 0)
+                    y = (j == 0) ? z : mir[20 - j]; // Z[0] mirrors itself
+                else
+                    y = mir[19 - j];
+                // X_a = (z + conj y), X_b = (z - conj y) / i   (the 1/2 lives in the window table)
+                const double ar = round_to_float(z.x + y.x), ai = round_to_float(z.y - y.y);
+                const double br = round_to_float(z.y + y.y), bi = round_to_float(y.x - z.x);
+                pa[j] = ar * ar + ai * ai;
+                pb[j] = br * br + bi * bi;
+            }
+            if (lane20 == 0) { // bin 200 = Z[200] of row 0 mirrors itself: both spectra are real there
+                const double ar = round_to_float(v[10].x + v[10].x), br = round_to_float(v[10].y + v[10].y);
+                pa[10] = ar * ar;
+                pb[10] = br * br;
             }
             __syncthreads(); // every thread has read its mirror values: overlay the matrix with the power spectra
             double *rowa = s_pow + (2 * pair) * kPowStride + lane20;
