@@ -24,9 +24,11 @@
 // consecutive frames of one utterance (8 frame pairs x 20 threads = 160 threads).  Everything a tile needs to
 // know (source offset, output offsets, edge flags) is one 64-byte host-built descriptor; descriptors run two
 // tiles ahead and the raw samples one tile ahead, both by cp.async (LDGSTS, no registers), so no thread ever
-// waits on a global load inside the loop.  The mel projection runs from a host-built balanced schedule of
-// short bands (MelSchedule): CTA-uniform, fully unrolled tap loops with four independent FMA chains per
-// thread, partial sums through shared memory, then a branch-free batch of table-driven log10.
+// waits on a global load inside the loop; tiles beyond a CTA's first three are taken from a global counter, so the
+// tail of the kernel does not depend on the tile-count remainder.  The mel projection runs from a host-built banded
+// table (MelSchedule): thread (frame, group) walks its own filters with warp-uniform, fully unrolled tap bodies (four
+// independent FMA chains), parks the floored sums in its own shared-memory slots and takes their log10 as one
+// branch-free, table-driven batch.  Launched with programmatic dependent launch (see aat_internal.cuh).
 #include "aat_internal.cuh"
 
 namespace aat {

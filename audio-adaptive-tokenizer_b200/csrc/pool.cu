@@ -21,7 +21,11 @@
 //     of its own rows.  No CTA waits on a waiter and the whole grid is co-resident, so there is neither
 //     a dependency chain nor a deadlock; flags are reset by their single consumer (graph-replay safe);
 //   * optional epilogue: float64 column sums of the pooled vectors (input of the dataset-mean
-//     allreduce) are accumulated per CTA and reduced in CTA order by a second tiny kernel.
+//     allreduce) are accumulated per CTA and reduced in CTA order by a second tiny kernel;
+//   * launched with programmatic dependent launch: the whole ring of embedding stages is requested before the
+//     kernel waits for its predecessor (the boundary scan, whose outputs are only the offsets), the first offsets
+//     window arrives by one bulk copy, and the owner of a cut segment looks at its neighbour's partial sums two
+//     stages before its last row (profiles/r1_pool_timeline*.txt, r1_pool_ab.txt).
 //
 // Algorithmic bytes per launch: n_rows*dim*e + S*dim*4 + (S+1)*8  (SURVEY.md §8d).
 #include <cuda_bf16.h>
