@@ -106,7 +106,7 @@ struct aat_ctx {
     int num_sms = 0;
     aat_config cfg{};
     double *window_half = nullptr; // device [400], 0.5 * window (exact scaling, folds the /2 of the two-frame split)
-    double2 *twiddle = nullptr;    // device [19 * 20], W_400^(k1 * n2) at [(k1 - 1) * 20 + n2], k1 = 1..19
+    double2 *twiddle = nullptr;    // device [7 * 20], W_400^(k1 * n2) for k1 = 1, 2, 3, 4, 5, 10, 15 (row-major over n2)
     double2 *log_table = nullptr;  // device [32], (1/c_i, -log10(1/c_i)) for the log-mel kernel's log10
     aat::MelSchedule mel{};
     aat::PoolScratch pool{};

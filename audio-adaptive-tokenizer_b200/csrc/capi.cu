@@ -187,14 +187,16 @@ static int init_context(aat_ctx *ctx, const double *window_host, const double *m
     int rc = upload(&ctx->window_half, win.data(), win.size());
     if (rc) return rc;
 
-    // W_400^(k1 * n2) for k1 = 1..19 (row k1 = 0 is all ones and never read), long double, rounded once
-    std::vector<double2> tw(19 * 20);
+    // W_400^(k1 * n2) for k1 = 1, 2, 3, 4, 5, 10, 15 (the kernel derives the other rows as products), long double,
+    // rounded once
+    const int tw_rows[7] = {1, 2, 3, 4, 5, 10, 15};
+    std::vector<double2> tw(7 * 20);
     const long double two_pi = 6.283185307179586476925286766559005768L;
-    for (int k1 = 1; k1 < 20; ++k1)
+    for (int r = 0; r < 7; ++r)
         for (int n2 = 0; n2 < 20; ++n2) {
-            const int e = (k1 * n2) % kNfft;
+            const int e = (tw_rows[r] * n2) % kNfft;
             const long double a = two_pi * (long double)e / (long double)kNfft;
-            tw[(k1 - 1) * 20 + n2] = make_double2((double)cosl(a), (double)-sinl(a));
+            tw[r * 20 + n2] = make_double2((double)cosl(a), (double)-sinl(a));
         }
     rc = upload(&ctx->twiddle, tw.data(), tw.size());
     if (rc) return rc;

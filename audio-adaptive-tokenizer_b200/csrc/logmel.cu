@@ -203,7 +203,7 @@ struct LogmelParams {
     LogmelConsts K;
 };
 
-constexpr int kTwiddles = 19 * 20;
+constexpr int kTwiddles = 7 * 20; // rows k1 = 1, 2, 3, 4, 5, 10, 15
 constexpr int kTileRing = 3; // descriptors: current tile, the tile whose samples are being fetched, the one after
 
 // Raw-sample staging for hop 160: frame pairs start 320 samples apart, a multiple of the 32 banks, so the lanes of
@@ -424,9 +424,23 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
                 v[n1] = make_double2((double)wa[ia] * w, (double)wa[ib] * w);
             }
             dft20(v, p.K);
+            // W_400^(n2 k1) for k1 = 5 j + i is (W^(5 j n2)) (W^(i n2)): seven table rows (k1 = 1..4, 5, 10, 15) and twelve
+            // complex products instead of nineteen 16-byte loads per thread — the shared-memory pipe is this kernel's
+            // busiest unit, the FP64 pipe is not.  One extra rounding per derived twiddle (1e-16 relative).
             ex[lane20] = v[0];
+            double2 w[5];
 #pragma unroll
-            for (int k1 = 1; k1 < 20; ++k1) ex[k1 * kRow + lane20] = cmul(v[k1], s_tw[(k1 - 1) * 20 + lane20]);
+            for (int i = 1; i < 5; ++i) {
+                w[i] = s_tw[(i - 1) * 20 + lane20];
+                ex[i * kRow + lane20] = cmul(v[i], w[i]);
+            }
+#pragma unroll
+            for (int j = 1; j < 4; ++j) {
+                const double2 a = s_tw[(3 + j) * 20 + lane20];
+                ex[(5 * j) * kRow + lane20] = cmul(v[5 * j], a);
+#pragma unroll
+                for (int i = 1; i < 5; ++i) ex[(5 * j + i) * kRow + lane20] = cmul(v[5 * j + i], cmul(a, w[i]));
+            }
         }
         if (tid == 0) *s_next = 3 * G + grabbed;
         __syncthreads();
