@@ -42,6 +42,8 @@ constexpr int kRow = 21;                     // padded row (double2 units): 21 i
 constexpr int kPairStride = 20 * kRow;       // 420 double2; 420 % 8 == 4 keeps neighbouring pairs on distinct banks
 constexpr int kPowStride = kBins;            // 201 doubles (odd)
 constexpr int kLogTable = 32;                // entries of the log10 table (|r| < 2^-6, degree-8 series: |error| < 3e-18)
+constexpr int kLogCopies = 8;                // shared-memory replicas: lane l reads copy l & 7, so the eight lanes of a
+                                             // quarter-warp hit eight different 16-byte bank groups whatever their indices
 
 // FP64 literals cost two UMOVs per use as immediates (and the compiler folds __constant__ initialisers back
 // into immediates); as kernel parameters they are constant-bank operands of DFMA/DADD, i.e. free.
@@ -164,7 +166,7 @@ __device__ __forceinline__ double fast_log10(double x, const double2 *__restrict
     const int e = (hi >> 20) - 1023;
     const int idx = (hi >> 15) & (kLogTable - 1);
     const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
-    const double2 t = table[idx];
+    const double2 t = table[idx * kLogCopies + (threadIdx.x & (kLogCopies - 1))];
     const double r = fma(m, t.x, -1.0);
     double q = K.k[7];
     q = fma(q, r, K.k[6]);
@@ -234,7 +236,7 @@ __host__ __device__ inline SmemLayout smem_layout(int raw_elems, int wave_bytes,
     L.acc = (L.mel + sizeof(float) * kFrames * (kMaxMels + 1) + 15) & ~size_t(15); // per-thread filter sums [13][160]
     L.raw = take((size_t)raw_elems * wave_bytes);
     L.tw = take(sizeof(double2) * kTwiddles);
-    L.logt = take(sizeof(double2) * kLogTable);
+    L.logt = take(sizeof(double2) * kLogTable * kLogCopies);
     L.mw = take(sizeof(double) * n_weights);
     L.fdesc = take(sizeof(uint32_t) * n_mels);
     L.tiles = take(sizeof(MelTile) * kTileRing);
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
     fetch_desc(blockIdx.x + gridDim.x, 1);
     cp_async_commit();
     for (int i = tid; i < kTwiddles; i += kThreads) s_tw[i] = p.twiddle[i];
-    for (int i = tid; i < kLogTable; i += kThreads) s_logt[i] = p.log_table[i];
+    for (int i = tid; i < kLogTable * kLogCopies; i += kThreads) s_logt[i] = p.log_table[i / kLogCopies];
     for (int i = tid; i < p.n_weights; i += kThreads) s_mw[i] = p.mel_weight[i];
     for (int i = tid; i < p.n_mels; i += kThreads) s_fdesc[i] = p.filter_desc[i];
     cp_async_wait<0>();
