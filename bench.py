@@ -230,11 +230,37 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.workload), "host": "cpu"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "host": host_description()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def host_description():
+    """What the CPU figures were measured on (state core count, CPU model and library versions)."""
+    info = {"cpu_count": os.cpu_count()}
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    info["cpu_model"] = line.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    for mod in ("numpy", "scipy", "transformers", "torch"):
+        try:
+            info[mod] = __import__(mod).__version__
+        except Exception:
+            info[mod] = None
+    try:
+        import torch
+
+        info["torch_threads"] = torch.get_num_threads()
+    except Exception:
+        pass
+    return info
 
 
 # ------------------------------------------------------------------------------------------- B200 arm
@@ -389,7 +415,8 @@ def run_b200(args):
             v, dt = cpu_reference_throughput(args.workload, n_sample)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"{n_sample} utterances of the workload (8 distinct, cycled), single "
-                                              f"process (datasets.map without num_proc), {dt:.1f} s of CPU work"}
+                                              f"process (datasets.map without num_proc), {dt:.1f} s of CPU work",
+                                    "host": host_description()}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
