@@ -18,6 +18,10 @@
  *     points copy host<->device themselves and synchronise before returning.
  *   - there is no CPU fallback: without a CUDA device every compute call fails with
  *     AAT_ERR_CUDA.
+ *   - aat_logmel, aat_boundaries and aat_segment_mean_pool are launched with programmatic dependent launch:
+ *     enqueued back to back on one stream, each kernel's prologue overlaps the tail of the one before it and waits
+ *     on the device before touching its predecessor's outputs.  Ordering against any other work on the stream is the
+ *     usual one.  A plan may have one launch of each in flight at a time (use one plan per stream).
  *
  * Packed batch layout ("plan"): a batch of B utterances with n_samples[b] samples each.
  *   wave      : concatenated samples, utterance b at wave_off[b] = sum_{i<b} n_samples[i]
