@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AAT_B200_LIB") or os.path.join(_HERE, "libaat_b200.so")  # override: profiles/ experiments
 CSRC_DIR = os.path.join(os.path.dirname(_HERE), "csrc")
 
+ABI_VERSION = 200  # AAT_B200_VERSION of include/aat_b200.h this binding was written against
 AAT_OK = 0
 AAT_ERR_INVALID = -1
 AAT_ERR_UNSUPPORTED = -2
@@ -23,6 +24,7 @@ AAT_ERR_TAIL = -5
 
 AAT_F32, AAT_F64, AAT_F16, AAT_BF16 = 0, 1, 2, 3
 AAT_NORM_ZSCORE, AAT_NORM_W2V2 = 0, 1
+AAT_POOL_ACCUMULATE, AAT_POOL_EMB_READY, AAT_POOL_ROWS_FROM_DEVICE = 1, 2, 4
 
 c_i32 = ctypes.c_int32
 c_i64 = ctypes.c_int64
@@ -76,8 +78,8 @@ SIGNATURES = {
     "aat_boundaries": (ctypes.c_int, [c_void] * 14),
     "aat_process_boarders": (ctypes.c_int, [c_void, c_i64, c_void, c_i64, c_void, c_void, c_i64, c_void, c_void, c_void]),
     "aat_segment_frame_csr": (ctypes.c_int, [c_void] * 8),
-    "aat_segment_mean_pool": (ctypes.c_int, [c_void, c_void, ctypes.c_int, c_i64, c_i32, c_void, c_i64, c_void, c_void,
-                                             c_void, ctypes.c_int, c_void]),
+    "aat_segment_mean_pool": (ctypes.c_int, [c_void, c_void, c_void, ctypes.c_int, c_i64, c_i32, c_void, c_i64, c_void,
+                                             c_void, c_void, ctypes.c_int, c_void]),
     "aat_colsum_accumulate": (ctypes.c_int, [c_void, c_void, c_void, c_i32, c_void]),
     "aat_colsum_finalize": (ctypes.c_int, [c_void, c_void, c_i32, c_void, c_void]),
     "aat_normalize": (ctypes.c_int, [c_void, c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, ctypes.c_int, c_void, c_void]),
@@ -86,6 +88,9 @@ SIGNATURES = {
                                             c_void]),
     "aat_scatter_mel_segments": (ctypes.c_int, [c_void, c_void, c_void, c_void, c_i64, c_i64, c_void, c_void, c_void]),
     "aat_masked_mean_pool": (ctypes.c_int, [c_void, c_void, ctypes.c_int, c_i64, c_i64, c_i32, c_void, c_void, c_void, c_void]),
+    "aat_synth_workspace_bytes": (c_i64, [c_void]),
+    "aat_synth_waveforms": (ctypes.c_int, [c_void, c_void, ctypes.c_uint64, c_i64, c_void, c_void, c_void]),
+    "aat_synth_normal": (ctypes.c_int, [c_void, c_void, c_i64, ctypes.c_uint64, c_void]),
     "aat_host_logmel": (ctypes.c_int, [c_void, c_void, ctypes.c_int, c_i64, c_void]),
     "aat_host_find_minimas": (ctypes.c_int, [c_void, c_void, c_i64, c_void, c_void]),
     "aat_host_process_boarders": (ctypes.c_int, [c_void, c_i64, c_void, c_i64, c_void, c_void, c_i64, c_void, c_void]),
@@ -124,6 +129,9 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)
             fn.restype = restype
             fn.argtypes = argtypes
+        if handle.aat_version() != ABI_VERSION:
+            raise ImportError(f"{LIB_PATH} has ABI version {handle.aat_version()}, this binding needs {ABI_VERSION}: "
+                              "rebuild it (make -C audio-adaptive-tokenizer_b200/csrc)")
         _lib = handle
     return _lib
 

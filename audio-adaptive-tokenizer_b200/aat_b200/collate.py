@@ -13,10 +13,10 @@ from . import _cabi
 from .tokenizer import PackedBatch
 
 
-def _stream():
+def _stream(device=None):
     import torch
 
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def _raise_on_status(status, what):
@@ -49,23 +49,26 @@ def normalize_waveforms(batch: PackedBatch, wave, mode: str = "zscore", out_dtyp
     out = torch.empty(batch.total_samples, dtype=out_dtype, device=wave.device)
     stats = torch.empty(2 * batch.n_utts, dtype=torch.float64, device=wave.device)
     _cabi.check(_cabi.lib().aat_normalize(batch.ctx.handle, batch.handle, wave.data_ptr(), codes[wave.dtype], modes[mode],
-                                          out.data_ptr(), codes[out_dtype], stats.data_ptr(), _stream()))
+                                          out.data_ptr(), codes[out_dtype], stats.data_ptr(), _stream(wave.device)))
     return (out, stats.view(batch.n_utts, 2)) if return_stats else out
 
 
-def pad_segment_boarders(batch: PackedBatch, s_max=None):
+def pad_segment_boarders(batch: PackedBatch, s_max=None, check: bool = True):
     """``_make_padded_segments_boarders`` on the device: ``(segments_boarders_padded, attention_mask)``,
-    both ``[B, S_max]`` int64.  ``s_max=None`` reads the largest segment count back from the device (one sync)."""
+    both ``[B, S_max]`` int64.  ``s_max=None`` reads the largest segment count back from the device (one sync).
+    ``check`` reads the status back (one sync) and raises when an utterance has more than ``s_max`` segments."""
     import torch
 
     if s_max is None:
         s_max = int(batch.seg_count.max().item())
     padded = torch.empty((batch.n_utts, s_max), dtype=torch.int64, device=batch.device)
     mask = torch.empty_like(padded)
-    status = torch.empty(batch.n_utts, dtype=torch.int32, device=batch.device)
+    status = torch.zeros(batch.n_utts, dtype=torch.int32, device=batch.device)
     _cabi.check(_cabi.lib().aat_pad_segment_boarders(batch.ctx.handle, batch.handle, batch.seg_len.data_ptr(),
                                                      batch.seg_count.data_ptr(), s_max, padded.data_ptr(),
-                                                     mask.data_ptr(), status.data_ptr(), _stream()))
+                                                     mask.data_ptr(), status.data_ptr(), _stream(batch.device)))
+    if check:
+        _raise_on_status(status, "pad_segment_boarders")
     return padded, mask
 
 
@@ -80,10 +83,10 @@ def scatter_segments(batch: PackedBatch, wave_padded, boarders_padded, max_segme
     B, s_max = boarders_padded.shape
     out = torch.empty((B, s_max, max_segment_frames), dtype=torch.float32, device=wave_padded.device)
     mask = torch.empty_like(out) if with_mask else None
-    status = torch.empty(B, dtype=torch.int32, device=wave_padded.device)
+    status = torch.zeros(B, dtype=torch.int32, device=wave_padded.device)
     _cabi.check(_cabi.lib().aat_scatter_segments(
         batch.ctx.handle, wave_padded.data_ptr(), int(wave_padded.shape[1]), B, boarders_padded.data_ptr(), s_max,
-        int(max_segment_frames), out.data_ptr(), mask.data_ptr() if with_mask else None, status.data_ptr(), _stream()))
+        int(max_segment_frames), out.data_ptr(), mask.data_ptr() if with_mask else None, status.data_ptr(), _stream(wave_padded.device)))
     if check:
         _raise_on_status(status, "scatter_segments")
     return (out, mask) if with_mask else out
@@ -99,10 +102,10 @@ def scatter_mel_segments(batch: PackedBatch, boarders_padded, max_segment_frames
     max_items = 1 + int(max_segment_frames) // hop
     B, s_max = boarders_padded.shape
     out = torch.empty((B, s_max, batch.n_mels, max_items), dtype=torch.float32, device=mel.device)
-    status = torch.empty(B, dtype=torch.int32, device=mel.device)
+    status = torch.zeros(B, dtype=torch.int32, device=mel.device)
     _cabi.check(_cabi.lib().aat_scatter_mel_segments(batch.ctx.handle, batch.handle, mel.data_ptr(),
                                                      boarders_padded.data_ptr(), s_max, max_items, out.data_ptr(),
-                                                     status.data_ptr(), _stream()))
+                                                     status.data_ptr(), _stream(mel.device)))
     if check:
         _raise_on_status(status, "scatter_mel_segments")
     return out
@@ -128,9 +131,9 @@ def masked_mean_pool(audio_embeds, audio_embeds_attention_mask):
     out = torch.empty((R, D), dtype=torch.float32, device=emb.device)
     row_mask = torch.empty(R, dtype=torch.int64, device=emb.device)
     ctx = default_context(emb.device.index)
-    with torch.cuda.device(emb.device):
-        _cabi.check(_cabi.lib().aat_masked_mean_pool(ctx.handle, emb.data_ptr(), _torch_dtype_code(emb.dtype), R, L, D,
-                                                     mask.data_ptr(), out.data_ptr(), row_mask.data_ptr(), _stream()))
+    _cabi.check(_cabi.lib().aat_masked_mean_pool(ctx.handle, emb.data_ptr(), _torch_dtype_code(emb.dtype), R, L, D,
+                                                 mask.data_ptr(), out.data_ptr(), row_mask.data_ptr(),
+                                                 _stream(emb.device)))
     return out, row_mask
 
 

@@ -30,16 +30,20 @@ def _torch_dtype_code(dtype) -> int:
     return code
 
 
-def _pool_device(ctx: Context, emb, seg_off, n_seg: int, n_seg_dev, out, colsum, stream, accumulate: bool = False):
-    """Raw K4 launch on CUDA tensors (no allocation, no sync)."""
+def _pool_device(ctx: Context, emb, seg_off, n_seg: int, n_seg_dev, out, colsum, stream, accumulate: bool = False,
+                 plan=None, emb_ready: bool = False, rows_from_device: bool = False):
+    """Raw K4 launch on CUDA tensors (no allocation, no sync).  ``plan`` is an ``aat_plan`` handle (its scratch is
+    used, so launches on different plans may overlap) or None (the context's scratch; such launches are serialised)."""
     if emb.dim() != 2 or not emb.is_contiguous():
         raise ValueError("emb must be a contiguous [T, D] tensor")
     if out.dtype.is_floating_point is False or out.element_size() != 4 or not out.is_contiguous():
         raise TypeError("out must be a contiguous float32 tensor")
+    flags = ((_cabi.AAT_POOL_ACCUMULATE if accumulate else 0) | (_cabi.AAT_POOL_EMB_READY if emb_ready else 0) |
+             (_cabi.AAT_POOL_ROWS_FROM_DEVICE if rows_from_device else 0))
     _cabi.check(_cabi.lib().aat_segment_mean_pool(
-        ctx.handle, emb.data_ptr(), _torch_dtype_code(emb.dtype), int(emb.shape[0]), int(emb.shape[1]),
+        ctx.handle, plan, emb.data_ptr(), _torch_dtype_code(emb.dtype), int(emb.shape[0]), int(emb.shape[1]),
         seg_off.data_ptr(), int(n_seg), n_seg_dev.data_ptr() if n_seg_dev is not None else None, out.data_ptr(),
-        colsum.data_ptr() if colsum is not None else None, 1 if accumulate else 0, stream))
+        colsum.data_ptr() if colsum is not None else None, flags, stream))
     return out
 
 
@@ -74,9 +78,8 @@ def mean_pool_segments(embeddings, seg_off=None, *, out=None, colsum=None, devic
         n_seg = int(off.numel()) - 1
         if out is None:
             out = torch.empty((n_seg, emb.shape[1]), dtype=torch.float32, device=emb.device)
-        with torch.cuda.device(emb.device):
-            stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-            _pool_device(ctx, emb, off, n_seg, None, out, colsum, stream)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(emb.device).cuda_stream)
+        _pool_device(ctx, emb, off, n_seg, None, out, colsum, stream)
         return out.view(1, n_seg, emb.shape[1])
 
     # host buffers: one C-ABI call does H2D, the kernel and D2H
@@ -131,7 +134,7 @@ class DatasetMean:
     def accumulate(self):
         import torch
 
-        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         _cabi.check(_cabi.lib().aat_colsum_accumulate(self.ctx.handle, self.acc.data_ptr(), self.batch.data_ptr(),
                                                       self.dim, stream))
 
@@ -147,7 +150,7 @@ class DatasetMean:
         import torch
 
         mean = torch.empty(self.dim, dtype=torch.float32, device=self.device)
-        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         _cabi.check(_cabi.lib().aat_colsum_finalize(self.ctx.handle, self.acc.data_ptr(), self.dim, mean.data_ptr(),
                                                     stream))
         return mean

@@ -1,6 +1,8 @@
 """Deterministic synthetic inputs for tests, goldens and bench.
 
-Host-side numpy generators only: this module produces *inputs*, never results.
+This module produces *inputs*, never results.  The numpy generators below run on the host (tests, goldens,
+the oracle's subset); ``device_bursty_batch`` / ``device_normal`` generate the same recipe ON the device from a
+counter-based RNG through the C ABI (``aat_synth_*``), for the benchmark's dataset-scale job.
 
 * ``bursty_speech`` – 16 kHz mono "syllable" audio: Gaussian noise times an
   envelope of voiced bursts U(80,600) ms (Hann-shaped, amplitude U(0.3,1.0))
@@ -77,3 +79,47 @@ def segment_frame_offsets(segment_lengths) -> np.ndarray:
 def mel_frames(n_samples: int, hop_length: int = 160) -> int:
     """``1 + N//hop`` — frame count of the centred STFT, TF:audio_utils.py:778."""
     return 1 + int(n_samples) // int(hop_length)
+
+
+# ---------------------------------------------------------------------------------------- on the device
+def device_bursty_batch(batch, seed_base: int, utt_index_base: int = 0, out=None):
+    """Packed float32 waveform of ``batch`` (a :class:`~aat_b200.tokenizer.PackedBatch`) generated on its device:
+    utterance ``b`` is bursty speech from seed ``seed_base + utt_index_base + b`` (Philox; the seed convention of
+    :func:`seed_for` when ``seed_base = 1000 * config``).  Enqueued on the current stream; returns ``out``."""
+    import ctypes
+
+    import torch
+
+    from . import _cabi
+
+    lib = _cabi.lib()
+    if out is None:
+        out = torch.empty(batch.total_samples, dtype=torch.float32, device=batch.device)
+    if out.dtype != torch.float32 or out.numel() != batch.total_samples or not out.is_contiguous():
+        raise TypeError("out must be a contiguous float32 CUDA tensor with the plan's total_samples entries")
+    ws = getattr(batch, "_synth_ws", None)
+    if ws is None:
+        ws = batch._synth_ws = torch.empty(int(lib.aat_synth_workspace_bytes(batch.handle)) + 16, dtype=torch.uint8,
+                                           device=batch.device)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(batch.device).cuda_stream)
+    _cabi.check(lib.aat_synth_waveforms(batch.ctx.handle, batch.handle, int(seed_base), int(utt_index_base),
+                                        out.data_ptr(), ws.data_ptr(), stream))
+    return out
+
+
+def device_normal(out, seed: int):
+    """Fill the float32 CUDA tensor ``out`` with N(0, 1) (random-init HuBERT-shaped embeddings); element ``i`` is a
+    pure function of ``(seed, i)``."""
+    import ctypes
+
+    import torch
+
+    from . import _cabi
+    from .context import default_context
+
+    if out.dtype != torch.float32 or not out.is_cuda or not out.is_contiguous():
+        raise TypeError("out must be a contiguous float32 CUDA tensor")
+    ctx = default_context(out.device.index)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(out.device).cuda_stream)
+    _cabi.check(_cabi.lib().aat_synth_normal(ctx.handle, out.data_ptr(), out.numel(), int(seed), stream))
+    return out

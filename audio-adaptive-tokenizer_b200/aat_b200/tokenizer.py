@@ -287,7 +287,9 @@ class PackedBatch:
         self.minima = torch.zeros(self.total_frames, dtype=torch.int64, device=dev)
         self.minima_count = torch.zeros(self.n_utts, dtype=torch.int32, device=dev)
         self.seg_off = torch.zeros(self.total_seg_slots + 1, dtype=torch.int64, device=dev)
-        self.n_seg = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._csr_totals = torch.zeros(2, dtype=torch.int64, device=dev)  # {segments, HuBERT frames} of the batch
+        self.n_seg = self._csr_totals[:1]
+        self.n_frames = self._csr_totals[1:]
         self.utt_seg_off = torch.zeros(self.n_utts + 1, dtype=torch.int64, device=dev)
 
     def close(self):
@@ -301,11 +303,11 @@ class PackedBatch:
         except Exception:
             pass
 
-    @staticmethod
-    def _stream():
+    def _stream(self):
+        """The caller's current stream ON THE PLAN'S DEVICE (which need not be the current device)."""
         import torch
 
-        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def pack(self, waveforms) -> "torch.Tensor":
         """List of 1-D tensors/arrays (or a [B, N] tensor) -> one packed 1-D CUDA tensor."""
@@ -358,13 +360,19 @@ class PackedBatch:
             self.n_seg.data_ptr(), self.utt_seg_off.data_ptr(), self._stream()))
         return self.seg_off, self.n_seg
 
-    def pool(self, emb, out, colsum=None, accumulate: bool = False):
+    def pool(self, emb, out, colsum=None, accumulate: bool = False, emb_ready: bool = False,
+             rows_from_device: bool = False):
         """K4 with the device-resident CSR of :meth:`frame_csr`.  ``out`` is [capacity, D] float32; ``colsum``
-        ([D+1] float64) receives the column sums of the pooled vectors, added to its content when ``accumulate``."""
+        ([D+1] float64) receives the column sums of the pooled vectors, added to its content when ``accumulate``.
+
+        emb_ready        : the previous launch on this stream is this batch's :meth:`boundaries` (or anything else that
+                           does not write ``emb``): the kernel may start fetching embeddings before that launch ends
+        rows_from_device : ``emb`` is an allocation of at least as many rows as the segments cover; the covered row
+                           count is taken from the device (written by :meth:`boundaries`) instead of ``emb.shape[0]``"""
         from .pooling import _pool_device
 
         return _pool_device(self.ctx, emb, self.seg_off, int(out.shape[0]), self.n_seg, out, colsum, self._stream(),
-                            accumulate)
+                            accumulate, plan=self.handle, emb_ready=emb_ready, rows_from_device=rows_from_device)
 
     # ---- host views (synchronising; for tests and the numpy-facing callers)
     def mel_of(self, b: int):

@@ -80,7 +80,9 @@ struct alignas(16) MelTile {
 };
 static_assert(sizeof(MelTile) == 64, "MelTile is copied as four 16-byte pieces");
 
-// Scratch for the pool kernel's cross-CTA partial sums.
+// Scratch for the pool kernel's cross-CTA partial sums.  One launch at a time may use a scratch block: a plan owns
+// one (a plan has one launch in flight at a time anyway), and the context owns the block used by calls without a plan,
+// whose launches are ordered against each other with an event (see launch_mean_pool).
 struct PoolScratch {
     int max_ctas = 0;
     int max_dim = 0;
@@ -109,7 +111,10 @@ struct aat_ctx {
     double2 *twiddle = nullptr;    // device [7 * 20], W_400^(k1 * n2) for k1 = 1, 2, 3, 4, 5, 10, 15 (row-major over n2)
     double2 *log_table = nullptr;  // device [32], (1/c_i, -log10(1/c_i)) for the log-mel kernel's log10
     aat::MelSchedule mel{};
-    aat::PoolScratch pool{};
+    aat::PoolScratch pool{};         // scratch of pool launches that name no plan
+    std::mutex pool_mutex;           // ... which are ordered against each other: each waits for `pool_done`, recorded
+    cudaEvent_t pool_done = nullptr; //     behind the previous one (on whatever stream that was)
+    bool pool_done_recorded = false;
     // staging for aat_host_* entry points (grown on demand, never inside stream capture)
     void *dev_scratch = nullptr;
     size_t dev_scratch_bytes = 0;
@@ -147,6 +152,10 @@ struct aat_plan {
     int32_t *d_chunk_first = nullptr;   // [B+1]
     double *d_norm_partial = nullptr;   // [norm_chunks, 3] (n, mean, M2)
     double *d_norm_stats = nullptr;     // [B, 2] (mean, population variance)
+    aat::PoolScratch pool{};            // cross-CTA scratch of the pool kernel (empty for the cached host-API plans)
+    // on-device synthetic inputs (aat_synth_waveforms): slots of the per-utterance burst tables in the caller's workspace
+    int64_t total_bursts = 0;
+    int64_t *d_burst_off = nullptr;     // [B+1]
 };
 
 namespace aat {
@@ -162,9 +171,9 @@ int launch_process_boarders(aat_ctx *ctx, int64_t n_samples, const int64_t *boar
                             int32_t *status, cudaStream_t stream);
 int launch_segment_frame_csr(aat_ctx *ctx, const aat_plan *plan, const int64_t *seg_len, const int32_t *seg_count,
                              int64_t *seg_off, int64_t *n_seg, int64_t *utt_seg_off, cudaStream_t stream);
-int launch_mean_pool(aat_ctx *ctx, const void *emb, int emb_dtype, int64_t n_rows, int32_t dim,
+int launch_mean_pool(aat_ctx *ctx, const aat_plan *plan, const void *emb, int emb_dtype, int64_t n_rows, int32_t dim,
                      const int64_t *seg_off, int64_t n_seg, const int64_t *n_seg_dev, float *out, double *colsum,
-                     bool colsum_accumulate, cudaStream_t stream);
+                     int flags, cudaStream_t stream);
 int launch_colsum_accumulate(double *acc, const double *colsum, int32_t dim, cudaStream_t stream);
 int launch_colsum_finalize(const double *acc, int32_t dim, float *mean, cudaStream_t stream);
 int launch_normalize(aat_ctx *ctx, const aat_plan *plan, const void *wave, int in_dtype, int mode, void *out,
@@ -177,10 +186,15 @@ int launch_scatter_mel_segments(aat_ctx *ctx, const aat_plan *plan, const float 
                                 int64_t s_max, int64_t max_items, float *out, int32_t *status, cudaStream_t stream);
 int launch_masked_mean_pool(const void *emb, int emb_dtype, int64_t n_rows, int64_t seq_len, int32_t dim,
                             const int64_t *mask, float *out, int64_t *row_mask, cudaStream_t stream);
+int64_t synth_burst_capacity(int sampling_rate, int64_t n_samples);
+size_t synth_workspace_bytes(const aat_plan *plan);
+int launch_synth_waveforms(aat_ctx *ctx, const aat_plan *plan, uint64_t seed_base, int64_t utt_index_base, float *wave,
+                           void *workspace, cudaStream_t stream);
+int launch_synth_normal(aat_ctx *ctx, float *out, int64_t n, uint64_t seed, cudaStream_t stream);
 constexpr int kNormChunk = 4096;
 int logmel_tables_init(aat_ctx *ctx);
-int pool_scratch_init(aat_ctx *ctx);
-void pool_scratch_free(aat_ctx *ctx);
+int pool_scratch_init(int num_sms, PoolScratch *ps);
+void pool_scratch_free(PoolScratch *ps);
 
 constexpr int kMelFramesPerTile = 16; // frames one CTA of the log-mel kernel produces
 

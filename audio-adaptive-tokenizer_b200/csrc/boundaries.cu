@@ -176,7 +176,8 @@ __device__ void build_frame_csr(int n_utts, const int64_t *seg_slot_off, const i
     }
     __syncthreads();
     if (tid == 0) {
-        *n_seg_out = s_seg[n_utts];
+        n_seg_out[0] = s_seg[n_utts];
+        n_seg_out[1] = s_frm[n_utts]; // the frames the CSR covers (AAT_POOL_ROWS_FROM_DEVICE)
         seg_off[s_seg[n_utts]] = s_frm[n_utts];
     }
     if (utt_seg_off_out)
@@ -688,7 +689,8 @@ __global__ void __launch_bounds__(kThreads) boundaries_kernel_t(const BoundaryPa
             if (p.utt_seg_off) p.utt_seg_off[utt] = base_seg;
             if (utt == p.n_utts - 1) {
                 if (p.utt_seg_off) p.utt_seg_off[p.n_utts] = base_seg + my_cnt;
-                *p.n_seg = base_seg + my_cnt;
+                p.n_seg[0] = base_seg + my_cnt;
+                p.n_seg[1] = base_frm + my_frm; // the frames the CSR covers (AAT_POOL_ROWS_FROM_DEVICE)
                 p.seg_off[base_seg + my_cnt] = base_frm + my_frm;
             }
             s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1); // after this CTA's look-back

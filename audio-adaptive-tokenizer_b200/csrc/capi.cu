@@ -39,6 +39,11 @@ struct DeviceGuard {
     }
 };
 
+// device entry points run on the context's device whatever the caller's current device is
+#define AAT_DEVICE_GUARD(ctx)                  \
+    DeviceGuard guard__((ctx)->device);         \
+    AAT_REQUIRE(guard__.ok, AAT_ERR_CUDA, "cudaSetDevice(%d) failed", (ctx)->device)
+
 template <typename T>
 int upload(T **dst, const T *src, size_t n)
 {
@@ -204,7 +209,8 @@ static int init_context(aat_ctx *ctx, const double *window_host, const double *m
     if ((rc = build_mel_schedule(ctx, mel_filters_host))) return rc;
 
     if ((rc = logmel_tables_init(ctx))) return rc;
-    if ((rc = pool_scratch_init(ctx))) return rc;
+    if ((rc = pool_scratch_init(ctx->num_sms, &ctx->pool))) return rc;
+    AAT_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->pool_done, cudaEventDisableTiming));
     AAT_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking));
     return AAT_OK;
 }
@@ -252,7 +258,8 @@ int aat_destroy(aat_ctx *ctx)
     cudaFree(ctx->log_table);
     cudaFree(ctx->mel.filter_desc);
     cudaFree(ctx->mel.weight);
-    pool_scratch_free(ctx);
+    pool_scratch_free(&ctx->pool);
+    if (ctx->pool_done) cudaEventDestroy(ctx->pool_done);
     if (ctx->dev_scratch) cudaFree(ctx->dev_scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->host_stream) cudaStreamDestroy(ctx->host_stream);
@@ -315,7 +322,9 @@ int aat_get_config(const aat_ctx *ctx, aat_config *out)
     return AAT_OK;
 }
 
-int aat_plan_create(aat_ctx *ctx, int32_t n_utts, const int64_t *n_samples_host, aat_plan **out)
+// with_pool_scratch: the cross-CTA scratch of the pool kernel (14.5 MB); the single-utterance plans cached for the
+// aat_host_* entry points never pool and go without.
+static int plan_create(aat_ctx *ctx, int32_t n_utts, const int64_t *n_samples_host, bool with_pool_scratch, aat_plan **out)
 {
     AAT_REQUIRE(ctx && out && (n_samples_host || n_utts == 0), AAT_ERR_INVALID, "aat_plan_create: NULL argument");
     AAT_REQUIRE(n_utts >= 0, AAT_ERR_INVALID, "aat_plan_create: negative n_utts");
@@ -329,6 +338,7 @@ int aat_plan_create(aat_ctx *ctx, int32_t n_utts, const int64_t *n_samples_host,
     plan->h_frame_off.assign(n_utts + 1, 0);
     plan->h_seg_slot_off.assign(n_utts + 1, 0);
     std::vector<int32_t> chunk_first(n_utts + 1, 0), chunk_utt;
+    std::vector<int64_t> burst_off(n_utts + 1, 0);
     std::vector<MelTile> tiles_desc;
     const int hop = ctx->cfg.hop_length, n_mels = ctx->cfg.num_mel_filters;
     const int64_t stage_pad = (((int64_t)(kMelFramesPerTile - 1) * hop + kNfft) + 3) & ~int64_t(3);
@@ -363,6 +373,7 @@ int aat_plan_create(aat_ctx *ctx, int32_t n_utts, const int64_t *n_samples_host,
             d.interior = (g0 >= 0 && g0 + stage_pad <= n) ? 1 : 0;
             tiles_desc.push_back(d);
         }
+        burst_off[b + 1] = burst_off[b] + synth_burst_capacity(ctx->cfg.sampling_rate, n);
         const int64_t chunks = (n + kNormChunk - 1) / kNormChunk;
         chunk_first[b + 1] = chunk_first[b] + (int32_t)chunks;
         chunk_utt.insert(chunk_utt.end(), (size_t)chunks, b);
@@ -378,11 +389,13 @@ int aat_plan_create(aat_ctx *ctx, int32_t n_utts, const int64_t *n_samples_host,
         (rc = upload(&plan->d_seg_slot_off, plan->h_seg_slot_off.data(), (size_t)n_utts + 1)) ||
         (rc = upload(&plan->d_mel_tile, tiles_desc.data(), tiles_desc.size())) ||
         (rc = upload(&plan->d_chunk_utt, chunk_utt.data(), chunk_utt.size())) ||
-        (rc = upload(&plan->d_chunk_first, chunk_first.data(), chunk_first.size()))) {
+        (rc = upload(&plan->d_chunk_first, chunk_first.data(), chunk_first.size())) ||
+        (rc = upload(&plan->d_burst_off, burst_off.data(), burst_off.size()))) {
         aat_plan_destroy(plan);
         return rc;
     }
     plan->norm_chunks = (int32_t)chunk_utt.size();
+    plan->total_bursts = burst_off[n_utts];
     if (cudaMalloc(&plan->d_norm_partial, sizeof(double) * 3 * (size_t)(plan->norm_chunks ? plan->norm_chunks : 1)) != cudaSuccess ||
         cudaMalloc(&plan->d_norm_stats, sizeof(double) * 2 * (size_t)(n_utts ? n_utts : 1)) != cudaSuccess) {
         aat_plan_destroy(plan);
@@ -399,8 +412,20 @@ int aat_plan_create(aat_ctx *ctx, int32_t n_utts, const int64_t *n_samples_host,
         aat_plan_destroy(plan);
         AAT_REQUIRE(false, AAT_ERR_CUDA, "aat_plan_create: out of device memory");
     }
+    if (with_pool_scratch) {
+        const int prc = pool_scratch_init(ctx->num_sms, &plan->pool);
+        if (prc != AAT_OK) {
+            aat_plan_destroy(plan);
+            return prc;
+        }
+    }
     *out = plan;
     return AAT_OK;
+}
+
+int aat_plan_create(aat_ctx *ctx, int32_t n_utts, const int64_t *n_samples_host, aat_plan **out)
+{
+    return plan_create(ctx, n_utts, n_samples_host, true, out);
 }
 
 int aat_plan_destroy(aat_plan *plan)
@@ -419,6 +444,8 @@ int aat_plan_destroy(aat_plan *plan)
     cudaFree(plan->d_chunk_first);
     cudaFree(plan->d_norm_partial);
     cudaFree(plan->d_norm_stats);
+    cudaFree(plan->d_burst_off);
+    pool_scratch_free(&plan->pool);
     delete plan;
     return AAT_OK;
 }
@@ -443,6 +470,7 @@ int aat_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave_dev, int wav
 {
     AAT_REQUIRE(ctx && plan && wave_dev && mel_dev, AAT_ERR_INVALID, "aat_logmel: NULL argument");
     AAT_REQUIRE(plan->ctx == ctx, AAT_ERR_INVALID, "aat_logmel: plan belongs to another context");
+    AAT_DEVICE_GUARD(ctx);
     return launch_logmel(ctx, plan, wave_dev, wave_dtype, mel_dev, amp_dev, static_cast<cudaStream_t>(stream));
 }
 
@@ -457,6 +485,7 @@ int aat_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel_dev, con
                 "aat_boundaries: NULL argument");
     AAT_REQUIRE(mel_dev || amp_dev, AAT_ERR_INVALID, "aat_boundaries: need mel_dev or amp_dev");
     AAT_REQUIRE(plan->ctx == ctx, AAT_ERR_INVALID, "aat_boundaries: plan belongs to another context");
+    AAT_DEVICE_GUARD(ctx);
     return launch_boundaries(ctx, plan, mel_dev, amp_dev, seg_start_dev, seg_len_dev, seg_count_dev, minima_dev,
                              minima_count_dev, status_dev, seg_off_dev, n_seg_dev, utt_seg_off_dev,
                              static_cast<cudaStream_t>(stream));
@@ -469,6 +498,7 @@ int aat_process_boarders(aat_ctx *ctx, int64_t n_samples, const int64_t *boarder
     AAT_REQUIRE(ctx && (boarders_dev || n_boarders == 0) && seg_start_dev && seg_len_dev && seg_count_dev && status_dev,
                 AAT_ERR_INVALID, "aat_process_boarders: NULL argument");
     AAT_REQUIRE(n_samples >= 0 && n_boarders >= 0 && capacity >= 0, AAT_ERR_INVALID, "aat_process_boarders: negative size");
+    AAT_DEVICE_GUARD(ctx);
     return launch_process_boarders(ctx, n_samples, boarders_dev, n_boarders, seg_start_dev, seg_len_dev, capacity,
                                    seg_count_dev, status_dev, static_cast<cudaStream_t>(stream));
 }
@@ -478,28 +508,35 @@ int aat_segment_frame_csr(aat_ctx *ctx, const aat_plan *plan, const int64_t *seg
 {
     AAT_REQUIRE(ctx && plan && seg_len_dev && seg_count_dev && seg_off_dev && n_seg_dev, AAT_ERR_INVALID,
                 "aat_segment_frame_csr: NULL argument");
+    AAT_DEVICE_GUARD(ctx);
     return launch_segment_frame_csr(ctx, plan, seg_len_dev, seg_count_dev, seg_off_dev, n_seg_dev, utt_seg_off_dev,
                                     static_cast<cudaStream_t>(stream));
 }
 
-int aat_segment_mean_pool(aat_ctx *ctx, const void *emb_dev, int emb_dtype, int64_t n_rows, int32_t dim,
-                          const int64_t *seg_off_dev, int64_t n_seg, const int64_t *n_seg_dev, float *out_dev,
-                          double *colsum_dev, int colsum_accumulate, void *stream)
+int aat_segment_mean_pool(aat_ctx *ctx, const aat_plan *plan, const void *emb_dev, int emb_dtype, int64_t n_rows,
+                          int32_t dim, const int64_t *seg_off_dev, int64_t n_seg, const int64_t *n_seg_dev,
+                          float *out_dev, double *colsum_dev, int flags, void *stream)
 {
     AAT_REQUIRE(ctx, AAT_ERR_INVALID, "aat_segment_mean_pool: NULL context");
-    return launch_mean_pool(ctx, emb_dev, emb_dtype, n_rows, dim, seg_off_dev, n_seg, n_seg_dev, out_dev, colsum_dev,
-                            colsum_accumulate != 0, static_cast<cudaStream_t>(stream));
+    AAT_REQUIRE(plan == nullptr || plan->ctx == ctx, AAT_ERR_INVALID, "aat_segment_mean_pool: plan belongs to another context");
+    AAT_REQUIRE((flags & ~(AAT_POOL_ACCUMULATE | AAT_POOL_EMB_READY | AAT_POOL_ROWS_FROM_DEVICE)) == 0, AAT_ERR_INVALID,
+                "aat_segment_mean_pool: unknown flag bits 0x%x", flags);
+    AAT_DEVICE_GUARD(ctx);
+    return launch_mean_pool(ctx, plan, emb_dev, emb_dtype, n_rows, dim, seg_off_dev, n_seg, n_seg_dev, out_dev,
+                            colsum_dev, flags, static_cast<cudaStream_t>(stream));
 }
 
 int aat_colsum_accumulate(aat_ctx *ctx, double *acc_dev, const double *colsum_dev, int32_t dim, void *stream)
 {
     AAT_REQUIRE(ctx && acc_dev && colsum_dev && dim > 0, AAT_ERR_INVALID, "aat_colsum_accumulate: bad argument");
+    AAT_DEVICE_GUARD(ctx);
     return launch_colsum_accumulate(acc_dev, colsum_dev, dim, static_cast<cudaStream_t>(stream));
 }
 
 int aat_colsum_finalize(aat_ctx *ctx, const double *acc_dev, int32_t dim, float *mean_dev, void *stream)
 {
     AAT_REQUIRE(ctx && acc_dev && mean_dev && dim > 0, AAT_ERR_INVALID, "aat_colsum_finalize: bad argument");
+    AAT_DEVICE_GUARD(ctx);
     return launch_colsum_finalize(acc_dev, dim, mean_dev, static_cast<cudaStream_t>(stream));
 }
 
@@ -508,6 +545,7 @@ int aat_normalize(aat_ctx *ctx, const aat_plan *plan, const void *wave_dev, int 
 {
     AAT_REQUIRE(ctx && plan && wave_dev && (out_dev || stats_dev), AAT_ERR_INVALID, "aat_normalize: NULL argument");
     AAT_REQUIRE(plan->ctx == ctx, AAT_ERR_INVALID, "aat_normalize: plan belongs to another context");
+    AAT_DEVICE_GUARD(ctx);
     return launch_normalize(ctx, plan, wave_dev, in_dtype, mode, out_dev, out_dtype, stats_dev,
                             static_cast<cudaStream_t>(stream));
 }
@@ -519,6 +557,7 @@ int aat_pad_segment_boarders(aat_ctx *ctx, const aat_plan *plan, const int64_t *
     AAT_REQUIRE(ctx && plan && seg_len_dev && seg_count_dev && boarders_dev && mask_dev && status_dev, AAT_ERR_INVALID,
                 "aat_pad_segment_boarders: NULL argument");
     AAT_REQUIRE(s_max >= 0, AAT_ERR_INVALID, "aat_pad_segment_boarders: negative s_max");
+    AAT_DEVICE_GUARD(ctx);
     return launch_pad_boarders(plan, seg_len_dev, seg_count_dev, s_max, boarders_dev, mask_dev, status_dev,
                                static_cast<cudaStream_t>(stream));
 }
@@ -531,6 +570,7 @@ int aat_scatter_segments(aat_ctx *ctx, const float *wave_padded_dev, int64_t n_m
                 "aat_scatter_segments: NULL argument");
     AAT_REQUIRE(n_max >= 0 && n_utts >= 0 && s_max >= 0 && max_frames >= 0, AAT_ERR_INVALID,
                 "aat_scatter_segments: negative size");
+    AAT_DEVICE_GUARD(ctx);
     return launch_scatter_segments(wave_padded_dev, n_max, n_utts, boarders_dev, s_max, max_frames, out_dev, mask_dev,
                                    status_dev, static_cast<cudaStream_t>(stream));
 }
@@ -541,6 +581,7 @@ int aat_scatter_mel_segments(aat_ctx *ctx, const aat_plan *plan, const float *me
     AAT_REQUIRE(ctx && plan && mel_dev && boarders_dev && out_dev && status_dev, AAT_ERR_INVALID,
                 "aat_scatter_mel_segments: NULL argument");
     AAT_REQUIRE(s_max >= 0 && max_items >= 0, AAT_ERR_INVALID, "aat_scatter_mel_segments: negative size");
+    AAT_DEVICE_GUARD(ctx);
     return launch_scatter_mel_segments(ctx, plan, mel_dev, boarders_dev, s_max, max_items, out_dev, status_dev,
                                        static_cast<cudaStream_t>(stream));
 }
@@ -550,8 +591,29 @@ int aat_masked_mean_pool(aat_ctx *ctx, const void *emb_dev, int emb_dtype, int64
 {
     AAT_REQUIRE(ctx && (emb_dev || n_rows == 0) && mask_dev && out_dev, AAT_ERR_INVALID, "aat_masked_mean_pool: NULL argument");
     AAT_REQUIRE(n_rows >= 0 && seq_len >= 0 && dim > 0, AAT_ERR_INVALID, "aat_masked_mean_pool: negative size");
+    AAT_DEVICE_GUARD(ctx);
     return launch_masked_mean_pool(emb_dev, emb_dtype, n_rows, seq_len, dim, mask_dev, out_dev, row_mask_dev,
                                    static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ synthetic inputs
+int64_t aat_synth_workspace_bytes(const aat_plan *plan) { return plan ? (int64_t)synth_workspace_bytes(plan) : -1; }
+
+int aat_synth_waveforms(aat_ctx *ctx, const aat_plan *plan, uint64_t seed_base, int64_t utt_index_base, float *wave_dev,
+                        void *workspace_dev, void *stream)
+{
+    AAT_REQUIRE(ctx && plan && wave_dev && workspace_dev, AAT_ERR_INVALID, "aat_synth_waveforms: NULL argument");
+    AAT_REQUIRE(plan->ctx == ctx, AAT_ERR_INVALID, "aat_synth_waveforms: plan belongs to another context");
+    AAT_DEVICE_GUARD(ctx);
+    return launch_synth_waveforms(ctx, plan, seed_base, utt_index_base, wave_dev, workspace_dev,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+int aat_synth_normal(aat_ctx *ctx, float *out_dev, int64_t n, uint64_t seed, void *stream)
+{
+    AAT_REQUIRE(ctx && (out_dev || n == 0) && n >= 0, AAT_ERR_INVALID, "aat_synth_normal: bad argument");
+    AAT_DEVICE_GUARD(ctx);
+    return launch_synth_normal(ctx, out_dev, n, seed, static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------------------------------------ host API
@@ -570,7 +632,7 @@ static int host_plan_for(aat_ctx *ctx, int64_t n_samples, aat_plan **out)
             return AAT_OK;
         }
     aat_plan *plan = nullptr;
-    int rc = aat_plan_create(ctx, 1, &n_samples, &plan);
+    int rc = plan_create(ctx, 1, &n_samples, false, &plan);
     if (rc) return rc;
     cache.insert(cache.begin(), std::make_pair(n_samples, plan));
     if (cache.size() > 8) {
@@ -780,8 +842,8 @@ int aat_host_mean_pool(aat_ctx *ctx, const void *emb_host, int emb_dtype, int64_
     cudaStream_t st = ctx->host_stream;
     if (emb_bytes) AAT_CUDA_CHECK(cudaMemcpyAsync(d_emb, emb_host, emb_bytes, cudaMemcpyHostToDevice, st));
     AAT_CUDA_CHECK(cudaMemcpyAsync(d_off, seg_off_host, off_bytes, cudaMemcpyHostToDevice, st));
-    rc = launch_mean_pool(ctx, d_emb, emb_dtype, n_rows, dim, d_off, n_seg, nullptr, d_out, colsum_host ? d_cs : nullptr,
-                          false, st);
+    rc = launch_mean_pool(ctx, nullptr, d_emb, emb_dtype, n_rows, dim, d_off, n_seg, nullptr, d_out,
+                          colsum_host ? d_cs : nullptr, 0, st);
     if (rc) return rc;
     if (out_bytes) AAT_CUDA_CHECK(cudaMemcpyAsync(out_host, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
     if (colsum_host) AAT_CUDA_CHECK(cudaMemcpyAsync(colsum_host, d_cs, cs_bytes, cudaMemcpyDeviceToHost, st));

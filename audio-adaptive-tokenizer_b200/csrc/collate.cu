@@ -397,9 +397,9 @@ int launch_normalize(aat_ctx *ctx, const aat_plan *plan, const void *wave, int i
 int launch_pad_boarders(const aat_plan *plan, const int64_t *seg_len, const int32_t *seg_count, int64_t s_max,
                         int64_t *boarders, int64_t *mask, int32_t *status, cudaStream_t stream)
 {
-    if (plan->n_utts == 0 || s_max == 0) return AAT_OK;
+    if (plan->n_utts == 0) return AAT_OK;
     AAT_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)plan->n_utts, stream));
-    const int warps = 4;
+    const int warps = 4; // s_max == 0 still runs: an utterance with segments must report AAT_ERR_CAPACITY
     pad_boarders_kernel<<<(plan->n_utts + warps - 1) / warps, warps * 32, 0, stream>>>(
         plan->n_utts, s_max, plan->d_seg_slot_off, seg_len, seg_count, boarders, mask, status);
     AAT_LAUNCH_CHECK();
@@ -409,9 +409,10 @@ int launch_pad_boarders(const aat_plan *plan, const int64_t *seg_len, const int3
 int launch_scatter_segments(const float *wave, int64_t n_max, int32_t n_utts, const int64_t *boarders, int64_t s_max,
                             int64_t max_frames, float *out, float *mask, int32_t *status, cudaStream_t stream)
 {
-    if (n_utts == 0 || s_max == 0 || max_frames == 0) return AAT_OK;
+    if (n_utts == 0) return AAT_OK;
+    AAT_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)n_utts, stream)); // also on the empty shapes below
+    if (s_max == 0 || max_frames == 0) return AAT_OK;
     AAT_REQUIRE((int64_t)n_utts * s_max < (int64_t)INT32_MAX, AAT_ERR_UNSUPPORTED, "aat_scatter_segments: too many rows");
-    AAT_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)n_utts, stream));
     scatter_segments_kernel<<<(unsigned)(n_utts * s_max), 256, 0, stream>>>(wave, n_max, boarders, s_max, max_frames, out,
                                                                           mask, status);
     AAT_LAUNCH_CHECK();
@@ -421,9 +422,10 @@ int launch_scatter_segments(const float *wave, int64_t n_max, int32_t n_utts, co
 int launch_scatter_mel_segments(aat_ctx *ctx, const aat_plan *plan, const float *mel, const int64_t *boarders,
                                 int64_t s_max, int64_t max_items, float *out, int32_t *status, cudaStream_t stream)
 {
-    if (plan->n_utts == 0 || s_max == 0 || max_items == 0) return AAT_OK;
+    if (plan->n_utts == 0) return AAT_OK;
+    AAT_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)plan->n_utts, stream)); // also on the empty shapes below
+    if (s_max == 0 || max_items == 0) return AAT_OK;
     AAT_REQUIRE((int64_t)plan->n_utts * s_max < (int64_t)INT32_MAX, AAT_ERR_UNSUPPORTED, "aat_scatter_mel_segments: too many rows");
-    AAT_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)plan->n_utts, stream));
     scatter_mel_segments_kernel<<<(unsigned)(plan->n_utts * s_max), 256, 0, stream>>>(
         mel, plan->d_frame_off, plan->d_n_samples, ctx->cfg.hop_length, ctx->cfg.num_mel_filters, boarders, s_max,
         max_items, out, status);

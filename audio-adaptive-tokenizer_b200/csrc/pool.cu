@@ -22,10 +22,17 @@
 //     a dependency chain nor a deadlock; flags are reset by their single consumer (graph-replay safe);
 //   * optional epilogue: float64 column sums of the pooled vectors (input of the dataset-mean
 //     allreduce) are accumulated per CTA and reduced in CTA order by a second tiny kernel;
-//   * launched with programmatic dependent launch: the whole ring of embedding stages is requested before the
-//     kernel waits for its predecessor (the boundary scan, whose outputs are only the offsets), the first offsets
-//     window arrives by one bulk copy, and the owner of a cut segment looks at its neighbour's partial sums two
-//     stages before its last row (profiles/r1_pool_timeline*.txt, r1_pool_ab.txt).
+//   * launched with programmatic dependent launch.  When the caller vouches that the kernel in front of this one on
+//     the stream does not write the embeddings (AAT_POOL_EMB_READY: the library's own boundary scan, whose outputs
+//     are only the offsets), the whole ring of embedding stages is requested before the kernel waits for that
+//     predecessor; otherwise nothing is read before the wait.  The first offsets window arrives by one bulk copy, and
+//     the owner of a cut segment looks at its neighbour's partial sums two stages before its last row
+//     (profiles/r1_pool_timeline*.txt, r1_pool_ab.txt);
+//   * the cross-CTA scratch (partial sums, flags, per-CTA column sums) belongs to the plan the launch names, or to the
+//     context for launches without a plan, which are ordered against each other by an event: two launches never share
+//     a scratch block while in flight.  An owner only ever waits for CTAs with a HIGHER index, which publish without
+//     waiting for anything, so with CTAs dispatched in index order the kernel makes progress whatever else occupies
+//     the SMs (a second pool launch on another stream, another tenant).
 //
 // Algorithmic bytes per launch: n_rows*dim*e + S*dim*4 + (S+1)*8  (SURVEY.md §8d).
 #include <cuda_bf16.h>
@@ -67,8 +74,8 @@ constexpr int kStageBytes = AAT_POOL_STAGE_KB * 1024; // 24 KB: 8 rows of 768 fp
 constexpr int kMaxConsumers = 256;
 constexpr int kMaxSlabs = 4; // 16-byte column slabs per consumer thread -> dim*e <= 16 KB
 constexpr int kMaxCtasPerSm = AAT_POOL_CTAS;
-// stages requested before the dependency wait (<= kStages); measured at config 2: 1 -> 0.1907 ms/step, 2 -> 0.1899,
-// 4 -> 0.1895, and the event-timed kernel alone is no slower (gpurun b18)
+// Stages requested before the dependency wait when the caller allows it (AAT_POOL_EMB_READY); measured at config 2:
+// 1 -> 0.1907 ms/step, 2 -> 0.1899, 4 -> 0.1895, and the event-timed kernel alone is no slower (gpurun b18).
 constexpr int kPreStages = kStages;
 constexpr int kOffCache = 256; // segment offsets of the CTA's neighbourhood kept in shared memory
 
@@ -209,6 +216,8 @@ struct PoolParams {
     int rows_per_stage;
     int slabs_per_row; // row_bytes / 16
     int n_consumers;
+    int pre_stages;    // stages requested before the dependency wait (0 unless the caller set AAT_POOL_EMB_READY)
+    int rows_from_dev; // n_seg_dev[1] holds the number of rows the CSR covers; n_rows is an upper bound
 };
 
 __device__ __forceinline__ int64_t cta_row_begin(int64_t c, int64_t n_rows, int64_t G) { return (c * n_rows) / G; }
@@ -281,9 +290,10 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
     const int n_consumers = p.n_consumers;
     const int64_t G = gridDim.x;
     const int64_t c = blockIdx.x;
-    const int64_t r0 = cta_row_begin(c, p.n_rows, G);
-    const int64_t r1 = cta_row_begin(c + 1, p.n_rows, G);
-    const int64_t n_chunks = (r1 - r0 + p.rows_per_stage - 1) / p.rows_per_stage;
+    int64_t n_rows = p.n_rows;
+    int64_t r0 = cta_row_begin(c, n_rows, G);
+    int64_t r1 = cta_row_begin(c + 1, n_rows, G);
+    int64_t n_chunks = (r1 - r0 + p.rows_per_stage - 1) / p.rows_per_stage;
     const size_t stage_stride = (size_t)p.rows_per_stage * p.row_bytes;
 
     if (tid == 0) {
@@ -304,16 +314,24 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
         mbar_expect_tx(&s_full[s], bytes);
         bulk_g2s(smem_raw + s * stage_stride, p.emb + (size_t)row * p.row_bytes, bytes, &s_full[s]);
     };
-    // The embedding rows are not written by the kernel in front of this one (the boundary scan), so the whole ring
-    // is requested before the dependency wait: under programmatic dependent launch it lands while that kernel is
-    // still running.  Segment offsets and counts are its outputs and are only touched after the wait.
+    // When the caller vouches that the embedding rows are not written by the kernel in front of this one (the
+    // library's boundary scan), the whole ring is requested before the dependency wait: under programmatic dependent
+    // launch it lands while that kernel is still running.  Segment offsets and counts are its outputs and are only
+    // touched after the wait.
     const bool producer = tid == n_consumers;
-    const int64_t n_pre = n_chunks < kPreStages ? n_chunks : kPreStages;
+    const int64_t n_pre = n_chunks < p.pre_stages ? n_chunks : p.pre_stages;
     if (producer)
         for (int64_t ch = 0; ch < n_pre; ++ch) issue_stage(ch);
     pdl_wait();
     pdl_launch_dependents();
-    const int64_t S_total = p.n_seg_dev ? min(*p.n_seg_dev, p.n_seg) : p.n_seg;
+    const int64_t S_total = p.n_seg_dev ? min(p.n_seg_dev[0], p.n_seg) : p.n_seg;
+    if (p.rows_from_dev) { // the rows the CSR covers, as counted on the device: nothing beyond them is streamed
+        const int64_t covered = p.n_seg_dev[1];
+        if (covered < n_rows) n_rows = covered < 0 ? 0 : covered;
+        r0 = cta_row_begin(c, n_rows, G);
+        r1 = cta_row_begin(c + 1, n_rows, G);
+        n_chunks = (r1 - r0 + p.rows_per_stage - 1) / p.rows_per_stage;
+    }
 
     if (tid >= n_consumers) {
         // ============================== producer warp ==============================
@@ -323,7 +341,7 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
         } else if (lane == 0 && r0 < r1) {
             // the offsets window goes ahead of the bulk of the stream: a plain load issued later would queue behind
             // ~28 MB of bulk traffic from all CTAs and take 3.5-6 us (profiles/r1_pool_timeline_before.txt)
-            const OffWindow w = first_window(p.seg_off, r0, p.n_rows, S_total);
+            const OffWindow w = first_window(p.seg_off, r0, n_rows, S_total);
             if (w.bulk) {
                 mbar_expect_tx(&s_offbar, (uint32_t)(w.count * sizeof(int64_t)));
                 bulk_g2s(s_off, p.seg_off + w.first, (uint32_t)(w.count * sizeof(int64_t)), &s_offbar);
@@ -380,7 +398,7 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
         };
         int64_t idx;
         {
-            const OffWindow w = first_window(p.seg_off, r0, p.n_rows, S_total);
+            const OffWindow w = first_window(p.seg_off, r0, n_rows, S_total);
             if (w.bulk) {
                 mbar_wait(&s_offbar, 0); // the producer's bulk copy of the window has landed
                 cache_base = w.first;
@@ -494,9 +512,9 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
                 } else {
                     // this CTA owns a segment that continues into later CTAs: add their pieces in CTA order
                     const int64_t last_row = seg_end - 1;
-                    int64_t ce = p.n_rows > 0 ? (last_row < p.n_rows ? (last_row * G) / p.n_rows : G - 1) : G - 1;
-                    while (ce + 1 < G && cta_row_begin(ce + 1, p.n_rows, G) <= last_row) ++ce;
-                    while (ce > c && cta_row_begin(ce, p.n_rows, G) > last_row) --ce;
+                    int64_t ce = n_rows > 0 ? (last_row < n_rows ? (last_row * G) / n_rows : G - 1) : G - 1;
+                    while (ce + 1 < G && cta_row_begin(ce + 1, n_rows, G) <= last_row) ++ce;
+                    while (ce > c && cta_row_begin(ce, n_rows, G) > last_row) --ce;
                     // the threads polled the flag at slightly different times: take the early path only if all saw it
                     const bool early = kEarlyCarry && ce == c + 1 && consumer_barrier_and(n_consumers, carry_flag != 0);
                     if (early) {
@@ -506,12 +524,13 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
                         for (int k = 0; k < kCols; ++k) sum[k] = reduce_acc(0, k) + carry[k];
                         write_pooled(0, sum, nrows);
                     } else {
-                        if (tid == 0) {
-                            for (int64_t m = c + 1; m <= ce; ++m) {
-                                if (cta_row_begin(m, p.n_rows, G) == cta_row_begin(m + 1, p.n_rows, G)) continue;
-                                while (ld_acquire(p.head_flag + m) == 0) {}
-                                p.head_flag[m] = 0; // single consumer resets: safe for CUDA-graph replays
-                            }
+                        // every consumer thread polls its share of the flags (a giant segment spans hundreds of CTAs:
+                        // one thread polling them one after the other paid a global round trip per CTA); a flag is
+                        // reset by the thread that saw it, its single consumer (safe for CUDA-graph replays)
+                        for (int64_t m = c + 1 + tid; m <= ce; m += n_consumers) {
+                            if (cta_row_begin(m, n_rows, G) == cta_row_begin(m + 1, n_rows, G)) continue;
+                            while (ld_acquire(p.head_flag + m) == 0) {}
+                            p.head_flag[m] = 0;
                         }
                         consumer_barrier(n_consumers);
 #pragma unroll
@@ -521,11 +540,27 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
                             if (slab < p.slabs_per_row) {
 #pragma unroll
                                 for (int k = 0; k < kCols; ++k) sum[k] = reduce_acc(j, k);
-                                for (int64_t m = c + 1; m <= ce; ++m) {
-                                    if (cta_row_begin(m, p.n_rows, G) == cta_row_begin(m + 1, p.n_rows, G)) continue;
+                                // the pieces are added in CTA order, but fetched eight CTAs at a time: the loads of a
+                                // batch are independent, so a giant segment costs a round trip per batch, not per CTA
+                                constexpr int kBatch = 8;
+                                const float *piece = p.head + (size_t)slab * kCols;
+                                for (int64_t m0 = c + 1; m0 <= ce; m0 += kBatch) {
+                                    float v[kBatch][kCols];
 #pragma unroll
-                                    for (int k = 0; k < kCols; ++k)
-                                        sum[k] += __ldcg(p.head + (size_t)m * p.dim + slab * kCols + k);
+                                    for (int b = 0; b < kBatch; ++b) {
+                                        const int64_t m = m0 + b;
+                                        const bool live = m <= ce && cta_row_begin(m, n_rows, G) != cta_row_begin(m + 1, n_rows, G);
+#pragma unroll
+                                        for (int k = 0; k < kCols; k += 4) {
+                                            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                                            if (live) x = __ldcg(reinterpret_cast<const float4 *>(piece + (size_t)m * p.dim + k));
+                                            v[b][k] = x.x, v[b][k + 1] = x.y, v[b][k + 2] = x.z, v[b][k + 3] = x.w;
+                                        }
+                                    }
+#pragma unroll
+                                    for (int b = 0; b < kBatch; ++b)
+#pragma unroll
+                                        for (int k = 0; k < kCols; ++k) sum[k] += v[b][k]; // + 0 for the slots past ce
                                 }
                             }
                             write_pooled(j, sum, nrows);
@@ -668,7 +703,8 @@ __global__ void colsum_finalize_kernel(const double *acc, int dim, float *mean)
 }
 
 template <typename EmbT, int kSlabs>
-int launch_typed(aat_ctx *ctx, PoolParams &p, size_t smem, bool colsum, cudaStream_t stream, int *grid_out)
+int launch_typed(aat_ctx *ctx, const PoolScratch &ps, PoolParams &p, size_t smem, bool colsum, cudaStream_t stream,
+                 int *grid_out)
 {
     const int threads = p.n_consumers + 32;
     auto kernel = colsum ? pool_kernel<EmbT, kSlabs, true> : pool_kernel<EmbT, kSlabs, false>;
@@ -681,7 +717,7 @@ int launch_typed(aat_ctx *ctx, PoolParams &p, size_t smem, bool colsum, cudaStre
     AAT_REQUIRE(per_sm >= 1, AAT_ERR_UNSUPPORTED, "aat_segment_mean_pool: kernel does not fit on an SM");
     if (per_sm > kMaxCtasPerSm) per_sm = kMaxCtasPerSm;
     int grid = ctx->num_sms * per_sm;
-    if (grid > ctx->pool.max_ctas) grid = ctx->pool.max_ctas;
+    if (grid > ps.max_ctas) grid = ps.max_ctas;
     // small inputs: give every CTA at least two stages of rows, otherwise one segment spans dozens of CTAs
     // and its owner spends longer collecting pieces than streaming
     const int64_t min_rows = 2 * (int64_t)p.rows_per_stage;
@@ -695,42 +731,41 @@ int launch_typed(aat_ctx *ctx, PoolParams &p, size_t smem, bool colsum, cudaStre
 }
 
 template <typename EmbT>
-int launch_slabs(aat_ctx *ctx, PoolParams &p, int slabs, size_t smem, bool colsum, cudaStream_t stream, int *grid_out)
+int launch_slabs(aat_ctx *ctx, const PoolScratch &ps, PoolParams &p, int slabs, size_t smem, bool colsum,
+                 cudaStream_t stream, int *grid_out)
 {
     switch (slabs) {
-    case 1: return launch_typed<EmbT, 1>(ctx, p, smem, colsum, stream, grid_out);
-    case 2: return launch_typed<EmbT, 2>(ctx, p, smem, colsum, stream, grid_out);
-    default: return launch_typed<EmbT, 4>(ctx, p, smem, colsum, stream, grid_out);
+    case 1: return launch_typed<EmbT, 1>(ctx, ps, p, smem, colsum, stream, grid_out);
+    case 2: return launch_typed<EmbT, 2>(ctx, ps, p, smem, colsum, stream, grid_out);
+    default: return launch_typed<EmbT, 4>(ctx, ps, p, smem, colsum, stream, grid_out);
     }
 }
 
 } // namespace
 
-int pool_scratch_init(aat_ctx *ctx)
+int pool_scratch_init(int num_sms, PoolScratch *ps)
 {
-    PoolScratch &ps = ctx->pool;
-    ps.max_ctas = ctx->num_sms * kMaxCtasPerSm;
-    if (ps.max_ctas > 512) ps.max_ctas = 512; // colsum_reduce_kernel covers 32 slices x 16 rows
-    ps.max_dim = 4096;
-    AAT_CUDA_CHECK(cudaMalloc(&ps.head, sizeof(float) * (size_t)ps.max_ctas * ps.max_dim));
-    AAT_CUDA_CHECK(cudaMalloc(&ps.head_flag, sizeof(int) * (size_t)ps.max_ctas));
-    AAT_CUDA_CHECK(cudaMalloc(&ps.colsum, sizeof(double) * (size_t)ps.max_ctas * ps.max_dim));
-    AAT_CUDA_CHECK(cudaMemset(ps.head_flag, 0, sizeof(int) * (size_t)ps.max_ctas));
+    ps->max_ctas = num_sms * kMaxCtasPerSm;
+    if (ps->max_ctas > 512) ps->max_ctas = 512; // colsum_reduce_kernel covers 32 slices x 16 rows
+    ps->max_dim = 4096;
+    AAT_CUDA_CHECK(cudaMalloc(&ps->head, sizeof(float) * (size_t)ps->max_ctas * ps->max_dim));
+    AAT_CUDA_CHECK(cudaMalloc(&ps->head_flag, sizeof(int) * (size_t)ps->max_ctas));
+    AAT_CUDA_CHECK(cudaMalloc(&ps->colsum, sizeof(double) * (size_t)ps->max_ctas * ps->max_dim));
+    AAT_CUDA_CHECK(cudaMemset(ps->head_flag, 0, sizeof(int) * (size_t)ps->max_ctas));
     return AAT_OK;
 }
 
-void pool_scratch_free(aat_ctx *ctx)
+void pool_scratch_free(PoolScratch *ps)
 {
-    PoolScratch &ps = ctx->pool;
-    cudaFree(ps.head);
-    cudaFree(ps.head_flag);
-    cudaFree(ps.colsum);
-    ps = PoolScratch{};
+    cudaFree(ps->head);
+    cudaFree(ps->head_flag);
+    cudaFree(ps->colsum);
+    *ps = PoolScratch{};
 }
 
-int launch_mean_pool(aat_ctx *ctx, const void *emb, int emb_dtype, int64_t n_rows, int32_t dim,
-                     const int64_t *seg_off, int64_t n_seg, const int64_t *n_seg_dev, float *out, double *colsum,
-                     bool colsum_accumulate, cudaStream_t stream)
+static int launch_mean_pool_on(aat_ctx *ctx, const PoolScratch &ps, const void *emb, int emb_dtype, int64_t n_rows,
+                               int32_t dim, const int64_t *seg_off, int64_t n_seg, const int64_t *n_seg_dev, float *out,
+                               double *colsum, int flags, cudaStream_t stream)
 {
     int esize;
     switch (emb_dtype) {
@@ -740,13 +775,16 @@ int launch_mean_pool(aat_ctx *ctx, const void *emb, int emb_dtype, int64_t n_row
     default:
         AAT_REQUIRE(false, AAT_ERR_UNSUPPORTED, "aat_segment_mean_pool: embedding dtype must be F32, F16 or BF16");
     }
+    const bool colsum_accumulate = (flags & AAT_POOL_ACCUMULATE) != 0;
     AAT_REQUIRE(dim > 0 && n_rows >= 0 && n_seg >= 0, AAT_ERR_INVALID, "aat_segment_mean_pool: negative size");
+    AAT_REQUIRE(!(flags & AAT_POOL_ROWS_FROM_DEVICE) || n_seg_dev != nullptr, AAT_ERR_INVALID,
+                "aat_segment_mean_pool: AAT_POOL_ROWS_FROM_DEVICE needs n_seg_dev");
     const int64_t row_bytes = (int64_t)dim * esize;
     AAT_REQUIRE(row_bytes % 16 == 0, AAT_ERR_UNSUPPORTED,
                 "aat_segment_mean_pool: dim * sizeof(element) = %lld must be a multiple of 16", (long long)row_bytes);
-    AAT_REQUIRE(row_bytes <= 16 * kMaxConsumers * kMaxSlabs && dim <= ctx->pool.max_dim, AAT_ERR_UNSUPPORTED,
+    AAT_REQUIRE(row_bytes <= 16 * kMaxConsumers * kMaxSlabs && dim <= ps.max_dim, AAT_ERR_UNSUPPORTED,
                 "aat_segment_mean_pool: dim %d too large (row must be <= %d bytes, dim <= %d)", dim,
-                16 * kMaxConsumers * kMaxSlabs, ctx->pool.max_dim);
+                16 * kMaxConsumers * kMaxSlabs, ps.max_dim);
     AAT_REQUIRE((reinterpret_cast<uintptr_t>(emb) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                 AAT_ERR_INVALID, "aat_segment_mean_pool: emb_dev and out_dev must be 16-byte aligned");
     if (n_seg == 0) {
@@ -762,14 +800,17 @@ int launch_mean_pool(aat_ctx *ctx, const void *emb, int emb_dtype, int64_t n_row
     p.seg_off = seg_off;
     p.n_seg_dev = n_seg_dev;
     p.out = out;
-    p.head = ctx->pool.head;
-    p.head_flag = ctx->pool.head_flag;
-    p.colsum = ctx->pool.colsum;
+    p.head = ps.head;
+    p.head_flag = ps.head_flag;
+    p.colsum = ps.colsum;
     p.n_rows = n_rows;
     p.n_seg = n_seg;
     p.dim = dim;
     p.row_bytes = (int)row_bytes;
     p.slabs_per_row = (int)(row_bytes / 16);
+    p.rows_from_dev = (flags & AAT_POOL_ROWS_FROM_DEVICE) ? 1 : 0;
+    // the row split is only known after the dependency wait when the row count lives on the device
+    p.pre_stages = ((flags & AAT_POOL_EMB_READY) && !p.rows_from_dev) ? kPreStages : 0;
     int consumers = ((p.slabs_per_row + 31) / 32) * 32;
     int slabs = 1;
     while (consumers > kMaxConsumers) {
@@ -784,18 +825,44 @@ int launch_mean_pool(aat_ctx *ctx, const void *emb, int emb_dtype, int64_t n_row
     int rc, grid = 0;
     const bool want_colsum = colsum != nullptr;
     if (emb_dtype == AAT_F32)
-        rc = launch_slabs<float>(ctx, p, slabs, smem, want_colsum, stream, &grid);
+        rc = launch_slabs<float>(ctx, ps, p, slabs, smem, want_colsum, stream, &grid);
     else if (emb_dtype == AAT_F16)
-        rc = launch_slabs<__half>(ctx, p, slabs, smem, want_colsum, stream, &grid);
+        rc = launch_slabs<__half>(ctx, ps, p, slabs, smem, want_colsum, stream, &grid);
     else
-        rc = launch_slabs<__nv_bfloat16>(ctx, p, slabs, smem, want_colsum, stream, &grid);
+        rc = launch_slabs<__nv_bfloat16>(ctx, ps, p, slabs, smem, want_colsum, stream, &grid);
     if (rc != AAT_OK) return rc;
     if (want_colsum) {
         AAT_MAX_SMEM_CARVEOUT(colsum_reduce_kernel);
         AAT_CUDA_CHECK(launch_pdl(colsum_reduce_kernel, dim3((dim + 31) / 32), dim3(32 * kReduceSlices), 0, stream,
-                                  (const double *)ctx->pool.colsum, grid, (int)dim, n_seg, n_seg_dev, colsum,
+                                  (const double *)ps.colsum, grid, (int)dim, n_seg, n_seg_dev, colsum,
                                   colsum_accumulate));
         AAT_LAUNCH_CHECK();
+    }
+    return AAT_OK;
+}
+
+int launch_mean_pool(aat_ctx *ctx, const aat_plan *plan, const void *emb, int emb_dtype, int64_t n_rows, int32_t dim,
+                     const int64_t *seg_off, int64_t n_seg, const int64_t *n_seg_dev, float *out, double *colsum,
+                     int flags, cudaStream_t stream)
+{
+    if (plan != nullptr && plan->pool.head != nullptr) // the plan's own scratch: one launch per plan in flight
+        return launch_mean_pool_on(ctx, plan->pool, emb, emb_dtype, n_rows, dim, seg_off, n_seg, n_seg_dev, out, colsum,
+                                   flags, stream);
+    // No plan: the context's scratch.  Launches that share it are ordered against each other whatever streams they
+    // are on: each waits for the event recorded behind the previous one.  (Inside a stream capture the event cannot
+    // be used — a captured stream may not depend on uncaptured work — so captured plan-less launches must not run
+    // concurrently with other plan-less launches; name a plan there.)
+    std::lock_guard<std::mutex> lock(ctx->pool_mutex);
+    cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+    AAT_CUDA_CHECK(cudaStreamIsCapturing(stream, &capturing));
+    const bool use_event = capturing == cudaStreamCaptureStatusNone;
+    if (use_event && ctx->pool_done_recorded) AAT_CUDA_CHECK(cudaStreamWaitEvent(stream, ctx->pool_done, 0));
+    const int rc = launch_mean_pool_on(ctx, ctx->pool, emb, emb_dtype, n_rows, dim, seg_off, n_seg, n_seg_dev, out,
+                                       colsum, flags, stream);
+    if (rc != AAT_OK) return rc;
+    if (use_event) {
+        AAT_CUDA_CHECK(cudaEventRecord(ctx->pool_done, stream));
+        ctx->pool_done_recorded = true;
     }
     return AAT_OK;
 }

@@ -5,27 +5,35 @@
 
 A *step* is one pass of the whole hot path over one batch of synthetic input: K1+K2 log-mel,
 K3 boundaries (+ frame CSR in its tail), K4 mean-pool (with the column-sum epilogue feeding the dataset mean).
-The default workload is BASELINE.json configs[1]: 64 x 16 s utterances, HuBERT-base 768-d embeddings
+The headline workload is BASELINE.json configs[1] ("c2"): 64 x 16 s utterances, HuBERT-base 768-d embeddings
 on one B200; with N GPUs every rank runs that batch on its own shard (weak scaling, no data-path
 collective) and the ranks meet once, in the dataset-mean allreduce, at the end of the timed region.
 
-One JSON line on stdout (rank 0).  `value` = whole-job audio-hours/s with inputs resident in HBM;
-`e2e` = the same metric through the public batched API with HOST (pinned) buffers, H2D/D2H inside the
-timed region; `roofline` = the pool kernel's algorithmic bytes / its CUDA-event duration measured in
-the timed region, against MEASURED_PEAKS.json; `cpu_baseline` = the oracle port of the reference's
-CPU path on a bounded sample.  `--impl reference` times that CPU path alone with all host cores.
+One JSON line on stdout (rank 0).
+  value        whole-job audio-hours/s with inputs resident in HBM (generated there by the library's counter-based
+               generator, `aat_synth_*`; distinct utterances in every rotating buffer set)
+  e2e          the same metric through the public batched API with HOST (pinned) buffers, H2D/D2H inside the timed
+               region, plus the plain pinned-copy rate measured in the same run (`copy_peak`) as its own roofline
+  roofline     the pool kernel: algorithmic bytes / duration, against MEASURED_PEAKS.json.  Two clocks are printed:
+               `us_per_launch` = K back-to-back launches on rotating inputs inside ONE event pair (the kernel's
+               sustained rate; an event pair around a single ~30 us kernel measures the pair as much as the kernel),
+               and `sampled_in_step` = event pairs around every n-th launch of the timed region
+  cpu_baseline the oracle port of the reference's CPU path on a bounded sample (rank 0, N = 1)
+  configs      sub-records of the other BASELINE configs measured in the same run: c1 (one 10 s clip through the numpy
+               API), c3 (256 x 20 s, D = 1024), c4 (8 x 30 min), and c5: the dataset job — >= 1000 synthetic
+               audio-hours of DISTINCT utterances sharded over the N ranks, generated on the device chunk by chunk
+               and consumed by the path, ending in the one allreduce of the dataset-mean embedding, whose value is
+               checked against an independent reduction
+`--impl reference` times the reference's CPU path (oracle port) alone with all host cores.
 
 The kernels of a step are chained by programmatic dependent launch (each one's prologue overlaps its
-predecessor's tail).  A CUDA event in front of a kernel switches that overlap off for that launch, so the pool
-kernel is event-timed on every `--pool-sample-every`-th launch of the timed region only (default 8): the
-sampled launches give the kernel's duration in isolation (what the roofline needs), the others run the way a
-user's loop runs them (what `value` measures).  `kernel_us` comes from an extra, untimed pass with events
-around every kernel.
+predecessor's tail).  `kernel_us` comes from an extra, untimed pass with events around every kernel.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -49,6 +57,8 @@ WORKLOADS = {
     "c4": (8, 28_800_000, 768, 3),
 }
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+C5_AUDIO_HOURS = 1000.0    # BASELINE.json configs[4]
+DEFAULT_ROTATE = 4
 
 
 def workload_name(name):
@@ -56,14 +66,23 @@ def workload_name(name):
     return f"configs[{idx}]: batch {b} x {n / 16000:g} s synthetic 16 kHz utterances, {d}-d HuBERT-shaped embeddings"
 
 
-def make_waves(name, rank):
-    from aat_b200 import synth
+def hubert_rows_upper_bound(n_samples, min_segment_frames=2000):
+    """Rows an utterance's segments can cover under the per-segment-encode convention: sum_i ((L_i - 400) // 320 + 1)
+    <= sum_i L_i / 320, and the segments add up to at most n_samples + min_segment_frames (zero-padded tail)."""
+    return (n_samples + min_segment_frames) // 320 + 2
 
-    b, n, _, idx = WORKLOADS[name]
-    if name == "c4":  # a 30-min stream takes seconds to synthesise: tile two distinct streams
-        base = [synth.bursty_speech(n, synth.seed_for(4, i)) for i in range(2)]
-        return [base[i % 2] for i in range(b)]
-    return [synth.bursty_speech(n, synth.seed_for(idx + 1, rank * b + i)) for i in range(b)]
+
+def workload_config(name, world, rotate):
+    """`config` of the JSON line: the workload only, identical in both arms (the driver compares them)."""
+    b, n, d, _ = WORKLOADS[name]
+    resident_mb = rotate * (b * n * 4 + b * hubert_rows_upper_bound(n) * d * 4) / 1e6
+    return {
+        "workload": workload_name(name), "batch_per_gpu": b, "samples_per_utterance": n, "dim": d,
+        "embedding_dtype": "f32", "segment_convention": "per-segment encode: n_i = (L_i - 400) // 320 + 1 frames",
+        "parallelism": f"utterance-sharded dp{world}, one allreduce of {d + 1} f64",
+        "l2": f"b200 arm: inputs rotate over {rotate} buffer sets of distinct utterances (~{resident_mb:.0f} MB) "
+              f"> 126 MB L2; reference arm: host memory",
+    }
 
 
 # ------------------------------------------------------------------------------------------- clocks
@@ -124,25 +143,45 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- CPU baseline
-def _cpu_tokenize_one(args):
-    """Reference CPU path for one utterance: log-mel + minima + merge/split + per-segment mean-pool."""
-    wave, dim, seed = args
+_LOCAL_ITEMS = []  # per-process inputs of the CPU arm (waveform, per-segment embeddings), built before the timed phase
+_TOK = []
+
+
+def _cpu_tokenizer():
+    if not _TOK:
+        from oracle import ref_port
+
+        _TOK.append(ref_port.RefTokenizer())
+    return _TOK[0]
+
+
+def _cpu_tokenize_one(item):
+    """Reference CPU path for one utterance: log-mel + minima + merge/split + per-segment mean-pool.  The embeddings
+    are inputs (the GPU arm's are resident before its timed region too): they were generated in `_prepare_local_items`
+    from this utterance's own segmentation."""
+    from oracle import ref_port
+
+    wave, embs = item
+    _cpu_tokenizer().segment_lengths(wave)
+    ref_port.mean_pool_segments(embs)
+
+
+def _prepare_local_items(name, n_local):
     import torch
 
     from aat_b200 import synth
-    from oracle import ref_port
 
-    tok = _cpu_tokenize_one.tok = getattr(_cpu_tokenize_one, "tok", None) or ref_port.RefTokenizer()
-    lengths, _, _ = tok.segment_lengths(wave)
-    frames = synth.hubert_frames(lengths)
-    g = torch.Generator().manual_seed(seed)
-    embs = [torch.randn(1, int(f), dim, generator=g) for f in frames]
-    t0 = time.perf_counter()
-    ref_port.mean_pool_segments(embs)
-    return time.perf_counter() - t0
-
-
-_LOCAL_WAVES = []  # per-process inputs of the CPU arm, generated before the timed phase
+    _, n, dim, idx = WORKLOADS[name]
+    n = min(n, 4_800_000)  # 30-min streams: time a 5-min slice per item, throughput is linear in length
+    items = []
+    for i in range(n_local):
+        wave = synth.bursty_speech(n, synth.seed_for(idx + 1, 5000 + i)).astype(np.float64)
+        lengths, _, _ = _cpu_tokenizer().segment_lengths(wave)  # untimed: fixes the embedding shapes
+        g = torch.Generator().manual_seed(i)
+        embs = [torch.randn(1, int(f), dim, generator=g) for f in synth.hubert_frames(lengths)]
+        items.append((wave, embs))
+    _LOCAL_ITEMS[:] = items
+    _cpu_tokenize_one(_LOCAL_ITEMS[0])  # warm imports (transformers, scipy)
 
 
 def _cpu_worker_init(name="c2", n_local=4):
@@ -157,36 +196,26 @@ def _cpu_worker_init(name="c2", n_local=4):
     import torch
 
     torch.set_num_threads(1)
-    _prepare_local_waves(name, n_local)
-
-
-def _prepare_local_waves(name, n_local):
-    from aat_b200 import synth
-
-    _, n, dim, idx = WORKLOADS[name]
-    n = min(n, 4_800_000)  # 30-min streams: time a 5-min slice per item, throughput is linear in length
-    _LOCAL_WAVES[:] = [(synth.bursty_speech(n, synth.seed_for(idx + 1, 5000 + i)).astype(np.float64), dim, i)
-                       for i in range(n_local)]
-    _cpu_tokenize_one(_LOCAL_WAVES[0])  # warm imports (transformers, scipy)
+    _prepare_local_items(name, n_local)
 
 
 def _cpu_task(i):
-    return _cpu_tokenize_one(_LOCAL_WAVES[i % len(_LOCAL_WAVES)])
+    _cpu_tokenize_one(_LOCAL_ITEMS[i % len(_LOCAL_ITEMS)])
 
 
 def _cpu_ready(_):
     time.sleep(0.05)  # keeps the task on this worker long enough for every worker to take one
-    return len(_LOCAL_WAVES)
+    return len(_LOCAL_ITEMS)
 
 
 def cpu_reference_throughput(name, n_utts, pool=None):
     """Audio-hours/s of the oracle port (reference algorithm, same third-party calls) on host cores: `n_utts`
     utterances of the workload, in this process or spread over a worker pool whose processes already hold
-    their inputs."""
+    their inputs (waveforms AND embeddings)."""
     _, n, dim, idx = WORKLOADS[name]
     n = min(n, 4_800_000)
-    if pool is None and not _LOCAL_WAVES:
-        _prepare_local_waves(name, 8)
+    if pool is None and not _LOCAL_ITEMS:
+        _prepare_local_items(name, 8)
     t0 = time.perf_counter()
     if pool is not None:
         pool.map(_cpu_task, range(n_utts), chunksize=1)
@@ -201,6 +230,7 @@ def run_reference(args):
     """`--impl reference`: the reference's CPU implementation of the path (oracle port: the reference
     is pure Python and /root/reference does not travel), all host cores, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
@@ -224,12 +254,12 @@ def run_reference(args):
             t_total += dt
     value = float(np.mean(vals))
     sample = (f"{per_step} utterances of {min(n, 4_800_000) / 16000:g} s per step, multiprocessing.Pool({cores}), "
-              f"inputs resident in the workers, 1 BLAS thread each")
+              f"inputs (waveforms and per-segment embeddings) resident in the workers, 1 BLAS thread each")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(args.steps, 1), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload), "host": "cpu"},
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64 (log-mel) / f32 (boundaries, pool)", "data": "synthetic",
+        "config": workload_config(args.workload, max(world, args.gpus), args.rotate),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "host": host_description()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -264,17 +294,408 @@ def host_description():
 
 
 # ------------------------------------------------------------------------------------------- B200 arm
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank (and therefore first-touch its pinned host buffers) on the NUMA node its GPU hangs off:
+    N ranks reading pinned memory of one node was what capped the round-1 e2e figure at N >= 4."""
+    try:
+        out = subprocess.run(["nvidia-smi", f"--id={local_rank}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=20).stdout.strip()
+        bus = out.lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"node": None, "note": "the platform reports no NUMA affinity for the GPU"}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"node": node, "cpus": len(allowed)}
+    except Exception as exc:  # best effort: a VM may not expose the topology
+        return {"node": None, "note": f"{type(exc).__name__}: {exc}"[:120]}
+
+
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+    return FALLBACK_HBM_GBS, "fallback of B200_PROFILING.md"
+
+
+class Workload:
+    """One BASELINE config resident on one GPU: R rotating buffer sets of distinct, device-generated utterances with
+    the embeddings their own segmentation calls for, and the step that runs the path over one set."""
+
+    def __init__(self, torch, tok, name, rank, local_rank, rotate):
+        from aat_b200 import synth
+        from aat_b200.pooling import DatasetMean
+
+        self.torch, self.name = torch, name
+        self.B, self.N, self.D, idx = WORKLOADS[name]
+        self.dev = torch.device("cuda", local_rank)
+        self.batch = tok.plan([self.N] * self.B)
+        B, D = self.B, self.D
+        per_set = B * self.N * 4 + B * hubert_rows_upper_bound(self.N) * D * 4
+        self.R = max(2, min(rotate, int(24e9 // per_set)))  # bounded HBM footprint for the long-form config
+        self.wave_sets, self.emb_sets, self.n_seg, self.n_rows = [], [], [], []
+        for s in range(self.R):
+            # distinct utterances in every set and on every rank (seed = 1000 * config + utterance index, SURVEY §8d)
+            wave = synth.device_bursty_batch(self.batch, 1000 * (idx + 1), (rank * self.R + s) * B)
+            self.batch.logmel(wave), self.batch.boundaries()  # one untimed pass fixes the segmentation, hence the embedding shape
+            torch.cuda.synchronize()
+            assert int(self.batch.status.min().item()) >= 0
+            n_seg = int(self.batch.n_seg.item())
+            n_rows = int(self.batch.seg_off[n_seg].item())
+            assert n_rows == int(self.batch.n_frames.item())
+            emb = torch.empty(n_rows, D, device=self.dev)
+            synth.device_normal(emb, 1234 + 97 * rank + s)
+            self.wave_sets.append(wave), self.emb_sets.append(emb), self.n_seg.append(n_seg), self.n_rows.append(n_rows)
+        self.out = torch.empty(self.batch.total_seg_slots, D, device=self.dev)
+        self.dm = DatasetMean(D, device=local_rank)
+        self.audio_hours_per_step = B * self.N / 16000 / 3600
+        self.pool_bytes = float(np.mean([r * D * 4 + s * D * 4 + (s + 1) * 8 for r, s in zip(self.n_rows, self.n_seg)]))
+
+    def step(self, i, colsum=True):
+        s = i % self.R
+        b = self.batch
+        b.logmel(self.wave_sets[s])
+        b.boundaries()  # also emits the packed frame CSR from the kernel's tail
+        # the launch in front of the pool kernel is this batch's boundary scan, which does not write embeddings
+        if colsum:
+            b.pool(self.emb_sets[s], self.out, colsum=self.dm.running_buffer(), accumulate=True, emb_ready=True)
+        else:  # diagnostic only: the dataset-mean epilogue is part of the step by default
+            b.pool(self.emb_sets[s], self.out, emb_ready=True)
+
+    def expected_sums(self, uses):
+        """Independent reduction of what `steps` steps must have accumulated: the pooled vectors of every buffer set
+        are summed by torch in float64 and weighted with how often the set was used."""
+        torch = self.torch
+        acc = torch.zeros(self.D + 1, dtype=torch.float64, device=self.dev)
+        for s in range(self.R):
+            if uses[s] == 0:
+                continue
+            self.batch.logmel(self.wave_sets[s]), self.batch.boundaries()
+            self.batch.pool(self.emb_sets[s], self.out)
+            torch.cuda.synchronize()
+            n_seg = int(self.batch.n_seg.item())
+            acc[: self.D] += uses[s] * self.out[:n_seg].double().sum(dim=0)
+            acc[self.D] += uses[s] * n_seg
+        return acc
+
+    def pool_roofline(self, _cabi, sampled, sample_every, traffic):
+        """Roofline of the pool kernel.  Back-to-back clock: 8 x R launches on the rotating sets inside one event pair."""
+        torch, b = self.torch, self.batch
+        peak, peak_src = hbm_peak()
+        reps = 8 * self.R
+        # per-set copies of the CSR, so that launch i pools set i % R with that set's own offsets
+        csr = []
+        for s in range(self.R):
+            b.logmel(self.wave_sets[s]), b.boundaries()
+            torch.cuda.synchronize()
+            csr.append((b.seg_off.clone(), b._csr_totals.clone()))
+        from aat_b200.pooling import _pool_device
+
+        stream = b._stream()
+
+        def launch(i):
+            s = i % self.R
+            seg_off, totals = csr[s]
+            _pool_device(b.ctx, self.emb_sets[s], seg_off, int(self.out.shape[0]), totals, self.out, None, stream,
+                         plan=b.handle, emb_ready=True)
+
+        for i in range(2 * self.R):
+            launch(i)
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(reps):
+                launch(i)
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / reps
+            best = us if best is None else min(best, us)
+        achieved = self.pool_bytes / (best * 1e-6) / 1e9
+        roof = {"kernel": "pool_kernel<float,1,false>" if self.D <= 1024 else "pool_kernel<float,k,false>", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": "ncu --set full capture of an earlier run of this command (profiles/pool_traffic.json), "
+                                  "not measured in this run" if traffic is not None else None,
+                "bytes_per_launch": self.pool_bytes, "us_per_launch": best, "launches_timed": reps,
+                "method": f"{reps} back-to-back launches over the {self.R} rotating input sets inside one CUDA-event "
+                          f"pair, best of 3 (no column-sum epilogue: the reduce kernel is a separate launch)",
+                "peak_source": peak_src}
+        if sampled is not None:
+            n, ms = sampled
+            if n:
+                us_s = ms / n * 1e3
+                a = self.pool_bytes / (us_s * 1e-6) / 1e9
+                roof["sampled_in_step"] = {"us_per_launch": us_s, "achieved": a, "frac": a / peak, "launches_timed": n,
+                                           "method": f"event pair around every {sample_every}th pool launch of the timed "
+                                                     f"region (an event in front of a kernel stops it overlapping its "
+                                                     f"predecessor, and the pair itself costs several us)"}
+        return roof
+
+
+def measure_workload(torch, dist, w, steps, warmup, world, sample_every, no_colsum=False, sampler=None):
+    """Warm-up, then exactly `steps` timed steps (+ the allreduce of the dataset mean) between barriers; returns the
+    timing record.  Device time by CUDA events, max over ranks."""
+    from aat_b200 import _cabi
+
+    dev = w.dev
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        w.step(i, not no_colsum)
+    barrier()
+    if sampler is not None:
+        t_spin = time.time()
+        while not sampler.samples and time.time() - t_spin < 2.0:  # keep the GPU busy until nvidia-smi is up
+            w.step(0, not no_colsum)
+            torch.cuda.synchronize()
+    w.dm.acc.zero_()  # the dataset mean is the mean of the TIMED steps
+    _cabi.profile_enable(w.batch.ctx.handle, ("pool",), every=sample_every)
+    launches0 = _cabi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    wall0 = time.time()
+    ev0.record()
+    for i in range(steps):
+        w.step(i, not no_colsum)
+    w.dm.allreduce()
+    mean_vec = w.dm.result()
+    ev1.record()
+    barrier()
+    wall1 = time.time()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = _cabi.launch_count() - launches0
+    prof = _cabi.profile_summary(w.batch.ctx.handle)
+    _cabi.profile_enable(w.batch.ctx.handle, ())
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+
+    # ---- the collective's result against an independent reduction (A9): per-set pooled sums by torch, weighted by use
+    # count, gathered from every rank and added in rank order (no NCCL reduction on the checking side)
+    check = None
+    if not no_colsum:
+        uses = [len(range(s, steps, w.R)) for s in range(w.R)]
+        mine = w.expected_sums(uses)
+        if world > 1:
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            want = torch.stack(parts).sum(dim=0)
+        else:
+            want = mine
+        got = w.dm.acc
+        assert int(got[w.D].item()) == int(want[w.D].item()), (got[w.D].item(), want[w.D].item())
+        scale = want[: w.D].abs().max().clamp_min(1e-300)
+        rel = float(((got[: w.D] - want[: w.D]).abs().max() / scale).item())
+        assert rel <= 1e-12, f"dataset-mean sums differ from the independent reduction by {rel:.3e}"
+        want_mean = (want[: w.D] / want[w.D]).float()
+        assert bool(torch.isfinite(mean_vec).all())
+        mean_err = float((mean_vec - want_mean).abs().max().item())
+        assert mean_err <= 1e-6 * float(want_mean.abs().max().clamp_min(1e-30).item()) + 1e-12
+        check = {"segments": int(want[w.D].item()), "max_rel_err_sums": rel, "max_abs_err_mean": mean_err,
+                 "against": "torch float64 sums of the pooled vectors of every buffer set x use count, all_gather'ed and "
+                            "added in rank order"}
+
+    # ---- per-kernel breakdown (untimed extra pass with every kernel instrumented)
+    _cabi.profile_enable(w.batch.ctx.handle, _cabi.KERNEL_NAMES)
+    for i in range(min(steps, 50)):
+        w.step(i, not no_colsum)
+    torch.cuda.synchronize()
+    breakdown = {k: (ms / n * 1e3 if n else None) for k, (n, ms) in _cabi.profile_summary(w.batch.ctx.handle).items()}
+    _cabi.profile_enable(w.batch.ctx.handle, ())
+    return {"elapsed_ms": elapsed_ms, "value": world * w.audio_hours_per_step * steps / (elapsed_ms / 1e3),
+            "ms_per_step": elapsed_ms / steps, "launches": int(launches), "sampled_pool": prof["pool"],
+            "kernel_us": breakdown, "wall": (wall0, wall1), "dataset_mean_check": check}
+
+
+def pool_traffic(name):
+    tpath = os.path.join(ROOT, "profiles", "pool_traffic.json")
+    if os.path.exists(tpath):
+        return json.load(open(tpath)).get(name)
+    return None
+
+
+def sub_record(torch, dist, tok, name, rank, local_rank, world, args):
+    """configs[...] sub-record of another BASELINE config, same machinery as the headline at fewer steps."""
+    from aat_b200 import _cabi
+
+    w = Workload(torch, tok, name, rank, local_rank, args.rotate)
+    steps = {"c3": 200, "c4": 60, "c2": 500}[name]
+    m = measure_workload(torch, dist, w, steps, 5, world, args.pool_sample_every)
+    roof = w.pool_roofline(_cabi, m["sampled_pool"], args.pool_sample_every, pool_traffic(name))
+    rec = {"workload": workload_name(name), "value": m["value"], "unit": UNIT, "steps": steps, "ms_per_step": m["ms_per_step"],
+           "kernel_us": m["kernel_us"], "roofline": roof, "segments_per_batch": w.n_seg, "hubert_frames_per_batch": w.n_rows,
+           "rotating_sets": w.R, "dataset_mean_check": m["dataset_mean_check"]}
+    del w
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_c1(torch, tok):
+    """BASELINE configs[0]: one 10 s clip through the reference-facing numpy API (host buffers in and out, one C-ABI
+    call each), with the oracle port on one host core beside it."""
+    from aat_b200 import AudioWaveform, mean_pool_segments, synth
+    from oracle import ref_port
+
+    n, dim = 160_000, 768
+    wave = synth.bursty_speech(n, synth.seed_for(1, 0))
+    awf = AudioWaveform(wave, 16000)
+    segments, mel = tok.tokenize(awf)
+    lengths = [s.waveform.shape[-1] for s in segments]
+    g = torch.Generator().manual_seed(0)
+    embs = [torch.randn(1, int(f), dim, generator=g) for f in synth.hubert_frames(lengths)]
+    ref = ref_port.RefTokenizer()
+    assert ref.segment_lengths(wave)[0] == lengths  # parity of what is being timed
+
+    def best_ms(fn, reps):
+        fn()
+        best = float("inf")
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            best = min(best, time.perf_counter() - t0)
+        return best * 1e3
+
+    gpu_tok = best_ms(lambda: tok.tokenize(awf), 30)
+    gpu_pool = best_ms(lambda: mean_pool_segments(embs), 30)
+    gpu_min = best_ms(lambda: tok.find_amplitude_minimas(mel), 30)
+    cpu_tok = best_ms(lambda: ref.segment_lengths(wave), 3)
+    cpu_pool = best_ms(lambda: ref_port.mean_pool_segments(embs), 10)
+    cpu_min = best_ms(lambda: ref.find_amplitude_minimas(mel), 10)
+    hours = n / 16000 / 3600
+    return {"workload": "configs[0]: single 10 s 16 kHz clip, batch 1, 768-d embeddings, numpy API (host in / host out)",
+            "value": hours / ((gpu_tok + gpu_pool) * 1e-3), "unit": UNIT, "segments": len(lengths),
+            "latency_ms": {"tokenize": gpu_tok, "mean_pool_segments(list)": gpu_pool, "find_amplitude_minimas": gpu_min},
+            "cpu_port_latency_ms": {"tokenize": cpu_tok, "mean_pool_segments(list)": cpu_pool, "find_amplitude_minimas": cpu_min},
+            "cpu_port_value": hours / ((cpu_tok + cpu_pool) * 1e-3), "method": "best of 30 calls, wall clock, one thread"}
+
+
+def run_c5(torch, dist, tok, rank, local_rank, world, args):
+    """BASELINE configs[4]: >= 1000 synthetic audio-hours of DISTINCT 16 s utterances sharded over the N ranks.  Every
+    rank generates its shard on the device chunk by chunk (counter-based generator; generation is outside the timed
+    brackets and reported beside them), runs the path over every batch of the chunk (timed, CUDA events), accumulates
+    the column sums on the device, and the ranks meet once in the allreduce of the dataset-mean embedding."""
+    from aat_b200 import synth
+    from aat_b200.pooling import DatasetMean
+
+    B, N, D, _ = WORKLOADS["c2"]
+    dev = torch.device("cuda", local_rank)
+    hours_per_batch = B * N / 16000 / 3600
+    total_batches = math.ceil(args.c5_hours / hours_per_batch)
+    per_rank = math.ceil(total_batches / world)
+    chunk = min(64, per_rank)  # 4096 utterances: 4.2 GB of waveforms + 10 GB of embeddings per chunk
+    rows_ub = B * hubert_rows_upper_bound(N)
+    batch = tok.plan([N] * B)
+    waves = torch.empty(chunk, batch.total_samples, dtype=torch.float32, device=dev)
+    embs = torch.empty(chunk, rows_ub, D, dtype=torch.float32, device=dev)
+    out = torch.empty(batch.total_seg_slots, D, device=dev)
+    dm = DatasetMean(D, device=local_rank)
+    status_min = torch.zeros(1, dtype=torch.int32, device=dev)
+    gen_ms = run_ms = 0.0
+    first_batch = rank * per_rank  # global batch index of this rank's shard
+
+    def generate(c0, n):
+        for k in range(n):
+            g = first_batch + c0 + k
+            synth.device_bursty_batch(batch, 5000, g * B, out=waves[k])  # seed = 1000 * config + utterance index
+            synth.device_normal(embs[k], 7_000_000 + g)
+
+    def consume(n, acc):
+        for k in range(n):
+            batch.logmel(waves[k]), batch.boundaries()
+            # embeddings are an allocation of the upper-bound row count: the rows the segments cover are read on the device
+            batch.pool(embs[k], out, colsum=acc, accumulate=True, rows_from_device=True)
+
+    # warm-up on the first chunk's first batches (untimed), then reset the accumulator
+    generate(0, min(chunk, 4))
+    consume(min(chunk, 4), dm.running_buffer())
+    torch.cuda.synchronize()
+    dm.acc.zero_()
+    audit = None
+    if world > 1:
+        dist.barrier()
+    done = 0
+    while done < per_rank:
+        n = min(chunk, per_rank - done)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        generate(done, n)
+        e[1].record()
+        consume(n, dm.running_buffer())
+        torch.minimum(status_min, batch.status.min().reshape(1), out=status_min)  # last batch of the chunk
+        e[2].record()
+        torch.cuda.synchronize()
+        gen_ms += e[0].elapsed_time(e[1])
+        run_ms += e[1].elapsed_time(e[2])
+        if done == 0:
+            # audit of the first chunk (untimed): the same batches again, every pooled vector summed by torch
+            chk = DatasetMean(D, device=local_rank)
+            ref = torch.zeros(D + 1, dtype=torch.float64, device=dev)
+            for k in range(min(n, 16)):
+                batch.logmel(waves[k]), batch.boundaries()
+                batch.pool(embs[k], out, colsum=chk.running_buffer(), accumulate=True, rows_from_device=True)
+                torch.cuda.synchronize()
+                s = int(batch.n_seg.item())
+                ref[:D] += out[:s].double().sum(dim=0)
+                ref[D] += s
+            rel = float(((chk.acc[:D] - ref[:D]).abs().max() / ref[:D].abs().max()).item())
+            assert int(chk.acc[D].item()) == int(ref[D].item()) and rel <= 1e-12, rel
+            audit = {"batches": min(n, 16), "segments": int(ref[D].item()), "max_rel_err_sums": rel}
+        done += n
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    dm.allreduce()
+    mean_vec = dm.result()
+    ev1.record()
+    torch.cuda.synchronize()
+    run_ms += ev0.elapsed_time(ev1)
+    assert int(status_min.item()) >= 0
+    t = torch.tensor([run_ms, gen_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    run_ms, gen_ms = float(t[0].item()), float(t[1].item())
+    hours = world * per_rank * hours_per_batch
+    segments = int(dm.acc[D].item())
+    utterances = world * per_rank * B
+    assert bool(torch.isfinite(mean_vec).all()) and 20 * utterances <= segments <= 60 * utterances
+    rec = {"workload": f"configs[4]: {hours:.1f} synthetic audio-hours = {utterances} distinct 16 s utterances sharded over "
+                       f"{world} GPU(s), {D}-d embeddings, NCCL allreduce of the dataset-mean embedding",
+           "audio_hours_processed": hours, "utterances": utterances, "segments": segments, "value": hours / (run_ms / 1e3),
+           "unit": UNIT, "device_seconds_path": run_ms / 1e3, "device_seconds_generation": gen_ms / 1e3,
+           "batches_per_rank": per_rank, "chunk_batches": chunk, "scaling": "strong (fixed 1000 audio-hours)",
+           "timing": "sum over chunks of CUDA-event brackets around the path (generation bracketed separately), + the "
+                     "allreduce and finalisation; max over ranks",
+           "dataset_mean": {"norm": float(mean_vec.norm().item()), "audit_first_chunk": audit}}
+    del waves, embs
+    torch.cuda.empty_cache()
+    return rec
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
 
     from aat_b200 import AdaptiveAudioAmplitudeTokenizer, _cabi
-    from aat_b200.pooling import DatasetMean
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    numa = bind_to_gpu_numa_node(local_rank)  # before any pinned allocation
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -293,121 +714,41 @@ def run_b200(args):
             os.dup2(saved, 1)
             os.close(saved)
 
-    B, N, D, _ = WORKLOADS[args.workload]
     tok = AdaptiveAudioAmplitudeTokenizer(device=local_rank)
-    waves = make_waves(args.workload, rank)
-    batch = tok.plan([N] * B)
-    host_wave = torch.from_numpy(np.concatenate(waves)).pin_memory()
-    R = args.rotate  # rotating input sets so that no step finds its inputs in the 126 MB L2
-    wave_sets = [host_wave.to(dev) for _ in range(R)]
-
-    # one untimed pass fixes the segmentation, hence the embedding shape
-    batch.logmel(wave_sets[0]), batch.boundaries()
-    torch.cuda.synchronize()
-    assert int(batch.status.min().item()) >= 0
-    n_seg = int(batch.n_seg.item())
-    n_rows = int(batch.seg_off[n_seg].item())
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    emb_sets = [torch.randn(n_rows, D, device=dev, generator=gen) for _ in range(R)]
-    out = torch.empty(batch.total_seg_slots, D, device=dev)
-    dm = DatasetMean(D, device=local_rank)
-    audio_hours_per_step = B * N / 16000 / 3600
-
-    def step(i):
-        s = i % R
-        batch.logmel(wave_sets[s])
-        batch.boundaries()  # also emits the packed frame CSR from the kernel's tail
-        if args.no_colsum:  # diagnostic only: the dataset-mean epilogue is part of the step by default
-            batch.pool(emb_sets[s], out)
-        else:
-            batch.pool(emb_sets[s], out, colsum=dm.running_buffer(), accumulate=True)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    w = Workload(torch, tok, args.workload, rank, local_rank, args.rotate)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for i in range(args.warmup):
-        step(i)
-    barrier()
-    t_spin = time.time()
-    while not sampler.samples and time.time() - t_spin < 2.0:  # keep the GPU busy until nvidia-smi is up
-        step(0)
-        torch.cuda.synchronize()
-
-    # ---- timed region: K steps + the one collective
-    # every 8th pool launch is bracketed by CUDA events (an event in front of a kernel keeps it from overlapping its
-    # predecessor's tail, so the other seven run the way a user's loop runs them)
-    _cabi.profile_enable(batch.ctx.handle, ("pool",), every=args.pool_sample_every)
-    launches0 = _cabi.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    wall0 = time.time()
-    ev0.record()
-    for i in range(args.steps):
-        step(i)
-    dm.allreduce()
-    mean_vec = dm.result()
-    ev1.record()
-    barrier()
-    wall1 = time.time()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    launches = _cabi.launch_count() - launches0
-    prof = _cabi.profile_summary(batch.ctx.handle)
-    _cabi.profile_enable(batch.ctx.handle, ())
-    clocks = sampler.stop(wall0, wall1)
-    assert args.no_colsum or bool(torch.isfinite(mean_vec).all())
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    value = world * audio_hours_per_step * args.steps / (elapsed_ms / 1e3)
-
-    # ---- per-kernel breakdown (untimed extra pass with every kernel instrumented)
-    _cabi.profile_enable(batch.ctx.handle, _cabi.KERNEL_NAMES)
-    for i in range(min(args.steps, 50)):
-        step(i)
-    torch.cuda.synchronize()
-    breakdown = {k: (ms / n * 1e3 if n else None) for k, (n, ms) in _cabi.profile_summary(batch.ctx.handle).items()}
-    _cabi.profile_enable(batch.ctx.handle, ())
-
-    # ---- roofline of the pool kernel (algorithmic bytes)
-    pool_launches, pool_ms = prof["pool"]
-    pool_bytes = n_rows * D * 4 + n_seg * D * 4 + (n_seg + 1) * 8
-    pool_us = pool_ms / max(pool_launches, 1) * 1e3
-    achieved = pool_bytes / (pool_us * 1e-6) / 1e9
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
-    else:
-        peak, peak_src = FALLBACK_HBM_GBS, "fallback of B200_PROFILING.md"
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "pool_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(args.workload)
-    roofline = {"kernel": "pool_kernel<float,1,true>", "bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "bytes_per_launch": pool_bytes,
-                "us_per_launch": pool_us, "launches_timed": pool_launches, "sampled": f"every {args.pool_sample_every}th launch of the timed region",
-                "peak_source": peak_src}
+    m = measure_workload(torch, dist, w, args.steps, args.warmup, world, args.pool_sample_every, args.no_colsum, sampler)
+    clocks = sampler.stop(*m["wall"])
+    roofline = w.pool_roofline(_cabi, m["sampled_pool"], args.pool_sample_every, pool_traffic(args.workload))
 
     # ---- e2e: same step through the public batched API with host (pinned) buffers
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(torch, dev, tok, batch, host_wave, emb_sets[0], out, n_seg, D, args, world, audio_hours_per_step)
+        e2e = run_e2e(torch, dev, w, args, world)
+        e2e["numa"] = numa
 
+    cfg = workload_config(args.workload, world, args.rotate)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64 (log-mel) / f32 (boundaries, pool)", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload), "batch_per_gpu": B, "samples_per_utterance": N, "dim": D,
-                   "segments_per_batch": n_seg, "hubert_frames_per_batch": n_rows,
-                   "parallelism": f"utterance-sharded dp{world}, one allreduce of {D + 1} f64",
-                   "l2": f"inputs rotate over {R} buffer sets ({R * (host_wave.numel() * 4 + n_rows * D * 4) / 1e6:.0f} MB) > 126 MB L2"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-        "kernel_us": breakdown,
+        "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 (log-mel) / f32 (boundaries, pool)", "data": "synthetic", "config": cfg,
+        "workload_detail": {"segments_per_batch": w.n_seg, "hubert_frames_per_batch": w.n_rows, "rotating_sets": w.R,
+                            "resident_mb": sum(x.numel() * 4 for x in w.wave_sets + w.emb_sets) / 1e6,
+                            "generator": "aat_synth_waveforms / aat_synth_normal (Philox 4x32-10, on the device)"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": m["launches"], "roofline": roofline,
+        "kernel_us": m["kernel_us"], "dataset_mean_check": m["dataset_mean_check"],
     }
+    if not args.no_configs and args.workload == "c2":
+        configs = {}
+        for name, fn in (("c3", lambda: sub_record(torch, dist, tok, "c3", rank, local_rank, world, args)),
+                         ("c4", lambda: sub_record(torch, dist, tok, "c4", rank, local_rank, world, args)),
+                         ("c5", lambda: run_c5(torch, dist, tok, rank, local_rank, world, args))):
+            # a failure is fatal on purpose: a silent partial record would read as coverage
+            configs[name] = fn()
+        if rank == 0:
+            configs["c1"] = run_c1(torch, tok)
+        line["configs"] = configs
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             _, t_probe = cpu_reference_throughput(args.workload, 8)
@@ -415,52 +756,102 @@ def run_b200(args):
             v, dt = cpu_reference_throughput(args.workload, n_sample)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"{n_sample} utterances of the workload (8 distinct, cycled), single "
-                                              f"process (datasets.map without num_proc), {dt:.1f} s of CPU work",
+                                              f"process (datasets.map without num_proc), {dt:.1f} s of CPU work; waveforms "
+                                              f"and embeddings resident before the clock starts",
                                     "host": host_description()}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
-def run_e2e(torch, dev, tok, batch, host_wave, emb_dev, out, n_seg, D, args, world, audio_hours_per_step):
-    """Host buffers in, host buffers out: every step copies its waveforms and embeddings from pinned host
-    memory, runs the path, and reads segment lengths and pooled vectors back.  Two streams ping-pong so
-    the next step's H2D overlaps this step's kernels (throughput metric over K steps)."""
+def measure_copy_peak(torch, dev, h2d_bytes, d2h_bytes, world):
+    """Plain pinned-memory copies of the e2e step's byte counts, H2D and D2H on two streams at once, all ranks at the
+    same time: what the host side of the box sustains, i.e. the roofline of the e2e figure."""
     import torch.distributed as dist
 
-    host_emb = emb_dev.cpu().pin_memory()
+    src = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
+    back_d = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8, device=dev)
+    back_h = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8).pin_memory()
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    reps = 10
+
+    def once():
+        with torch.cuda.stream(s_in):
+            dst.copy_(src, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            back_h.copy_(back_d, non_blocking=True)
+
+    once()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) / reps  # seconds per step's worth of copies
+
+
+def run_e2e(torch, dev, w, args, world):
+    """Host buffers in, host buffers out: every step copies its waveforms and embeddings from pinned host
+    memory, runs the path, and reads segment lengths and pooled vectors back.  Three streams: H2D of step i + 1,
+    kernels of step i and D2H of step i - 1 overlap (throughput metric over K steps)."""
+    import torch.distributed as dist
+
+    batch, D = w.batch, w.D
+    host_wave = w.wave_sets[0].cpu().pin_memory()
+    host_emb = w.emb_sets[0].cpu().pin_memory()
+    n_seg = w.n_seg[0]
     n_slots = batch.total_seg_slots
     bufs = []
     for _ in range(2):
         bufs.append({
-            "stream": torch.cuda.Stream(device=dev),
-            "wave": torch.empty_like(host_wave, device=dev),
-            "emb": torch.empty_like(emb_dev),
+            "wave": torch.empty_like(w.wave_sets[0]), "emb": torch.empty_like(w.emb_sets[0]),
+            "out": torch.empty(n_slots, D, device=dev), "seg_len": torch.empty_like(batch.seg_len),
+            "seg_count": torch.empty_like(batch.seg_count),
             "pooled_host": torch.empty((n_seg, D), dtype=torch.float32).pin_memory(),
             "len_host": torch.empty(n_slots, dtype=torch.int64).pin_memory(),
             "count_host": torch.empty(batch.n_utts, dtype=torch.int32).pin_memory(),
+            "in_free": None, "out_free": None,
         })
     h2d = host_wave.numel() * 4 + host_emb.numel() * 4
     d2h = n_seg * D * 4 + n_slots * 8 + batch.n_utts * 4
-    compute = torch.cuda.Stream(device=dev)  # kernels share the plan's output buffers: keep them on one stream
+    s_in, s_run, s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
 
     def e2e_step(i):
         b = bufs[i % 2]
-        with torch.cuda.stream(b["stream"]):
+        with torch.cuda.stream(s_in):
+            if b["in_free"] is not None:
+                s_in.wait_event(b["in_free"])  # the kernels that read this input pair two steps ago are done
             b["wave"].copy_(host_wave, non_blocking=True)
             b["emb"].copy_(host_emb, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record()
-        with torch.cuda.stream(compute):
-            compute.wait_event(ready)
+        with torch.cuda.stream(s_run):
+            s_run.wait_event(ready)
+            if b["out_free"] is not None:
+                s_run.wait_event(b["out_free"])  # the D2H that read this output pair two steps ago is done
             batch.logmel(b["wave"]), batch.boundaries()
-            batch.pool(b["emb"], out)
-            b["pooled_host"].copy_(out[:n_seg], non_blocking=True)
-            b["len_host"].copy_(batch.seg_len, non_blocking=True)
-            b["count_host"].copy_(batch.seg_count, non_blocking=True)
-            done = torch.cuda.Event()
-            done.record()
-        b["stream"].wait_event(done)  # the next reuse of this buffer pair waits for this step
+            batch.pool(b["emb"], b["out"], emb_ready=True)
+            # the plan's segment buffers are rewritten by the next step: hand the D2H stream its own copy (device to
+            # device, 0.2 MB) so that result copies never hold the next step's kernels back
+            b["seg_len"].copy_(batch.seg_len, non_blocking=True)
+            b["seg_count"].copy_(batch.seg_count, non_blocking=True)
+            b["in_free"] = torch.cuda.Event()
+            b["in_free"].record()
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(b["in_free"])
+            b["pooled_host"].copy_(b["out"][:n_seg], non_blocking=True)
+            b["len_host"].copy_(b["seg_len"], non_blocking=True)
+            b["count_host"].copy_(b["seg_count"], non_blocking=True)
+            b["out_free"] = torch.cuda.Event()
+            b["out_free"].record()
 
     steps = max(4, min(args.steps, 40))
     for i in range(2):
@@ -469,13 +860,8 @@ def run_e2e(torch, dev, tok, batch, host_wave, emb_dev, out, n_seg, D, args, wor
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
     for i in range(steps):
         e2e_step(i)
-    compute.synchronize()
-    torch.cuda.synchronize()
-    ev1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     t = torch.tensor([wall], dtype=torch.float64, device=dev)
@@ -483,9 +869,21 @@ def run_e2e(torch, dev, tok, batch, host_wave, emb_dev, out, n_seg, D, args, wor
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     wall = float(t.item())
     assert int(bufs[0]["count_host"].sum()) == n_seg
-    return {"value": world * audio_hours_per_step * steps / wall, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": 1e3 * wall / steps,
-            "api": "PackedBatch.logmel/boundaries/pool on pinned host tensors, 2-deep copy/compute pipeline"}
+    # parity of the host-side result with the device-resident path on the same input set
+    batch.logmel(w.wave_sets[0]), batch.boundaries()
+    batch.pool(w.emb_sets[0], w.out)
+    torch.cuda.synchronize()
+    assert torch.equal(bufs[0]["pooled_host"], w.out[:n_seg].cpu())
+    copy_s = measure_copy_peak(torch, dev, h2d, d2h, world)
+    step_s = wall / steps
+    return {"value": world * w.audio_hours_per_step * steps / wall, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": 1e3 * step_s,
+            "copy_peak": {"ms_per_step": 1e3 * copy_s, "h2d_gbs_per_gpu": h2d / copy_s / 1e9,
+                          "how": "the step's H2D and D2H byte counts as plain pinned-memory copies on two streams, all "
+                                 "ranks at once, same run"},
+            "frac_of_copy_peak": copy_s / step_s,
+            "api": "PackedBatch.logmel/boundaries/pool on pinned host tensors; H2D, kernels and D2H on three streams "
+                   "(2 buffer pairs)"}
 
 
 def main():
@@ -495,10 +893,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
-    ap.add_argument("--rotate", type=int, default=4)
+    ap.add_argument("--rotate", type=int, default=DEFAULT_ROTATE)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the c1/c3/c4/c5 sub-records (profiling runs)")
     ap.add_argument("--no-colsum", action="store_true", help="diagnostic: pool without the column-sum epilogue")
+    ap.add_argument("--c5-hours", type=float, default=C5_AUDIO_HOURS, help="audio-hours of the dataset job (configs[4])")
     ap.add_argument("--pool-sample-every", type=int, default=8, help="event-time every n-th pool launch of the timed region")
     args = ap.parse_args()
     if args.impl == "reference":

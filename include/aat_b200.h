@@ -21,7 +21,12 @@
  *   - aat_logmel, aat_boundaries and aat_segment_mean_pool are launched with programmatic dependent launch:
  *     enqueued back to back on one stream, each kernel's prologue overlaps the tail of the one before it and waits
  *     on the device before touching its predecessor's outputs.  Ordering against any other work on the stream is the
- *     usual one.  A plan may have one launch of each in flight at a time (use one plan per stream).
+ *     usual one: nothing a kernel of this library reads is touched before that wait, unless the caller opts in
+ *     (AAT_POOL_EMB_READY).  A plan may have one launch of each in flight at a time (use one plan per stream): the
+ *     plan owns the kernels' device-side scheduling state (tile counter, completion ticket, look-back words, the
+ *     pool kernel's cross-CTA partial sums).  Plans on different streams are independent and may run concurrently.
+ *   - device entry points run on the context's device whatever the calling thread's current device is; `stream`
+ *     must belong to that device.
  *
  * Packed batch layout ("plan"): a batch of B utterances with n_samples[b] samples each.
  *   wave      : concatenated samples, utterance b at wave_off[b] = sum_{i<b} n_samples[i]
@@ -45,7 +50,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define AAT_B200_VERSION 100 /* 0.1.0 */
+#define AAT_B200_VERSION 200 /* 0.2.0: aat_segment_mean_pool takes a plan and flags; n_seg_dev holds {S, frames} */
 
 typedef enum aat_status {
     AAT_OK = 0,
@@ -167,7 +172,8 @@ int aat_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave_dev, int wav
  *                  (ref:src/aat/tokenizer.py:177-181)
  * seg_off_dev, n_seg_dev, utt_seg_off_dev : optional (NULL = skip); when given, the kernel also emits the packed
  *                  frame CSR (every utterance's CTA writes its own slice after a look-back over the utterances
- *                  before it), exactly what aat_segment_frame_csr would write
+ *                  before it), exactly what aat_segment_frame_csr would write; n_seg_dev is int64 [2]:
+ *                  {S, seg_off[S]} = segments of the batch and the HuBERT frames they cover
  * One launch per plan may be in flight at a time (the plan owns the completion ticket and the look-back words). */
 int aat_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel_dev, const float *amp_dev,
                    int64_t *seg_start_dev, int64_t *seg_len_dev, int32_t *seg_count_dev, int64_t *minima_dev,
@@ -184,7 +190,7 @@ int aat_process_boarders(aat_ctx *ctx, int64_t n_samples, const int64_t *boarder
  * Per-segment encode convention consumed by ref:scripts/mean_hubert_embeddings.py:18-20:
  * n_i = max(0, (L_i - 400) / 320 + 1) frames (TF:models/hubert/modeling_hubert.py:675-688).
  * seg_off_dev   : int64 [total_seg_slots + 1]; entries [0, S] are written
- * n_seg_dev     : int64 [1]; S = total number of segments in the batch
+ * n_seg_dev     : int64 [2]; {S, seg_off[S]}: total number of segments in the batch and the frames they cover
  * utt_seg_off_dev : optional int64 [n_utts+1]; first packed segment index of each utterance */
 int aat_segment_frame_csr(aat_ctx *ctx, const aat_plan *plan, const int64_t *seg_len_dev,
                           const int32_t *seg_count_dev, int64_t *seg_off_dev, int64_t *n_seg_dev,
@@ -194,16 +200,33 @@ int aat_segment_frame_csr(aat_ctx *ctx, const aat_plan *plan, const int64_t *seg
  * Replaces `torch.cat([x.mean(dim=1, keepdim=True).to(float32) for x in embs], dim=1)`
  * (ref:scripts/mean_hubert_embeddings.py:19-20) on the packed layout
  *   emb_dev [n_rows, dim] row-major (AAT_F32 / AAT_F16 / AAT_BF16) + seg_off_dev [S+1] (frame units).
+ * plan      : optional.  The kernel needs scratch for the partial sums of segments that straddle two CTAs; a plan
+ *             owns such a block (like every other device-side state of a step), so launches that name different
+ *             plans may run concurrently on different streams.  NULL = the context's block: such launches are
+ *             ordered against each other with an event (whatever their streams), and must not be captured into a
+ *             CUDA graph concurrently with other plan-less launches.
  * out_dev   : float32 [S, dim]; an empty segment yields NaN, as torch's mean does
+ * n_rows    : rows of emb_dev; rows outside [seg_off[0], seg_off[S]) belong to no segment and are ignored
  * n_seg     : S when n_seg_dev is NULL; otherwise an upper bound and S is read from n_seg_dev[0]
  * colsum_dev: optional float64 [dim+1]: column sums over the S pooled vectors and, last, S itself
  *             (input of the dataset-level mean allreduce)
- * colsum_accumulate : 0 = colsum_dev is overwritten; 1 = this batch's sums are ADDED to colsum_dev
- *             (running totals over batches without a separate kernel)
+ * flags     : bit set of aat_pool_flags
  * One pass over emb; dim * sizeof(element) must be a multiple of 16 and emb_dev 16-byte aligned. */
-int aat_segment_mean_pool(aat_ctx *ctx, const void *emb_dev, int emb_dtype, int64_t n_rows, int32_t dim,
-                          const int64_t *seg_off_dev, int64_t n_seg, const int64_t *n_seg_dev, float *out_dev,
-                          double *colsum_dev, int colsum_accumulate, void *stream);
+typedef enum aat_pool_flags {
+    AAT_POOL_ACCUMULATE = 1,       /* this batch's column sums are ADDED to colsum_dev (running totals over batches
+                                      without a separate kernel); default: colsum_dev is overwritten */
+    AAT_POOL_EMB_READY = 2,        /* the caller vouches that the kernel enqueued immediately before this call on
+                                      `stream` does not write emb_dev (true when it is aat_boundaries): the kernel may
+                                      then request embedding rows before it waits for that predecessor.  Without the
+                                      flag nothing is read before the wait, so any producer of emb_dev may precede
+                                      the call, including kernels that trigger their dependents early */
+    AAT_POOL_ROWS_FROM_DEVICE = 4  /* n_rows is an upper bound (the allocation); the rows the CSR covers are read
+                                      from n_seg_dev[1] as written by aat_boundaries / aat_segment_frame_csr, and
+                                      nothing beyond them is streamed */
+} aat_pool_flags;
+int aat_segment_mean_pool(aat_ctx *ctx, const aat_plan *plan, const void *emb_dev, int emb_dtype, int64_t n_rows,
+                          int32_t dim, const int64_t *seg_off_dev, int64_t n_seg, const int64_t *n_seg_dev,
+                          float *out_dev, double *colsum_dev, int flags, void *stream);
 
 /* acc_dev[0..dim] += colsum_dev[0..dim] (float64), for accumulating over batches before the allreduce. */
 int aat_colsum_accumulate(aat_ctx *ctx, double *acc_dev, const double *colsum_dev, int32_t dim, void *stream);
@@ -257,6 +280,20 @@ int aat_scatter_mel_segments(aat_ctx *ctx, const aat_plan *plan, const float *me
  * row_mask_dev (optional) [n_rows] int64 = 1 where the row has a valid frame (the segment-level mask). */
 int aat_masked_mean_pool(aat_ctx *ctx, const void *emb_dev, int emb_dtype, int64_t n_rows, int64_t seq_len, int32_t dim,
                          const int64_t *mask_dev, float *out_dev, int64_t *row_mask_dev, void *stream);
+
+/* ------------------------------------------------------------------ synthetic inputs, generated on the device
+ * For the benchmark's dataset-scale job (BASELINE config 5: 1000 audio-hours of DISTINCT utterances) and for tests:
+ * inputs of the path, never results.  Counter-based (Philox 4x32-10): sample i of utterance u is a pure function
+ * of (seed_base + utt_index_base + u, i), so any rank can generate any shard.  Recipe of SURVEY.md section 8d, the
+ * one aat_b200/synth.py implements on the host: Gaussian noise times an envelope of Hann-shaped bursts of
+ * U(80,600) ms, amplitude U(0.3,1.0), separated by pauses of U(30,250) ms at a 1e-3 floor.
+ * wave_dev      : packed float32 waveform of the plan (aat_plan_total_samples entries)
+ * workspace_dev : aat_synth_workspace_bytes(plan) bytes, 16-byte aligned (burst tables) */
+int64_t aat_synth_workspace_bytes(const aat_plan *plan);
+int aat_synth_waveforms(aat_ctx *ctx, const aat_plan *plan, uint64_t seed_base, int64_t utt_index_base, float *wave_dev,
+                        void *workspace_dev, void *stream);
+/* out_dev[i] ~ N(0, 1), i < n: random-init HuBERT-shaped embeddings.  out_dev 16-byte aligned. */
+int aat_synth_normal(aat_ctx *ctx, float *out_dev, int64_t n, uint64_t seed, void *stream);
 
 /* ------------------------------------------------------------------ host-buffer entry points
  * Same operations for callers that hold numpy arrays, exactly like the reference's methods:

@@ -9,6 +9,8 @@ Bars (BASELINE.json north_star):
 """
 import hashlib
 
+import os
+
 import numpy as np
 import pytest
 
@@ -514,22 +516,35 @@ def test_back_to_back_steps_match_synchronised_steps(tok):
 
 
 def test_two_plans_on_two_streams_are_independent(tok):
-    """Tile counter, completion ticket and look-back words belong to the plan: two plans driven concurrently from two
-    streams give what they give alone."""
+    """Tile counter, completion ticket, look-back words and the pool kernel's cross-CTA scratch belong to the plan: two
+    plans driven concurrently from two streams — whole steps, pool included, with long segments so that every CTA
+    boundary of the pool kernel cuts one — give what they give alone."""
     import torch
 
     from aat_b200 import synth
 
-    specs = [[64000] * 24, [160000, 31999, 256000, 8000, 96000, 48000, 20000, 131072]]
-    plans, waves, want = [], [], []
-    for k, lengths in enumerate(specs):
-        batch = tok.plan(lengths)
+    # long max duration => segments of hundreds of HuBERT frames: the pool kernel's carry path runs at every CTA boundary
+    from aat_b200 import AdaptiveAudioAmplitudeTokenizer
+
+    tok_long = AdaptiveAudioAmplitudeTokenizer(max_segment_duration_milliseconds=20000, max_amplitude_for_minima=1000)
+    specs = [(tok, [64000] * 24, 768), (tok_long, [160000, 31999, 256000, 8000, 96000, 48000, 20000, 131072] * 4, 1024)]
+    plans, waves, embs, outs, want = [], [], [], [], []
+    for k, (t, lengths, dim) in enumerate(specs):
+        batch = t.plan(lengths)
         wave = batch.pack([torch.from_numpy(synth.bursty_speech(n, 8800 + 50 * k + i)) for i, n in enumerate(lengths)])
         batch.logmel(wave), batch.boundaries()
         torch.cuda.synchronize()
         n_seg = int(batch.n_seg.item())
-        want.append((batch.mel.clone(), batch.seg_count.clone(), batch.seg_off[: n_seg + 1].clone(), n_seg))
-        plans.append(batch), waves.append(wave)
+        n_rows = int(batch.n_frames.item())
+        assert n_rows == int(batch.seg_off[n_seg].item())
+        emb = torch.randn(n_rows, dim, device="cuda", generator=torch.Generator(device="cuda").manual_seed(k))
+        out = torch.zeros(batch.total_seg_slots, dim, device="cuda")
+        batch.pool(emb, out, emb_ready=True)
+        torch.cuda.synchronize()
+        want.append((batch.mel.clone(), batch.seg_count.clone(), batch.seg_off[: n_seg + 1].clone(), n_seg, out[:n_seg].clone()))
+        plans.append(batch), waves.append(wave), embs.append(emb), outs.append(out)
+    # the second plan's segments are long enough to be cut by the pool kernel's CTA boundaries
+    assert float(np.diff(want[1][2].cpu().numpy()).max()) > 400
     streams = [torch.cuda.Stream(), torch.cuda.Stream()]
     torch.cuda.synchronize()
     for rep in range(20):
@@ -537,12 +552,78 @@ def test_two_plans_on_two_streams_are_independent(tok):
             with torch.cuda.stream(streams[k]):
                 plans[k].logmel(waves[k])
                 plans[k].boundaries()
+                outs[k].zero_()
+                plans[k].pool(embs[k], outs[k], emb_ready=(rep % 2 == 0))
     torch.cuda.synchronize()
     for k in (0, 1):
-        mel, count, off, n_seg = want[k]
+        mel, count, off, n_seg, pooled = want[k]
         assert int(plans[k].n_seg.item()) == n_seg
         assert torch.equal(plans[k].mel, mel) and torch.equal(plans[k].seg_count, count)
         assert torch.equal(plans[k].seg_off[: n_seg + 1], off)
+        assert torch.equal(outs[k][:n_seg], pooled)
+
+
+def test_pool_launches_without_a_plan_are_serialised_across_streams(c_oracle):
+    """mean_pool_segments names no plan, so its launches share the context's scratch block; the library orders them
+    against each other whatever streams they come from.  Long segments: every CTA boundary needs the scratch."""
+    import torch
+
+    from aat_b200 import mean_pool_segments
+
+    rng = np.random.default_rng(77)
+    cases = []
+    for k in range(2):
+        n_rows = 30000 + 5000 * k
+        emb = torch.from_numpy(rng.standard_normal((n_rows, 768), dtype=np.float32)).cuda()
+        off = _random_offsets(rng, n_rows, 400, 1500)
+        want = mean_pool_segments(emb, off).clone()
+        cases.append((emb, torch.from_numpy(off).cuda(), off, want))
+    assert_pooled_close(cases[0][3].cpu().numpy()[0], c_oracle.mean_pool_f64(cases[0][0].cpu().numpy(), cases[0][2]))
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    got = [[], []]
+    for rep in range(15):
+        for k in (0, 1):
+            with torch.cuda.stream(streams[k]):
+                got[k].append(mean_pool_segments(cases[k][0], cases[k][1]))
+    torch.cuda.synchronize()
+    for k in (0, 1):
+        for g in got[k]:
+            assert torch.equal(g, cases[k][3])
+
+
+def test_pool_flags_row_count_from_the_device_and_early_fetch(tok):
+    """AAT_POOL_ROWS_FROM_DEVICE: the embedding tensor is an allocation larger than what the segments cover and the
+    covered row count comes from the boundary kernel; AAT_POOL_EMB_READY only changes when rows are requested."""
+    import torch
+
+    from aat_b200 import synth
+
+    lengths = [256000] * 16
+    batch = tok.plan(lengths)
+    wave = synth.device_bursty_batch(batch, 2000, 0)
+    batch.logmel(wave), batch.boundaries()
+    torch.cuda.synchronize()
+    n_seg, n_rows = int(batch.n_seg.item()), int(batch.n_frames.item())
+    assert n_rows == int(batch.seg_off[n_seg].item()) and 30 * 16 <= n_seg <= 40 * 16
+    big = torch.randn(n_rows + 5000, 768, device="cuda")
+    exact = big[:n_rows].clone()
+    out = torch.zeros(batch.total_seg_slots, 768, device="cuda")
+    want = batch.pool(exact, out)[:n_seg].clone()
+    for kw in (dict(rows_from_device=True), dict(emb_ready=True), dict(rows_from_device=True, emb_ready=True)):
+        out.zero_()
+        src = big if kw.get("rows_from_device") else exact
+        # whole steps, so that the pool launch really follows the boundary kernel
+        batch.logmel(wave), batch.boundaries()
+        got = batch.pool(src, out, **kw)[:n_seg]
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), kw
+    cs = torch.zeros(769, dtype=torch.float64, device="cuda")
+    batch.logmel(wave), batch.boundaries()
+    batch.pool(big, out, colsum=cs, rows_from_device=True)
+    torch.cuda.synchronize()
+    assert int(cs[768].item()) == n_seg
+    assert torch.allclose(cs[:768], want.double().sum(dim=0), rtol=1e-12, atol=1e-9)
 
 
 def test_profile_sampling_records_every_nth_launch(tok):
@@ -778,3 +859,122 @@ def test_masked_mean_pool_in_padded_layout():
         assert torch.equal(rows.cpu(), want_rows)
         assert torch.allclose(got.cpu().double(), want, rtol=tol, atol=tol)
         assert float(got[5].abs().max()) == 0.0
+
+
+# ----------------------------------------------------------------------------------------- on-device synthetic inputs
+def test_device_generator_is_counter_based_and_exercises_the_ragged_path(tok):
+    """aat_synth_*: utterance u is a pure function of (seed, u) whatever batch it is generated in; the recipe yields the
+    31-36 segments per 16 s the survey validated for the host generator; embeddings are N(0, 1)."""
+    import torch
+
+    from aat_b200 import synth
+
+    B, N = 8, 256000
+    batch = tok.plan([N] * B)
+    a = synth.device_bursty_batch(batch, 5000, 40).clone()
+    b = synth.device_bursty_batch(batch, 5000, 40)
+    assert torch.equal(a, b)                                    # deterministic
+    c = synth.device_bursty_batch(batch, 5000, 44)
+    assert torch.equal(c[: 4 * N], a[4 * N:])                    # utterance 44..47 is the same wherever it is generated
+    assert not torch.equal(c[4 * N:], a[: 4 * N])
+    ragged = tok.plan([N, 100, 31999, 4097])                     # another plan shape, same utterance
+    d = synth.device_bursty_batch(ragged, 5000, 40)
+    assert torch.equal(d[:N], a[:N]) and torch.equal(d[N + 100: N + 100 + 31999], a[2 * N: 2 * N + 31999])
+    x = a.view(B, N).double()
+    assert abs(float(x.mean())) < 1e-3 and 0.05 < float(x.std()) < 0.6 and float(x.abs().max()) < 6.0
+    assert float(x.abs().view(B, -1, 160).amax(dim=2).min()) < 0.02   # pauses sit at the 1e-3 floor
+    batch.logmel(a), batch.boundaries()
+    torch.cuda.synchronize()
+    counts = batch.seg_count.cpu().numpy()
+    assert counts.min() >= 25 and counts.max() <= 42, counts
+    # ... and the host path agrees with the device path on the device-generated audio (bit-exact segment lengths)
+    from oracle import ref_port
+
+    ref = ref_port.RefTokenizer()
+    w0 = a[:N].cpu().numpy()
+    assert batch.segments_of(0)[1].tolist() == ref.segment_lengths(w0)[0]
+    e = torch.empty(1_000_003, device="cuda")
+    synth.device_normal(e, 9)
+    e2 = torch.empty(1_000_003, device="cuda")
+    synth.device_normal(e2, 9)
+    assert torch.equal(e, e2) and abs(float(e.mean())) < 5e-3 and abs(float(e.std()) - 1.0) < 5e-3
+    assert abs(float((e ** 4).mean()) - 3.0) < 0.05                  # Gaussian kurtosis
+    synth.device_normal(e2, 10)
+    assert not torch.equal(e, e2)
+
+
+def test_pad_segment_boarders_reports_overflow(tok):
+    import torch
+
+    from aat_b200 import _cabi, collate, synth
+
+    batch = tok.plan([256000, 64000])
+    batch.logmel(synth.device_bursty_batch(batch, 2000, 0)), batch.boundaries()
+    torch.cuda.synchronize()
+    s_max = int(batch.seg_count.max().item())
+    padded, mask = collate.pad_segment_boarders(batch)
+    assert padded.shape == (2, s_max) and int(mask.sum().item()) == int(batch.seg_count.sum().item())
+    with pytest.raises(_cabi.AatError):
+        collate.pad_segment_boarders(batch, s_max=s_max - 1)
+
+
+def _two_gpu_worker(rank, world, port, out_path):
+    import torch
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    # the tokenizer names its device explicitly while the CURRENT device stays 0 on both ranks until set below
+    from aat_b200 import AdaptiveAudioAmplitudeTokenizer, synth
+    from aat_b200.pooling import DatasetMean
+
+    tok = AdaptiveAudioAmplitudeTokenizer(device=rank)
+    dev = torch.device("cuda", rank)
+    batch = tok.plan([256000] * 8)
+    dm = DatasetMean(768, device=rank)
+    ref = torch.zeros(769, dtype=torch.float64, device=dev)
+    out = torch.zeros(batch.total_seg_slots, 768, device=dev)
+    emb = torch.empty(8 * 810, 768, device=dev)
+    for step in range(3):
+        # launched from a thread whose current device is cuda:0 on BOTH ranks: the entry points must run on the plan's device
+        wave = synth.device_bursty_batch(batch, 3000, (rank * 3 + step) * 8)
+        synth.device_normal(emb, 100 * rank + step)
+        batch.logmel(wave), batch.boundaries()
+        batch.pool(emb, out, colsum=dm.running_buffer(), accumulate=True, rows_from_device=True)
+        torch.cuda.synchronize(dev)
+        s = int(batch.n_seg.item())
+        ref[:768] += out[:s].double().sum(dim=0)
+        ref[768] += s
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    dm.allreduce()
+    mean = dm.result()
+    parts = [torch.empty_like(ref) for _ in range(world)]
+    dist.all_gather(parts, ref)
+    want = torch.stack(parts).sum(dim=0)
+    rel = float(((dm.acc[:768] - want[:768]).abs().max() / want[:768].abs().max()).item())
+    ok = int(dm.acc[768].item()) == int(want[768].item()) and rel <= 1e-12
+    ok = ok and torch.allclose(mean, (want[:768] / want[768]).float(), rtol=1e-6, atol=1e-9)
+    if rank == 0:
+        with open(out_path, "w") as f:
+            f.write("ok" if ok else f"mismatch rel={rel}")
+    dist.destroy_process_group()
+
+
+def test_dataset_mean_allreduce_on_two_gpus(tmp_path):
+    """A9 at N > 1: DatasetMean.allreduce (NCCL) + result against an independently reduced value (torch float64 sums of
+    the pooled vectors, all_gather'ed and added in rank order), to 1e-12.  Also exercises a tokenizer bound to a device
+    that is not the thread's current device."""
+    import socket
+
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "result.txt")
+    mp.spawn(_two_gpu_worker, args=(2, port, out), nprocs=2, join=True)
+    assert open(out).read() == "ok"

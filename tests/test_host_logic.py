@@ -84,7 +84,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_cabi.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _cabi.lib().aat_version() == 100
+    assert _cabi.lib().aat_version() == _cabi.ABI_VERSION == int(re.search(r'#define AAT_B200_VERSION (\d+)', open(os.path.join(ROOT, 'include', 'aat_b200.h')).read()).group(1))
 
 
 def test_config_struct_layout_matches_header():
