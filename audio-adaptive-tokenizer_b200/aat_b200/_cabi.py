@@ -74,7 +74,7 @@ SIGNATURES = {
     "aat_plan_total_frames": (c_i64, [c_void]),
     "aat_plan_total_seg_slots": (c_i64, [c_void]),
     "aat_plan_offsets": (ctypes.c_int, [c_void, c_void, c_void, c_void]),
-    "aat_logmel": (ctypes.c_int, [c_void, c_void, c_void, ctypes.c_int, c_void, c_void, c_void]),
+    "aat_logmel": (ctypes.c_int, [c_void, c_void, c_void, ctypes.c_int, c_void, c_void, c_void, c_void]),
     "aat_boundaries": (ctypes.c_int, [c_void] * 14),
     "aat_process_boarders": (ctypes.c_int, [c_void, c_i64, c_void, c_i64, c_void, c_void, c_i64, c_void, c_void, c_void]),
     "aat_segment_frame_csr": (ctypes.c_int, [c_void] * 8),
@@ -87,6 +87,9 @@ SIGNATURES = {
     "aat_scatter_segments": (ctypes.c_int, [c_void, c_void, c_i64, c_i32, c_void, c_i64, c_i64, c_void, c_void, c_void,
                                             c_void]),
     "aat_scatter_mel_segments": (ctypes.c_int, [c_void, c_void, c_void, c_void, c_i64, c_i64, c_void, c_void, c_void]),
+    "aat_scatter_mel_tiles": (ctypes.c_int, [c_void, c_i32, c_void, c_void, c_void, c_void, c_void, c_i64, c_i64, c_void, c_void,
+                                             c_void]),
+    "aat_normalize_padded": (ctypes.c_int, [c_void, c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_i64, c_void, c_void, c_void]),
     "aat_masked_mean_pool": (ctypes.c_int, [c_void, c_void, ctypes.c_int, c_i64, c_i64, c_i32, c_void, c_void, c_void, c_void]),
     "aat_synth_workspace_bytes": (c_i64, [c_void]),
     "aat_synth_waveforms": (ctypes.c_int, [c_void, c_void, ctypes.c_uint64, c_i64, c_void, c_void, c_void]),

@@ -111,6 +111,153 @@ def scatter_mel_segments(batch: PackedBatch, boarders_padded, max_segment_frames
     return out
 
 
+def normalize_waveforms_padded(batch: PackedBatch, wave, mode: str = "w2v2", n_max=None, with_mask: bool = True):
+    """Per-utterance normalisation written straight into the feature extractor's padded layout
+    (``audio_processor(waveforms, padding=True, return_tensors="pt")``, ref:src/aat/training/collate.py:301-304):
+    returns ``(input_values [B, N_max] float32, attention_mask [B, N_max] int64 or None)``."""
+    import torch
+
+    modes = {"zscore": _cabi.AAT_NORM_ZSCORE, "w2v2": _cabi.AAT_NORM_W2V2}
+    codes = {torch.float32: _cabi.AAT_F32, torch.float64: _cabi.AAT_F64}
+    if wave.dtype not in codes or not wave.is_cuda or not wave.is_contiguous() or wave.numel() != batch.total_samples:
+        raise TypeError("wave must be a contiguous packed CUDA tensor (float32 or float64) matching the plan")
+    if n_max is None:
+        n_max = int(batch.n_samples.max()) if batch.n_utts else 0
+    out = torch.empty((batch.n_utts, n_max), dtype=torch.float32, device=wave.device)
+    mask = torch.empty((batch.n_utts, n_max), dtype=torch.int64, device=wave.device) if with_mask else None
+    _cabi.check(_cabi.lib().aat_normalize_padded(batch.ctx.handle, batch.handle, wave.data_ptr(), codes[wave.dtype],
+                                                 modes[mode], out.data_ptr(), int(n_max),
+                                                 mask.data_ptr() if with_mask else None, None, _stream(wave.device)))
+    return out, mask
+
+
+def scatter_mel_tiles(batch: PackedBatch, mel, mel_elem_off, mel_frames, mel_row_stride, boarders_padded,
+                      max_segment_frames: int, check: bool = True):
+    """:func:`scatter_mel_segments` for mel blocks described by three int64 device arrays (first element, columns, row
+    stride per utterance) — column slices of the packed log-mel, as the n-word cropping leaves them."""
+    import torch
+
+    hop = int(batch.tokenizer.hop_length)
+    max_items = 1 + int(max_segment_frames) // hop
+    B, s_max = boarders_padded.shape
+    out = torch.empty((B, s_max, batch.n_mels, max_items), dtype=torch.float32, device=mel.device)
+    status = torch.zeros(B, dtype=torch.int32, device=mel.device)
+    _cabi.check(_cabi.lib().aat_scatter_mel_tiles(batch.ctx.handle, B, mel.data_ptr(), mel_elem_off.data_ptr(),
+                                                  mel_frames.data_ptr(), mel_row_stride.data_ptr(),
+                                                  boarders_padded.data_ptr(), s_max, max_items, out.data_ptr(),
+                                                  status.data_ptr(), _stream(mel.device)))
+    if check:
+        _raise_on_status(status, "scatter_mel_tiles")
+    return out
+
+
+def collate_batch(tokenizer, waveforms, *, audio_encoder_type: str = "hubert", segmentation: str = "adaptive",
+                  uniform_segmentation_frames_per_segment=None, word_crops=None, device=None):
+    """The audio tensors of ``TokenizedAudioWaveformCollator.__call__`` (ref:src/aat/training/collate.py:255-352),
+    built on the GPU from raw waveforms: z-score (:135-152) -> log-mel -> adaptive (or uniform, :141-149) segmentation
+    -> optional n-word cropping (:169-212) -> the feature extractor's normalisation and padding (:301-304) -> padded
+    boarders (:242-253) -> waveform tiles + mask (:321-335) or log-mel tiles (:337-342).  Text columns are not produced.
+
+    waveforms  : list of 1-D float arrays (float64, as HF ``datasets`` delivers ``item['audio']['array']``)
+    audio_encoder_type : "hubert" / "wav2vec2" (waveform tiles) or "efficient_net" (log-mel tiles)
+    segmentation : "adaptive" or "uniform" (then ``uniform_segmentation_frames_per_segment`` is required)
+    word_crops : optional list with, per item, None or ``dict(word_start=[...], word_end=[...], word_start_idx=int,
+                 n_words=int)`` — the draws the reference takes from ``random`` (:122, :176) are the caller's
+
+    Returns a dict with the reference's keys (``segments_boarders_padded``, ``segments_boarders_attention_mask``,
+    ``segments_max_frame_len``, ``batched_segments``, ``segments_waveforms_mask``, ``batched_segments_melspectrograms``,
+    ``segments_count``) as CUDA tensors, plus ``audio_input_values`` / ``audio_attention_mask`` (the processor's output,
+    None for efficient_net) and ``batch`` (the :class:`PackedBatch` holding the packed log-mel).  Raises where the
+    reference raises (a segment longer than the tile, a slice past the padded waveform).  Everything but the integer
+    cropping arithmetic and the (tiny) boarder tables runs in the library's kernels."""
+    import numpy as np
+    import torch
+
+    if segmentation not in ("adaptive", "uniform"):
+        raise ValueError(f"Unhandled segmentation type: {segmentation}")
+    waves = [np.asarray(w) for w in waveforms]
+    if any(w.ndim != 1 for w in waves):
+        raise AssertionError("channel dim is not supported for waveform")
+    B = len(waves)
+    lengths = [int(w.shape[0]) for w in waves]
+    batch = tokenizer.plan(lengths, device=device)
+    dev = batch.device
+    raw = batch.pack([torch.from_numpy(np.ascontiguousarray(w, dtype=np.float64)) for w in waves])
+    hop = int(tokenizer.hop_length)
+    max_frames = int(tokenizer.max_segment_frames)
+
+    # z-score fused into the log-mel kernel's staging (what the collator caches as `melspec`), boundaries
+    batch.logmel(raw, znorm_stats=batch.waveform_stats(raw))
+    if segmentation == "adaptive":
+        batch.boundaries()
+        status = batch.status.cpu().numpy()
+        if (status < 0).any():
+            bad = int(np.argmax(status < 0))
+            raise _cabi.AatError(int(status[bad]), f"boundary kernel reported an error for utterance {bad}")
+        counts = batch.seg_count.cpu().numpy()
+        seg_len = batch.seg_len.cpu().numpy()
+        raw_lengths = [seg_len[int(batch.seg_slot_off[b]): int(batch.seg_slot_off[b]) + int(counts[b])] for b in range(B)]
+    else:
+        if not uniform_segmentation_frames_per_segment:
+            raise ValueError("uniform segmentation needs uniform_segmentation_frames_per_segment")
+        raw_lengths = [uniform_segment_lengths(n, int(uniform_segmentation_frames_per_segment)) for n in lengths]
+
+    # n-word cropping: integer arithmetic on the host, slices taken on the device
+    boarders, wave_rng, mel_rng = [], [], []
+    for b in range(B):
+        crop = word_crops[b] if word_crops is not None else None
+        n_mel = 1 + lengths[b] // hop
+        if crop is None:
+            boarders.append(np.cumsum(raw_lengths[b]))
+            wave_rng.append((0, lengths[b]))
+            mel_rng.append((0, n_mel))
+        else:
+            kept, wr, mr, _ = crop_to_words(raw_lengths[b], crop["word_start"], crop["word_end"], crop["word_start_idx"],
+                                            crop["n_words"], int(tokenizer.sampling_rate), hop,
+                                            int(tokenizer.running_mean_points), lengths[b], n_mel)
+            boarders.append(np.asarray(kept, dtype=np.int64))
+            wave_rng.append(wr)
+            mel_rng.append(mr)
+    s_max = max(len(x) for x in boarders)
+    padded_h = np.zeros((B, s_max), dtype=np.int64)
+    mask_h = np.zeros((B, s_max), dtype=np.int64)
+    for b, sb in enumerate(boarders):
+        padded_h[b, : len(sb)] = sb
+        mask_h[b, : len(sb)] = 1
+    padded = torch.from_numpy(padded_h).to(dev)
+    result = {
+        "segments_boarders_padded": padded,
+        "segments_boarders_attention_mask": torch.from_numpy(mask_h).to(dev),
+        "segments_max_frame_len": torch.tensor([int(np.max(x)) for x in raw_lengths], device=dev),
+        "segments_count": s_max, "batch": batch,
+        "batched_segments": None, "segments_waveforms_mask": None, "batched_segments_melspectrograms": None,
+        "audio_input_values": None, "audio_attention_mask": None,
+    }
+
+    if audio_encoder_type != "efficient_net":
+        cropped = any(r != (0, n) for r, n in zip(wave_rng, lengths))
+        if cropped:
+            crop_batch = tokenizer.plan([hi - lo for lo, hi in wave_rng], device=device)
+            crop_raw = torch.cat([raw[int(batch.wave_off[b]) + lo: int(batch.wave_off[b]) + hi]
+                                  for b, (lo, hi) in enumerate(wave_rng)])
+        else:
+            crop_batch, crop_raw = batch, raw
+        values, attention = normalize_waveforms_padded(crop_batch, crop_raw, "w2v2")
+        assert values.shape[1] > 0
+        segs, seg_mask = scatter_segments(crop_batch, values, padded, max_frames)
+        result.update(audio_input_values=values, audio_attention_mask=attention, batched_segments=segs,
+                      segments_waveforms_mask=seg_mask)
+    else:
+        n_mels = batch.n_mels
+        off = [n_mels * int(batch.frame_off[b]) + lo for b, (lo, hi) in enumerate(mel_rng)]
+        frames = [hi - lo for lo, hi in mel_rng]
+        stride = [1 + lengths[b] // hop for b in range(B)]
+        as_dev = lambda v: torch.tensor(v, dtype=torch.int64, device=dev)  # noqa: E731
+        result["batched_segments_melspectrograms"] = scatter_mel_tiles(batch, batch.mel, as_dev(off), as_dev(frames),
+                                                                       as_dev(stride), padded, max_frames)
+    return result
+
+
 def masked_mean_pool(audio_embeds, audio_embeds_attention_mask):
     """Mean over the valid frames of ``audio_embeds [R, L, D]`` under ``audio_embeds_attention_mask [R, L]`` —
     the ``SegmentProjectionEnum.mean`` pooling that ``AslmModel.audio_embeddings_projection`` leaves as

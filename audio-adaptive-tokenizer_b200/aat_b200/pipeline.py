@@ -1,0 +1,112 @@
+"""Batches in flight on several streams: the offline tokenization job as a software pipeline.
+
+Utterance batches are independent, and the three kernels of a step stress different parts of the
+chip: the log-mel kernel is bound by the FP64 / shared-memory pipes and leaves HBM idle, the boundary scan is one
+latency-bound CTA per utterance (8 to 256 of the 148 x 3 CTA slots) and the pool kernel is bound by HBM and leaves the
+arithmetic pipes idle.  Run strictly one after the other (one plan, one stream) every kernel's weak side is exposed; with
+``depth`` plans on ``depth`` streams the boundary scan and the pool of batch *i* overlap the log-mel of batch *i + 1*.
+
+Every slot owns a plan (hence its own device-side scheduling state and pool scratch, see include/aat_b200.h), its own
+output buffer and its own running column sums, so slots share nothing and the results are exactly what the serial
+loop gives (tests/test_gpu_parity.py::test_pipelined_steps_match_serial_steps).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+from .pooling import DatasetMean
+from .tokenizer import AdaptiveAudioAmplitudeTokenizer, PackedBatch
+
+
+class _Slot:
+    def __init__(self, torch, tokenizer, n_samples, dim, device, priority):
+        self.batch: PackedBatch = tokenizer.plan(n_samples, device=device)
+        dev = self.batch.device
+        self.stream = torch.cuda.Stream(device=dev, priority=priority)
+        self.out = torch.empty(self.batch.total_seg_slots, dim, dtype=torch.float32, device=dev)
+        self.mean = DatasetMean(dim, device=dev.index)
+        self.done = torch.cuda.Event()
+        self.stats = None  # [B, 2] waveform statistics of the fused z-score (allocated on first use)
+
+
+class TokenizerPipeline:
+    """``depth`` batches of one shape in flight.
+
+    >>> pipe = TokenizerPipeline(tok, [256000] * 64, dim=768)
+    >>> for wave, emb in batches:          # packed CUDA tensors (PackedBatch layout)
+    ...     slot = pipe.submit(wave, emb)  # log-mel -> boundaries -> pool (+ column sums) on the slot's stream
+    >>> mean = pipe.dataset_mean()         # joins the streams, adds the slots' sums, allreduce, finalise
+
+    ``submit`` returns the slot; ``slot.done`` is recorded behind its kernels, ``slot.batch`` holds the segment
+    tables and ``slot.out[:n_seg]`` the pooled vectors — valid until the slot is submitted to again (``depth`` submits
+    later), so consume or copy them after ``slot.done.synchronize()`` / ``stream.wait_event(slot.done)``."""
+
+    def __init__(self, tokenizer: AdaptiveAudioAmplitudeTokenizer, n_samples: Sequence[int], dim: int, depth: int = 2,
+                 device=None, priorities: Optional[Sequence[int]] = None):
+        import torch
+
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.torch = torch
+        self.dim = int(dim)
+        pr = list(priorities) if priorities is not None else [0] * depth
+        self.slots: List[_Slot] = [_Slot(torch, tokenizer, n_samples, self.dim, device, pr[k]) for k in range(depth)]
+        self.device = self.slots[0].batch.device
+        self.submitted = 0
+
+    def fork(self):
+        """Make every slot's stream wait for the caller's current stream (inputs produced there, an event recorded
+        there).  ``submit(..., inputs_ready=True)`` then needs no per-step dependency."""
+        cur = self.torch.cuda.current_stream(self.device)
+        for slot in self.slots:
+            slot.stream.wait_stream(cur)
+
+    def submit(self, wave, emb, colsum: bool = True, znorm: bool = False, rows_from_device: bool = False,
+               inputs_ready: bool = False) -> _Slot:
+        """One step over one batch on the next slot's stream.  ``wave`` / ``emb`` must be ready on the CALLER's current
+        stream: the slot's stream is made to wait for it, unless ``inputs_ready`` says they have been for long (resident
+        inputs, or after :meth:`fork`) — an event wait between two steps of a slot costs the overlap of the second
+        step's first kernel with the first step's last.  ``znorm`` applies the call sites' z-score inside the log-mel
+        kernel; ``rows_from_device`` as in :meth:`PackedBatch.pool`."""
+        torch = self.torch
+        slot = self.slots[self.submitted % len(self.slots)]
+        self.submitted += 1
+        if not inputs_ready:
+            slot.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(slot.stream):
+            b = slot.batch
+            if znorm:
+                slot.stats = b.waveform_stats(wave, out=slot.stats)
+                b.logmel(wave, znorm_stats=slot.stats)
+            else:
+                b.logmel(wave)
+            b.boundaries()
+            # the launch in front of the pool kernel is this slot's boundary scan, which does not write embeddings
+            b.pool(emb, slot.out, colsum=slot.mean.running_buffer() if colsum else None, accumulate=colsum,
+                   emb_ready=not rows_from_device, rows_from_device=rows_from_device)
+            slot.done.record()
+        return slot
+
+    def join(self):
+        """Make the caller's current stream wait for everything submitted so far (no host synchronisation)."""
+        cur = self.torch.cuda.current_stream(self.device)
+        for slot in self.slots:
+            cur.wait_stream(slot.stream)
+
+    def reset_sums(self):
+        self.join()
+        for slot in self.slots:
+            slot.mean.acc.zero_()
+        self.fork()  # later submits see the zeroed sums
+
+    def dataset_mean(self, group=None) -> DatasetMean:
+        """Joins the streams and returns slot 0's :class:`DatasetMean` holding the sums of ALL slots, allreduced
+        (one SUM allreduce of ``dim + 1`` float64).  Call ``.result()`` on it for the mean vector."""
+        self.join()
+        total = self.slots[0].mean
+        for slot in self.slots[1:]:
+            total.acc += slot.mean.acc
+            slot.mean.acc.zero_()
+        total.allreduce(group)
+        self.fork()  # later submits are ordered behind the additions above
+        return total

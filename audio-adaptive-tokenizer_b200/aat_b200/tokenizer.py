@@ -320,8 +320,26 @@ class PackedBatch:
             raise ValueError("waveform lengths do not match the plan")
         return torch.cat([p.reshape(-1) for p in parts]).to(self.device)
 
-    def logmel(self, wave, with_amp: bool = True):
-        """K1+K2 on a packed waveform tensor (float32 or float64, CUDA).  Returns the packed mel."""
+    def waveform_stats(self, wave, out=None):
+        """Per-utterance (mean, population variance) of a packed waveform in float64 -> ``[B, 2]`` CUDA tensor: one pass
+        over the samples (N2).  Feed it to :meth:`logmel` as ``znorm_stats`` for the fused z-score."""
+        import torch
+
+        dt = {torch.float32: _cabi.AAT_F32, torch.float64: _cabi.AAT_F64}.get(wave.dtype)
+        if dt is None or not wave.is_cuda or not wave.is_contiguous() or wave.numel() != self.total_samples:
+            raise TypeError("wave must be a contiguous packed CUDA tensor (float32 or float64) matching the plan")
+        if out is None:
+            out = torch.empty((self.n_utts, 2), dtype=torch.float64, device=self.device)
+        _cabi.check(_cabi.lib().aat_normalize(self.ctx.handle, self.handle, wave.data_ptr(), dt, _cabi.AAT_NORM_ZSCORE,
+                                              None, _cabi.AAT_F64, out.data_ptr(), self._stream()))
+        return out
+
+    def logmel(self, wave, with_amp: bool = True, znorm_stats=None):
+        """K1+K2 on a packed waveform tensor (float32 or float64, CUDA).  Returns the packed mel.
+
+        znorm_stats : optional ``[B, 2]`` float64 CUDA tensor from :meth:`waveform_stats`; the samples are then
+                      z-scored ``(x - mean) / (std + 1e-6)`` in float64 as they are staged (what the reference's call
+                      sites do before ``get_melspec``), without a normalised copy of the waveform"""
         import torch
 
         if not (isinstance(wave, torch.Tensor) and wave.is_cuda and wave.is_contiguous()):
@@ -331,8 +349,12 @@ class PackedBatch:
         dt = {torch.float32: _cabi.AAT_F32, torch.float64: _cabi.AAT_F64}.get(wave.dtype)
         if dt is None:
             raise TypeError("waveform dtype must be float32 or float64")
-        _cabi.check(_cabi.lib().aat_logmel(self.ctx.handle, self.handle, wave.data_ptr(), dt, self.mel.data_ptr(),
-                                           self.amp.data_ptr() if with_amp else None, self._stream()))
+        if znorm_stats is not None and (znorm_stats.dtype != torch.float64 or znorm_stats.numel() != 2 * self.n_utts or
+                                        not znorm_stats.is_cuda or not znorm_stats.is_contiguous()):
+            raise TypeError("znorm_stats must be a contiguous [B, 2] float64 CUDA tensor (waveform_stats())")
+        _cabi.check(_cabi.lib().aat_logmel(self.ctx.handle, self.handle, wave.data_ptr(), dt,
+                                           znorm_stats.data_ptr() if znorm_stats is not None else None,
+                                           self.mel.data_ptr(), self.amp.data_ptr() if with_amp else None, self._stream()))
         return self.mel
 
     def boundaries(self, mel=None, use_amp: bool = True, with_minima: bool = True, with_csr: bool = True):

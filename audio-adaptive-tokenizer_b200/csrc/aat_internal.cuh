@@ -76,7 +76,7 @@ struct alignas(16) MelTile {
     int32_t T;        // frames of the utterance (row stride of its mel block)
     int32_t valid;    // frames of this tile that exist (1..kMelFramesPerTile); 0 marks "no tile"
     int32_t interior; // the whole staged range lies inside the utterance (no reflection needed)
-    int32_t pad_;
+    int32_t utt;      // utterance index (per-utterance statistics of the fused z-score)
 };
 static_assert(sizeof(MelTile) == 64, "MelTile is copied as four 16-byte pieces");
 
@@ -161,8 +161,8 @@ struct aat_plan {
 namespace aat {
 
 // kernels' host launchers (defined in the .cu files)
-int launch_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave, int wave_dtype, float *mel, float *amp,
-                  cudaStream_t stream);
+int launch_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave, int wave_dtype, const double *znorm_stats,
+                  float *mel, float *amp, cudaStream_t stream);
 int launch_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel, const float *amp, int64_t *seg_start,
                       int64_t *seg_len, int32_t *seg_count, int64_t *minima, int32_t *minima_count, int32_t *status,
                       int64_t *seg_off, int64_t *n_seg, int64_t *utt_seg_off, cudaStream_t stream);
@@ -182,8 +182,12 @@ int launch_pad_boarders(const aat_plan *plan, const int64_t *seg_len, const int3
                         int64_t *boarders, int64_t *mask, int32_t *status, cudaStream_t stream);
 int launch_scatter_segments(const float *wave, int64_t n_max, int32_t n_utts, const int64_t *boarders, int64_t s_max,
                             int64_t max_frames, float *out, float *mask, int32_t *status, cudaStream_t stream);
-int launch_scatter_mel_segments(aat_ctx *ctx, const aat_plan *plan, const float *mel, const int64_t *boarders,
-                                int64_t s_max, int64_t max_items, float *out, int32_t *status, cudaStream_t stream);
+int launch_scatter_mel_segments(aat_ctx *ctx, const aat_plan *plan, int32_t n_utts, const float *mel,
+                                const int64_t *mel_elem_off, const int64_t *mel_frames, const int64_t *mel_row_stride,
+                                const int64_t *boarders, int64_t s_max, int64_t max_items, float *out, int32_t *status,
+                                cudaStream_t stream);
+int launch_normalize_padded(aat_ctx *ctx, const aat_plan *plan, const void *wave, int in_dtype, int mode, float *out,
+                            int64_t n_max, int64_t *mask, double *stats, cudaStream_t stream);
 int launch_masked_mean_pool(const void *emb, int emb_dtype, int64_t n_rows, int64_t seq_len, int32_t dim,
                             const int64_t *mask, float *out, int64_t *row_mask, cudaStream_t stream);
 int64_t synth_burst_capacity(int sampling_rate, int64_t n_samples);

@@ -371,6 +371,7 @@ static int plan_create(aat_ctx *ctx, int32_t n_utts, const int64_t *n_samples_ho
             d.T = (int32_t)T;
             d.valid = (int32_t)(T - f0 < kMelFramesPerTile ? T - f0 : kMelFramesPerTile);
             d.interior = (g0 >= 0 && g0 + stage_pad <= n) ? 1 : 0;
+            d.utt = b;
             tiles_desc.push_back(d);
         }
         burst_off[b + 1] = burst_off[b] + synth_burst_capacity(ctx->cfg.sampling_rate, n);
@@ -465,13 +466,14 @@ int aat_plan_offsets(const aat_plan *plan, int64_t *wave_off_host, int64_t *fram
 }
 
 // ------------------------------------------------------------------------------------------------ device API
-int aat_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave_dev, int wave_dtype, float *mel_dev,
-               float *amp_dev, void *stream)
+int aat_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave_dev, int wave_dtype, const double *znorm_stats_dev,
+               float *mel_dev, float *amp_dev, void *stream)
 {
     AAT_REQUIRE(ctx && plan && wave_dev && mel_dev, AAT_ERR_INVALID, "aat_logmel: NULL argument");
     AAT_REQUIRE(plan->ctx == ctx, AAT_ERR_INVALID, "aat_logmel: plan belongs to another context");
     AAT_DEVICE_GUARD(ctx);
-    return launch_logmel(ctx, plan, wave_dev, wave_dtype, mel_dev, amp_dev, static_cast<cudaStream_t>(stream));
+    return launch_logmel(ctx, plan, wave_dev, wave_dtype, znorm_stats_dev, mel_dev, amp_dev,
+                         static_cast<cudaStream_t>(stream));
 }
 
 int aat_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel_dev, const float *amp_dev,
@@ -582,8 +584,36 @@ int aat_scatter_mel_segments(aat_ctx *ctx, const aat_plan *plan, const float *me
                 "aat_scatter_mel_segments: NULL argument");
     AAT_REQUIRE(s_max >= 0 && max_items >= 0, AAT_ERR_INVALID, "aat_scatter_mel_segments: negative size");
     AAT_DEVICE_GUARD(ctx);
-    return launch_scatter_mel_segments(ctx, plan, mel_dev, boarders_dev, s_max, max_items, out_dev, status_dev,
+    return launch_scatter_mel_segments(ctx, plan, plan->n_utts, mel_dev, nullptr, nullptr, nullptr, boarders_dev, s_max,
+                                       max_items, out_dev, status_dev, static_cast<cudaStream_t>(stream));
+}
+
+int aat_scatter_mel_tiles(aat_ctx *ctx, int32_t n_utts, const float *mel_dev, const int64_t *mel_elem_off_dev,
+                          const int64_t *mel_frames_dev, const int64_t *mel_row_stride_dev, const int64_t *boarders_dev,
+                          int64_t s_max, int64_t max_items, float *out_dev, int32_t *status_dev, void *stream)
+{
+    AAT_REQUIRE(ctx && mel_dev && mel_elem_off_dev && mel_frames_dev && mel_row_stride_dev && boarders_dev && out_dev &&
+                    status_dev,
+                AAT_ERR_INVALID, "aat_scatter_mel_tiles: NULL argument");
+    AAT_REQUIRE(n_utts >= 0 && s_max >= 0 && max_items >= 0, AAT_ERR_INVALID, "aat_scatter_mel_tiles: negative size");
+    AAT_DEVICE_GUARD(ctx);
+    return launch_scatter_mel_segments(ctx, nullptr, n_utts, mel_dev, mel_elem_off_dev, mel_frames_dev, mel_row_stride_dev,
+                                       boarders_dev, s_max, max_items, out_dev, status_dev,
                                        static_cast<cudaStream_t>(stream));
+}
+
+int aat_normalize_padded(aat_ctx *ctx, const aat_plan *plan, const void *wave_dev, int in_dtype, int mode, float *out_dev,
+                         int64_t n_max, int64_t *mask_dev, double *stats_dev, void *stream)
+{
+    AAT_REQUIRE(ctx && plan && wave_dev && out_dev, AAT_ERR_INVALID, "aat_normalize_padded: NULL argument");
+    AAT_REQUIRE(plan->ctx == ctx, AAT_ERR_INVALID, "aat_normalize_padded: plan belongs to another context");
+    AAT_REQUIRE(n_max >= 0, AAT_ERR_INVALID, "aat_normalize_padded: negative n_max");
+    for (int64_t n : plan->h_n_samples)
+        AAT_REQUIRE(n <= n_max, AAT_ERR_INVALID, "aat_normalize_padded: an utterance of %lld samples does not fit n_max = %lld",
+                    (long long)n, (long long)n_max);
+    AAT_DEVICE_GUARD(ctx);
+    return launch_normalize_padded(ctx, plan, wave_dev, in_dtype, mode, out_dev, n_max, mask_dev, stats_dev,
+                                   static_cast<cudaStream_t>(stream));
 }
 
 int aat_masked_mean_pool(aat_ctx *ctx, const void *emb_dev, int emb_dtype, int64_t n_rows, int64_t seq_len, int32_t dim,
@@ -700,7 +730,7 @@ static int host_pipeline(aat_ctx *ctx, const void *wave_host, int wave_dtype, in
     if (need_wave) {
         memcpy(h_wave, wave_host, wsize * n_samples);
         AAT_TRY_CUDA(cudaMemcpyAsync(d_wave, h_wave, wsize * n_samples, cudaMemcpyHostToDevice, st));
-        rc = launch_logmel(ctx, plan, d_wave, wave_dtype, d_mel, want_boundaries ? d_amp : nullptr, st);
+        rc = launch_logmel(ctx, plan, d_wave, wave_dtype, nullptr, d_mel, want_boundaries ? d_amp : nullptr, st);
         if (rc) return fail(rc);
         if (mel_out_host) AAT_TRY_CUDA(cudaMemcpyAsync(h_mel, d_mel, sizeof(float) * M * T, cudaMemcpyDeviceToHost, st));
     } else {

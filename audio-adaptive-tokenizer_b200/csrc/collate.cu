@@ -119,6 +119,33 @@ wave_apply_norm_kernel(const InT *wave, OutT *out, const int64_t *n_samples, con
     }
 }
 
+// Same affine map, written straight into the feature extractor's padded layout: out[b, :n_b] = normalised samples,
+// out[b, n_b:] = 0 (padding_value), mask[b, :] = 1 / 0 (ref:src/aat/training/collate.py:301-304: the processor call
+// with padding=True).  grid = (chunks of the padded row, utterances).
+template <typename InT>
+__global__ void __launch_bounds__(kStatThreads)
+wave_apply_norm_padded_kernel(const InT *wave, float *out, int64_t *mask, const int64_t *n_samples, const int64_t *wave_off,
+                              int64_t n_max, const double *stats, int mode)
+{
+    const int utt = blockIdx.y;
+    const int64_t n = n_samples[utt];
+    const int64_t j0 = (int64_t)blockIdx.x * kStatChunk;
+    const int64_t end = (n_max - j0 < kStatChunk) ? n_max : j0 + kStatChunk;
+    const double mean = stats[2 * utt], var = stats[2 * utt + 1];
+    const InT *src = wave + wave_off[utt];
+    float *dst = out + (size_t)utt * n_max;
+    int64_t *m = mask ? mask + (size_t)utt * n_max : nullptr;
+    const double denom64 = sqrt(var) + 1e-6;
+    const float mf = (float)mean;
+    const float denom32 = sqrtf(__fadd_rn((float)var, 1e-7f));
+    for (int64_t i = j0 + threadIdx.x; i < end; i += kStatThreads) {
+        float v = 0.0f;
+        if (i < n) v = (mode == 0) ? (float)(((double)src[i] - mean) / denom64) : __fdiv_rn(__fsub_rn((float)src[i], mf), denom32);
+        dst[i] = v;
+        if (m) m[i] = i < n ? 1 : 0;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- N1
 __global__ void pad_boarders_kernel(int n_utts, int64_t s_max, const int64_t *seg_slot_off, const int64_t *seg_len,
                                     const int32_t *seg_count, int64_t *boarders, int64_t *mask, int32_t *status)
@@ -196,15 +223,19 @@ scatter_segments_kernel(const float *wave, int64_t n_max, const int64_t *boarder
 }
 
 // grid = B * s_max rows; out[b, s, mel, :cols] = mel_b[mel, prev/hop : boarder/hop], rest 0
+// Utterance b's mel is a C-contiguous (n_mels, T_b) block: either the plan's packed layout (frame_off / n_samples) or,
+// when mel_elem_off / mel_frames are given, any blocks the caller describes (cropped mels of the n-word path).
 __global__ void __launch_bounds__(256)
-scatter_mel_segments_kernel(const float *mel, const int64_t *frame_off, const int64_t *n_samples, int hop, int n_mels,
+scatter_mel_segments_kernel(const float *mel, const int64_t *frame_off, const int64_t *n_samples,
+                            const int64_t *mel_elem_off, const int64_t *mel_frames, const int64_t *mel_row_stride, int hop, int n_mels,
                             const int64_t *boarders, int64_t s_max, int64_t max_items, float *out, int32_t *status)
 {
     const int64_t row = blockIdx.x;
     const int64_t b = row / s_max, s = row - b * s_max;
     const int64_t *brow = boarders + b * s_max;
     const int64_t end = brow[s];
-    const int64_t T = 1 + n_samples[b] / hop;
+    const int64_t T = mel_frames ? mel_frames[b] : 1 + n_samples[b] / hop;  // columns of the block (slices clamp here)
+    const int64_t stride = mel_row_stride ? mel_row_stride[b] : T;          // elements between its rows
     float *o = out + (size_t)row * n_mels * max_items;
     int64_t c0 = 0, cols = 0;
     if (s == 0 || end != 0) {
@@ -220,12 +251,12 @@ scatter_mel_segments_kernel(const float *mel, const int64_t *frame_off, const in
         }
         if (cols < 0) cols = 0;
     }
-    const float *src = mel + (size_t)n_mels * frame_off[b] + c0;
+    const float *src = mel + (mel_elem_off ? (size_t)mel_elem_off[b] : (size_t)n_mels * frame_off[b]) + c0;
     // a warp per mel row, lanes along time: coalesced reads of the source row and of the tile row, no divisions
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const int items = (int)max_items, ncols = (int)cols;
     for (int r = warp; r < n_mels; r += n_warps) {
-        const float *srow = src + (size_t)r * T;
+        const float *srow = src + (size_t)r * stride;
         float *orow = o + (size_t)r * items;
         for (int c = lane; c < items; c += 32) orow[c] = (c < ncols) ? srow[c] : 0.0f;
     }
@@ -419,16 +450,38 @@ int launch_scatter_segments(const float *wave, int64_t n_max, int32_t n_utts, co
     return AAT_OK;
 }
 
-int launch_scatter_mel_segments(aat_ctx *ctx, const aat_plan *plan, const float *mel, const int64_t *boarders,
+int launch_scatter_mel_segments(aat_ctx *ctx, const aat_plan *plan, int32_t n_utts, const float *mel,
+                                const int64_t *mel_elem_off, const int64_t *mel_frames, const int64_t *mel_row_stride,
+                                const int64_t *boarders,
                                 int64_t s_max, int64_t max_items, float *out, int32_t *status, cudaStream_t stream)
 {
-    if (plan->n_utts == 0) return AAT_OK;
-    AAT_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)plan->n_utts, stream)); // also on the empty shapes below
+    if (n_utts == 0) return AAT_OK;
+    AAT_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)n_utts, stream)); // also on the empty shapes below
     if (s_max == 0 || max_items == 0) return AAT_OK;
-    AAT_REQUIRE((int64_t)plan->n_utts * s_max < (int64_t)INT32_MAX, AAT_ERR_UNSUPPORTED, "aat_scatter_mel_segments: too many rows");
-    scatter_mel_segments_kernel<<<(unsigned)(plan->n_utts * s_max), 256, 0, stream>>>(
-        mel, plan->d_frame_off, plan->d_n_samples, ctx->cfg.hop_length, ctx->cfg.num_mel_filters, boarders, s_max,
-        max_items, out, status);
+    AAT_REQUIRE((int64_t)n_utts * s_max < (int64_t)INT32_MAX, AAT_ERR_UNSUPPORTED, "aat_scatter_mel_segments: too many rows");
+    scatter_mel_segments_kernel<<<(unsigned)(n_utts * s_max), 256, 0, stream>>>(
+        mel, plan ? plan->d_frame_off : nullptr, plan ? plan->d_n_samples : nullptr, mel_elem_off, mel_frames,
+        mel_row_stride, ctx->cfg.hop_length, ctx->cfg.num_mel_filters, boarders, s_max, max_items, out, status);
+    AAT_LAUNCH_CHECK();
+    return AAT_OK;
+}
+
+int launch_normalize_padded(aat_ctx *ctx, const aat_plan *plan, const void *wave, int in_dtype, int mode, float *out,
+                            int64_t n_max, int64_t *mask, double *stats, cudaStream_t stream)
+{
+    AAT_REQUIRE(in_dtype == AAT_F32 || in_dtype == AAT_F64, AAT_ERR_UNSUPPORTED, "aat_normalize_padded: input dtype must be F32 or F64");
+    AAT_REQUIRE(mode == 0 || mode == 1, AAT_ERR_INVALID, "aat_normalize_padded: unknown mode %d", mode);
+    if (plan->n_utts == 0 || n_max == 0) return AAT_OK;
+    double *st = stats ? stats : plan->d_norm_stats;
+    const int rc = launch_normalize(ctx, plan, wave, in_dtype, mode, nullptr, AAT_F32, st, stream); // statistics only
+    if (rc != AAT_OK) return rc;
+    const dim3 grid((unsigned)((n_max + kStatChunk - 1) / kStatChunk), (unsigned)plan->n_utts);
+    if (in_dtype == AAT_F32)
+        wave_apply_norm_padded_kernel<float><<<grid, kStatThreads, 0, stream>>>(
+            static_cast<const float *>(wave), out, mask, plan->d_n_samples, plan->d_wave_off, n_max, st, mode);
+    else
+        wave_apply_norm_padded_kernel<double><<<grid, kStatThreads, 0, stream>>>(
+            static_cast<const double *>(wave), out, mask, plan->d_n_samples, plan->d_wave_off, n_max, st, mode);
     AAT_LAUNCH_CHECK();
     return AAT_OK;
 }

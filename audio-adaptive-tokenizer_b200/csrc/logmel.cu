@@ -186,6 +186,7 @@ __device__ __forceinline__ double fast_log10(double x, const double2 *__restrict
 __device__ __noinline__ double slow_log10(double x) { return log10(x); }
 
 struct LogmelParams {
+    const double *znorm; // optional [2 * n_utts] (mean, population variance): fused z-score of the samples
     const void *wave;
     float *mel;
     float *amp;
@@ -319,7 +320,23 @@ __device__ __noinline__ void fetch_edge_tile(WaveT *dst, const WaveT *utt, int64
         cp_async<(int)sizeof(WaveT)>(dst + i + gap * (i / kRawBlock), utt + reflect_index(g0 + i, n));
 }
 
-template <typename WaveT, bool kHop160>
+// Fused z-score (x - mean) / (std + 1e-6) of the call sites (ref:src/aat/training/collate.py:135-152,
+// ref:scripts/audio_tokenization_melspec.py:40) in float64, applied where a sample is widened for the transform, so a
+// normalised copy of the waveform is never written or re-read.  The quotient is correctly rounded like numpy's division
+// without a division per sample: with r = RN(1 / d) taken once per tile, q = RN(t * r) is within an ulp of t / d, the
+// remainder t - q * d is exact in one FMA, and RN(q + rem * r) is the correctly rounded quotient (Markstein) — three
+// operations on the FP64 pipe instead of the ~10 of a division.
+struct Znorm {
+    double mean, d, r;
+    __device__ __forceinline__ double operator()(double x) const
+    {
+        const double t = __dsub_rn(x, mean);
+        const double q = __dmul_rn(t, r);
+        return fma(fma(-q, d, t), r, q);
+    }
+};
+
+template <typename WaveT, bool kHop160, bool kZnorm>
 __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -414,6 +431,13 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
         // ---- pass 1: thread n2 transforms x[20 n1 + n2] over n1, applies W_400^(n2 k1) ----
         {
             double2 v[20];
+            Znorm zn{0.0, 1.0, 1.0};
+            if (kZnorm) {
+                const int u = s_tiles[slot].utt;
+                zn.mean = __ldg(p.znorm + 2 * u);
+                zn.d = __dadd_rn(__dsqrt_rn(__ldg(p.znorm + 2 * u + 1)), 1e-6);
+                zn.r = __drcp_rn(zn.d);
+            }
             const WaveT *wa = s_rawbuf + pair * (kHop160 ? kRawBlock + kGap : 2 * p.hop) + lane20;
             const int hop = kHop160 ? 160 : p.hop;
 #pragma unroll
@@ -423,7 +447,10 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
                 // the offsets that cross into the next 320-sample block are known at compile time.
                 const int ia = 20 * n1 + (kHop160 && 20 * n1 >= kRawBlock ? kGap : 0);
                 const int ib = hop + 20 * n1 + (kHop160 && 160 + 20 * n1 >= kRawBlock ? kGap : 0);
-                v[n1] = make_double2((double)wa[ia] * w, (double)wa[ib] * w);
+                if (kZnorm)
+                    v[n1] = make_double2(zn((double)wa[ia]) * w, zn((double)wa[ib]) * w);
+                else
+                    v[n1] = make_double2((double)wa[ia] * w, (double)wa[ib] * w);
             }
             dft20(v, p.K);
             // W_400^(n2 k1) for k1 = 5 j + i is (W^(5 j n2)) (W^(i n2)): seven table rows (k1 = 1..4, 5, 10, 15) and twelve
@@ -598,13 +625,21 @@ int logmel_tables_init(aat_ctx *ctx)
     return AAT_OK;
 }
 
-int launch_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave, int wave_dtype, float *mel, float *amp,
-                  cudaStream_t stream)
+template <typename WaveT>
+static auto pick_logmel_kernel(bool hop160, bool znorm)
+{
+    if (hop160) return znorm ? logmel_kernel<WaveT, true, true> : logmel_kernel<WaveT, true, false>;
+    return znorm ? logmel_kernel<WaveT, false, true> : logmel_kernel<WaveT, false, false>;
+}
+
+int launch_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave, int wave_dtype, const double *znorm_stats,
+                  float *mel, float *amp, cudaStream_t stream)
 {
     AAT_REQUIRE(wave_dtype == AAT_F32 || wave_dtype == AAT_F64, AAT_ERR_UNSUPPORTED,
                 "aat_logmel: waveform dtype must be AAT_F32 or AAT_F64 (got %d)", wave_dtype);
     if (plan->mel_tiles == 0) return AAT_OK;
     LogmelParams p{};
+    p.znorm = znorm_stats;
     p.wave = wave;
     p.mel = mel;
     p.amp = amp;
@@ -627,8 +662,8 @@ int launch_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave, int wave
     const bool hop160 = p.hop == 160;
     const int gap = hop160 ? (wave_dtype == AAT_F32 ? raw_gap<float>() : raw_gap<double>()) : 0;
     const size_t smem = smem_layout(raw_elems(p.stage_pad, gap), wave_bytes, p.n_mels, p.n_weights).total;
-    auto kernel = wave_dtype == AAT_F32 ? (hop160 ? logmel_kernel<float, true> : logmel_kernel<float, false>)
-                                        : (hop160 ? logmel_kernel<double, true> : logmel_kernel<double, false>);
+    const bool znorm = znorm_stats != nullptr;
+    auto kernel = wave_dtype == AAT_F32 ? pick_logmel_kernel<float>(hop160, znorm) : pick_logmel_kernel<double>(hop160, znorm);
     AAT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AAT_MAX_SMEM_CARVEOUT(kernel);
     int per_sm = 0;

@@ -331,9 +331,9 @@ class Workload:
     """One BASELINE config resident on one GPU: R rotating buffer sets of distinct, device-generated utterances with
     the embeddings their own segmentation calls for, and the step that runs the path over one set."""
 
-    def __init__(self, torch, tok, name, rank, local_rank, rotate):
+    def __init__(self, torch, tok, name, rank, local_rank, rotate, depth=2):
         from aat_b200 import synth
-        from aat_b200.pooling import DatasetMean
+        from aat_b200.pipeline import TokenizerPipeline
 
         self.torch, self.name = torch, name
         self.B, self.N, self.D, idx = WORKLOADS[name]
@@ -356,20 +356,17 @@ class Workload:
             synth.device_normal(emb, 1234 + 97 * rank + s)
             self.wave_sets.append(wave), self.emb_sets.append(emb), self.n_seg.append(n_seg), self.n_rows.append(n_rows)
         self.out = torch.empty(self.batch.total_seg_slots, D, device=self.dev)
-        self.dm = DatasetMean(D, device=local_rank)
+        # the step runs through the public pipeline object: `depth` plans on `depth` streams, so that the boundary scan
+        # and the pool of one batch overlap the log-mel of the next (depth 1 = strictly serial, kept for the A/B)
+        self.depth = depth
+        self.pipes = {d: TokenizerPipeline(tok, [self.N] * B, D, depth=d, device=local_rank) for d in sorted({1, depth})}
         self.audio_hours_per_step = B * self.N / 16000 / 3600
         self.pool_bytes = float(np.mean([r * D * 4 + s * D * 4 + (s + 1) * 8 for r, s in zip(self.n_rows, self.n_seg)]))
 
-    def step(self, i, colsum=True):
+    def step(self, i, colsum=True, depth=None):
         s = i % self.R
-        b = self.batch
-        b.logmel(self.wave_sets[s])
-        b.boundaries()  # also emits the packed frame CSR from the kernel's tail
-        # the launch in front of the pool kernel is this batch's boundary scan, which does not write embeddings
-        if colsum:
-            b.pool(self.emb_sets[s], self.out, colsum=self.dm.running_buffer(), accumulate=True, emb_ready=True)
-        else:  # diagnostic only: the dataset-mean epilogue is part of the step by default
-            b.pool(self.emb_sets[s], self.out, emb_ready=True)
+        self.pipes[self.depth if depth is None else depth].submit(self.wave_sets[s], self.emb_sets[s], colsum=colsum,
+                                                                   inputs_ready=True)
 
     def expected_sums(self, uses):
         """Independent reduction of what `steps` steps must have accumulated: the pooled vectors of every buffer set
@@ -442,12 +439,16 @@ class Workload:
         return roof
 
 
-def measure_workload(torch, dist, w, steps, warmup, world, sample_every, no_colsum=False, sampler=None):
+def measure_workload(torch, dist, w, steps, warmup, world, sample_every, no_colsum=False, sampler=None, depth=None,
+                     breakdown=True):
     """Warm-up, then exactly `steps` timed steps (+ the allreduce of the dataset mean) between barriers; returns the
     timing record.  Device time by CUDA events, max over ranks."""
     from aat_b200 import _cabi
 
     dev = w.dev
+    depth = w.depth if depth is None else depth
+    pipe = w.pipes[depth]
+    ctx_handle = w.batch.ctx.handle
 
     def barrier():
         if world > 1:
@@ -455,31 +456,32 @@ def measure_workload(torch, dist, w, steps, warmup, world, sample_every, no_cols
         torch.cuda.synchronize()
 
     for i in range(warmup):
-        w.step(i, not no_colsum)
+        w.step(i, not no_colsum, depth)
     barrier()
     if sampler is not None:
         t_spin = time.time()
         while not sampler.samples and time.time() - t_spin < 2.0:  # keep the GPU busy until nvidia-smi is up
-            w.step(0, not no_colsum)
+            w.step(0, not no_colsum, depth)
             torch.cuda.synchronize()
-    w.dm.acc.zero_()  # the dataset mean is the mean of the TIMED steps
-    _cabi.profile_enable(w.batch.ctx.handle, ("pool",), every=sample_every)
+    pipe.reset_sums()  # the dataset mean is the mean of the TIMED steps
+    _cabi.profile_enable(ctx_handle, ("pool",), every=sample_every)
     launches0 = _cabi.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     wall0 = time.time()
     ev0.record()
+    pipe.fork()  # the slots' streams start behind ev0
     for i in range(steps):
-        w.step(i, not no_colsum)
-    w.dm.allreduce()
-    mean_vec = w.dm.result()
+        w.step(i, not no_colsum, depth)
+    dm = pipe.dataset_mean()  # joins the streams, adds the slots' sums, allreduce
+    mean_vec = dm.result()
     ev1.record()
     barrier()
     wall1 = time.time()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = _cabi.launch_count() - launches0
-    prof = _cabi.profile_summary(w.batch.ctx.handle)
-    _cabi.profile_enable(w.batch.ctx.handle, ())
+    prof = _cabi.profile_summary(ctx_handle)
+    _cabi.profile_enable(ctx_handle, ())
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -497,7 +499,7 @@ def measure_workload(torch, dist, w, steps, warmup, world, sample_every, no_cols
             want = torch.stack(parts).sum(dim=0)
         else:
             want = mine
-        got = w.dm.acc
+        got = dm.acc
         assert int(got[w.D].item()) == int(want[w.D].item()), (got[w.D].item(), want[w.D].item())
         scale = want[: w.D].abs().max().clamp_min(1e-300)
         rel = float(((got[: w.D] - want[: w.D]).abs().max() / scale).item())
@@ -510,16 +512,25 @@ def measure_workload(torch, dist, w, steps, warmup, world, sample_every, no_cols
                  "against": "torch float64 sums of the pooled vectors of every buffer set x use count, all_gather'ed and "
                             "added in rank order"}
 
-    # ---- per-kernel breakdown (untimed extra pass with every kernel instrumented)
-    _cabi.profile_enable(w.batch.ctx.handle, _cabi.KERNEL_NAMES)
-    for i in range(min(steps, 50)):
-        w.step(i, not no_colsum)
-    torch.cuda.synchronize()
-    breakdown = {k: (ms / n * 1e3 if n else None) for k, (n, ms) in _cabi.profile_summary(w.batch.ctx.handle).items()}
-    _cabi.profile_enable(w.batch.ctx.handle, ())
+    # ---- per-kernel breakdown (untimed extra pass, strictly serial, with every kernel instrumented)
+    kernel_us = None
+    if breakdown:
+        _cabi.profile_enable(ctx_handle, _cabi.KERNEL_NAMES)
+        for i in range(min(steps, 50)):
+            w.step(i, not no_colsum, 1)
+        torch.cuda.synchronize()
+        kernel_us = {k: (ms / n * 1e3 if n else None) for k, (n, ms) in _cabi.profile_summary(ctx_handle).items()}
+        _cabi.profile_enable(ctx_handle, ())
     return {"elapsed_ms": elapsed_ms, "value": world * w.audio_hours_per_step * steps / (elapsed_ms / 1e3),
             "ms_per_step": elapsed_ms / steps, "launches": int(launches), "sampled_pool": prof["pool"],
-            "kernel_us": breakdown, "wall": (wall0, wall1), "dataset_mean_check": check}
+            "kernel_us": kernel_us, "wall": (wall0, wall1), "dataset_mean_check": check, "depth": depth}
+
+
+def schedule_note(depth):
+    if depth == 1:
+        return "one plan, one stream: log-mel -> boundaries -> pool strictly one after the other"
+    return (f"aat_b200.pipeline.TokenizerPipeline, {depth} plans on {depth} streams: boundaries and pool of one batch overlap "
+            f"the log-mel of the next")
 
 
 def pool_traffic(name):
@@ -533,11 +544,14 @@ def sub_record(torch, dist, tok, name, rank, local_rank, world, args):
     """configs[...] sub-record of another BASELINE config, same machinery as the headline at fewer steps."""
     from aat_b200 import _cabi
 
-    w = Workload(torch, tok, name, rank, local_rank, args.rotate)
+    w = Workload(torch, tok, name, rank, local_rank, args.rotate, args.depth)
     steps = {"c3": 200, "c4": 60, "c2": 500}[name]
     m = measure_workload(torch, dist, w, steps, 5, world, args.pool_sample_every)
-    roof = w.pool_roofline(_cabi, m["sampled_pool"], args.pool_sample_every, pool_traffic(name))
+    serial = measure_workload(torch, dist, w, steps, 5, world, args.pool_sample_every, depth=1, breakdown=False)
+    roof = w.pool_roofline(_cabi, serial["sampled_pool"], args.pool_sample_every, pool_traffic(name))
     rec = {"workload": workload_name(name), "value": m["value"], "unit": UNIT, "steps": steps, "ms_per_step": m["ms_per_step"],
+           "schedule": schedule_note(m["depth"]),
+           "serial": {"value": serial["value"], "ms_per_step": serial["ms_per_step"], "schedule": schedule_note(1)},
            "kernel_us": m["kernel_us"], "roofline": roof, "segments_per_batch": w.n_seg, "hubert_frames_per_batch": w.n_rows,
            "rotating_sets": w.R, "dataset_mean_check": m["dataset_mean_check"]}
     del w
@@ -715,12 +729,16 @@ def run_b200(args):
             os.close(saved)
 
     tok = AdaptiveAudioAmplitudeTokenizer(device=local_rank)
-    w = Workload(torch, tok, args.workload, rank, local_rank, args.rotate)
+    w = Workload(torch, tok, args.workload, rank, local_rank, args.rotate, args.depth)
     sampler = ClockSampler(local_rank)
     sampler.start()
     m = measure_workload(torch, dist, w, args.steps, args.warmup, world, args.pool_sample_every, args.no_colsum, sampler)
     clocks = sampler.stop(*m["wall"])
-    roofline = w.pool_roofline(_cabi, m["sampled_pool"], args.pool_sample_every, pool_traffic(args.workload))
+    serial = m
+    if args.depth != 1:  # same-run A/B: the strictly serial schedule (round 1's step)
+        serial = measure_workload(torch, dist, w, max(50, args.steps // 4), 5, world, args.pool_sample_every, args.no_colsum,
+                                  depth=1, breakdown=False)
+    roofline = w.pool_roofline(_cabi, serial["sampled_pool"], args.pool_sample_every, pool_traffic(args.workload))
 
     # ---- e2e: same step through the public batched API with host (pinned) buffers
     e2e = None
@@ -738,6 +756,8 @@ def run_b200(args):
                             "generator": "aat_synth_waveforms / aat_synth_normal (Philox 4x32-10, on the device)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": m["launches"], "roofline": roofline,
         "kernel_us": m["kernel_us"], "dataset_mean_check": m["dataset_mean_check"],
+        "schedule": schedule_note(m["depth"]),
+        "serial": {"value": serial["value"], "ms_per_step": serial["ms_per_step"], "schedule": schedule_note(1)},
     }
     if not args.no_configs and args.workload == "c2":
         configs = {}
@@ -894,6 +914,7 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
     ap.add_argument("--rotate", type=int, default=DEFAULT_ROTATE)
+    ap.add_argument("--depth", type=int, default=2, help="batches in flight (plans x streams) of the step's pipeline; 1 = serial")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-configs", action="store_true", help="skip the c1/c3/c4/c5 sub-records (profiling runs)")

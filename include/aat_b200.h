@@ -147,12 +147,17 @@ int aat_plan_offsets(const aat_plan *plan, int64_t *wave_off_host, int64_t *fram
  * n_fft at hop, window, real DFT in float64, spectrum rounded to complex64, |.|^2 in float64,
  * mel projection, max(1e-10, .), log10, float32.
  * wave_dev   : packed samples, AAT_F32 or AAT_F64
+ * znorm_stats_dev : optional float64 [2 * n_utts] (mean, population variance per utterance, as aat_normalize writes
+ *              into stats_dev): the call-site normalisation (x - mean) / (std + 1e-6) in float64
+ *              (ref:src/aat/training/collate.py:135-152, ref:scripts/audio_tokenization_melspec.py:40) is then applied
+ *              to every sample as it is staged, bit for bit what aat_normalize(AAT_NORM_ZSCORE, float64 out) followed
+ *              by this call gives, without writing or re-reading a normalised waveform.  NULL = samples as they are
  * mel_dev    : packed (n_mels, T_b) float32 blocks (see layout above)
  * amp_dev    : optional (may be NULL) float32 per frame: -10 * mean over mels of the float32
  *              log-mel, accumulated in the order numpy uses (ref:src/aat/tokenizer.py:67)
  * One launch per plan may be in flight at a time (the plan owns the kernel's tile counter). */
-int aat_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave_dev, int wave_dtype, float *mel_dev,
-               float *amp_dev, void *stream);
+int aat_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave_dev, int wave_dtype, const double *znorm_stats_dev,
+               float *mel_dev, float *amp_dev, void *stream);
 
 /* ------------------------------------------------------------------ K3: boundaries
  * Replaces find_amplitude_minimas + pretokenize + process_segments_boarders
@@ -249,6 +254,13 @@ typedef enum aat_norm_mode {
 int aat_normalize(aat_ctx *ctx, const aat_plan *plan, const void *wave_dev, int in_dtype, int mode, void *out_dev,
                   int out_dtype, double *stats_dev, void *stream);
 
+/* The same normalisation written straight into the feature extractor's padded layout
+ * (ref:src/aat/training/collate.py:301-304, the processor call with padding=True):
+ * out_dev [n_utts, n_max] float32 = normalised samples, zeros behind each utterance's end;
+ * mask_dev (optional) [n_utts, n_max] int64 = the processor's attention_mask.  Every utterance must fit n_max. */
+int aat_normalize_padded(aat_ctx *ctx, const aat_plan *plan, const void *wave_dev, int in_dtype, int mode, float *out_dev,
+                         int64_t n_max, int64_t *mask_dev, double *stats_dev, void *stream);
+
 /* `_make_padded_segments_boarders` (ref:src/aat/training/collate.py:242-253) on the output of aat_boundaries:
  * boarders_dev [n_utts, s_max] = cumulative segment ends (the collator's `frames_boarders`, :158), zero padded;
  * mask_dev [n_utts, s_max] = 1 for real segments.  status_dev [n_utts] gets AAT_ERR_CAPACITY when an utterance
@@ -271,6 +283,14 @@ int aat_scatter_segments(aat_ctx *ctx, const float *wave_padded_dev, int64_t n_m
  * mel_dev is the packed log-mel of the plan. */
 int aat_scatter_mel_segments(aat_ctx *ctx, const aat_plan *plan, const float *mel_dev, const int64_t *boarders_dev,
                              int64_t s_max, int64_t max_items, float *out_dev, int32_t *status_dev, void *stream);
+
+/* The same scatter from mel blocks the caller describes instead of a plan's packed layout: utterance b's mel has
+ * n_mels rows of mel_frames_dev[b] columns, row r starting at element mel_elem_off_dev[b] + r * mel_row_stride_dev[b]
+ * of mel_dev — e.g. the cropped mels of the collator's n-word path (ref:src/aat/training/collate.py:208-212), which
+ * are column slices (views) of the full ones.  All three arrays are int64 [n_utts]. */
+int aat_scatter_mel_tiles(aat_ctx *ctx, int32_t n_utts, const float *mel_dev, const int64_t *mel_elem_off_dev,
+                          const int64_t *mel_frames_dev, const int64_t *mel_row_stride_dev, const int64_t *boarders_dev,
+                          int64_t s_max, int64_t max_items, float *out_dev, int32_t *status_dev, void *stream);
 
 /* Masked mean over the valid frames of the padded layout: the
  * `SegmentProjectionEnum.mean` branch that the reference leaves as NotImplementedError

@@ -1,10 +1,12 @@
 """ORACLE (test infrastructure, not product code) — port of the collator's ragged -> padded layout and of
 the waveform normalisations either side of the hot path.
 
-PARITY UNPINNED for these rows: `aat.training.collate` does not import in the build container
-(`from transformers.trainer import ALL_LAYERNORM_LAYERS` fails on transformers 5.5.0, and `__call__` needs
-HF Hub processors), so no golden vector could be produced by the live reference.  The loops below are a
-statement-by-statement restatement of the cited lines; the tests compare the CUDA path with them.
+Pinned (round 2): tests/golden/make_collate_golden.py imports the UNMODIFIED `aat.training.collate` from
+/root/reference/src (placeholder modules for the absent `efficientnet_pytorch` and for
+`transformers.trainer.ALL_LAYERNORM_LAYERS`, a locally built Wav2Vec2FeatureExtractor instead of the hub download) and
+commits what `TokenizedAudioWaveformCollator.__call__` / `_initial_process_segments` return for six batches
+(tests/golden/collate_v1.npz).  tests/test_collate_golden.py checks the loops below — a statement-by-statement
+restatement of the cited lines — against those fixtures bit for bit, and the CUDA path against the same fixtures.
 
   ref:src/aat/training/collate.py:242-253   _make_padded_segments_boarders
   ref:src/aat/training/collate.py:309-346   batched_segments / segments_waveforms_mask / melspectrogram tiles

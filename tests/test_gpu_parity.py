@@ -626,6 +626,53 @@ def test_pool_flags_row_count_from_the_device_and_early_fetch(tok):
     assert torch.allclose(cs[:768], want.double().sum(dim=0), rtol=1e-12, atol=1e-9)
 
 
+def test_pipelined_steps_match_serial_steps(tok):
+    """aat_b200.pipeline.TokenizerPipeline: with 2 or 3 plans on as many streams (boundaries and pool of one batch
+    overlapping the log-mel of the next) every step gives bit for bit what the strictly serial loop gives, with and
+    without the fused z-score; the dataset mean agrees to float64 rounding (the slots' sums are added in another order)."""
+    import torch
+
+    from aat_b200 import synth
+    from aat_b200.pipeline import TokenizerPipeline
+
+    lengths = [48000, 160000, 3000, 96000, 256000, 20000, 131072, 64000] * 3
+    dim = 512
+    plan = tok.plan(lengths)
+    sets = [synth.device_bursty_batch(plan, 9000, 24 * k).clone() for k in range(5)]
+    rows_ub = sum((n + 2000) // 320 + 2 for n in lengths)
+    embs = [synth.device_normal(torch.empty(rows_ub, dim, device="cuda"), 70 + k) for k in range(5)]
+    first_mel = {}
+    for znorm in (False, True):
+        results = {}
+        for depth in (1, 2, 3):
+            pipe = TokenizerPipeline(tok, lengths, dim, depth=depth)
+            got = []
+            for it in range(11):
+                k = it % 5
+                slot = pipe.submit(sets[k], embs[k], znorm=znorm, rows_from_device=True, inputs_ready=True)
+                with torch.cuda.stream(slot.stream):  # copies ordered behind the step, ahead of the slot's reuse
+                    got.append((slot.batch.mel.clone(), slot.batch.seg_len.clone(), slot.batch.seg_count.clone(),
+                                slot.batch.seg_off.clone(), slot.batch._csr_totals.clone(), slot.out.clone()))
+            dm = pipe.dataset_mean()
+            mean = dm.result()
+            torch.cuda.synchronize()
+            results[depth] = (got, dm.acc.clone(), mean.clone())
+        ref_steps, ref_acc, ref_mean = results[1]
+        assert int(ref_acc[dim].item()) == sum(int(g[4][0].item()) for g in ref_steps)
+        for depth in (2, 3):
+            steps, acc, mean = results[depth]
+            for it, (a, b) in enumerate(zip(ref_steps, steps)):
+                n_seg = int(a[4][0].item())
+                assert torch.equal(a[4], b[4]), (depth, it)
+                assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]), (depth, it)
+                assert torch.equal(a[3][: n_seg + 1], b[3][: n_seg + 1]), (depth, it)
+                assert torch.equal(a[5][:n_seg], b[5][:n_seg]), (depth, it)
+            assert int(acc[dim].item()) == int(ref_acc[dim].item())
+            assert torch.allclose(acc, ref_acc, rtol=1e-13, atol=1e-9) and torch.allclose(mean, ref_mean, rtol=1e-6, atol=1e-9)
+        first_mel[znorm] = results[1][0][0][0]
+    assert not torch.equal(first_mel[False], first_mel[True])  # the fused z-score really normalised
+
+
 def test_profile_sampling_records_every_nth_launch(tok):
     import torch
 
@@ -733,6 +780,47 @@ def test_znorm_then_logmel_matches_reference_golden(tok, golden):
     torch.cuda.synchronize()
     assert_mel_close(batch.mel_of(0).cpu().numpy(), golden.get("c2_16s_znorm", "mel"), min_exact=0.999)
     assert batch.segments_of(0)[1].tolist() == golden.get("c2_16s_znorm", "lengths").tolist()
+
+
+def test_fused_znorm_is_bit_identical_to_the_separate_pass(tok, golden):
+    """aat_logmel with znorm_stats: the z-score applied while the samples are staged (reciprocal + one exact-remainder
+    correction instead of a division per sample) gives bit for bit the log-mel of the separately normalised float64
+    waveform, for float64 and float32 input, including utterances shorter than one frame and a DC offset."""
+    import torch
+
+    from aat_b200 import collate, synth
+
+    lengths = [256000, 4097, 100, 70001, 31999, 1]
+    waves = [synth.bursty_speech(n, 640 + i).astype(np.float64) * (1.0 + 3.0 * i) + (0.0 if i % 2 else 2.5)
+             for i, n in enumerate(lengths)]
+    batch = tok.plan(lengths)
+    for dtype in (torch.float64, torch.float32):
+        packed = batch.pack([torch.from_numpy(w) for w in waves]).to(dtype)
+        normed = collate.normalize_waveforms(batch, packed, "zscore")  # float64 out
+        batch.logmel(normed)
+        batch.boundaries()
+        torch.cuda.synchronize()
+        want = (batch.mel.clone(), batch.amp.clone(), batch.seg_len.clone(), batch.seg_count.clone())
+        stats = batch.waveform_stats(packed)
+        batch.mel.zero_(), batch.amp.zero_()
+        batch.logmel(packed, znorm_stats=stats)
+        batch.boundaries()
+        torch.cuda.synchronize()
+        assert torch.equal(batch.mel, want[0]) and torch.equal(batch.amp, want[1])
+        assert torch.equal(batch.seg_count, want[3])
+        for b in range(len(lengths)):
+            w = waves[b] if dtype == torch.float64 else waves[b].astype(np.float32).astype(np.float64)
+            assert abs(float(stats[b, 0]) - w.mean()) <= 1e-12 * max(1.0, abs(w.mean()))
+            assert abs(float(stats[b, 1]) - w.var()) <= 1e-11 * max(w.var(), 1e-300)
+    # against the live reference's mel of the numpy-normalised waveform
+    raw = synth.bursty_speech(256000, synth.seed_for(2, 2)).astype(np.float64)
+    one = tok.plan([raw.size])
+    d_raw = torch.from_numpy(raw).cuda()
+    one.logmel(d_raw, znorm_stats=one.waveform_stats(d_raw))
+    one.boundaries()
+    torch.cuda.synchronize()
+    assert_mel_close(one.mel_of(0).cpu().numpy(), golden.get("c2_16s_znorm", "mel"), min_exact=0.999)
+    assert one.segments_of(0)[1].tolist() == golden.get("c2_16s_znorm", "lengths").tolist()
 
 
 def test_padded_layout_matches_collator_port(tok):
