@@ -100,6 +100,7 @@ SIGNATURES = {
     "aat_host_tokenize": (ctypes.c_int, [c_void, c_void, ctypes.c_int, c_i64, c_void, c_void, c_void, c_void, c_void,
                                          c_void, c_i64, c_void, c_void]),
     "aat_host_mean_pool": (ctypes.c_int, [c_void, c_void, ctypes.c_int, c_i64, c_i32, c_void, c_i64, c_void, c_void]),
+    "aat_host_mean_pool_list": (ctypes.c_int, [c_void, c_void, c_void, c_i64, ctypes.c_int, c_i32, c_void, c_void]),
     "aat_segment_capacity": (c_i64, [ctypes.POINTER(AatConfig), c_i64]),
     "aat_num_mel_frames": (c_i64, [ctypes.POINTER(AatConfig), c_i64]),
 }

@@ -65,7 +65,25 @@ def mean_pool_segments(embeddings, seg_off=None, *, out=None, colsum=None, devic
         for x in parts:
             if x.dim() != 3 or x.shape[0] != 1:
                 raise ValueError("each embedding must have shape [1, n_i, D]")
+        dim = int(parts[0].shape[2])
+        if any(int(x.shape[2]) != dim or x.dtype != parts[0].dtype for x in parts):
+            raise RuntimeError("Sizes / dtypes of the per-segment tensors must match except in dimension 1")
         lengths = [int(x.shape[1]) for x in parts]
+        if all(not x.is_cuda for x in parts):
+            # host list (what torch.load gives for one file of the reference): one C-ABI call, every tensor copied once
+            # into pinned staging — no torch.cat on the host first
+            parts = [x if x.is_contiguous() else x.contiguous() for x in parts]
+            n_seg = len(parts)
+            ptrs = (ctypes.c_void_p * n_seg)(*[x.data_ptr() for x in parts])
+            rows = (ctypes.c_int64 * n_seg)(*lengths)
+            res = torch.empty((1, n_seg, dim), dtype=torch.float32)
+            cs = np.empty(dim + 1, dtype=np.float64) if colsum is not None else None
+            ctx = default_context(device)
+            _cabi.check(_cabi.lib().aat_host_mean_pool_list(ctx.handle, ptrs, rows, n_seg, _torch_dtype_code(parts[0].dtype),
+                                                            dim, res.data_ptr(), cs.ctypes.data if cs is not None else None))
+            if colsum is not None:
+                colsum[...] = torch.from_numpy(cs) if isinstance(colsum, torch.Tensor) else cs
+            return res
         off = np.zeros(len(parts) + 1, dtype=np.int64)
         np.cumsum(lengths, out=off[1:])
         packed = torch.cat([x.reshape(x.shape[1], x.shape[2]) for x in parts], dim=0)

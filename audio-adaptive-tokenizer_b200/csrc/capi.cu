@@ -741,12 +741,11 @@ static int host_pipeline(aat_ctx *ctx, const void *wave_host, int wave_dtype, in
         rc = launch_boundaries(ctx, plan, d_mel, need_wave ? d_amp : nullptr, d_seg_start, d_seg_len, d_seg_count,
                                d_minima, d_min_count, d_status, nullptr, nullptr, nullptr, st);
         if (rc) return fail(rc);
-        AAT_TRY_CUDA(cudaMemcpyAsync(h_seg_count, d_seg_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        AAT_TRY_CUDA(cudaMemcpyAsync(h_min_count, d_min_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        AAT_TRY_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        AAT_TRY_CUDA(cudaMemcpyAsync(h_seg_start, d_seg_start, sizeof(int64_t) * slots, cudaMemcpyDeviceToHost, st));
-        AAT_TRY_CUDA(cudaMemcpyAsync(h_seg_len, d_seg_len, sizeof(int64_t) * slots, cudaMemcpyDeviceToHost, st));
-        if (minima_host) AAT_TRY_CUDA(cudaMemcpyAsync(h_minima, d_minima, sizeof(int64_t) * T, cudaMemcpyDeviceToHost, st));
+        // segment tables, minima and the three counters sit back to back in both arenas (same layout): ONE copy
+        // (each cudaMemcpyAsync costs 3-5 us of host time, and this path is latency-bound)
+        const size_t span = (size_t)(reinterpret_cast<unsigned char *>(d_status) - reinterpret_cast<unsigned char *>(d_seg_start)) +
+                            sizeof(int32_t);
+        AAT_TRY_CUDA(cudaMemcpyAsync(h_seg_start, d_seg_start, span, cudaMemcpyDeviceToHost, st));
     }
     AAT_TRY_CUDA(cudaStreamSynchronize(st));
 #undef AAT_TRY_CUDA
@@ -878,6 +877,64 @@ int aat_host_mean_pool(aat_ctx *ctx, const void *emb_host, int emb_dtype, int64_
     if (out_bytes) AAT_CUDA_CHECK(cudaMemcpyAsync(out_host, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
     if (colsum_host) AAT_CUDA_CHECK(cudaMemcpyAsync(colsum_host, d_cs, cs_bytes, cudaMemcpyDeviceToHost, st));
     AAT_CUDA_CHECK(cudaStreamSynchronize(st));
+    return AAT_OK;
+}
+
+// The reference's own calling convention for the pooling (ref:scripts/mean_hubert_embeddings.py:18-20): a list of
+// per-segment tensors [1, n_i, D] in host memory.  Every tensor is copied once, straight into the pinned staging
+// buffer (no host-side concatenation first), and the DMA of a filled chunk overlaps the CPU copy of the next one.
+int aat_host_mean_pool_list(aat_ctx *ctx, const void *const *seg_ptrs_host, const int64_t *seg_rows_host, int64_t n_seg,
+                            int emb_dtype, int32_t dim, float *out_host, double *colsum_host)
+{
+    AAT_REQUIRE(ctx && (n_seg == 0 || (seg_ptrs_host && seg_rows_host && out_host)), AAT_ERR_INVALID,
+                "aat_host_mean_pool_list: NULL argument");
+    AAT_REQUIRE(n_seg >= 0 && dim > 0, AAT_ERR_INVALID, "aat_host_mean_pool_list: negative size");
+    AAT_REQUIRE(emb_dtype == AAT_F32 || emb_dtype == AAT_F16 || emb_dtype == AAT_BF16, AAT_ERR_UNSUPPORTED,
+                "aat_host_mean_pool_list: embedding dtype must be F32, F16 or BF16");
+    const size_t esize = dtype_size(emb_dtype);
+    int64_t n_rows = 0;
+    for (int64_t i = 0; i < n_seg; ++i) {
+        AAT_REQUIRE(seg_rows_host[i] >= 0 && (seg_rows_host[i] == 0 || seg_ptrs_host[i]), AAT_ERR_INVALID,
+                    "aat_host_mean_pool_list: segment %lld has a negative length or a NULL pointer", (long long)i);
+        n_rows += seg_rows_host[i];
+    }
+    DeviceGuard guard(ctx->device);
+    std::lock_guard<std::mutex> lock(ctx->host_mutex);
+    const size_t row_bytes = esize * (size_t)dim;
+    const size_t emb_bytes = row_bytes * (size_t)n_rows, out_bytes = sizeof(float) * (size_t)n_seg * dim;
+    const size_t off_bytes = sizeof(int64_t) * ((size_t)n_seg + 1), cs_bytes = sizeof(double) * ((size_t)dim + 1);
+    const size_t total = align256(emb_bytes) + align256(out_bytes) + align256(off_bytes) + align256(cs_bytes);
+    int rc = ensure_scratch(ctx, total, total);
+    if (rc) return rc;
+    Arena d(ctx->dev_scratch), h(ctx->pinned);
+    unsigned char *d_emb = d.take<unsigned char>(emb_bytes), *h_emb = h.take<unsigned char>(emb_bytes);
+    float *d_out = d.take<float>((size_t)n_seg * dim), *h_out = h.take<float>((size_t)n_seg * dim);
+    int64_t *d_off = d.take<int64_t>((size_t)n_seg + 1), *h_off = h.take<int64_t>((size_t)n_seg + 1);
+    double *d_cs = d.take<double>((size_t)dim + 1), *h_cs = h.take<double>((size_t)dim + 1);
+    cudaStream_t st = ctx->host_stream;
+    constexpr size_t kChunk = 256 * 1024; // DMA granularity: large enough to run at PCIe speed, small enough to overlap
+    size_t filled = 0, sent = 0;
+    h_off[0] = 0;
+    for (int64_t i = 0; i < n_seg; ++i) {
+        const size_t bytes = row_bytes * (size_t)seg_rows_host[i];
+        if (bytes) memcpy(h_emb + filled, seg_ptrs_host[i], bytes);
+        filled += bytes;
+        h_off[i + 1] = h_off[i] + seg_rows_host[i];
+        if (filled - sent >= kChunk) {
+            AAT_CUDA_CHECK(cudaMemcpyAsync(d_emb + sent, h_emb + sent, filled - sent, cudaMemcpyHostToDevice, st));
+            sent = filled;
+        }
+    }
+    if (filled > sent) AAT_CUDA_CHECK(cudaMemcpyAsync(d_emb + sent, h_emb + sent, filled - sent, cudaMemcpyHostToDevice, st));
+    AAT_CUDA_CHECK(cudaMemcpyAsync(d_off, h_off, off_bytes, cudaMemcpyHostToDevice, st));
+    rc = launch_mean_pool(ctx, nullptr, d_emb, emb_dtype, n_rows, dim, d_off, n_seg, nullptr, d_out,
+                          colsum_host ? d_cs : nullptr, 0, st);
+    if (rc) return rc;
+    if (out_bytes) AAT_CUDA_CHECK(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    if (colsum_host) AAT_CUDA_CHECK(cudaMemcpyAsync(h_cs, d_cs, cs_bytes, cudaMemcpyDeviceToHost, st));
+    AAT_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (out_bytes) memcpy(out_host, h_out, out_bytes);
+    if (colsum_host) memcpy(colsum_host, h_cs, cs_bytes);
     return AAT_OK;
 }
 

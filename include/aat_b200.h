@@ -346,6 +346,13 @@ int aat_host_tokenize(aat_ctx *ctx, const void *wave_host, int wave_dtype, int64
 int aat_host_mean_pool(aat_ctx *ctx, const void *emb_host, int emb_dtype, int64_t n_rows, int32_t dim,
                        const int64_t *seg_off_host, int64_t n_seg, float *out_host, double *colsum_host);
 
+/* The same on the reference's own argument: a LIST of per-segment tensors [1, n_i, dim] in host memory
+ * (ref:scripts/mean_hubert_embeddings.py:18: what torch.load returns for one file).  seg_ptrs_host[i] points at the
+ * n_i x dim contiguous elements of segment i, seg_rows_host[i] = n_i.  Every tensor is copied once, straight into the
+ * library's pinned staging buffer (no concatenation on the host first). */
+int aat_host_mean_pool_list(aat_ctx *ctx, const void *const *seg_ptrs_host, const int64_t *seg_rows_host, int64_t n_seg,
+                            int emb_dtype, int32_t dim, float *out_host, double *colsum_host);
+
 /* Upper bound on the segments one utterance can produce (slot capacity used by plans). */
 int64_t aat_segment_capacity(const aat_config *cfg, int64_t n_samples);
 /* 1 + n_samples / hop (TF:audio_utils.py:778 with centre padding). */

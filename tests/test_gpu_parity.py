@@ -229,6 +229,30 @@ def test_pool_matches_reference_golden(golden, case):
     assert_pooled_close(got2.cpu().numpy(), ref)
 
 
+def test_pool_host_list_path_copies_each_tensor_once():
+    """The reference's list-of-[1, n_i, D] argument on the host goes through aat_host_mean_pool_list: float16 tensors,
+    a non-contiguous one, an empty one, and the column sums."""
+    import torch
+
+    from aat_b200 import mean_pool_segments
+    from oracle import ref_port
+
+    g = torch.Generator().manual_seed(5)
+    lens = [7, 74, 1, 33, 0, 12]
+    for dtype in (torch.float32, torch.float16):
+        lst = [torch.randn(1, n, 768, generator=g).to(dtype) for n in lens]
+        lst[1] = torch.randn(1, 768, 74, generator=g).to(dtype).transpose(1, 2)  # non-contiguous view
+        keep = [x for x in lst if x.shape[1] > 0]
+        want = ref_port.mean_pool_segments(keep).numpy()[0]
+        cs = np.zeros(769)
+        got = mean_pool_segments(lst, colsum=cs).numpy()[0]
+        assert got.shape == (len(lens), 768) and np.all(np.isnan(got[4]))
+        live = np.asarray([n > 0 for n in lens])
+        tol = 1e-6 if dtype == torch.float32 else 2e-3
+        np.testing.assert_allclose(got[live], want, rtol=tol, atol=tol)
+        assert cs[768] == len(lens)
+
+
 def _random_offsets(rng, n_rows, lo, hi):
     cuts = [0]
     while cuts[-1] < n_rows:
