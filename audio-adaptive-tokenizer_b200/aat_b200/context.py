@@ -92,9 +92,19 @@ def get_context(config: _cabi.AatConfig, window: np.ndarray, mel_filters: np.nda
         return ctx
 
 
+_default: dict = {}
+
+
 def default_context(device=None) -> Context:
-    """Context with the reference's default constructor arguments (used by the pooling entry point)."""
+    """Context with the reference's default constructor arguments (used by the pooling entry point).  Remembered per
+    (process, device): building the constant tables and the cache key costs more than a small pooling call."""
+    device = _default_device() if device is None else int(device)
+    hit = _default.get((os.getpid(), device))
+    if hit is not None and hit.handle is not None:
+        return hit
     from .constants import hann_window_periodic, mel_filter_bank_slaney
 
     cfg = make_config(12, 2000, 24000, 400, 160, 64, 16000, 15)
-    return get_context(cfg, hann_window_periodic(400), mel_filter_bank_slaney(201, 64, 0.0, 8000.0, 16000), device)
+    ctx = get_context(cfg, hann_window_periodic(400), mel_filter_bank_slaney(201, 64, 0.0, 8000.0, 16000), device)
+    _default[(os.getpid(), device)] = ctx
+    return ctx

@@ -71,12 +71,25 @@ class AdaptiveAudioAmplitudeTokenizer:
 
     # ------------------------------------------------------------------ native context
     def __getstate__(self):
-        return dict(self.__dict__)  # plain attributes only: the native context lives in a per-process cache
+        state = dict(self.__dict__)  # plain attributes only: the native context lives in a per-process cache
+        state.pop("_ctx_memo", None)
+        return state
 
     def _ctx(self) -> Context:
+        """The native context of this tokenizer's configuration on its device, in this process.  Looked up in the
+        per-process cache once and remembered on the instance (the cache key hashes 100 KB of constant tables, which is
+        half the latency of a single-clip call); a forked or unpickled copy looks it up again.  Like the reference's
+        object, the tokenizer is immutable after construction: change an attribute and build a new one."""
+        import os
+
+        memo = self.__dict__.get("_ctx_memo")
+        if memo is not None and memo[0] == os.getpid() and memo[1] == self.device and memo[2].handle is not None:
+            return memo[2]
         cfg = make_config(self.running_mean_points, self.min_segment_frames, self.max_segment_frames, self.n_fft,
                           self.hop_length, self.num_mel_filters, self.sampling_rate, self.max_amplitude_for_minima)
-        return get_context(cfg, self.window_fn, self.mel_filters, self.device)
+        ctx = get_context(cfg, self.window_fn, self.mel_filters, self.device)
+        self._ctx_memo = (os.getpid(), self.device, ctx)
+        return ctx
 
     def _segment_capacity(self, n_samples: int) -> int:
         cfg = self._ctx().config

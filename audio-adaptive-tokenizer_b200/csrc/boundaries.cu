@@ -21,10 +21,9 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kChunk = 512; // mel frames per pipeline stage
-// 96 registers x 256 threads = 24 576: a CTA of this kernel then fits on an SM beside TWO CTAs of the log-mel kernel
-// (2 x 160 x 128 = 40 960 of the 65 536 registers), so the scan of one batch can run beside the next batch's log-mel
-// when batches are pipelined (aat_b200/pipeline.py); at the compiler's own choice of 128 it needed an SM with one.
-constexpr int kMaxRegs = 96;
+// Tried and rejected (gpurun r2_b4): capping the kernel at 96 registers so that a CTA fits beside two log-mel CTAs
+// (for the pipelined schedule of aat_b200/pipeline.py) slowed the serial scan of 30-min streams from 628 to 678 us and
+// bought no overlap — where the log-mel kernel's free slots end up is not under our control.
 
 // The merge/split state machine runs on ONE thread and is sequential in `prev`, so its cost per boarder is
 // instruction latency.  It is templated on the index type: 32-bit arithmetic (no carry chains, single-instruction
@@ -395,7 +394,7 @@ __device__ unsigned long long g_bnd_trace[256 * 32];
 __device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(kWorkers) : "memory"); }
 
 template <int kChunk>
-__global__ void __maxnreg__(kMaxRegs) boundaries_kernel_t(const BoundaryParams p)
+__global__ void __launch_bounds__(kThreads) boundaries_kernel_t(const BoundaryParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *s_amp = reinterpret_cast<float *>(smem_raw);          // [2][kChunk]

@@ -207,8 +207,6 @@ struct LogmelParams {
 };
 
 constexpr int kTwiddles = 7 * 20; // rows k1 = 1, 2, 3, 4, 5, 10, 15
-constexpr int64_t kLongStreamFrames = 20000; // >= 200 s at hop 160: the boundary scan then takes >= 70 us
-constexpr int kMaxReservedSlots = 32;
 constexpr int kTileRing = 3; // descriptors: current tile, the tile whose samples are being fetched, the one after
 
 // Raw-sample staging for hop 160: frame pairs start 320 samples apart, a multiple of the 32 banks, so the lanes of
@@ -672,13 +670,10 @@ int launch_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave, int wave
     AAT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
     AAT_REQUIRE(per_sm >= 1, AAT_ERR_UNSUPPORTED, "aat_logmel: kernel does not fit on an SM (%zu bytes of shared memory)", smem);
     int grid = ctx->num_sms * per_sm;
-    // Long streams: the boundary scan of such a batch runs for hundreds of microseconds on one CTA per utterance.  When
-    // batches are pipelined over several plans and streams (aat_b200/pipeline.py) it should run beside the NEXT batch's
-    // log-mel, but this kernel's persistent CTAs fill every SM's shared memory and the scan's CTAs would have to wait
-    // for the whole kernel to drain.  Leaving one CTA slot per utterance free costs this kernel < 1 % of its CTAs here
-    // and hides the scan completely (config 4: 2.20 -> 1.97 ms per step, profiles/r2_pipeline_ab.txt).
-    if (plan->max_frames >= kLongStreamFrames && plan->n_utts <= kMaxReservedSlots && grid > 4 * plan->n_utts)
-        grid -= plan->n_utts;
+    // Tried and rejected (gpurun r2_b3 / r2_b4): leaving one CTA slot per utterance free on long streams, so that the
+    // previous batch's boundary scan could run beside this kernel in the pipelined schedule (aat_b200/pipeline.py):
+    // the free slots do not end up one per SM, the scan's 256-thread CTAs did not fit them, and nothing overlapped
+    // (config 4: 2.20 -> 2.23 ms per step at depth 2).  A third batch in flight does hide the scan (2.07 ms).
     if (grid > plan->mel_tiles) grid = plan->mel_tiles;
     ProfileScope prof(ctx, AAT_K_LOGMEL, stream);
     AAT_CUDA_CHECK(launch_pdl(kernel, dim3(grid), dim3(kThreads), smem, stream, p));

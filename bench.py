@@ -331,7 +331,7 @@ class Workload:
     """One BASELINE config resident on one GPU: R rotating buffer sets of distinct, device-generated utterances with
     the embeddings their own segmentation calls for, and the step that runs the path over one set."""
 
-    def __init__(self, torch, tok, name, rank, local_rank, rotate, depth=2):
+    def __init__(self, torch, tok, name, rank, local_rank, rotate, depth=3):
         from aat_b200 import synth
         from aat_b200.pipeline import TokenizerPipeline
 
@@ -914,7 +914,7 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
     ap.add_argument("--rotate", type=int, default=DEFAULT_ROTATE)
-    ap.add_argument("--depth", type=int, default=2, help="batches in flight (plans x streams) of the step's pipeline; 1 = serial")
+    ap.add_argument("--depth", type=int, default=3, help="batches in flight (plans x streams) of the step's pipeline; 1 = serial")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-configs", action="store_true", help="skip the c1/c3/c4/c5 sub-records (profiling runs)")
