@@ -78,6 +78,11 @@ constexpr int kMaxCtasPerSm = AAT_POOL_CTAS;
 // 1 -> 0.1907 ms/step, 2 -> 0.1899, 4 -> 0.1895, and the event-timed kernel alone is no slower (gpurun b18).
 constexpr int kPreStages = kStages;
 constexpr int kOffCache = 256; // segment offsets of the CTA's neighbourhood kept in shared memory
+// A segment that spans many CTAs (ragged stress: one giant segment) is reduced in two levels: the first CTA of every
+// aligned group of kGroup CTAs that lie wholly inside the segment adds its group's pieces and publishes ONE group
+// piece, and the owner adds group pieces.  With one level the owner fetched ~295 pieces, 8 per round trip (+75 us at
+// config-3 size, profiles/r2_pool_sweep.txt); now it is <= 2 + (296 / 16 + 2 * 15) / 8 round trips.
+constexpr int kGroup = 16;
 
 // ---------------------------------------------------------------- PTX helpers (mbarrier + bulk copy)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -216,6 +221,7 @@ struct PoolParams {
     int rows_per_stage;
     int slabs_per_row; // row_bytes / 16
     int n_consumers;
+    int group_base;    // first row of head / head_flag that holds group pieces (= the scratch block's max_ctas)
     int pre_stages;    // stages requested before the dependency wait (0 unless the caller set AAT_POOL_EMB_READY)
     int rows_from_dev; // n_seg_dev[1] holds the number of rows the CSR covers; n_rows is an upper bound
 };
@@ -478,10 +484,77 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
             }
         };
 
+        // last CTA that holds rows of a segment ending at seg_end
+        auto last_cta_of = [&](int64_t seg_end_) {
+            const int64_t last_row = seg_end_ - 1;
+            int64_t ce = n_rows > 0 ? (last_row < n_rows ? (last_row * G) / n_rows : G - 1) : G - 1;
+            while (ce + 1 < G && cta_row_begin(ce + 1, n_rows, G) <= last_row) ++ce;
+            while (ce > c && cta_row_begin(ce, n_rows, G) > last_row) --ce;
+            return ce;
+        };
+        const bool every_cta_has_rows = n_rows >= G; // both sides of the group protocol evaluate the same condition
+        // sum[j][k] += pieces lo..hi (rows of `pieces`, published under `flags`), in index order.  Every consumer thread
+        // polls its share of the flags (one thread polling them one after the other paid a global round trip per
+        // piece) and resets what it saw — a flag has a single consumer, so the reset is safe for CUDA-graph replays;
+        // the pieces are then fetched eight at a time: the loads of a batch are independent, so the cost is a round
+        // trip per batch, not per piece.
+        auto collect = [&](float (&sum)[kSlabs][kCols], const float *pieces, int *flags, int64_t lo, int64_t hi,
+                           bool skip_rowless) {
+            if (lo > hi) return;
+            for (int64_t m = lo + tid; m <= hi; m += n_consumers) {
+                if (skip_rowless && cta_row_begin(m, n_rows, G) == cta_row_begin(m + 1, n_rows, G)) continue;
+                while (ld_acquire(flags + m) == 0) {}
+                flags[m] = 0;
+            }
+            consumer_barrier(n_consumers);
+            constexpr int kBatch = 8;
+#pragma unroll
+            for (int j = 0; j < kSlabs; ++j) {
+                const int slab = tid + j * n_consumers;
+                if (slab >= p.slabs_per_row) continue;
+                const float *piece = pieces + (size_t)slab * kCols;
+                for (int64_t m0 = lo; m0 <= hi; m0 += kBatch) {
+                    float v[kBatch][kCols];
+#pragma unroll
+                    for (int b = 0; b < kBatch; ++b) {
+                        const int64_t m = m0 + b;
+                        const bool live = m <= hi && !(skip_rowless && cta_row_begin(m, n_rows, G) == cta_row_begin(m + 1, n_rows, G));
+#pragma unroll
+                        for (int k = 0; k < kCols; k += 4) {
+                            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (live) x = __ldcg(reinterpret_cast<const float4 *>(piece + (size_t)m * p.dim + k));
+                            v[b][k] = x.x, v[b][k + 1] = x.y, v[b][k + 2] = x.z, v[b][k + 3] = x.w;
+                        }
+                    }
+#pragma unroll
+                    for (int b = 0; b < kBatch; ++b)
+#pragma unroll
+                        for (int k = 0; k < kCols; ++k) sum[j][k] += v[b][k]; // + 0 for the slots past hi
+                }
+            }
+        };
+        // publish sum[j][k] as piece `row` of the scratch (release flag by one thread after the barrier: the release is
+        // cumulative, so it also covers the other consumers' stores that the barrier ordered before it)
+        auto publish = [&](const float (&sum)[kSlabs][kCols], int64_t row_idx) {
+            float *dst = p.head + (size_t)row_idx * p.dim;
+#pragma unroll
+            for (int j = 0; j < kSlabs; ++j) {
+                const int slab = tid + j * n_consumers;
+                if (slab < p.slabs_per_row)
+#pragma unroll
+                    for (int k = 0; k < kCols; k += 4)
+                        *reinterpret_cast<float4 *>(dst + (size_t)slab * kCols + k) =
+                            make_float4(sum[j][k], sum[j][k + 1], sum[j][k + 2], sum[j][k + 3]);
+            }
+            consumer_barrier(n_consumers);
+            if (tid == 0) st_release(p.head_flag + row_idx, 1);
+        };
+
         // flush the accumulators for the segment that ends (or is cut) at `row_end`.
         // Ownership rule for a segment cut by CTA boundaries: the CTA that holds its FIRST row owns it.
-        // Every other CTA publishes its piece as soon as it has it and never waits before publishing;
-        // the owner waits only at the very end of its own rows.  So no CTA ever waits on a waiter.
+        // Every other CTA publishes its piece as soon as it has it and never waits before publishing (a group leader
+        // waits, after its own last row, for CTAs with a higher index only); the owner waits only at the very end of
+        // its own rows.  So no CTA ever waits on a waiter.
         auto flush = [&](int64_t row_end) {
             if (!in_gap) {
                 const bool starts_before = seg_begin < r0;
@@ -489,18 +562,19 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
                 const float nrows = (float)(seg_end - seg_begin);
                 if (starts_before) {
                     // end piece (or, when it also ends_after, a middle piece) of an earlier CTA's segment
-                    float *dst = p.head + (size_t)c * p.dim;
+                    float sum[kSlabs][kCols];
 #pragma unroll
-                    for (int j = 0; j < kSlabs; ++j) {
-                        const int slab = tid + j * n_consumers;
-                        if (slab < p.slabs_per_row)
+                    for (int j = 0; j < kSlabs; ++j)
 #pragma unroll
-                            for (int k = 0; k < kCols; ++k) dst[(size_t)slab * kCols + k] = reduce_acc(j, k);
+                        for (int k = 0; k < kCols; ++k) sum[j][k] = reduce_acc(j, k);
+                    const bool leader = ends_after && every_cta_has_rows && (c % kGroup) == 0 &&
+                                        last_cta_of(seg_end) >= c + kGroup - 1;
+                    if (leader) { // this CTA's group lies wholly inside the segment: one group piece instead of 16
+                        collect(sum, p.head, p.head_flag, c + 1, c + kGroup - 1, false);
+                        publish(sum, p.group_base + c / kGroup);
+                    } else {
+                        publish(sum, c);
                     }
-                    consumer_barrier(n_consumers);
-                    // release store by one thread after the barrier: the release is cumulative, so it also
-                    // covers the other consumers' partial-sum stores that the barrier ordered before it
-                    if (tid == 0) st_release(p.head_flag + c, 1);
                 } else if (!ends_after) {
 #pragma unroll
                     for (int j = 0; j < kSlabs; ++j) {
@@ -511,10 +585,7 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
                     }
                 } else {
                     // this CTA owns a segment that continues into later CTAs: add their pieces in CTA order
-                    const int64_t last_row = seg_end - 1;
-                    int64_t ce = n_rows > 0 ? (last_row < n_rows ? (last_row * G) / n_rows : G - 1) : G - 1;
-                    while (ce + 1 < G && cta_row_begin(ce + 1, n_rows, G) <= last_row) ++ce;
-                    while (ce > c && cta_row_begin(ce, n_rows, G) > last_row) --ce;
+                    const int64_t ce = last_cta_of(seg_end);
                     // the threads polled the flag at slightly different times: take the early path only if all saw it
                     const bool early = kEarlyCarry && ce == c + 1 && consumer_barrier_and(n_consumers, carry_flag != 0);
                     if (early) {
@@ -524,47 +595,22 @@ __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolPara
                         for (int k = 0; k < kCols; ++k) sum[k] = reduce_acc(0, k) + carry[k];
                         write_pooled(0, sum, nrows);
                     } else {
-                        // every consumer thread polls its share of the flags (a giant segment spans hundreds of CTAs:
-                        // one thread polling them one after the other paid a global round trip per CTA); a flag is
-                        // reset by the thread that saw it, its single consumer (safe for CUDA-graph replays)
-                        for (int64_t m = c + 1 + tid; m <= ce; m += n_consumers) {
-                            if (cta_row_begin(m, n_rows, G) == cta_row_begin(m + 1, n_rows, G)) continue;
-                            while (ld_acquire(p.head_flag + m) == 0) {}
-                            p.head_flag[m] = 0;
+                        float sum[kSlabs][kCols];
+#pragma unroll
+                        for (int j = 0; j < kSlabs; ++j)
+#pragma unroll
+                            for (int k = 0; k < kCols; ++k) sum[j][k] = reduce_acc(j, k);
+                        const int64_t g0 = c / kGroup + 1;                 // first aligned group behind this CTA
+                        const int64_t g1 = (ce + 1) / kGroup - 1;          // last group that ends at or before ce
+                        if (every_cta_has_rows && g0 <= g1) {
+                            collect(sum, p.head, p.head_flag, c + 1, g0 * kGroup - 1, false);
+                            collect(sum, p.head + (size_t)p.group_base * p.dim, p.head_flag + p.group_base, g0, g1, false);
+                            collect(sum, p.head, p.head_flag, (g1 + 1) * kGroup, ce, false);
+                        } else {
+                            collect(sum, p.head, p.head_flag, c + 1, ce, true);
                         }
-                        consumer_barrier(n_consumers);
 #pragma unroll
-                        for (int j = 0; j < kSlabs; ++j) {
-                            const int slab = tid + j * n_consumers;
-                            float sum[kCols];
-                            if (slab < p.slabs_per_row) {
-#pragma unroll
-                                for (int k = 0; k < kCols; ++k) sum[k] = reduce_acc(j, k);
-                                // the pieces are added in CTA order, but fetched eight CTAs at a time: the loads of a
-                                // batch are independent, so a giant segment costs a round trip per batch, not per CTA
-                                constexpr int kBatch = 8;
-                                const float *piece = p.head + (size_t)slab * kCols;
-                                for (int64_t m0 = c + 1; m0 <= ce; m0 += kBatch) {
-                                    float v[kBatch][kCols];
-#pragma unroll
-                                    for (int b = 0; b < kBatch; ++b) {
-                                        const int64_t m = m0 + b;
-                                        const bool live = m <= ce && cta_row_begin(m, n_rows, G) != cta_row_begin(m + 1, n_rows, G);
-#pragma unroll
-                                        for (int k = 0; k < kCols; k += 4) {
-                                            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                                            if (live) x = __ldcg(reinterpret_cast<const float4 *>(piece + (size_t)m * p.dim + k));
-                                            v[b][k] = x.x, v[b][k + 1] = x.y, v[b][k + 2] = x.z, v[b][k + 3] = x.w;
-                                        }
-                                    }
-#pragma unroll
-                                    for (int b = 0; b < kBatch; ++b)
-#pragma unroll
-                                        for (int k = 0; k < kCols; ++k) sum[k] += v[b][k]; // + 0 for the slots past ce
-                                }
-                            }
-                            write_pooled(j, sum, nrows);
-                        }
+                        for (int j = 0; j < kSlabs; ++j) write_pooled(j, sum[j], nrows);
                     }
                 }
             }
@@ -748,10 +794,11 @@ int pool_scratch_init(int num_sms, PoolScratch *ps)
     ps->max_ctas = num_sms * kMaxCtasPerSm;
     if (ps->max_ctas > 512) ps->max_ctas = 512; // colsum_reduce_kernel covers 32 slices x 16 rows
     ps->max_dim = 4096;
-    AAT_CUDA_CHECK(cudaMalloc(&ps->head, sizeof(float) * (size_t)ps->max_ctas * ps->max_dim));
-    AAT_CUDA_CHECK(cudaMalloc(&ps->head_flag, sizeof(int) * (size_t)ps->max_ctas));
+    const size_t pieces = (size_t)ps->max_ctas + (size_t)ps->max_ctas / kGroup + 1; // per-CTA pieces, then group pieces
+    AAT_CUDA_CHECK(cudaMalloc(&ps->head, sizeof(float) * pieces * ps->max_dim));
+    AAT_CUDA_CHECK(cudaMalloc(&ps->head_flag, sizeof(int) * pieces));
     AAT_CUDA_CHECK(cudaMalloc(&ps->colsum, sizeof(double) * (size_t)ps->max_ctas * ps->max_dim));
-    AAT_CUDA_CHECK(cudaMemset(ps->head_flag, 0, sizeof(int) * (size_t)ps->max_ctas));
+    AAT_CUDA_CHECK(cudaMemset(ps->head_flag, 0, sizeof(int) * pieces));
     return AAT_OK;
 }
 
@@ -803,6 +850,7 @@ static int launch_mean_pool_on(aat_ctx *ctx, const PoolScratch &ps, const void *
     p.head = ps.head;
     p.head_flag = ps.head_flag;
     p.colsum = ps.colsum;
+    p.group_base = ps.max_ctas;
     p.n_rows = n_rows;
     p.n_seg = n_seg;
     p.dim = dim;
