@@ -26,73 +26,124 @@ namespace {
 constexpr int kStatThreads = 256;
 constexpr int kStatPer = 16;                         // samples per thread
 constexpr int kStatChunk = kStatThreads * kStatPer;  // 4096 samples per CTA
+static_assert(kStatChunk == kNormChunk, "the plan's chunk tables are built for kNormChunk samples");
 
-__device__ __forceinline__ double block_sum(double v, double *s_red)
+struct Moments { // (count, mean, sum of squared deviations) of a set of samples
+    double n, mean, m2;
+};
+// Chan et al.: moments of the union of two disjoint sets (robust against a DC offset; a fixed merge tree keeps the
+// result deterministic)
+__device__ __forceinline__ Moments merge(const Moments &a, const Moments &b)
 {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 0) s_red[warp] = v;
-    __syncthreads();
-    double t = 0.0;
-#pragma unroll
-    for (int w = 0; w < kStatThreads / 32; ++w) t += s_red[w]; // fixed order: deterministic
-    return t;
+    const double tot = a.n + b.n;
+    if (tot == 0.0) return Moments{0.0, 0.0, 0.0};
+    const double delta = b.mean - a.mean;
+    const double w = b.n / tot;
+    return Moments{tot, fma(delta, w, a.mean), a.m2 + b.m2 + delta * delta * (a.n * w)};
+}
+__device__ __forceinline__ Moments shfl_xor(const Moments &v, int d)
+{
+    return Moments{__shfl_xor_sync(0xffffffffu, v.n, d), __shfl_xor_sync(0xffffffffu, v.mean, d),
+                   __shfl_xor_sync(0xffffffffu, v.m2, d)};
 }
 
-// grid = total chunks (chunk_utt / chunk_first tables as for the mel tiles); partial[chunk] = (n, mean, M2)
+// 16 samples of thread `t` of a chunk.  Slot s of thread t is sample slot_index<WaveT>(s, t) of the chunk: 16-byte
+// vector q = s / kVec of the thread is vector q * 256 + t of the chunk, so every load / store instruction of a warp
+// covers one contiguous 512-byte range.  Whole, aligned chunks move by 16-byte accesses, the others element by element.
+template <typename T>
+__device__ __forceinline__ int slot_index(int s, int t)
+{
+    constexpr int kVec = 16 / (int)sizeof(T);
+    return ((s / kVec) * kStatThreads + t) * kVec + (s % kVec);
+}
+template <typename WaveT>
+__device__ __forceinline__ void load16(const WaveT *src, int64_t len, int t, double (&v)[kStatPer])
+{
+    constexpr int kVec = 16 / (int)sizeof(WaveT);
+    if (len == kStatChunk && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+        for (int q = 0; q < kStatPer / kVec; ++q) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(src) + q * kStatThreads + t);
+            const WaveT *e = reinterpret_cast<const WaveT *>(&raw);
+#pragma unroll
+            for (int k = 0; k < kVec; ++k) v[q * kVec + k] = (double)e[k];
+        }
+    } else {
+#pragma unroll
+        for (int s = 0; s < kStatPer; ++s) {
+            const int i = slot_index<WaveT>(s, t);
+            v[s] = (i < len) ? (double)src[i] : 0.0;
+        }
+    }
+}
+
+// grid = total chunks (chunk_utt / chunk_first tables as for the mel tiles); partial[chunk] = (n, mean, M2).
+// Per thread: exact two-pass moments of its 16 samples in registers; then a shuffle tree and one shared-memory hop.
 template <typename WaveT>
 __global__ void __launch_bounds__(kStatThreads)
 wave_chunk_stats_kernel(const WaveT *wave, const int64_t *n_samples, const int64_t *wave_off, const int32_t *chunk_utt,
                         const int32_t *chunk_first, double *partial)
 {
-    __shared__ double s_red[kStatThreads / 32];
+    __shared__ Moments s_part[kStatThreads / 32];
     const int utt = chunk_utt[blockIdx.x];
     const int64_t c = blockIdx.x - chunk_first[utt];
     const int64_t n = n_samples[utt];
     const int64_t j0 = c * kStatChunk;
     const int64_t len = (n - j0 < kStatChunk) ? n - j0 : kStatChunk;
-    const WaveT *src = wave + wave_off[utt] + j0;
     double v[kStatPer];
+    load16(wave + wave_off[utt] + j0, len, threadIdx.x, v);
+    int cnt = 0;
     double s = 0.0;
 #pragma unroll
     for (int k = 0; k < kStatPer; ++k) {
-        const int i = threadIdx.x + k * kStatThreads;
-        v[k] = (i < len) ? (double)src[i] : 0.0;
-        s += v[k];
+        s += v[k]; // slots past the end hold 0
+        cnt += slot_index<WaveT>(k, threadIdx.x) < len ? 1 : 0;
     }
-    const double mean = block_sum(s, s_red) / (double)len;
-    double q = 0.0;
+    Moments m{(double)cnt, cnt ? s / (double)cnt : 0.0, 0.0};
 #pragma unroll
     for (int k = 0; k < kStatPer; ++k) {
-        const int i = threadIdx.x + k * kStatThreads;
-        const double d = v[k] - mean;
-        q += (i < len) ? d * d : 0.0;
+        const double d = v[k] - m.mean;
+        m.m2 += (slot_index<WaveT>(k, threadIdx.x) < len) ? d * d : 0.0;
     }
-    const double m2 = block_sum(q, s_red);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { // lane l merges with lane l ^ d: the lower lane's set first, on both sides
+        const Moments o = shfl_xor(m, d);
+        m = (threadIdx.x & d) ? merge(o, m) : merge(m, o);
+    }
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = m;
+    __syncthreads();
     if (threadIdx.x == 0) {
-        partial[3 * (size_t)blockIdx.x + 0] = (double)len;
-        partial[3 * (size_t)blockIdx.x + 1] = mean;
-        partial[3 * (size_t)blockIdx.x + 2] = m2;
+        Moments t = s_part[0];
+#pragma unroll
+        for (int w = 1; w < kStatThreads / 32; ++w) t = merge(t, s_part[w]);
+        partial[3 * (size_t)blockIdx.x + 0] = t.n;
+        partial[3 * (size_t)blockIdx.x + 1] = t.mean;
+        partial[3 * (size_t)blockIdx.x + 2] = t.m2;
     }
 }
 
-// one thread per utterance merges its chunk statistics in order (Chan et al.): stats[2b] = mean, [2b+1] = population variance
+// one WARP per utterance merges its chunk moments: lane l takes chunks l, l + 32, ... in order, then a shuffle tree
+// (a 30-min stream has 7 000 chunks: one thread walking them was 180 us).  stats[2b] = mean, [2b+1] = population variance
 __global__ void wave_merge_stats_kernel(int n_utts, const int32_t *chunk_first, const double *partial, double *stats)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (b >= n_utts) return;
-    double n = 0.0, mean = 0.0, m2 = 0.0;
-    for (int c = chunk_first[b]; c < chunk_first[b + 1]; ++c) {
-        const double nb = partial[3 * (size_t)c], mb = partial[3 * (size_t)c + 1], qb = partial[3 * (size_t)c + 2];
-        const double tot = n + nb, delta = mb - mean;
-        mean += delta * (nb / tot);
-        m2 += qb + delta * delta * (n * nb / tot);
-        n = tot;
+    const int c0 = chunk_first[b], c1 = chunk_first[b + 1];
+    // contiguous runs per lane keep the merge order the order of the samples
+    const int per = (c1 - c0 + 31) / 32;
+    Moments m{0.0, 0.0, 0.0};
+    for (int c = c0 + lane * per; c < c1 && c < c0 + (lane + 1) * per; ++c)
+        m = merge(m, Moments{partial[3 * (size_t)c], partial[3 * (size_t)c + 1], partial[3 * (size_t)c + 2]});
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const Moments o = shfl_xor(m, d);
+        m = (lane & d) ? merge(o, m) : merge(m, o);
     }
-    stats[2 * b] = mean;
-    stats[2 * b + 1] = (n > 0.0) ? m2 / n : 0.0;
+    if (lane == 0) {
+        stats[2 * b] = m.mean;
+        stats[2 * b + 1] = (m.n > 0.0) ? m.m2 / m.n : 0.0;
+    }
 }
 
 template <typename InT, typename OutT>
@@ -105,17 +156,34 @@ wave_apply_norm_kernel(const InT *wave, OutT *out, const int64_t *n_samples, con
     const int64_t n = n_samples[utt];
     const int64_t j0 = c * kStatChunk;
     const int64_t len = (n - j0 < kStatChunk) ? n - j0 : kStatChunk;
-    const double mean = stats[2 * utt], var = stats[2 * utt + 1];
     const InT *src = wave + wave_off[utt] + j0;
     OutT *dst = out + wave_off[utt] + j0;
-    if (mode == 0) { // z-score, float64 arithmetic as numpy does for float64 input
-        const double denom = sqrt(var) + 1e-6;
-        for (int i = threadIdx.x; i < len; i += kStatThreads) dst[i] = (OutT)(((double)src[i] - mean) / denom);
+    double v[kStatPer];
+    load16(src, len, threadIdx.x, v);
+    alignas(16) OutT r[kStatPer];
+    if (mode == 0) { // z-score, float64 arithmetic as numpy does for float64 input (correctly rounded quotient)
+        const Znorm zn = Znorm::from_stats(stats, utt);
+#pragma unroll
+        for (int k = 0; k < kStatPer; ++k) r[k] = (OutT)zn(v[k]);
     } else { // wav2vec2 feature extractor: float32 arithmetic on the float32-rounded statistics
-        const float mf = (float)mean;
-        const float denom = sqrtf(__fadd_rn((float)var, 1e-7f));
-        for (int i = threadIdx.x; i < len; i += kStatThreads)
-            dst[i] = (OutT)__fdiv_rn(__fsub_rn((float)src[i], mf), denom);
+        const float mf = (float)stats[2 * utt];
+        const float denom = sqrtf(__fadd_rn((float)stats[2 * utt + 1], 1e-7f));
+#pragma unroll
+        for (int k = 0; k < kStatPer; ++k) r[k] = (OutT)__fdiv_rn(__fsub_rn((float)v[k], mf), denom);
+    }
+    // r[] is in the INPUT type's slot order; when both types have the same width the 16-byte vectors line up and whole
+    // chunks are stored as vectors, otherwise every value goes to its own position (still 4- or 8-byte coalesced)
+    if (sizeof(InT) == sizeof(OutT) && len == kStatChunk && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        constexpr int kVec = 16 / (int)sizeof(OutT);
+#pragma unroll
+        for (int q = 0; q < kStatPer / kVec; ++q)
+            reinterpret_cast<uint4 *>(dst)[q * kStatThreads + threadIdx.x] = reinterpret_cast<const uint4 *>(r)[q];
+    } else {
+#pragma unroll
+        for (int s = 0; s < kStatPer; ++s) {
+            const int i = slot_index<InT>(s, threadIdx.x);
+            if (i < len) dst[i] = r[s];
+        }
     }
 }
 
@@ -135,12 +203,12 @@ wave_apply_norm_padded_kernel(const InT *wave, float *out, int64_t *mask, const 
     const InT *src = wave + wave_off[utt];
     float *dst = out + (size_t)utt * n_max;
     int64_t *m = mask ? mask + (size_t)utt * n_max : nullptr;
-    const double denom64 = sqrt(var) + 1e-6;
+    const Znorm zn = Znorm::from_stats(stats, utt);
     const float mf = (float)mean;
     const float denom32 = sqrtf(__fadd_rn((float)var, 1e-7f));
     for (int64_t i = j0 + threadIdx.x; i < end; i += kStatThreads) {
         float v = 0.0f;
-        if (i < n) v = (mode == 0) ? (float)(((double)src[i] - mean) / denom64) : __fdiv_rn(__fsub_rn((float)src[i], mf), denom32);
+        if (i < n) v = (mode == 0) ? (float)zn((double)src[i]) : __fdiv_rn(__fsub_rn((float)src[i], mf), denom32);
         dst[i] = v;
         if (m) m[i] = i < n ? 1 : 0;
     }
@@ -252,13 +320,27 @@ scatter_mel_segments_kernel(const float *mel, const int64_t *frame_off, const in
         if (cols < 0) cols = 0;
     }
     const float *src = mel + (mel_elem_off ? (size_t)mel_elem_off[b] : (size_t)n_mels * frame_off[b]) + c0;
-    // a warp per mel row, lanes along time: coalesced reads of the source row and of the tile row, no divisions
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    const int items = (int)max_items, ncols = (int)cols;
-    for (int r = warp; r < n_mels; r += n_warps) {
-        const float *srow = src + (size_t)r * stride;
-        float *orow = o + (size_t)r * items;
-        for (int c = lane; c < items; c += 32) orow[c] = (c < ncols) ? srow[c] : 0.0f;
+    // The tile [n_mels, max_items] is one contiguous, 16-byte aligned range: every thread writes 16-byte vectors of
+    // consecutive tile elements (a row of 151 floats is not a multiple of 16 bytes, so a warp per row left every row
+    // with ragged sectors at both ends: 0.49 of the HBM peak, profiles/r1_collate_bw.txt); the source elements of a
+    // vector are consecutive in the mel row except where the vector wraps to the next row.
+    const int items = (int)max_items, ncols = (int)cols, total = n_mels * items;
+    if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        for (int e0 = 4 * (int)threadIdx.x; e0 < total; e0 += 4 * (int)blockDim.x) {
+            int r = e0 / items, c = e0 - r * items;
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v[u] = (c < ncols) ? src[(size_t)r * stride + c] : 0.0f;
+                if (++c == items) c = 0, ++r;
+            }
+            *reinterpret_cast<float4 *>(o + e0) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    } else {
+        for (int e = (int)threadIdx.x; e < total; e += (int)blockDim.x) {
+            const int r = e / items, c = e - r * items;
+            o[e] = (c < ncols) ? src[(size_t)r * stride + c] : 0.0f;
+        }
     }
 }
 
@@ -408,8 +490,8 @@ int launch_normalize(aat_ctx *ctx, const aat_plan *plan, const void *wave, int i
             static_cast<const double *>(wave), plan->d_n_samples, plan->d_wave_off, plan->d_chunk_utt, plan->d_chunk_first,
             plan->d_norm_partial);
     AAT_LAUNCH_CHECK();
-    wave_merge_stats_kernel<<<(plan->n_utts + 127) / 128, 128, 0, stream>>>(plan->n_utts, plan->d_chunk_first,
-                                                                            plan->d_norm_partial, st);
+    wave_merge_stats_kernel<<<(plan->n_utts + 3) / 4, 128, 0, stream>>>(plan->n_utts, plan->d_chunk_first,
+                                                                        plan->d_norm_partial, st);
     AAT_LAUNCH_CHECK();
     if (out == nullptr) return AAT_OK; // statistics only
 #define AAT_APPLY(IN, OUT)                                                                                         \

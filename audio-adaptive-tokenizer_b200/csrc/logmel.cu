@@ -322,20 +322,8 @@ __device__ __noinline__ void fetch_edge_tile(WaveT *dst, const WaveT *utt, int64
 
 // Fused z-score (x - mean) / (std + 1e-6) of the call sites (ref:src/aat/training/collate.py:135-152,
 // ref:scripts/audio_tokenization_melspec.py:40) in float64, applied where a sample is widened for the transform, so a
-// normalised copy of the waveform is never written or re-read.  The quotient is correctly rounded like numpy's division
-// without a division per sample: with r = RN(1 / d) taken once per tile, q = RN(t * r) is within an ulp of t / d, the
-// remainder t - q * d is exact in one FMA, and RN(q + rem * r) is the correctly rounded quotient (Markstein) — three
-// operations on the FP64 pipe instead of the ~10 of a division.
-struct Znorm {
-    double mean, d, r;
-    __device__ __forceinline__ double operator()(double x) const
-    {
-        const double t = __dsub_rn(x, mean);
-        const double q = __dmul_rn(t, r);
-        return fma(fma(-q, d, t), r, q);
-    }
-};
-
+// normalised copy of the waveform is never written or re-read: the Znorm functor of aat_internal.cuh (correctly rounded
+// quotient in three FP64 operations), the very one aat_normalize applies, so fused and separate passes agree bit for bit.
 template <typename WaveT, bool kHop160, bool kZnorm>
 __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams p)
 {
@@ -432,12 +420,7 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
         {
             double2 v[20];
             Znorm zn{0.0, 1.0, 1.0};
-            if (kZnorm) {
-                const int u = s_tiles[slot].utt;
-                zn.mean = __ldg(p.znorm + 2 * u);
-                zn.d = __dadd_rn(__dsqrt_rn(__ldg(p.znorm + 2 * u + 1)), 1e-6);
-                zn.r = __drcp_rn(zn.d);
-            }
+            if (kZnorm) zn = Znorm::from_stats(p.znorm, s_tiles[slot].utt);
             const WaveT *wa = s_rawbuf + pair * (kHop160 ? kRawBlock + kGap : 2 * p.hop) + lane20;
             const int hop = kHop160 ? 160 : p.hop;
 #pragma unroll

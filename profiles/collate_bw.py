@@ -46,15 +46,27 @@ def main():
     rows = []
     t = timed(lambda: collate.normalize_waveforms(batch, packed, "w2v2"))
     rows.append(("normalize w2v2 f32->f32 (3 kernels)", B * N * 4 * 3, t))  # stats read + apply read + write
-    t = timed(lambda: collate.normalize_waveforms(batch, packed.double(), "zscore"))
-    rows.append(("normalize zscore f64->f64 (incl. cast)", B * N * 8 * 3, t))
+    packed64 = packed.double()
+    t = timed(lambda: collate.normalize_waveforms(batch, packed64, "zscore"))
+    rows.append(("normalize zscore f64->f64 (3 kernels)", B * N * 8 * 3, t))
+    t = timed(lambda: collate.normalize_waveforms_padded(batch, packed, "w2v2", n_max=n_max))
+    rows.append(("normalize_padded w2v2 + mask", B * N * 4 * 2 + B * n_max * 12, t))
+    stats = torch.empty(B, 2, dtype=torch.float64, device="cuda")
+    t = timed(lambda: batch.waveform_stats(packed, out=stats))
+    rows.append(("waveform_stats f32 (2 kernels)", B * N * 4, t))
+    t_plain = timed(lambda: batch.logmel(packed))
+    t_fused = timed(lambda: batch.logmel(packed, znorm_stats=stats))
+    t_sep = timed(lambda: batch.logmel(collate.normalize_waveforms(batch, packed, "zscore")))
     t = timed(lambda: collate.scatter_segments(batch, wave_padded, padded, F, check=False))
     rows.append(("scatter_segments + mask", B * s_max * F * 4 * 2 + B * N * 4, t))
     t = timed(lambda: collate.scatter_mel_segments(batch, padded, F, check=False))
     rows.append(("scatter_mel_segments", B * s_max * 64 * (1 + F // 160) * 4 + batch.mel.numel() * 4, t))
     for name, nbytes, us in rows:
         print(f"{name:34s} {nbytes / 1e6:15.1f} {us:9.1f} {nbytes / us / 1e3:8.0f} {nbytes / us / 1e3 / peak:6.3f}")
-    print("# times include torch.empty of the outputs (caching allocator) and, for zscore, the float64 cast of the input")
+    print("# times include torch.empty of the outputs (caching allocator)")
+    print(f"# z-scored log-mel of the batch: log-mel alone {t_plain:.1f} us; statistics + fused z-score "
+          f"{timed(lambda: batch.logmel(packed, znorm_stats=batch.waveform_stats(packed, out=stats))):.1f} us "
+          f"(log-mel kernel with the fused z-score {t_fused:.1f} us); separate normalise (float64 copy) + log-mel {t_sep:.1f} us")
 
 
 if __name__ == "__main__":
