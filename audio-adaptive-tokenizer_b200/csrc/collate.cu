@@ -77,14 +77,29 @@ __device__ __forceinline__ void load16(const WaveT *src, int64_t len, int t, dou
     }
 }
 
+// sum over the CTA, returned to every thread: shuffle tree per warp, one shared-memory hop, fixed order (deterministic)
+__device__ __forceinline__ double block_sum(double v, double *s_red)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kStatThreads / 32; ++w) t += s_red[w];
+    return t;
+}
+
 // grid = total chunks (chunk_utt / chunk_first tables as for the mel tiles); partial[chunk] = (n, mean, M2).
-// Per thread: exact two-pass moments of its 16 samples in registers; then a shuffle tree and one shared-memory hop.
+// Two-pass moments of the chunk with the samples held in registers: sum -> mean -> sum of squared deviations.  Plain
+// additions only (merging per-thread moments with Chan's formula cost a float64 division per shuffle step: 50 us per
+// config-2 batch against the 10 us the 65 MB take at the HBM peak; gpurun r2_t7).
 template <typename WaveT>
 __global__ void __launch_bounds__(kStatThreads)
 wave_chunk_stats_kernel(const WaveT *wave, const int64_t *n_samples, const int64_t *wave_off, const int32_t *chunk_utt,
                         const int32_t *chunk_first, double *partial)
 {
-    __shared__ Moments s_part[kStatThreads / 32];
+    __shared__ double s_red[2][kStatThreads / 32];
     const int utt = chunk_utt[blockIdx.x];
     const int64_t c = blockIdx.x - chunk_first[utt];
     const int64_t n = n_samples[utt];
@@ -92,33 +107,21 @@ wave_chunk_stats_kernel(const WaveT *wave, const int64_t *n_samples, const int64
     const int64_t len = (n - j0 < kStatChunk) ? n - j0 : kStatChunk;
     double v[kStatPer];
     load16(wave + wave_off[utt] + j0, len, threadIdx.x, v);
-    int cnt = 0;
     double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < kStatPer; ++k) {
-        s += v[k]; // slots past the end hold 0
-        cnt += slot_index<WaveT>(k, threadIdx.x) < len ? 1 : 0;
-    }
-    Moments m{(double)cnt, cnt ? s / (double)cnt : 0.0, 0.0};
+    for (int k = 0; k < kStatPer; ++k) s += v[k]; // slots past the end hold 0
+    const double mean = block_sum(s, s_red[0]) / (double)len;
+    double q = 0.0;
 #pragma unroll
     for (int k = 0; k < kStatPer; ++k) {
-        const double d = v[k] - m.mean;
-        m.m2 += (slot_index<WaveT>(k, threadIdx.x) < len) ? d * d : 0.0;
+        const double d = v[k] - mean;
+        q += (len == kStatChunk || slot_index<WaveT>(k, threadIdx.x) < len) ? d * d : 0.0;
     }
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { // lane l merges with lane l ^ d: the lower lane's set first, on both sides
-        const Moments o = shfl_xor(m, d);
-        m = (threadIdx.x & d) ? merge(o, m) : merge(m, o);
-    }
-    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = m;
-    __syncthreads();
+    const double m2 = block_sum(q, s_red[1]);
     if (threadIdx.x == 0) {
-        Moments t = s_part[0];
-#pragma unroll
-        for (int w = 1; w < kStatThreads / 32; ++w) t = merge(t, s_part[w]);
-        partial[3 * (size_t)blockIdx.x + 0] = t.n;
-        partial[3 * (size_t)blockIdx.x + 1] = t.mean;
-        partial[3 * (size_t)blockIdx.x + 2] = t.m2;
+        partial[3 * (size_t)blockIdx.x + 0] = (double)len;
+        partial[3 * (size_t)blockIdx.x + 1] = mean;
+        partial[3 * (size_t)blockIdx.x + 2] = m2;
     }
 }
 
@@ -326,12 +329,19 @@ scatter_mel_segments_kernel(const float *mel, const int64_t *frame_off, const in
     // vector are consecutive in the mel row except where the vector wraps to the next row.
     const int items = (int)max_items, ncols = (int)cols, total = n_mels * items;
     if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        if (ncols == 0) { // a padding tile (no segment in this slot): zeros, no loads
+            for (int e0 = 4 * (int)threadIdx.x; e0 < total; e0 += 4 * (int)blockDim.x)
+                *reinterpret_cast<float4 *>(o + e0) = make_float4(0.f, 0.f, 0.f, 0.f);
+            return;
+        }
+        const bool narrow = (int64_t)n_mels * stride < (int64_t)INT32_MAX; // 32-bit source offsets
         for (int e0 = 4 * (int)threadIdx.x; e0 < total; e0 += 4 * (int)blockDim.x) {
             int r = e0 / items, c = e0 - r * items;
             float v[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                v[u] = (c < ncols) ? src[(size_t)r * stride + c] : 0.0f;
+                v[u] = 0.0f;
+                if (c < ncols) v[u] = narrow ? __ldg(src + (r * (int)stride + c)) : __ldg(src + ((size_t)r * stride + c));
                 if (++c == items) c = 0, ++r;
             }
             *reinterpret_cast<float4 *>(o + e0) = make_float4(v[0], v[1], v[2], v[3]);
