@@ -297,9 +297,9 @@ scatter_segments_kernel(const float *wave, int64_t n_max, const int64_t *boarder
 // Utterance b's mel is a C-contiguous (n_mels, T_b) block: either the plan's packed layout (frame_off / n_samples) or,
 // when mel_elem_off / mel_frames are given, any blocks the caller describes (cropped mels of the n-word path).
 __global__ void __launch_bounds__(256)
-scatter_mel_segments_kernel(const float *mel, const int64_t *frame_off, const int64_t *n_samples,
+scatter_mel_segments_kernel(const float *__restrict__ mel, const int64_t *frame_off, const int64_t *n_samples,
                             const int64_t *mel_elem_off, const int64_t *mel_frames, const int64_t *mel_row_stride, int hop, int n_mels,
-                            const int64_t *boarders, int64_t s_max, int64_t max_items, float *out, int32_t *status)
+                            const int64_t *boarders, int64_t s_max, int64_t max_items, float *__restrict__ out, int32_t *status)
 {
     const int64_t row = blockIdx.x;
     const int64_t b = row / s_max, s = row - b * s_max;

@@ -13,13 +13,25 @@ from aat_b200 import AdaptiveAudioAmplitudeTokenizer, collate, synth
 
 
 def timed(fn, reps=20):
+    """us per call on the DEVICE: the call is captured into a CUDA graph and the graph is replayed, so that the host
+    side of the call (torch.empty, ctypes, two or three launches: 20-30 us, more than some of these kernels take) is
+    not what is measured."""
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            fn()
     for _ in range(3):
-        fn()
+        g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        fn()
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps * 1e3
@@ -63,7 +75,7 @@ def main():
     rows.append(("scatter_mel_segments", B * s_max * 64 * (1 + F // 160) * 4 + batch.mel.numel() * 4, t))
     for name, nbytes, us in rows:
         print(f"{name:34s} {nbytes / 1e6:15.1f} {us:9.1f} {nbytes / us / 1e3:8.0f} {nbytes / us / 1e3 / peak:6.3f}")
-    print("# times include torch.empty of the outputs (caching allocator)")
+    print("# device time per call (each call captured into a CUDA graph and replayed 20 times)")
     print(f"# z-scored log-mel of the batch: log-mel alone {t_plain:.1f} us; statistics + fused z-score "
           f"{timed(lambda: batch.logmel(packed, znorm_stats=batch.waveform_stats(packed, out=stats))):.1f} us "
           f"(log-mel kernel with the fused z-score {t_fused:.1f} us); separate normalise (float64 copy) + log-mel {t_sep:.1f} us")
