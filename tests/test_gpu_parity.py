@@ -764,6 +764,68 @@ def test_config2_full_size_properties(tok):
     assert_pooled_close(p1[:40].cpu().numpy(), want)
 
 
+def _full_size_properties(tok, B, N, D, config, oracle_utts):
+    """Size-independent properties of a whole BASELINE-sized batch (device-generated audio), vectorised on
+    the device, plus bit-exact oracle parity of the segment lengths on a sample of utterances."""
+    import torch
+
+    from aat_b200 import synth
+    from oracle import ref_port
+
+    batch = tok.plan([N] * B)
+    wave = synth.device_bursty_batch(batch, 1000 * config, 0)
+    batch.logmel(wave), batch.boundaries()
+    torch.cuda.synchronize()
+    assert int(batch.status.min().item()) >= 0
+    cap = int(batch.seg_slot_off[1])
+    lens = batch.seg_len.view(B, cap)
+    starts = batch.seg_start.view(B, cap)
+    count = batch.seg_count.long()
+    live = torch.arange(cap, device="cuda")[None, :] < count[:, None]
+    total = (lens * live).sum(dim=1)
+    tail = (batch.status & 1).bool()
+    assert bool((total >= N).all()) and bool(((total > N) == tail).all())             # sum of lengths >= N, > iff padded tail
+    assert int(lens[live].min()) >= tok.min_segment_frames and int(lens[live].max()) <= tok.max_segment_frames
+    want_starts = torch.cumsum(lens * live, dim=1) - lens * live                        # starts = exclusive cumsum of lengths
+    assert bool((starts[live] == want_starts[live]).all())
+    n_seg = int(batch.n_seg.item())
+    assert n_seg == int(count.sum().item())
+    seg_off = batch.seg_off[: n_seg + 1]
+    frames = torch.clamp((lens[live] - 400) // 320 + 1, min=0)                        # row-major == packed order
+    assert bool((seg_off[1:] - seg_off[:-1] == frames).all()) and int(seg_off[0]) == 0
+    assert int(batch.n_frames.item()) == int(seg_off[-1].item())
+    ref = ref_port.RefTokenizer()
+    for b in oracle_utts:
+        w = wave[b * N:(b + 1) * N].cpu().numpy()
+        c, o = int(count[b]), b * cap
+        assert batch.seg_len[o:o + c].tolist() == ref.segment_lengths(w)[0], b
+    # pooling: the frame-weighted checksum  sum_s n_s * pooled[s] == column sums of E, and a sample against torch
+    n_rows = int(seg_off[-1].item())
+    emb = synth.device_normal(torch.empty(n_rows, D, device="cuda"), 11)
+    out = torch.empty(batch.total_seg_slots, D, device="cuda")
+    cs = torch.zeros(D + 1, dtype=torch.float64, device="cuda")
+    pooled = batch.pool(emb, out, colsum=cs)[:n_seg]
+    torch.cuda.synchronize()
+    lhs = (pooled.double() * frames.double()[:, None]).sum(dim=0)
+    rhs = emb.double().sum(dim=0)
+    assert torch.allclose(lhs, rhs, rtol=1e-6, atol=2e-3 * (n_rows / 5e4) ** 0.5)
+    assert int(cs[D].item()) == n_seg and torch.allclose(cs[:D], pooled.double().sum(dim=0), rtol=1e-12, atol=1e-9)
+    k = min(n_seg, 64)
+    off = seg_off[: k + 1].cpu().numpy()
+    want = ref_port.mean_pool_csr(emb[: off[-1]].cpu(), off).numpy()[0]
+    assert_pooled_close(pooled[:k].cpu().numpy(), want)
+
+
+def test_config3_full_size_properties(tok):
+    """BASELINE config 3: 256 x 20 s, HuBERT-large 1024-d."""
+    _full_size_properties(tok, 256, 320000, 1024, 3, oracle_utts=(0, 101, 255))
+
+
+def test_config4_full_size_properties(tok):
+    """BASELINE config 4: 8 x 30-min streams, 768-d (one stream checked against the oracle: ~4 s of CPU)."""
+    _full_size_properties(tok, 8, 28_800_000, 768, 4, oracle_utts=(5,))
+
+
 # ----------------------------------------------------------------------------------------- N1 / N2 (SURVEY §8f)
 def test_waveform_normalisations(tok):
     import torch
