@@ -42,7 +42,7 @@ class TokenizerPipeline:
     later), so consume or copy them after ``slot.done.synchronize()`` / ``stream.wait_event(slot.done)``."""
 
     def __init__(self, tokenizer: AdaptiveAudioAmplitudeTokenizer, n_samples: Sequence[int], dim: int, depth: int = 2,
-                 device=None, priorities: Optional[Sequence[int]] = None):
+                 device=None, priorities: Optional[Sequence[int]] = None, fused_amp: bool = True):
         import torch
 
         if depth < 1:
@@ -53,6 +53,10 @@ class TokenizerPipeline:
         self.slots: List[_Slot] = [_Slot(torch, tokenizer, n_samples, self.dim, device, pr[k]) for k in range(depth)]
         self.device = self.slots[0].batch.device
         self.submitted = 0
+        # True: the log-mel kernel also emits the amplitude curve the boundary scan starts from (its fused epilogue);
+        # False: the boundary scan derives it from the mel itself (one more pass over the mel, in the kernel that the
+        # pipeline hides behind the next batch's log-mel).  Same results either way (tested).
+        self.fused_amp = bool(fused_amp)
 
     def fork(self):
         """Make every slot's stream wait for the caller's current stream (inputs produced there, an event recorded
@@ -77,10 +81,10 @@ class TokenizerPipeline:
             b = slot.batch
             if znorm:
                 slot.stats = b.waveform_stats(wave, out=slot.stats)
-                b.logmel(wave, znorm_stats=slot.stats)
+                b.logmel(wave, with_amp=self.fused_amp, znorm_stats=slot.stats)
             else:
-                b.logmel(wave)
-            b.boundaries()
+                b.logmel(wave, with_amp=self.fused_amp)
+            b.boundaries(use_amp=self.fused_amp)
             # the launch in front of the pool kernel is this slot's boundary scan, which does not write embeddings
             b.pool(emb, slot.out, colsum=slot.mean.running_buffer() if colsum else None, accumulate=colsum,
                    emb_ready=not rows_from_device, rows_from_device=rows_from_device)

@@ -331,7 +331,7 @@ class Workload:
     """One BASELINE config resident on one GPU: R rotating buffer sets of distinct, device-generated utterances with
     the embeddings their own segmentation calls for, and the step that runs the path over one set."""
 
-    def __init__(self, torch, tok, name, rank, local_rank, rotate, depth=3):
+    def __init__(self, torch, tok, name, rank, local_rank, rotate, depth=3, fused_amp=True):
         from aat_b200 import synth
         from aat_b200.pipeline import TokenizerPipeline
 
@@ -359,7 +359,8 @@ class Workload:
         # the step runs through the public pipeline object: `depth` plans on `depth` streams, so that the boundary scan
         # and the pool of one batch overlap the log-mel of the next (depth 1 = strictly serial, kept for the A/B)
         self.depth = depth
-        self.pipes = {d: TokenizerPipeline(tok, [self.N] * B, D, depth=d, device=local_rank) for d in sorted({1, depth})}
+        self.pipes = {d: TokenizerPipeline(tok, [self.N] * B, D, depth=d, device=local_rank, fused_amp=fused_amp)
+                      for d in sorted({1, depth})}
         self.audio_hours_per_step = B * self.N / 16000 / 3600
         self.pool_bytes = float(np.mean([r * D * 4 + s * D * 4 + (s + 1) * 8 for r, s in zip(self.n_rows, self.n_seg)]))
 
@@ -733,7 +734,7 @@ def run_b200(args):
             os.close(saved)
 
     tok = AdaptiveAudioAmplitudeTokenizer(device=local_rank)
-    w = Workload(torch, tok, args.workload, rank, local_rank, args.rotate, args.depth)
+    w = Workload(torch, tok, args.workload, rank, local_rank, args.rotate, args.depth, not args.unfused_amp)
     sampler = ClockSampler(local_rank)
     sampler.start()
     m = measure_workload(torch, dist, w, args.steps, args.warmup, world, args.pool_sample_every, args.no_colsum, sampler)
@@ -923,6 +924,7 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
     ap.add_argument("--rotate", type=int, default=DEFAULT_ROTATE)
     ap.add_argument("--depth", type=int, default=3, help="batches in flight (plans x streams) of the step's pipeline; 1 = serial")
+    ap.add_argument("--unfused-amp", action="store_true", help="diagnostic: the boundary scan derives the amplitude curve from the mel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-configs", action="store_true", help="skip the c1/c3/c4/c5 sub-records (profiling runs)")
