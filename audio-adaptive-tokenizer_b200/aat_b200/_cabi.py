@@ -75,6 +75,7 @@ SIGNATURES = {
     "aat_plan_total_seg_slots": (c_i64, [c_void]),
     "aat_plan_offsets": (ctypes.c_int, [c_void, c_void, c_void, c_void]),
     "aat_logmel": (ctypes.c_int, [c_void, c_void, c_void, ctypes.c_int, c_void, c_void, c_void, c_void]),
+    "aat_amplitude": (ctypes.c_int, [c_void, c_void, c_void, c_void, c_void]),
     "aat_boundaries": (ctypes.c_int, [c_void] * 14),
     "aat_process_boarders": (ctypes.c_int, [c_void, c_i64, c_void, c_i64, c_void, c_void, c_i64, c_void, c_void, c_void]),
     "aat_segment_frame_csr": (ctypes.c_int, [c_void] * 8),

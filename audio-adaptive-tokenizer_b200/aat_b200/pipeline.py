@@ -54,8 +54,10 @@ class TokenizerPipeline:
         self.device = self.slots[0].batch.device
         self.submitted = 0
         # True: the log-mel kernel also emits the amplitude curve the boundary scan starts from (its fused epilogue);
-        # False: the boundary scan derives it from the mel itself (one more pass over the mel, in the kernel that the
-        # pipeline hides behind the next batch's log-mel).  Same results either way (tested).
+        # False: a separate, fully parallel pass over the mel (aat_amplitude) does, between the two kernels.  Bit-identical
+        # results (tested).  With several batches in flight the separate pass hides behind the next batch's log-mel,
+        # while the epilogue costs the log-mel kernel — the one kernel nothing hides — a CTA barrier and a serial
+        # 64-term chain per tile.
         self.fused_amp = bool(fused_amp)
 
     def fork(self):
@@ -84,7 +86,9 @@ class TokenizerPipeline:
                 b.logmel(wave, with_amp=self.fused_amp, znorm_stats=slot.stats)
             else:
                 b.logmel(wave, with_amp=self.fused_amp)
-            b.boundaries(use_amp=self.fused_amp)
+            if not self.fused_amp:
+                b.amplitude()
+            b.boundaries()
             # the launch in front of the pool kernel is this slot's boundary scan, which does not write embeddings
             b.pool(emb, slot.out, colsum=slot.mean.running_buffer() if colsum else None, accumulate=colsum,
                    emb_ready=not rows_from_device, rows_from_device=rows_from_device)

@@ -370,6 +370,16 @@ class PackedBatch:
                                            self.mel.data_ptr(), self.amp.data_ptr() if with_amp else None, self._stream()))
         return self.mel
 
+    def amplitude(self, mel=None):
+        """``-10 * mel.mean(axis=0)`` of every utterance in numpy's float32 order (ref:src/aat/tokenizer.py:67) into
+        ``self.amp``: what :meth:`logmel` writes with ``with_amp=True``, as a separate, fully parallel pass."""
+        src = self.mel if mel is None else mel
+        if src.numel() != self.n_mels * self.total_frames or not src.is_cuda or not src.is_contiguous():
+            raise ValueError("mel must be a contiguous packed CUDA tensor matching the plan")
+        _cabi.check(_cabi.lib().aat_amplitude(self.ctx.handle, self.handle, src.data_ptr(), self.amp.data_ptr(),
+                                              self._stream()))
+        return self.amp
+
     def boundaries(self, mel=None, use_amp: bool = True, with_minima: bool = True, with_csr: bool = True):
         """K3.  ``mel=None`` uses this batch's own mel (and the fused amplitude curve when ``use_amp``);
         pass a packed float32 CUDA tensor to segment somebody else's mel (e.g. the reference's).

@@ -166,6 +166,7 @@ int launch_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave, int wave
 int launch_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel, const float *amp, int64_t *seg_start,
                       int64_t *seg_len, int32_t *seg_count, int64_t *minima, int32_t *minima_count, int32_t *status,
                       int64_t *seg_off, int64_t *n_seg, int64_t *utt_seg_off, cudaStream_t stream);
+int launch_amplitude(aat_ctx *ctx, const aat_plan *plan, const float *mel, float *amp, cudaStream_t stream);
 int launch_process_boarders(aat_ctx *ctx, int64_t n_samples, const int64_t *boarders, int64_t n_boarders,
                             int64_t *seg_start, int64_t *seg_len, int64_t capacity, int32_t *seg_count,
                             int32_t *status, cudaStream_t stream);

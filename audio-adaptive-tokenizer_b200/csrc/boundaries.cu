@@ -716,6 +716,38 @@ extern "C" __attribute__((visibility("default"))) int aat_debug_bnd_trace(unsign
 namespace {
 #endif
 
+// Stand-alone amplitude curve: amp[t] = -10 * mean_r(mel[r][t]) with numpy's arithmetic (rows added in order in
+// float32, exact division by the row count; ref:src/aat/tokenizer.py:67).  One thread per frame, consecutive threads on
+// consecutive frames (every row access of a warp is one 128-byte line), the loads of 16 rows in flight before the
+// dependent additions consume them.  This is the log-mel kernel's fused epilogue as a separate, fully parallel pass:
+// the pipelined schedule (aat_b200/pipeline.py) prefers it, because there the extra pass over the mel (L2-resident at
+// batch sizes up to ~100 MB of mel) hides behind the next batch's log-mel, while the epilogue inside the log-mel kernel
+// costs that kernel a CTA barrier and a serial 64-term chain per tile (5 % of its time).
+__global__ void __launch_bounds__(256)
+amplitude_kernel(const float *__restrict__ mel, float *__restrict__ amp, const int64_t *n_samples, const int64_t *frame_off,
+                 int hop, int n_mels)
+{
+    pdl_wait(); // the log-mel kernel's mel
+    pdl_launch_dependents();
+    const int utt = blockIdx.y;
+    const int64_t T = 1 + n_samples[utt] / hop;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const int64_t fbase = frame_off[utt];
+    const float *col = mel + (size_t)n_mels * fbase + t;
+    float acc = col[0];
+    int r = 1;
+    for (; r + 16 <= n_mels; r += 16) {
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = __ldg(col + (size_t)(r + k) * T);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc = __fadd_rn(acc, v[k]);
+    }
+    for (; r < n_mels; ++r) acc = __fadd_rn(acc, __ldg(col + (size_t)r * T));
+    amp[fbase + t] = __fmul_rn(-10.0f, __fdiv_rn(acc, (float)n_mels));
+}
+
 __global__ void process_boarders_kernel(int64_t n_samples, const int64_t *boarders, int64_t n_boarders,
                                         int64_t min_frames, int64_t max_frames, int64_t *seg_start, int64_t *seg_len,
                                         int64_t capacity, int32_t *seg_count, int32_t *status)
@@ -790,6 +822,17 @@ int launch_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel, cons
     }
     if (seg_off != nullptr && !fuse_csr) // batch too large for the fused epilogue's scratch: separate kernel
         return launch_segment_frame_csr(ctx, plan, seg_len, seg_count, seg_off, n_seg, utt_seg_off, stream);
+    return AAT_OK;
+}
+
+int launch_amplitude(aat_ctx *ctx, const aat_plan *plan, const float *mel, float *amp, cudaStream_t stream)
+{
+    if (plan->n_utts == 0 || plan->max_frames == 0) return AAT_OK;
+    AAT_MAX_SMEM_CARVEOUT(amplitude_kernel);
+    const dim3 grid((unsigned)((plan->max_frames + 255) / 256), (unsigned)plan->n_utts);
+    AAT_CUDA_CHECK(launch_pdl(amplitude_kernel, grid, dim3(256), 0, stream, mel, amp, (const int64_t *)plan->d_n_samples,
+                              (const int64_t *)plan->d_frame_off, (int)ctx->cfg.hop_length, (int)ctx->cfg.num_mel_filters));
+    AAT_LAUNCH_CHECK();
     return AAT_OK;
 }
 

@@ -476,6 +476,15 @@ int aat_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave_dev, int wav
                          static_cast<cudaStream_t>(stream));
 }
 
+int aat_amplitude(aat_ctx *ctx, const aat_plan *plan, const float *mel_dev, float *amp_dev, void *stream)
+{
+    AAT_REQUIRE(ctx && plan && mel_dev && amp_dev, AAT_ERR_INVALID, "aat_amplitude: NULL argument");
+    AAT_REQUIRE(plan->ctx == ctx, AAT_ERR_INVALID, "aat_amplitude: plan belongs to another context");
+    AAT_REQUIRE(plan->n_utts <= 65535, AAT_ERR_UNSUPPORTED, "aat_amplitude: at most 65535 utterances per plan");
+    AAT_DEVICE_GUARD(ctx);
+    return launch_amplitude(ctx, plan, mel_dev, amp_dev, static_cast<cudaStream_t>(stream));
+}
+
 int aat_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel_dev, const float *amp_dev,
                    int64_t *seg_start_dev, int64_t *seg_len_dev, int32_t *seg_count_dev, int64_t *minima_dev,
                    int32_t *minima_count_dev, int32_t *status_dev, int64_t *seg_off_dev, int64_t *n_seg_dev,

@@ -924,7 +924,7 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
     ap.add_argument("--rotate", type=int, default=DEFAULT_ROTATE)
     ap.add_argument("--depth", type=int, default=3, help="batches in flight (plans x streams) of the step's pipeline; 1 = serial")
-    ap.add_argument("--unfused-amp", action="store_true", help="diagnostic: the boundary scan derives the amplitude curve from the mel")
+    ap.add_argument("--unfused-amp", action="store_true", help="amplitude curve by the separate pass (aat_amplitude) instead of the log-mel kernel's epilogue")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-configs", action="store_true", help="skip the c1/c3/c4/c5 sub-records (profiling runs)")

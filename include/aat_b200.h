@@ -159,6 +159,11 @@ int aat_plan_offsets(const aat_plan *plan, int64_t *wave_off_host, int64_t *fram
 int aat_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave_dev, int wave_dtype, const double *znorm_stats_dev,
                float *mel_dev, float *amp_dev, void *stream);
 
+/* The amplitude curve alone: amp_dev[frame] = -10 * mean over mels of mel_dev, in numpy's float32 order
+ * (ref:src/aat/tokenizer.py:67) — what aat_logmel's fused epilogue writes, as a separate fully parallel pass over
+ * a packed log-mel (the plan's, or the reference's own).  Pipelined schedules prefer it: see aat_b200/pipeline.py. */
+int aat_amplitude(aat_ctx *ctx, const aat_plan *plan, const float *mel_dev, float *amp_dev, void *stream);
+
 /* ------------------------------------------------------------------ K3: boundaries
  * Replaces find_amplitude_minimas + pretokenize + process_segments_boarders
  * (ref:src/aat/tokenizer.py:55-92, 121-139, 141-183).  Bit-exact: sequential float32

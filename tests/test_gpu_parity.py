@@ -419,6 +419,34 @@ def test_packed_batch_matches_per_utterance_path(tok, golden):
     assert torch.equal(batch.seg_off[: total + 1], before[2][: total + 1]) and torch.equal(batch.utt_seg_off, before[3])
 
 
+def test_amplitude_pass_equals_the_fused_epilogue(tok, golden):
+    """aat_amplitude = the log-mel kernel's fused epilogue = numpy's -10 * mel.mean(axis=0), bit for bit."""
+    import torch
+
+    from aat_b200 import synth
+
+    lengths = [160000, 100, 31999, 256000, 2080]
+    batch = tok.plan(lengths)
+    wave = synth.device_bursty_batch(batch, 4000, 0)
+    batch.logmel(wave, with_amp=True)
+    torch.cuda.synchronize()
+    fused = batch.amp.clone()
+    batch.amp.zero_()
+    batch.logmel(wave, with_amp=False)
+    batch.amplitude()
+    torch.cuda.synchronize()
+    assert torch.equal(batch.amp, fused)
+    mel = batch.mel_of(3).cpu().numpy()
+    o0 = int(batch.frame_off[3])
+    assert np.array_equal(fused[o0:o0 + mel.shape[1]].cpu().numpy(), -10 * mel.mean(axis=0))
+    # on the reference's own mel
+    case = "c1_10s"
+    one = tok.plan([golden.cases[case]["n_samples"]])
+    ref_mel = golden.get(case, "mel")
+    amp = one.amplitude(torch.from_numpy(ref_mel).reshape(-1).cuda()).cpu().numpy()
+    assert np.array_equal(amp, -10 * ref_mel.mean(axis=0))
+
+
 def test_packed_batch_segments_reference_mel(tok, golden):
     """Device path fed the reference's own mel frames: bit-exact offsets."""
     import torch
@@ -668,8 +696,8 @@ def test_pipelined_steps_match_serial_steps(tok):
     first_mel = {}
     for znorm in (False, True):
         results = {}
-        for depth in (1, 2, 3):
-            pipe = TokenizerPipeline(tok, lengths, dim, depth=depth)
+        for depth in (1, 2, 3, -3):  # -3: three batches in flight, amplitude curve by the separate pass
+            pipe = TokenizerPipeline(tok, lengths, dim, depth=abs(depth), fused_amp=depth > 0)
             got = []
             for it in range(11):
                 k = it % 5
@@ -683,7 +711,7 @@ def test_pipelined_steps_match_serial_steps(tok):
             results[depth] = (got, dm.acc.clone(), mean.clone())
         ref_steps, ref_acc, ref_mean = results[1]
         assert int(ref_acc[dim].item()) == sum(int(g[4][0].item()) for g in ref_steps)
-        for depth in (2, 3):
+        for depth in (2, 3, -3):
             steps, acc, mean = results[depth]
             for it, (a, b) in enumerate(zip(ref_steps, steps)):
                 n_seg = int(a[4][0].item())
