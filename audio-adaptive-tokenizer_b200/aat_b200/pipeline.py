@@ -30,7 +30,7 @@ class _Slot:
 
 
 class TokenizerPipeline:
-    """``depth`` batches of one shape in flight.
+    """``depth`` batches of one shape in flight (default: :meth:`default_depth`).
 
     >>> pipe = TokenizerPipeline(tok, [256000] * 64, dim=768)
     >>> for wave, emb in batches:          # packed CUDA tensors (PackedBatch layout)
@@ -41,10 +41,21 @@ class TokenizerPipeline:
     tables and ``slot.out[:n_seg]`` the pooled vectors — valid until the slot is submitted to again (``depth`` submits
     later), so consume or copy them after ``slot.done.synchronize()`` / ``stream.wait_event(slot.done)``."""
 
-    def __init__(self, tokenizer: AdaptiveAudioAmplitudeTokenizer, n_samples: Sequence[int], dim: int, depth: int = 2,
-                 device=None, priorities: Optional[Sequence[int]] = None, fused_amp: bool = True):
+    @staticmethod
+    def default_depth(n_samples: Sequence[int], sampling_rate: int = 16000) -> int:
+        """Batches in flight when the caller does not say: 4, or 6 for long streams (>= 200 s), whose boundary scan is a
+        long serial chain on a handful of CTAs and needs more neighbours to hide behind (measured on a B200,
+        profiles/r2_pipeline_ab.txt: 64 x 16 s is best at 4, 8 x 30 min keeps gaining up to 6)."""
+        longest = max((int(n) for n in n_samples), default=0)
+        return 6 if longest >= 200 * sampling_rate else 4
+
+    def __init__(self, tokenizer: AdaptiveAudioAmplitudeTokenizer, n_samples: Sequence[int], dim: int,
+                 depth: Optional[int] = None, device=None, priorities: Optional[Sequence[int]] = None,
+                 fused_amp: bool = True):
         import torch
 
+        if depth is None:
+            depth = self.default_depth(n_samples, int(tokenizer.sampling_rate))
         if depth < 1:
             raise ValueError("depth must be >= 1")
         self.torch = torch

@@ -331,7 +331,7 @@ class Workload:
     """One BASELINE config resident on one GPU: R rotating buffer sets of distinct, device-generated utterances with
     the embeddings their own segmentation calls for, and the step that runs the path over one set."""
 
-    def __init__(self, torch, tok, name, rank, local_rank, rotate, depth=3, fused_amp=True):
+    def __init__(self, torch, tok, name, rank, local_rank, rotate, depth=0, fused_amp=True):
         from aat_b200 import synth
         from aat_b200.pipeline import TokenizerPipeline
 
@@ -358,7 +358,7 @@ class Workload:
         self.out = torch.empty(self.batch.total_seg_slots, D, device=self.dev)
         # the step runs through the public pipeline object: `depth` plans on `depth` streams, so that the boundary scan
         # and the pool of one batch overlap the log-mel of the next (depth 1 = strictly serial, kept for the A/B)
-        self.depth = depth
+        self.depth = depth = depth if depth > 0 else TokenizerPipeline.default_depth([self.N] * B)
         self.pipes = {d: TokenizerPipeline(tok, [self.N] * B, D, depth=d, device=local_rank, fused_amp=fused_amp)
                       for d in sorted({1, depth})}
         self.audio_hours_per_step = B * self.N / 16000 / 3600
@@ -616,7 +616,7 @@ def run_c5(torch, dist, tok, rank, local_rank, world, args):
     chunk = min(64, per_rank)  # 4096 utterances: 4.2 GB of waveforms + 10 GB of embeddings per chunk
     rows_ub = B * hubert_rows_upper_bound(N)
     batch = tok.plan([N] * B)  # generator layout + the audit's plan
-    pipe = TokenizerPipeline(tok, [N] * B, D, depth=args.depth, device=local_rank)
+    pipe = TokenizerPipeline(tok, [N] * B, D, depth=args.depth if args.depth > 0 else None, device=local_rank)
     waves = torch.empty(chunk, batch.total_samples, dtype=torch.float32, device=dev)
     embs = torch.empty(chunk, rows_ub, D, dtype=torch.float32, device=dev)
     out = torch.empty(batch.total_seg_slots, D, device=dev)
@@ -695,7 +695,7 @@ def run_c5(torch, dist, tok, rank, local_rank, world, args):
            "audio_hours_processed": hours, "utterances": utterances, "segments": segments, "value": hours / (run_ms / 1e3),
            "unit": UNIT, "device_seconds_path": run_ms / 1e3, "device_seconds_generation": gen_ms / 1e3,
            "batches_per_rank": per_rank, "chunk_batches": chunk, "scaling": "strong (fixed 1000 audio-hours)",
-           "schedule": schedule_note(args.depth),
+           "schedule": schedule_note(len(pipe.slots)),
            "timing": "sum over chunks of CUDA-event brackets around the path (generation bracketed separately), + the "
                      "allreduce and finalisation; max over ranks",
            "dataset_mean": {"norm": float(mean_vec.norm().item()), "audit_first_chunk": audit}}
@@ -740,7 +740,7 @@ def run_b200(args):
     m = measure_workload(torch, dist, w, args.steps, args.warmup, world, args.pool_sample_every, args.no_colsum, sampler)
     clocks = sampler.stop(*m["wall"])
     serial = m
-    if args.depth != 1:  # same-run A/B: the strictly serial schedule (round 1's step)
+    if w.depth != 1:  # same-run A/B: the strictly serial schedule (round 1's step)
         serial = measure_workload(torch, dist, w, max(50, args.steps // 4), 5, world, args.pool_sample_every, args.no_colsum,
                                   depth=1, breakdown=False)
     roofline = w.pool_roofline(_cabi, serial["sampled_pool"], args.pool_sample_every, pool_traffic(args.workload))
@@ -923,7 +923,8 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
     ap.add_argument("--rotate", type=int, default=DEFAULT_ROTATE)
-    ap.add_argument("--depth", type=int, default=3, help="batches in flight (plans x streams) of the step's pipeline; 1 = serial")
+    ap.add_argument("--depth", type=int, default=0,
+                    help="batches in flight (plans x streams) of the step's pipeline; 1 = serial, 0 = the pipeline's own default")
     ap.add_argument("--unfused-amp", action="store_true", help="amplitude curve by the separate pass (aat_amplitude) instead of the log-mel kernel's epilogue")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
