@@ -90,61 +90,39 @@ __device__ __forceinline__ double block_sum(double v, double *s_red)
     return t;
 }
 
-// partial[chunk] = (n, mean, M2) of every 4096-sample chunk (chunk_utt / chunk_first tables as for the mel tiles).
+// grid = total chunks (chunk_utt / chunk_first tables as for the mel tiles); partial[chunk] = (n, mean, M2).
 // Two-pass moments of the chunk with the samples held in registers: sum -> mean -> sum of squared deviations.  Plain
 // additions only (merging per-thread moments with Chan's formula cost a float64 division per shuffle step: 50 us per
-// config-2 batch against the 10 us the 65 MB take at the HBM peak; gpurun r2_t7).  Persistent CTAs walk the chunks with
-// the NEXT chunk's samples (and table entries) already in flight while the current one is reduced: a CTA per chunk
-// paid three dependent table loads, the sample loads and two block reductions back to back, 4 us for 16 KB.
+// config-2 batch against the 10 us the 65 MB take at the HBM peak; gpurun r2_t7).  One CTA per chunk: persistent CTAs
+// with the next chunk's samples in flight were tried and are slower (32 vs 23 us: fewer loads in flight in total).
 template <typename WaveT>
 __global__ void __launch_bounds__(kStatThreads)
 wave_chunk_stats_kernel(const WaveT *wave, const int64_t *n_samples, const int64_t *wave_off, const int32_t *chunk_utt,
-                        const int32_t *chunk_first, int n_chunks, double *partial)
+                        const int32_t *chunk_first, double *partial)
 {
-    __shared__ double s_red[2][2][kStatThreads / 32];
-    pdl_wait(); // the waveform may come from the kernel in front
-    pdl_launch_dependents();
-    int ch = blockIdx.x;
-    if (ch >= n_chunks) return;
-    auto describe = [&](int chunk, const WaveT *&src, int64_t &len) {
-        const int utt = chunk_utt[chunk];
-        const int64_t j0 = (int64_t)(chunk - chunk_first[utt]) * kStatChunk;
-        const int64_t n = n_samples[utt];
-        len = (n - j0 < kStatChunk) ? n - j0 : kStatChunk;
-        src = wave + wave_off[utt] + j0;
-    };
-    const WaveT *src;
-    int64_t len;
-    double v[kStatPer], nv[kStatPer];
-    describe(ch, src, len);
-    load16(src, len, threadIdx.x, v);
-    for (int it = 0; ch < n_chunks; ch += gridDim.x, ++it) {
-        const int nx = ch + gridDim.x;
-        int64_t nlen = 0;
-        if (nx < n_chunks) { // next chunk's loads fly while this one is reduced
-            const WaveT *nsrc;
-            describe(nx, nsrc, nlen);
-            load16(nsrc, nlen, threadIdx.x, nv);
-        }
-        double s = 0.0;
+    __shared__ double s_red[2][kStatThreads / 32];
+    const int utt = chunk_utt[blockIdx.x];
+    const int64_t c = blockIdx.x - chunk_first[utt];
+    const int64_t n = n_samples[utt];
+    const int64_t j0 = c * kStatChunk;
+    const int64_t len = (n - j0 < kStatChunk) ? n - j0 : kStatChunk;
+    double v[kStatPer];
+    load16(wave + wave_off[utt] + j0, len, threadIdx.x, v);
+    double s = 0.0;
 #pragma unroll
-        for (int k = 0; k < kStatPer; ++k) s += v[k]; // slots past the end hold 0
-        const double mean = block_sum(s, s_red[it & 1][0]) / (double)len;
-        double q = 0.0;
+    for (int k = 0; k < kStatPer; ++k) s += v[k]; // slots past the end hold 0
+    const double mean = block_sum(s, s_red[0]) / (double)len;
+    double q = 0.0;
 #pragma unroll
-        for (int k = 0; k < kStatPer; ++k) {
-            const double d = v[k] - mean;
-            q += (len == kStatChunk || slot_index<WaveT>(k, threadIdx.x) < len) ? d * d : 0.0;
-        }
-        const double m2 = block_sum(q, s_red[it & 1][1]);
-        if (threadIdx.x == 0) {
-            partial[3 * (size_t)ch + 0] = (double)len;
-            partial[3 * (size_t)ch + 1] = mean;
-            partial[3 * (size_t)ch + 2] = m2;
-        }
-        len = nlen;
-#pragma unroll
-        for (int k = 0; k < kStatPer; ++k) v[k] = nv[k];
+    for (int k = 0; k < kStatPer; ++k) {
+        const double d = v[k] - mean;
+        q += (len == kStatChunk || slot_index<WaveT>(k, threadIdx.x) < len) ? d * d : 0.0;
+    }
+    const double m2 = block_sum(q, s_red[1]);
+    if (threadIdx.x == 0) {
+        partial[3 * (size_t)blockIdx.x + 0] = (double)len;
+        partial[3 * (size_t)blockIdx.x + 1] = mean;
+        partial[3 * (size_t)blockIdx.x + 2] = m2;
     }
 }
 
@@ -152,8 +130,6 @@ wave_chunk_stats_kernel(const WaveT *wave, const int64_t *n_samples, const int64
 // (a 30-min stream has 7 000 chunks: one thread walking them was 180 us).  stats[2b] = mean, [2b+1] = population variance
 __global__ void wave_merge_stats_kernel(int n_utts, const int32_t *chunk_first, const double *partial, double *stats)
 {
-    pdl_wait(); // the chunk moments
-    pdl_launch_dependents();
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (b >= n_utts) return;
@@ -523,27 +499,23 @@ int launch_masked_mean_pool(const void *emb, int emb_dtype, int64_t n_rows, int6
 int launch_normalize(aat_ctx *ctx, const aat_plan *plan, const void *wave, int in_dtype, int mode, void *out,
                      int out_dtype, double *stats, cudaStream_t stream)
 {
+    (void)ctx;
     AAT_REQUIRE(in_dtype == AAT_F32 || in_dtype == AAT_F64, AAT_ERR_UNSUPPORTED, "aat_normalize: input dtype must be F32 or F64");
     AAT_REQUIRE(out_dtype == AAT_F32 || out_dtype == AAT_F64, AAT_ERR_UNSUPPORTED, "aat_normalize: output dtype must be F32 or F64");
     AAT_REQUIRE(mode == 0 || mode == 1, AAT_ERR_INVALID, "aat_normalize: unknown mode %d", mode);
     if (plan->norm_chunks == 0) return AAT_OK;
     double *st = stats ? stats : plan->d_norm_stats;
-    // the two statistics kernels (and whatever library kernel follows: the log-mel kernel reads the statistics behind
-    // its own dependency wait) are chained by programmatic dependent launch
-    const int stat_grid = plan->norm_chunks < ctx->num_sms * 8 ? plan->norm_chunks : ctx->num_sms * 8;
     if (in_dtype == AAT_F32)
-        AAT_CUDA_CHECK(launch_pdl(wave_chunk_stats_kernel<float>, dim3(stat_grid), dim3(kStatThreads), 0, stream,
-                                  static_cast<const float *>(wave), (const int64_t *)plan->d_n_samples,
-                                  (const int64_t *)plan->d_wave_off, (const int32_t *)plan->d_chunk_utt,
-                                  (const int32_t *)plan->d_chunk_first, (int)plan->norm_chunks, plan->d_norm_partial));
+        wave_chunk_stats_kernel<float><<<plan->norm_chunks, kStatThreads, 0, stream>>>(
+            static_cast<const float *>(wave), plan->d_n_samples, plan->d_wave_off, plan->d_chunk_utt, plan->d_chunk_first,
+            plan->d_norm_partial);
     else
-        AAT_CUDA_CHECK(launch_pdl(wave_chunk_stats_kernel<double>, dim3(stat_grid), dim3(kStatThreads), 0, stream,
-                                  static_cast<const double *>(wave), (const int64_t *)plan->d_n_samples,
-                                  (const int64_t *)plan->d_wave_off, (const int32_t *)plan->d_chunk_utt,
-                                  (const int32_t *)plan->d_chunk_first, (int)plan->norm_chunks, plan->d_norm_partial));
+        wave_chunk_stats_kernel<double><<<plan->norm_chunks, kStatThreads, 0, stream>>>(
+            static_cast<const double *>(wave), plan->d_n_samples, plan->d_wave_off, plan->d_chunk_utt, plan->d_chunk_first,
+            plan->d_norm_partial);
     AAT_LAUNCH_CHECK();
-    AAT_CUDA_CHECK(launch_pdl(wave_merge_stats_kernel, dim3((plan->n_utts + 3) / 4), dim3(128), 0, stream, (int)plan->n_utts,
-                              (const int32_t *)plan->d_chunk_first, (const double *)plan->d_norm_partial, st));
+    wave_merge_stats_kernel<<<(plan->n_utts + 3) / 4, 128, 0, stream>>>(plan->n_utts, plan->d_chunk_first,
+                                                                        plan->d_norm_partial, st);
     AAT_LAUNCH_CHECK();
     if (out == nullptr) return AAT_OK; // statistics only
 #define AAT_APPLY(IN, OUT)                                                                                         \

@@ -16,6 +16,11 @@ def timed(fn, reps=20):
     """us per call on the DEVICE: the call is captured into a CUDA graph and the graph is replayed, so that the host
     side of the call (torch.empty, ctypes, two or three launches: 20-30 us, more than some of these kernels take) is
     not what is measured."""
+    if os.environ.get("AAT_NO_GRAPH"):  # under ncu: plain launches
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        return float("nan")
     side = torch.cuda.Stream()
     with torch.cuda.stream(side):
         for _ in range(3):
