@@ -56,8 +56,11 @@ __device__ __forceinline__ int slot_index(int s, int t)
     constexpr int kVec = 16 / (int)sizeof(T);
     return ((s / kVec) * kStatThreads + t) * kVec + (s % kVec);
 }
+// The samples stay in their own type in registers (16 floats are 16 registers, 16 doubles 32): with the converted
+// copies the statistics kernel needed 56 registers, four CTAs per SM, and left the memory system idle during its two
+// block reductions (33 % DRAM utilisation, ncu r2_prof_collate); they are widened where they are used.
 template <typename WaveT>
-__device__ __forceinline__ void load16(const WaveT *src, int64_t len, int t, double (&v)[kStatPer])
+__device__ __forceinline__ void load16(const WaveT *src, int64_t len, int t, WaveT (&v)[kStatPer])
 {
     constexpr int kVec = 16 / (int)sizeof(WaveT);
     if (len == kStatChunk && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
@@ -66,13 +69,13 @@ __device__ __forceinline__ void load16(const WaveT *src, int64_t len, int t, dou
             const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(src) + q * kStatThreads + t);
             const WaveT *e = reinterpret_cast<const WaveT *>(&raw);
 #pragma unroll
-            for (int k = 0; k < kVec; ++k) v[q * kVec + k] = (double)e[k];
+            for (int k = 0; k < kVec; ++k) v[q * kVec + k] = e[k];
         }
     } else {
 #pragma unroll
         for (int s = 0; s < kStatPer; ++s) {
             const int i = slot_index<WaveT>(s, t);
-            v[s] = (i < len) ? (double)src[i] : 0.0;
+            v[s] = (i < len) ? src[i] : (WaveT)0;
         }
     }
 }
@@ -96,7 +99,7 @@ __device__ __forceinline__ double block_sum(double v, double *s_red)
 // config-2 batch against the 10 us the 65 MB take at the HBM peak; gpurun r2_t7).  One CTA per chunk: persistent CTAs
 // with the next chunk's samples in flight were tried and are slower (32 vs 23 us: fewer loads in flight in total).
 template <typename WaveT>
-__global__ void __launch_bounds__(kStatThreads)
+__global__ void __launch_bounds__(kStatThreads, sizeof(WaveT) == 4 ? 8 : 5)
 wave_chunk_stats_kernel(const WaveT *wave, const int64_t *n_samples, const int64_t *wave_off, const int32_t *chunk_utt,
                         const int32_t *chunk_first, double *partial)
 {
@@ -106,16 +109,16 @@ wave_chunk_stats_kernel(const WaveT *wave, const int64_t *n_samples, const int64
     const int64_t n = n_samples[utt];
     const int64_t j0 = c * kStatChunk;
     const int64_t len = (n - j0 < kStatChunk) ? n - j0 : kStatChunk;
-    double v[kStatPer];
+    WaveT v[kStatPer];
     load16(wave + wave_off[utt] + j0, len, threadIdx.x, v);
     double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < kStatPer; ++k) s += v[k]; // slots past the end hold 0
+    for (int k = 0; k < kStatPer; ++k) s += (double)v[k]; // slots past the end hold 0
     const double mean = block_sum(s, s_red[0]) / (double)len;
     double q = 0.0;
 #pragma unroll
     for (int k = 0; k < kStatPer; ++k) {
-        const double d = v[k] - mean;
+        const double d = (double)v[k] - mean;
         q += (len == kStatChunk || slot_index<WaveT>(k, threadIdx.x) < len) ? d * d : 0.0;
     }
     const double m2 = block_sum(q, s_red[1]);
@@ -151,7 +154,7 @@ __global__ void wave_merge_stats_kernel(int n_utts, const int32_t *chunk_first, 
 }
 
 template <typename InT, typename OutT>
-__global__ void __launch_bounds__(kStatThreads)
+__global__ void __launch_bounds__(kStatThreads, sizeof(InT) + sizeof(OutT) == 8 ? 8 : 5)
 wave_apply_norm_kernel(const InT *wave, OutT *out, const int64_t *n_samples, const int64_t *wave_off,
                        const int32_t *chunk_utt, const int32_t *chunk_first, const double *stats, int mode)
 {
@@ -162,13 +165,13 @@ wave_apply_norm_kernel(const InT *wave, OutT *out, const int64_t *n_samples, con
     const int64_t len = (n - j0 < kStatChunk) ? n - j0 : kStatChunk;
     const InT *src = wave + wave_off[utt] + j0;
     OutT *dst = out + wave_off[utt] + j0;
-    double v[kStatPer];
+    InT v[kStatPer];
     load16(src, len, threadIdx.x, v);
     alignas(16) OutT r[kStatPer];
     if (mode == 0) { // z-score, float64 arithmetic as numpy does for float64 input (correctly rounded quotient)
         const Znorm zn = Znorm::from_stats(stats, utt);
 #pragma unroll
-        for (int k = 0; k < kStatPer; ++k) r[k] = (OutT)zn(v[k]);
+        for (int k = 0; k < kStatPer; ++k) r[k] = (OutT)zn((double)v[k]);
     } else { // wav2vec2 feature extractor: float32 arithmetic on the float32-rounded statistics
         const float mf = (float)stats[2 * utt];
         const float denom = sqrtf(__fadd_rn((float)stats[2 * utt + 1], 1e-7f));
