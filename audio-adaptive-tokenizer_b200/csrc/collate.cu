@@ -338,30 +338,34 @@ scatter_mel_segments_kernel(const float *__restrict__ mel, const int64_t *frame_
                 *reinterpret_cast<float4 *>(o + e0) = make_float4(0.f, 0.f, 0.f, 0.f);
             return;
         }
-        const bool narrow = (int64_t)n_mels * stride < (int64_t)INT32_MAX; // 32-bit source offsets
-        // four vectors per trip, all sixteen loads issued before the first store: a thread has ~10 vectors, and one
-        // dependent load -> store round trip per vector was what the kernel spent its time on
-        constexpr int kTrip = 4;
-        const int step = 4 * (int)blockDim.x;
-        for (int e0 = 4 * (int)threadIdx.x; e0 < total; e0 += kTrip * step) {
-            float v[kTrip][4];
-#pragma unroll
-            for (int t = 0; t < kTrip; ++t) {
-                const int e = e0 + t * step;
-                int r = e / items, c = e - r * items;
+        // The kernel was bound by instruction issue (79 % issue utilisation, 31 M warp instructions for 128 MB: a
+        // division, four wrap tests and 64-bit offsets per 16-byte vector; ncu r2_prof_scatter_mel): the row of a vector
+        // now comes from one multiply-high, and the 35 of 38 vectors per row that do not wrap take a straight path.
+        const unsigned magic = 0xFFFFFFFFu / (unsigned)items + 1u; // e / items == umulhi(e, magic) for e, items < 2^16
+        const bool small = items >= 2 && total < 65536 && (int64_t)n_mels * stride < (int64_t)INT32_MAX;
+        const int step = 4 * (int)blockDim.x, istride = (int)stride;
+        for (int e = 4 * (int)threadIdx.x; e < total; e += step) {
+            int r = small ? (int)__umulhi((unsigned)e, magic) : e / items;
+            int c = e - r * items;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (small && c + 4 <= items) {
+                const float *p = src + (r * istride + c);
+                const int left = ncols - c; // columns of the segment at or behind c
+                if (left >= 4) {
+                    v[0] = __ldg(p), v[1] = __ldg(p + 1), v[2] = __ldg(p + 2), v[3] = __ldg(p + 3);
+                } else if (left > 0) {
+                    v[0] = __ldg(p);
+                    if (left > 1) v[1] = __ldg(p + 1);
+                    if (left > 2) v[2] = __ldg(p + 2);
+                }
+            } else {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    v[t][u] = 0.0f;
-                    if (e < total && c < ncols)
-                        v[t][u] = narrow ? __ldg(src + (r * (int)stride + c)) : __ldg(src + ((size_t)r * stride + c));
+                    if (c < ncols) v[u] = __ldg(src + ((size_t)r * stride + c));
                     if (++c == items) c = 0, ++r;
                 }
             }
-#pragma unroll
-            for (int t = 0; t < kTrip; ++t) {
-                const int e = e0 + t * step;
-                if (e < total) *reinterpret_cast<float4 *>(o + e) = make_float4(v[t][0], v[t][1], v[t][2], v[t][3]);
-            }
+            *reinterpret_cast<float4 *>(o + e) = make_float4(v[0], v[1], v[2], v[3]);
         }
     } else {
         for (int e = (int)threadIdx.x; e < total; e += (int)blockDim.x) {
