@@ -305,28 +305,37 @@ scatter_mel_segments_kernel(const float *__restrict__ mel, const int64_t *frame_
                             const int64_t *mel_elem_off, const int64_t *mel_frames, const int64_t *mel_row_stride, int hop, int n_mels,
                             const int64_t *boarders, int64_t s_max, int64_t max_items, float *__restrict__ out, int32_t *status)
 {
+    // The tile's geometry (four 64-bit divisions, a chain of dependent table loads) is worked out by ONE thread: done
+    // by all 256 it was two thirds of the kernel's instructions (ncu: 21 M warp instructions for 128 MB).
+    __shared__ int64_t s_geo[4]; // source offset, row stride, columns to copy
     const int64_t row = blockIdx.x;
-    const int64_t b = row / s_max, s = row - b * s_max;
-    const int64_t *brow = boarders + b * s_max;
-    const int64_t end = brow[s];
-    const int64_t T = mel_frames ? mel_frames[b] : 1 + n_samples[b] / hop;  // columns of the block (slices clamp here)
-    const int64_t stride = mel_row_stride ? mel_row_stride[b] : T;          // elements between its rows
-    float *o = out + (size_t)row * n_mels * max_items;
-    int64_t c0 = 0, cols = 0;
-    if (s == 0 || end != 0) {
-        const int64_t begin = (s == 0) ? 0 : brow[s - 1];
-        c0 = begin / hop;
-        int64_t c1 = end / hop;
-        if (c1 > T) c1 = T; // numpy slicing clamps at the array end
-        if (c0 > T) c0 = T;
-        cols = c1 - c0;
-        if (cols > max_items) { // the reference fails on the shape mismatch
-            if (threadIdx.x == 0) atomicMin(status + b, (int32_t)AAT_ERR_INVALID);
-            cols = max_items;
+    if (threadIdx.x == 0) {
+        const int64_t b = row / s_max, s = row - b * s_max;
+        const int64_t *brow = boarders + b * s_max;
+        const int64_t end = brow[s];
+        const int64_t T = mel_frames ? mel_frames[b] : 1 + n_samples[b] / hop; // columns of the block (slices clamp here)
+        int64_t c0 = 0, cols = 0;
+        if (s == 0 || end != 0) {
+            const int64_t begin = (s == 0) ? 0 : brow[s - 1];
+            c0 = begin / hop;
+            int64_t c1 = end / hop;
+            if (c1 > T) c1 = T; // numpy slicing clamps at the array end
+            if (c0 > T) c0 = T;
+            cols = c1 - c0;
+            if (cols > max_items) { // the reference fails on the shape mismatch
+                atomicMin(status + b, (int32_t)AAT_ERR_INVALID);
+                cols = max_items;
+            }
+            if (cols < 0) cols = 0;
         }
-        if (cols < 0) cols = 0;
+        s_geo[0] = (mel_elem_off ? mel_elem_off[b] : (int64_t)n_mels * frame_off[b]) + c0;
+        s_geo[1] = mel_row_stride ? mel_row_stride[b] : T; // elements between the block's rows
+        s_geo[2] = cols;
     }
-    const float *src = mel + (mel_elem_off ? (size_t)mel_elem_off[b] : (size_t)n_mels * frame_off[b]) + c0;
+    __syncthreads();
+    const float *src = mel + s_geo[0];
+    const int64_t stride = s_geo[1], cols = s_geo[2];
+    float *o = out + (size_t)row * n_mels * max_items;
     // The tile [n_mels, max_items] is one contiguous, 16-byte aligned range: every thread writes 16-byte vectors of
     // consecutive tile elements (a row of 151 floats is not a multiple of 16 bytes, so a warp per row left every row
     // with ragged sectors at both ends: 0.49 of the HBM peak, profiles/r1_collate_bw.txt); the source elements of a
