@@ -764,6 +764,9 @@ int launch_typed(aat_ctx *ctx, const PoolScratch &ps, PoolParams &p, size_t smem
     if (per_sm > kMaxCtasPerSm) per_sm = kMaxCtasPerSm;
     int grid = ctx->num_sms * per_sm;
     if (grid > ps.max_ctas) grid = ps.max_ctas;
+    // (More, smaller CTAs handed out in waves by the hardware, as a cheap form of dynamic balancing, were tried:
+    //  2 / 3 waves cost 30.2 -> 34.4 / 43.5 us at config-2 size, every new CTA pays the ramp again, and gain 0.4 % at
+    //  config-4 size; gpurun r2, AAT_POOL_WAVES experiment.)
     // small inputs: give every CTA at least two stages of rows, otherwise one segment spans dozens of CTAs
     // and its owner spends longer collecting pieces than streaming
     const int64_t min_rows = 2 * (int64_t)p.rows_per_stage;
