@@ -70,6 +70,7 @@ class TokenizerPipeline:
         # while the epilogue costs the log-mel kernel — the one kernel nothing hides — a CTA barrier and a serial
         # 64-term chain per tile.
         self.fused_amp = bool(fused_amp)
+        self._reduced = False  # dataset_mean() has folded (and allreduced) the sums: reset_sums() before the next pass
 
     def fork(self):
         """Make every slot's stream wait for the caller's current stream (inputs produced there, an event recorded
@@ -86,6 +87,9 @@ class TokenizerPipeline:
         step's first kernel with the first step's last.  ``znorm`` applies the call sites' z-score inside the log-mel
         kernel; ``rows_from_device`` as in :meth:`PackedBatch.pool`."""
         torch = self.torch
+        if colsum and self._reduced:
+            raise RuntimeError("the running sums were folded and allreduced by dataset_mean(); call reset_sums() before "
+                               "accumulating another pass (adding to them would count the other ranks twice)")
         slot = self.slots[self.submitted % len(self.slots)]
         self.submitted += 1
         if not inputs_ready:
@@ -116,6 +120,7 @@ class TokenizerPipeline:
         self.join()
         for slot in self.slots:
             slot.mean.acc.zero_()
+        self._reduced = False
         self.fork()  # later submits see the zeroed sums
 
     def dataset_mean(self, group=None) -> DatasetMean:
@@ -127,5 +132,6 @@ class TokenizerPipeline:
             total.acc += slot.mean.acc
             slot.mean.acc.zero_()
         total.allreduce(group)
+        self._reduced = True
         self.fork()  # later submits are ordered behind the additions above
         return total

@@ -422,8 +422,9 @@ class Workload:
         achieved = self.pool_bytes / (best * 1e-6) / 1e9
         roof = {"kernel": "pool_kernel<float,1,false>" if self.D <= 1024 else "pool_kernel<float,k,false>", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": "ncu --set full capture of an earlier run of this command (profiles/pool_traffic.json), "
-                                  "not measured in this run" if traffic is not None else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel "
+                                  "at this workload (profiles/pool_traffic.json, profiles/r2_prof_pool*.txt); not measured "
+                                  "in this run" if traffic is not None else None,
                 "bytes_per_launch": self.pool_bytes, "us_per_launch": best, "launches_timed": reps,
                 "method": f"{reps} back-to-back launches over the {self.R} rotating input sets inside one CUDA-event "
                           f"pair, best of 3 (no column-sum epilogue: the reduce kernel is a separate launch)",
@@ -516,6 +517,7 @@ def measure_workload(torch, dist, w, steps, warmup, world, sample_every, no_cols
     # ---- per-kernel breakdown (untimed extra pass, strictly serial, with every kernel instrumented)
     kernel_us = None
     if breakdown:
+        w.pipes[1].reset_sums()
         _cabi.profile_enable(ctx_handle, _cabi.KERNEL_NAMES)
         for i in range(min(steps, 50)):
             w.step(i, not no_colsum, 1)
@@ -564,7 +566,7 @@ def run_c1(torch, tok):
     """BASELINE configs[0]: one 10 s clip through the reference-facing numpy API (host buffers in and out, one C-ABI
     call each), with the oracle port on one host core beside it."""
     from aat_b200 import AudioWaveform, mean_pool_segments, synth
-    from oracle import ref_port
+    from oracle import ref_port  # this config's cpu_baseline leg: the port is timed beside the product and checks it
 
     n, dim = 160_000, 768
     wave = synth.bursty_speech(n, synth.seed_for(1, 0))

@@ -709,6 +709,11 @@ def test_pipelined_steps_match_serial_steps(tok):
             mean = dm.result()
             torch.cuda.synchronize()
             results[depth] = (got, dm.acc.clone(), mean.clone())
+            with pytest.raises(RuntimeError):  # the sums are folded: another pass needs reset_sums() first
+                pipe.submit(sets[0], embs[0], rows_from_device=True, inputs_ready=True)
+            pipe.reset_sums()
+            pipe.submit(sets[0], embs[0], znorm=znorm, rows_from_device=True, inputs_ready=True)
+            torch.cuda.synchronize()
         ref_steps, ref_acc, ref_mean = results[1]
         assert int(ref_acc[dim].item()) == sum(int(g[4][0].item()) for g in ref_steps)
         for depth in (2, 3, -3):
