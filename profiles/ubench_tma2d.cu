@@ -1,4 +1,7 @@
-// A/B of the two ways the TMA engine can feed the pool kernel's shared-memory ring:
+// Pure read-stream micro-benchmark of the pool kernel's mechanism, three questions:
+//   * how fast can this grid / ring / consumer arrangement stream at all (the ceiling the pool kernel is judged by);
+//   * does dynamic work distribution win back the uneven finish of the CTAs (variant C below);
+//   * A/B of the two ways the TMA engine can feed the ring:
 //   (A) 1-D bulk copies  cp.async.bulk.shared::cluster.global            (what csrc/pool.cu ships: SASS UBLKCP)
 //   (B) 2-D tensor-map tile loads  cp.async.bulk.tensor.2d ... .tile     (SASS UTMALDG)
 // Same persistent grid (2 CTAs per SM), same 4 x 24 KB ring, same consumers (one 16-byte column slab per thread, four
@@ -122,6 +125,76 @@ __global__ void __launch_bounds__(kThreads) stream_kernel(const float *emb, cons
     *reinterpret_cast<float4 *>(out + c * kDim + tid * 4) = o;
 }
 
+// (C) dynamic balancing: every CTA first streams a static share (kStaticPct % of a fair share), then takes chunks of
+// kDynStages stages from a global counter until the rows are used up — how much of the pool kernel's uneven finish
+// (profiles/r1_pool_timeline.txt) dynamic work distribution could win back.
+__device__ unsigned int g_next_chunk;
+template <int kStaticPct, int kDynStages>
+__global__ void __launch_bounds__(kThreads) stream_dynamic_kernel(const float *emb, int64_t n_rows, float *out)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
+    __shared__ int64_t s_row[kStages]; // first row of the stage (-1: no more work)
+    const int tid = threadIdx.x;
+    const int64_t G = gridDim.x, c = blockIdx.x;
+    const int64_t stages_total = n_rows / kRowsPerStage;
+    const int64_t static_stages = (stages_total * kStaticPct / 100) / G; // per CTA
+    const int64_t dyn_begin = static_stages * G;                          // first dynamic stage
+    const int64_t n_dyn_chunks = (stages_total - dyn_begin + kDynStages - 1) / kDynStages;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&s_full[s], 1), mbar_init(&s_empty[s], kConsumers / 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == kConsumers) { // producer: static share, then chunks from the counter; a stage with row -1 ends the stream
+        int64_t issued = 0;
+        auto issue = [&](int64_t stage_idx) {
+            const int s = (int)(issued % kStages);
+            if (issued >= kStages) mbar_wait(&s_empty[s], (uint32_t)(((issued / kStages) - 1) & 1));
+            s_row[s] = stage_idx;
+            if (stage_idx >= 0) {
+                mbar_expect_tx(&s_full[s], kStageBytes);
+                bulk_g2s(smem + s * kStageBytes, emb + stage_idx * kRowsPerStage * kDim, kStageBytes, &s_full[s]);
+            } else {
+                mbar_arrive(&s_full[s]);
+            }
+            ++issued;
+        };
+        for (int64_t i = 0; i < static_stages; ++i) issue(c * static_stages + i);
+        for (;;) {
+            const unsigned int k = atomicAdd(&g_next_chunk, 1u);
+            if ((int64_t)k >= n_dyn_chunks) break;
+            for (int j = 0; j < kDynStages; ++j) {
+                const int64_t st = dyn_begin + (int64_t)k * kDynStages + j;
+                if (st < stages_total) issue(st);
+            }
+        }
+        issue(-1);
+        return;
+    }
+    if (tid > kConsumers) return;
+    float acc[4][4] = {};
+    for (int64_t ch = 0;; ++ch) {
+        const int s = (int)(ch % kStages);
+        mbar_wait(&s_full[s], (uint32_t)((ch / kStages) & 1));
+        if (s_row[s] < 0) break;
+        const float *stage = reinterpret_cast<const float *>(smem + s * kStageBytes);
+#pragma unroll
+        for (int r = 0; r < kRowsPerStage; ++r) {
+            const float4 x = *reinterpret_cast<const float4 *>(stage + r * kDim + tid * 4);
+            acc[r & 3][0] += x.x, acc[r & 3][1] += x.y, acc[r & 3][2] += x.z, acc[r & 3][3] += x.w;
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&s_empty[s]);
+    }
+    float4 o;
+    o.x = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
+    o.y = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
+    o.z = (acc[0][2] + acc[1][2]) + (acc[2][2] + acc[3][2]);
+    o.w = (acc[0][3] + acc[1][3]) + (acc[2][3] + acc[3][3]);
+    *reinterpret_cast<float4 *>(out + c * kDim + tid * 4) = o;
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                              const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -142,11 +215,14 @@ int main()
     printf("# %s, %d SMs; grid %d x %d threads, ring %d x %d KB; float32 [rows, %d] streamed once, 4 rotating inputs,\n", prop.name,
            prop.multiProcessorCount, grid, kThreads, kStages, kStageBytes / 1024, kDim);
     printf("# 32 launches back to back inside one event pair, best of 5\n");
-    printf("%10s %10s %22s %22s\n", "rows", "MB", "1-D bulk: us   GB/s", "2-D tensor map: us   GB/s");
+    printf("%10s %10s %22s %22s %28s %28s\n", "rows", "MB", "1-D bulk: us   GB/s", "2-D tensor map: us   GB/s",
+           "75% static + dyn(2): us GB/s", "50% static + dyn(2): us GB/s");
     float *out = nullptr;
     CK(cudaMalloc(&out, sizeof(float) * (size_t)grid * kDim));
     CK(cudaFuncSetAttribute(stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStages * kStageBytes));
     CK(cudaFuncSetAttribute(stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStages * kStageBytes));
+    CK(cudaFuncSetAttribute(stream_dynamic_kernel<75, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStages * kStageBytes));
+    CK(cudaFuncSetAttribute(stream_dynamic_kernel<50, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStages * kStageBytes));
     for (int64_t n_rows : {49568LL, 255744LL, 719872LL}) {
         const int R = n_rows * kDim * 4 > 1500000000LL ? 2 : 4;
         std::vector<float *> emb(R);
@@ -165,13 +241,21 @@ int main()
                 return 1;
             }
         }
-        double us[2];
-        for (int variant = 0; variant < 2; ++variant) {
+        double us[4];
+        for (int variant = 0; variant < 4; ++variant) {
             auto launch = [&](int i) {
+                if (variant >= 2) {
+                    unsigned int zero = 0; // the counter is reset by a tiny async copy in front of every launch
+                    CK(cudaMemcpyToSymbolAsync(g_next_chunk, &zero, sizeof(zero), 0, cudaMemcpyHostToDevice));
+                }
                 if (variant == 0)
                     stream_kernel<false><<<grid, kThreads, kStages * kStageBytes>>>(emb[i % R], maps[i % R], n_rows, out);
-                else
+                else if (variant == 1)
                     stream_kernel<true><<<grid, kThreads, kStages * kStageBytes>>>(emb[i % R], maps[i % R], n_rows, out);
+                else if (variant == 2)
+                    stream_dynamic_kernel<75, 2><<<grid, kThreads, kStages * kStageBytes>>>(emb[i % R], n_rows, out);
+                else
+                    stream_dynamic_kernel<50, 2><<<grid, kThreads, kStages * kStageBytes>>>(emb[i % R], n_rows, out);
             };
             for (int i = 0; i < 8; ++i) launch(i);
             CK(cudaDeviceSynchronize());
@@ -192,7 +276,8 @@ int main()
             us[variant] = best * 1e3 / 32;
         }
         const double mb = (double)n_rows * kDim * 4 / 1e6;
-        printf("%10lld %10.1f %12.2f %9.0f %14.2f %9.0f\n", (long long)n_rows, mb, us[0], mb / us[0] * 1e3, us[1], mb / us[1] * 1e3);
+        printf("%10lld %10.1f %12.2f %9.0f %14.2f %9.0f %18.2f %9.0f %18.2f %9.0f\n", (long long)n_rows, mb, us[0], mb / us[0] * 1e3, us[1],
+               mb / us[1] * 1e3, us[2], mb / us[2] * 1e3, us[3], mb / us[3] * 1e3);
         for (int i = 0; i < R; ++i) CK(cudaFree(emb[i]));
     }
     return 0;
