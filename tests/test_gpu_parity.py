@@ -289,6 +289,66 @@ def test_pool_ragged_against_oracle(c_oracle, dim):
     assert_pooled_close(got, c_oracle.mean_pool_f64(emb, off))
 
 
+def test_pool_randomised_carry_paths_against_torch():
+    """The cross-CTA carry has many paths: early look at the neighbour, single pieces, aligned groups of 16 CTAs with a
+    leader, stragglers before and after the groups, segments that end exactly on a CTA boundary, leading / trailing
+    rows outside every segment, a row count taken from the device that is smaller than the allocation.  Sixty random
+    layouts (sizes chosen so that the grid is full: 296 CTAs) against a float64 torch reduction."""
+    import torch
+
+    from aat_b200 import AdaptiveAudioAmplitudeTokenizer
+    from aat_b200.pooling import _pool_device
+
+    rng = np.random.default_rng(2024)
+    tok = AdaptiveAudioAmplitudeTokenizer()
+    plan = tok.plan([16000])  # lends its pool scratch
+    stream = plan._stream()
+    for case in range(60):
+        dim = int(rng.choice([64, 256, 768, 1024, 2048]))
+        rows_per_stage = max(1, (24 * 1024) // (dim * 4))
+        n_rows = int(rng.integers(296 * 2 * rows_per_stage, 296 * 6 * rows_per_stage))
+        kind = case % 6
+        if kind == 0:    # a few giants among ordinary segments
+            lens = rng.integers(1, 40, size=n_rows)
+            for _ in range(3):
+                lens[rng.integers(0, lens.size)] = rng.integers(n_rows // 20, n_rows // 2)
+        elif kind == 1:  # one segment over (almost) everything
+            lens = np.asarray([n_rows - int(rng.integers(0, 50))])
+        elif kind == 2:  # segments about one CTA long: every boundary is cut, some end exactly on it
+            per_cta = n_rows / 296.0
+            lens = np.maximum(1, rng.normal(per_cta, per_cta * 0.3, size=600).astype(np.int64))
+        elif kind == 3:  # segments of 10..40 CTAs: groups with stragglers on both sides
+            per_cta = n_rows / 296.0
+            lens = (per_cta * rng.integers(10, 40, size=40)).astype(np.int64) + rng.integers(0, 7, size=40)
+        elif kind == 4:  # tiny segments
+            lens = rng.integers(1, 4, size=n_rows)
+        else:            # Zipf
+            lens = np.minimum(rng.zipf(1.4, size=n_rows), n_rows // 2)
+        first = int(rng.integers(0, 30)) if case % 2 else 0   # rows in front of the first segment
+        off = first + np.concatenate([[0], np.cumsum(lens)])
+        off = off[off <= n_rows - (int(rng.integers(0, 30)) if case % 3 == 0 else 0)]
+        if off.size < 2:
+            off = np.asarray([first, n_rows])
+        off = off.astype(np.int64)
+        S = off.size - 1
+        alloc = n_rows + (int(rng.integers(1, 2000)) if case % 4 == 1 else 0)  # allocation larger than the covered rows
+        emb = torch.randn(alloc, dim, device="cuda")
+        d_off = torch.from_numpy(off).cuda()
+        out = torch.full((S, dim), float("nan"), device="cuda")
+        totals = torch.tensor([S, int(off[-1])], dtype=torch.int64, device="cuda")
+        from_dev = alloc != n_rows
+        _pool_device(plan.ctx, emb, d_off, S, totals, out, None, stream, plan=plan.handle, rows_from_device=from_dev)
+        torch.cuda.synchronize()
+        cs = torch.zeros(alloc + 1, dim, dtype=torch.float64, device="cuda")
+        cs[1:] = torch.cumsum(emb.double(), dim=0)
+        n = (d_off[1:] - d_off[:-1]).double()
+        want = ((cs[d_off[1:]] - cs[d_off[:-1]]) / n[:, None]).float()
+        ok = n > 0
+        err = (out[ok].double() - want[ok].double()).norm(dim=1) / want[ok].double().norm(dim=1).clamp_min(1e-30)
+        assert float(err.max()) <= 1e-5, (case, kind, dim, n_rows, S, float(err.max()))
+        assert bool(torch.isnan(out[~ok]).all())
+
+
 def test_pool_empty_segments_gaps_and_degenerate_shapes(c_oracle):
     import torch
 
