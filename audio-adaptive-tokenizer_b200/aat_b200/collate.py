@@ -114,7 +114,8 @@ def scatter_mel_segments(batch: PackedBatch, boarders_padded, max_segment_frames
 def normalize_waveforms_padded(batch: PackedBatch, wave, mode: str = "w2v2", n_max=None, with_mask: bool = True):
     """Per-utterance normalisation written straight into the feature extractor's padded layout
     (``audio_processor(waveforms, padding=True, return_tensors="pt")``, ref:src/aat/training/collate.py:301-304):
-    returns ``(input_values [B, N_max] float32, attention_mask [B, N_max] int64 or None)``."""
+    returns ``(input_values [B, N_max] float32, attention_mask [B, N_max] int32 or None)`` (the dtypes the feature
+    extractor returns)."""
     import torch
 
     modes = {"zscore": _cabi.AAT_NORM_ZSCORE, "w2v2": _cabi.AAT_NORM_W2V2}
@@ -124,7 +125,7 @@ def normalize_waveforms_padded(batch: PackedBatch, wave, mode: str = "w2v2", n_m
     if n_max is None:
         n_max = int(batch.n_samples.max()) if batch.n_utts else 0
     out = torch.empty((batch.n_utts, n_max), dtype=torch.float32, device=wave.device)
-    mask = torch.empty((batch.n_utts, n_max), dtype=torch.int64, device=wave.device) if with_mask else None
+    mask = torch.empty((batch.n_utts, n_max), dtype=torch.int32, device=wave.device) if with_mask else None
     _cabi.check(_cabi.lib().aat_normalize_padded(batch.ctx.handle, batch.handle, wave.data_ptr(), codes[wave.dtype],
                                                  modes[mode], out.data_ptr(), int(n_max),
                                                  mask.data_ptr() if with_mask else None, None, _stream(wave.device)))

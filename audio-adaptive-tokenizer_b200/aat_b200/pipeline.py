@@ -12,6 +12,7 @@ loop gives (tests/test_gpu_parity.py::test_pipelined_steps_match_serial_steps).
 """
 from __future__ import annotations
 
+import ctypes
 from typing import List, Optional, Sequence
 
 from .pooling import DatasetMean
@@ -23,6 +24,7 @@ class _Slot:
         self.batch: PackedBatch = tokenizer.plan(n_samples, device=device)
         dev = self.batch.device
         self.stream = torch.cuda.Stream(device=dev, priority=priority)
+        self.handle = ctypes.c_void_p(self.stream.cuda_stream)  # passed straight to the C ABI: no current-stream switch
         self.out = torch.empty(self.batch.total_seg_slots, dim, dtype=torch.float32, device=dev)
         self.mean = DatasetMean(dim, device=dev.index)
         self.done = torch.cuda.Event()
@@ -94,20 +96,19 @@ class TokenizerPipeline:
         self.submitted += 1
         if not inputs_ready:
             slot.stream.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(slot.stream):
-            b = slot.batch
-            if znorm:
-                slot.stats = b.waveform_stats(wave, out=slot.stats)
-                b.logmel(wave, with_amp=self.fused_amp, znorm_stats=slot.stats)
-            else:
-                b.logmel(wave, with_amp=self.fused_amp)
-            if not self.fused_amp:
-                b.amplitude()
-            b.boundaries()
-            # the launch in front of the pool kernel is this slot's boundary scan, which does not write embeddings
-            b.pool(emb, slot.out, colsum=slot.mean.running_buffer() if colsum else None, accumulate=colsum,
-                   emb_ready=not rows_from_device, rows_from_device=rows_from_device)
-            slot.done.record()
+        b, st = slot.batch, slot.handle  # the slot's stream goes straight to the C ABI (no current-stream switch)
+        if znorm:
+            slot.stats = b.waveform_stats(wave, out=slot.stats, stream=st)
+            b.logmel(wave, with_amp=self.fused_amp, znorm_stats=slot.stats, stream=st)
+        else:
+            b.logmel(wave, with_amp=self.fused_amp, stream=st)
+        if not self.fused_amp:
+            b.amplitude(stream=st)
+        b.boundaries(stream=st)
+        # the launch in front of the pool kernel is this slot's boundary scan, which does not write embeddings
+        b.pool(emb, slot.out, colsum=slot.mean.running_buffer() if colsum else None, accumulate=colsum,
+               emb_ready=not rows_from_device, rows_from_device=rows_from_device, stream=st)
+        slot.done.record(slot.stream)
         return slot
 
     def join(self):

@@ -316,11 +316,17 @@ class PackedBatch:
         except Exception:
             pass
 
-    def _stream(self):
-        """The caller's current stream ON THE PLAN'S DEVICE (which need not be the current device)."""
-        import torch
+    def _stream(self, stream=None):
+        """``stream`` as a ``cudaStream_t`` handle: a ``torch.cuda.Stream``, a raw handle (``c_void_p`` / int), or — None —
+        the caller's current stream ON THE PLAN'S DEVICE (which need not be the current device).  Passing the stream
+        explicitly saves the current-stream switch (``with torch.cuda.stream(...)``) in loops that drive several streams."""
+        if stream is None:
+            import torch
 
-        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        if isinstance(stream, ctypes.c_void_p):
+            return stream
+        return ctypes.c_void_p(getattr(stream, "cuda_stream", stream))
 
     def pack(self, waveforms) -> "torch.Tensor":
         """List of 1-D tensors/arrays (or a [B, N] tensor) -> one packed 1-D CUDA tensor."""
@@ -333,7 +339,7 @@ class PackedBatch:
             raise ValueError("waveform lengths do not match the plan")
         return torch.cat([p.reshape(-1) for p in parts]).to(self.device)
 
-    def waveform_stats(self, wave, out=None):
+    def waveform_stats(self, wave, out=None, stream=None):
         """Per-utterance (mean, population variance) of a packed waveform in float64 -> ``[B, 2]`` CUDA tensor: one pass
         over the samples (N2).  Feed it to :meth:`logmel` as ``znorm_stats`` for the fused z-score."""
         import torch
@@ -344,10 +350,10 @@ class PackedBatch:
         if out is None:
             out = torch.empty((self.n_utts, 2), dtype=torch.float64, device=self.device)
         _cabi.check(_cabi.lib().aat_normalize(self.ctx.handle, self.handle, wave.data_ptr(), dt, _cabi.AAT_NORM_ZSCORE,
-                                              None, _cabi.AAT_F64, out.data_ptr(), self._stream()))
+                                              None, _cabi.AAT_F64, out.data_ptr(), self._stream(stream)))
         return out
 
-    def logmel(self, wave, with_amp: bool = True, znorm_stats=None):
+    def logmel(self, wave, with_amp: bool = True, znorm_stats=None, stream=None):
         """K1+K2 on a packed waveform tensor (float32 or float64, CUDA).  Returns the packed mel.
 
         znorm_stats : optional ``[B, 2]`` float64 CUDA tensor from :meth:`waveform_stats`; the samples are then
@@ -367,20 +373,21 @@ class PackedBatch:
             raise TypeError("znorm_stats must be a contiguous [B, 2] float64 CUDA tensor (waveform_stats())")
         _cabi.check(_cabi.lib().aat_logmel(self.ctx.handle, self.handle, wave.data_ptr(), dt,
                                            znorm_stats.data_ptr() if znorm_stats is not None else None,
-                                           self.mel.data_ptr(), self.amp.data_ptr() if with_amp else None, self._stream()))
+                                           self.mel.data_ptr(), self.amp.data_ptr() if with_amp else None,
+                                           self._stream(stream)))
         return self.mel
 
-    def amplitude(self, mel=None):
+    def amplitude(self, mel=None, stream=None):
         """``-10 * mel.mean(axis=0)`` of every utterance in numpy's float32 order (ref:src/aat/tokenizer.py:67) into
         ``self.amp``: what :meth:`logmel` writes with ``with_amp=True``, as a separate, fully parallel pass."""
         src = self.mel if mel is None else mel
         if src.numel() != self.n_mels * self.total_frames or not src.is_cuda or not src.is_contiguous():
             raise ValueError("mel must be a contiguous packed CUDA tensor matching the plan")
         _cabi.check(_cabi.lib().aat_amplitude(self.ctx.handle, self.handle, src.data_ptr(), self.amp.data_ptr(),
-                                              self._stream()))
+                                              self._stream(stream)))
         return self.amp
 
-    def boundaries(self, mel=None, use_amp: bool = True, with_minima: bool = True, with_csr: bool = True):
+    def boundaries(self, mel=None, use_amp: bool = True, with_minima: bool = True, with_csr: bool = True, stream=None):
         """K3.  ``mel=None`` uses this batch's own mel (and the fused amplitude curve when ``use_amp``);
         pass a packed float32 CUDA tensor to segment somebody else's mel (e.g. the reference's).
         ``with_csr`` also fills ``seg_off`` / ``n_seg`` / ``utt_seg_off`` (what :meth:`frame_csr` computes)
@@ -395,7 +402,7 @@ class PackedBatch:
             self.seg_count.data_ptr(), self.minima.data_ptr() if with_minima else None,
             self.minima_count.data_ptr() if with_minima else None, self.status.data_ptr(),
             self.seg_off.data_ptr() if with_csr else None, self.n_seg.data_ptr() if with_csr else None,
-            self.utt_seg_off.data_ptr() if with_csr else None, self._stream()))
+            self.utt_seg_off.data_ptr() if with_csr else None, self._stream(stream)))
         return self.seg_len, self.seg_count
 
     def frame_csr(self):
@@ -406,7 +413,7 @@ class PackedBatch:
         return self.seg_off, self.n_seg
 
     def pool(self, emb, out, colsum=None, accumulate: bool = False, emb_ready: bool = False,
-             rows_from_device: bool = False):
+             rows_from_device: bool = False, stream=None):
         """K4 with the device-resident CSR of :meth:`frame_csr`.  ``out`` is [capacity, D] float32; ``colsum``
         ([D+1] float64) receives the column sums of the pooled vectors, added to its content when ``accumulate``.
 
@@ -416,8 +423,9 @@ class PackedBatch:
                            count is taken from the device (written by :meth:`boundaries`) instead of ``emb.shape[0]``"""
         from .pooling import _pool_device
 
-        return _pool_device(self.ctx, emb, self.seg_off, int(out.shape[0]), self.n_seg, out, colsum, self._stream(),
-                            accumulate, plan=self.handle, emb_ready=emb_ready, rows_from_device=rows_from_device)
+        return _pool_device(self.ctx, emb, self.seg_off, int(out.shape[0]), self.n_seg, out, colsum,
+                            self._stream(stream), accumulate, plan=self.handle, emb_ready=emb_ready,
+                            rows_from_device=rows_from_device)
 
     # ---- host views (synchronising; for tests and the numpy-facing callers)
     def mel_of(self, b: int):

@@ -188,7 +188,7 @@ int launch_scatter_mel_segments(aat_ctx *ctx, const aat_plan *plan, int32_t n_ut
                                 const int64_t *boarders, int64_t s_max, int64_t max_items, float *out, int32_t *status,
                                 cudaStream_t stream);
 int launch_normalize_padded(aat_ctx *ctx, const aat_plan *plan, const void *wave, int in_dtype, int mode, float *out,
-                            int64_t n_max, int64_t *mask, double *stats, cudaStream_t stream);
+                            int64_t n_max, int32_t *mask, double *stats, cudaStream_t stream);
 int launch_masked_mean_pool(const void *emb, int emb_dtype, int64_t n_rows, int64_t seq_len, int32_t dim,
                             const int64_t *mask, float *out, int64_t *row_mask, cudaStream_t stream);
 int64_t synth_burst_capacity(int sampling_rate, int64_t n_samples);

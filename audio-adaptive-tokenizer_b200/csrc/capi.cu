@@ -612,7 +612,7 @@ int aat_scatter_mel_tiles(aat_ctx *ctx, int32_t n_utts, const float *mel_dev, co
 }
 
 int aat_normalize_padded(aat_ctx *ctx, const aat_plan *plan, const void *wave_dev, int in_dtype, int mode, float *out_dev,
-                         int64_t n_max, int64_t *mask_dev, double *stats_dev, void *stream)
+                         int64_t n_max, int32_t *mask_dev, double *stats_dev, void *stream)
 {
     AAT_REQUIRE(ctx && plan && wave_dev && out_dev, AAT_ERR_INVALID, "aat_normalize_padded: NULL argument");
     AAT_REQUIRE(plan->ctx == ctx, AAT_ERR_INVALID, "aat_normalize_padded: plan belongs to another context");

@@ -199,25 +199,37 @@ wave_apply_norm_kernel(const InT *wave, OutT *out, const int64_t *n_samples, con
 // with padding=True).  grid = (chunks of the padded row, utterances).
 template <typename InT>
 __global__ void __launch_bounds__(kStatThreads)
-wave_apply_norm_padded_kernel(const InT *wave, float *out, int64_t *mask, const int64_t *n_samples, const int64_t *wave_off,
-                              int64_t n_max, const double *stats, int mode)
+wave_apply_norm_padded_kernel(const InT *__restrict__ wave, float *__restrict__ out, int32_t *__restrict__ mask,
+                              const int64_t *n_samples, const int64_t *wave_off, int64_t n_max, const double *stats, int mode)
 {
     const int utt = blockIdx.y;
     const int64_t n = n_samples[utt];
     const int64_t j0 = (int64_t)blockIdx.x * kStatChunk;
     const int64_t end = (n_max - j0 < kStatChunk) ? n_max : j0 + kStatChunk;
-    const double mean = stats[2 * utt], var = stats[2 * utt + 1];
     const InT *src = wave + wave_off[utt];
     float *dst = out + (size_t)utt * n_max;
-    int64_t *m = mask ? mask + (size_t)utt * n_max : nullptr;
+    int32_t *m = mask ? mask + (size_t)utt * n_max : nullptr;
     const Znorm zn = Znorm::from_stats(stats, utt);
-    const float mf = (float)mean;
-    const float denom32 = sqrtf(__fadd_rn((float)var, 1e-7f));
-    for (int64_t i = j0 + threadIdx.x; i < end; i += kStatThreads) {
-        float v = 0.0f;
-        if (i < n) v = (mode == 0) ? (float)zn((double)src[i]) : __fdiv_rn(__fsub_rn((float)src[i], mf), denom32);
-        dst[i] = v;
-        if (m) m[i] = i < n ? 1 : 0;
+    const float mf = (float)stats[2 * utt];
+    const float denom32 = sqrtf(__fadd_rn((float)stats[2 * utt + 1], 1e-7f));
+    auto norm = [&](int64_t i) -> float {
+        if (i >= n) return 0.0f; // padding_value
+        return (mode == 0) ? (float)zn((double)src[i]) : __fdiv_rn(__fsub_rn((float)src[i], mf), denom32);
+    };
+    // rows of the padded layout start 16-byte aligned when n_max is a multiple of 4: four samples per thread and trip,
+    // one 16-byte store for the values and one for the mask (the packed source is read with coalesced scalar loads)
+    const bool vec = (n_max & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                     (m == nullptr || (reinterpret_cast<uintptr_t>(mask) & 15) == 0);
+    if (vec) {
+        for (int64_t i = j0 + 4 * (int64_t)threadIdx.x; i < end; i += 4 * kStatThreads) {
+            *reinterpret_cast<float4 *>(dst + i) = make_float4(norm(i), norm(i + 1), norm(i + 2), norm(i + 3));
+            if (m) *reinterpret_cast<int4 *>(m + i) = make_int4(i < n, i + 1 < n, i + 2 < n, i + 3 < n);
+        }
+    } else {
+        for (int64_t i = j0 + threadIdx.x; i < end; i += kStatThreads) {
+            dst[i] = norm(i);
+            if (m) m[i] = i < n ? 1 : 0;
+        }
     }
 }
 
@@ -589,7 +601,7 @@ int launch_scatter_mel_segments(aat_ctx *ctx, const aat_plan *plan, int32_t n_ut
 }
 
 int launch_normalize_padded(aat_ctx *ctx, const aat_plan *plan, const void *wave, int in_dtype, int mode, float *out,
-                            int64_t n_max, int64_t *mask, double *stats, cudaStream_t stream)
+                            int64_t n_max, int32_t *mask, double *stats, cudaStream_t stream)
 {
     AAT_REQUIRE(in_dtype == AAT_F32 || in_dtype == AAT_F64, AAT_ERR_UNSUPPORTED, "aat_normalize_padded: input dtype must be F32 or F64");
     AAT_REQUIRE(mode == 0 || mode == 1, AAT_ERR_INVALID, "aat_normalize_padded: unknown mode %d", mode);

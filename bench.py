@@ -473,8 +473,10 @@ def measure_workload(torch, dist, w, steps, warmup, world, sample_every, no_cols
     wall0 = time.time()
     ev0.record()
     pipe.fork()  # the slots' streams start behind ev0
+    host0 = time.perf_counter()
     for i in range(steps):
         w.step(i, not no_colsum, depth)
+    host_us = (time.perf_counter() - host0) * 1e6 / steps  # what the host needs to enqueue a step (must stay below ms_per_step)
     dm = pipe.dataset_mean()  # joins the streams, adds the slots' sums, allreduce
     mean_vec = dm.result()
     ev1.record()
@@ -526,7 +528,8 @@ def measure_workload(torch, dist, w, steps, warmup, world, sample_every, no_cols
         _cabi.profile_enable(ctx_handle, ())
     return {"elapsed_ms": elapsed_ms, "value": world * w.audio_hours_per_step * steps / (elapsed_ms / 1e3),
             "ms_per_step": elapsed_ms / steps, "launches": int(launches), "sampled_pool": prof["pool"],
-            "kernel_us": kernel_us, "wall": (wall0, wall1), "dataset_mean_check": check, "depth": depth}
+            "kernel_us": kernel_us, "wall": (wall0, wall1), "dataset_mean_check": check, "depth": depth,
+            "host_enqueue_us_per_step": host_us}
 
 
 def schedule_note(depth):
@@ -763,7 +766,7 @@ def run_b200(args):
                             "generator": "aat_synth_waveforms / aat_synth_normal (Philox 4x32-10, on the device)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": m["launches"], "roofline": roofline,
         "kernel_us": m["kernel_us"], "dataset_mean_check": m["dataset_mean_check"],
-        "schedule": schedule_note(m["depth"]),
+        "schedule": schedule_note(m["depth"]), "host_enqueue_us_per_step": m["host_enqueue_us_per_step"],
         "serial": {"value": serial["value"], "ms_per_step": serial["ms_per_step"], "schedule": schedule_note(1)},
     }
     if not args.no_configs and args.workload == "c2":

@@ -262,9 +262,9 @@ int aat_normalize(aat_ctx *ctx, const aat_plan *plan, const void *wave_dev, int 
 /* The same normalisation written straight into the feature extractor's padded layout
  * (ref:src/aat/training/collate.py:301-304, the processor call with padding=True):
  * out_dev [n_utts, n_max] float32 = normalised samples, zeros behind each utterance's end;
- * mask_dev (optional) [n_utts, n_max] int64 = the processor's attention_mask.  Every utterance must fit n_max. */
+ * mask_dev (optional) [n_utts, n_max] int32 = the processor's attention_mask (the feature extractor returns int32).  Every utterance must fit n_max. */
 int aat_normalize_padded(aat_ctx *ctx, const aat_plan *plan, const void *wave_dev, int in_dtype, int mode, float *out_dev,
-                         int64_t n_max, int64_t *mask_dev, double *stats_dev, void *stream);
+                         int64_t n_max, int32_t *mask_dev, double *stats_dev, void *stream);
 
 /* `_make_padded_segments_boarders` (ref:src/aat/training/collate.py:242-253) on the output of aat_boundaries:
  * boarders_dev [n_utts, s_max] = cumulative segment ends (the collator's `frames_boarders`, :158), zero padded;

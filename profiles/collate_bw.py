@@ -67,7 +67,7 @@ def main():
     t = timed(lambda: collate.normalize_waveforms(batch, packed64, "zscore"))
     rows.append(("normalize zscore f64->f64 (3 kernels)", B * N * 8 * 3, t))
     t = timed(lambda: collate.normalize_waveforms_padded(batch, packed, "w2v2", n_max=n_max))
-    rows.append(("normalize_padded w2v2 + mask", B * N * 4 * 2 + B * n_max * 12, t))
+    rows.append(("normalize_padded w2v2 + mask", B * N * 4 * 2 + B * n_max * 8, t))
     stats = torch.empty(B, 2, dtype=torch.float64, device="cuda")
     t = timed(lambda: batch.waveform_stats(packed, out=stats))
     rows.append(("waveform_stats f32 (2 kernels)", B * N * 4, t))
