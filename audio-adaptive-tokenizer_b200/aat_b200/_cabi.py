@@ -51,6 +51,14 @@ class AatConfig(ctypes.Structure):
     ]
 
 
+class AatStepBuffers(ctypes.Structure):
+    """``struct aat_step_buffers`` (include/aat_b200.h)."""
+
+    _fields_ = [(name, ctypes.c_void_p) for name in
+                ("mel", "amp", "seg_start", "seg_len", "seg_count", "minima", "minima_count", "status", "seg_off", "n_seg",
+                 "utt_seg_off", "znorm_stats")]
+
+
 class AatError(RuntimeError):
     def __init__(self, status: int, message: str):
         super().__init__(f"aat_b200 status {status}: {message}")
@@ -81,6 +89,8 @@ SIGNATURES = {
     "aat_segment_frame_csr": (ctypes.c_int, [c_void] * 8),
     "aat_segment_mean_pool": (ctypes.c_int, [c_void, c_void, c_void, ctypes.c_int, c_i64, c_i32, c_void, c_i64, c_void,
                                              c_void, c_void, ctypes.c_int, c_void]),
+    "aat_tokenize_and_pool": (ctypes.c_int, [c_void, c_void, ctypes.POINTER(AatStepBuffers), c_void, ctypes.c_int, ctypes.c_int,
+                                             c_void, ctypes.c_int, c_i64, c_i32, c_void, c_i64, c_void, ctypes.c_int, c_void]),
     "aat_colsum_accumulate": (ctypes.c_int, [c_void, c_void, c_void, c_i32, c_void]),
     "aat_colsum_finalize": (ctypes.c_int, [c_void, c_void, c_i32, c_void, c_void]),
     "aat_normalize": (ctypes.c_int, [c_void, c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, ctypes.c_int, c_void, c_void]),

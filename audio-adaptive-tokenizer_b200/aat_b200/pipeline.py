@@ -97,17 +97,20 @@ class TokenizerPipeline:
         if not inputs_ready:
             slot.stream.wait_stream(torch.cuda.current_stream(self.device))
         b, st = slot.batch, slot.handle  # the slot's stream goes straight to the C ABI (no current-stream switch)
-        if znorm:
-            slot.stats = b.waveform_stats(wave, out=slot.stats, stream=st)
-            b.logmel(wave, with_amp=self.fused_amp, znorm_stats=slot.stats, stream=st)
+        if self.fused_amp:  # the whole step in one foreign call
+            b.step(wave, emb, slot.out, colsum=slot.mean.running_buffer() if colsum else None, accumulate=colsum,
+                   znorm=znorm, rows_from_device=rows_from_device, stream=st)
         else:
-            b.logmel(wave, with_amp=self.fused_amp, stream=st)
-        if not self.fused_amp:
+            if znorm:
+                slot.stats = b.waveform_stats(wave, out=slot.stats, stream=st)
+                b.logmel(wave, with_amp=False, znorm_stats=slot.stats, stream=st)
+            else:
+                b.logmel(wave, with_amp=False, stream=st)
             b.amplitude(stream=st)
-        b.boundaries(stream=st)
-        # the launch in front of the pool kernel is this slot's boundary scan, which does not write embeddings
-        b.pool(emb, slot.out, colsum=slot.mean.running_buffer() if colsum else None, accumulate=colsum,
-               emb_ready=not rows_from_device, rows_from_device=rows_from_device, stream=st)
+            b.boundaries(stream=st)
+            # the launch in front of the pool kernel is this slot's boundary scan, which does not write embeddings
+            b.pool(emb, slot.out, colsum=slot.mean.running_buffer() if colsum else None, accumulate=colsum,
+                   emb_ready=not rows_from_device, rows_from_device=rows_from_device, stream=st)
         slot.done.record(slot.stream)
         return slot
 

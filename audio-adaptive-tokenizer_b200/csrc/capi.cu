@@ -537,6 +537,32 @@ int aat_segment_mean_pool(aat_ctx *ctx, const aat_plan *plan, const void *emb_de
                             colsum_dev, flags, static_cast<cudaStream_t>(stream));
 }
 
+int aat_tokenize_and_pool(aat_ctx *ctx, const aat_plan *plan, const aat_step_buffers *bufs, const void *wave_dev,
+                          int wave_dtype, int znorm, const void *emb_dev, int emb_dtype, int64_t n_rows, int32_t dim,
+                          float *out_dev, int64_t out_capacity, double *colsum_dev, int pool_flags, void *stream)
+{
+    AAT_REQUIRE(ctx && plan && bufs && wave_dev && out_dev, AAT_ERR_INVALID, "aat_tokenize_and_pool: NULL argument");
+    AAT_REQUIRE(plan->ctx == ctx, AAT_ERR_INVALID, "aat_tokenize_and_pool: plan belongs to another context");
+    AAT_REQUIRE(bufs->mel && bufs->amp && bufs->seg_start && bufs->seg_len && bufs->seg_count && bufs->status &&
+                    bufs->seg_off && bufs->n_seg,
+                AAT_ERR_INVALID, "aat_tokenize_and_pool: a required step buffer is NULL");
+    AAT_REQUIRE(!znorm || bufs->znorm_stats, AAT_ERR_INVALID, "aat_tokenize_and_pool: znorm needs bufs->znorm_stats");
+    AAT_REQUIRE((pool_flags & ~(AAT_POOL_ACCUMULATE | AAT_POOL_EMB_READY | AAT_POOL_ROWS_FROM_DEVICE)) == 0, AAT_ERR_INVALID,
+                "aat_tokenize_and_pool: unknown flag bits 0x%x", pool_flags);
+    AAT_DEVICE_GUARD(ctx);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc;
+    if (znorm && (rc = launch_normalize(ctx, plan, wave_dev, wave_dtype, AAT_NORM_ZSCORE, nullptr, AAT_F64, bufs->znorm_stats, st)))
+        return rc;
+    if ((rc = launch_logmel(ctx, plan, wave_dev, wave_dtype, znorm ? bufs->znorm_stats : nullptr, bufs->mel, bufs->amp, st)))
+        return rc;
+    if ((rc = launch_boundaries(ctx, plan, bufs->mel, bufs->amp, bufs->seg_start, bufs->seg_len, bufs->seg_count, bufs->minima,
+                                bufs->minima_count, bufs->status, bufs->seg_off, bufs->n_seg, bufs->utt_seg_off, st)))
+        return rc;
+    return launch_mean_pool(ctx, plan, emb_dev, emb_dtype, n_rows, dim, bufs->seg_off, out_capacity, bufs->n_seg, out_dev,
+                            colsum_dev, pool_flags, st);
+}
+
 int aat_colsum_accumulate(aat_ctx *ctx, double *acc_dev, const double *colsum_dev, int32_t dim, void *stream)
 {
     AAT_REQUIRE(ctx && acc_dev && colsum_dev && dim > 0, AAT_ERR_INVALID, "aat_colsum_accumulate: bad argument");

@@ -238,6 +238,31 @@ int aat_segment_mean_pool(aat_ctx *ctx, const aat_plan *plan, const void *emb_de
                           int32_t dim, const int64_t *seg_off_dev, int64_t n_seg, const int64_t *n_seg_dev,
                           float *out_dev, double *colsum_dev, int flags, void *stream);
 
+/* ------------------------------------------------------------------ one step in one call
+ * aat_logmel (with the fused z-score when `znorm` is non-zero: statistics by aat_normalize into bufs->znorm_stats
+ * first) -> aat_boundaries (with the packed frame CSR) -> aat_segment_mean_pool, enqueued back to back on `stream`:
+ * exactly the launches the separate calls make, for loops that drive many steps per second from an interpreted host
+ * language (three or four foreign calls per step cost more host time than one; aat_b200/pipeline.py).
+ * bufs: the plan-sized device buffers of the separate entry points, same meaning and sizes; minima / minima_count /
+ * utt_seg_off / znorm_stats may be NULL (znorm_stats only when znorm is 0). */
+typedef struct aat_step_buffers {
+    float *mel;            /* aat_logmel: mel_dev                       */
+    float *amp;            /* aat_logmel: amp_dev (required here)       */
+    int64_t *seg_start;    /* aat_boundaries ...                        */
+    int64_t *seg_len;
+    int32_t *seg_count;
+    int64_t *minima;
+    int32_t *minima_count;
+    int32_t *status;
+    int64_t *seg_off;
+    int64_t *n_seg;        /* int64 [2]                                 */
+    int64_t *utt_seg_off;
+    double *znorm_stats;   /* float64 [2 * n_utts]                      */
+} aat_step_buffers;
+int aat_tokenize_and_pool(aat_ctx *ctx, const aat_plan *plan, const aat_step_buffers *bufs, const void *wave_dev,
+                          int wave_dtype, int znorm, const void *emb_dev, int emb_dtype, int64_t n_rows, int32_t dim,
+                          float *out_dev, int64_t out_capacity, double *colsum_dev, int pool_flags, void *stream);
+
 /* acc_dev[0..dim] += colsum_dev[0..dim] (float64), for accumulating over batches before the allreduce. */
 int aat_colsum_accumulate(aat_ctx *ctx, double *acc_dev, const double *colsum_dev, int32_t dim, void *stream);
 /* mean_dev[d] = float32(acc_dev[d] / acc_dev[dim]) — after the SUM allreduce of acc_dev over ranks. */
