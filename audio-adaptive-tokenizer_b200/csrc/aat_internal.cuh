@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <map>
 #include <mutex>
 #include <utility>
 #include <cstdarg>
@@ -42,8 +43,16 @@ extern std::atomic<int64_t> g_launch_count;
 
 // Every kernel of the library asks for the same (maximum) shared-memory carve-out, so the SMs are not
 // drained and reconfigured between the kernels of a step (they differ widely in shared-memory footprint).
-#define AAT_MAX_SMEM_CARVEOUT(kernel) \
-    AAT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
+// Function attributes and occupancy are per-device facts that do not change between launches: they are set / asked
+// once per (context, kernel) and remembered — ten driver calls per step were half of the host time of a step.
+struct KernelSetup {
+    size_t max_smem = 0;   // cudaFuncAttributeMaxDynamicSharedMemorySize already granted
+    bool carveout = false; // cudaFuncAttributePreferredSharedMemoryCarveout already set
+    int occ_threads = 0;   // occupancy answer for (occ_threads, occ_smem)
+    size_t occ_smem = 0;
+    int occ = 0;
+};
+#define AAT_MAX_SMEM_CARVEOUT(kernel) AAT_CUDA_CHECK(aat::prepare_kernel(ctx, kernel, 0, 0, nullptr))
 
 #define AAT_LAUNCH_CHECK()                         \
     do {                                           \
@@ -126,6 +135,8 @@ struct aat_ctx {
     std::mutex host_mutex;
     std::vector<std::pair<int64_t, aat_plan *>> host_plans;
     aat::Profiler prof{};
+    std::mutex setup_mutex;
+    std::map<const void *, aat::KernelSetup> kernel_setup; // keyed by the kernel's host function pointer
 };
 
 struct aat_plan {
@@ -253,6 +264,35 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// Grants `smem` bytes of dynamic shared memory to `kernel`, asks for the maximum carve-out, and (when per_sm is given)
+// returns the resident CTAs per SM for (threads, smem) — each at most once per context and kernel.
+template <typename K>
+inline cudaError_t prepare_kernel(aat_ctx *ctx, K kernel, int threads, size_t smem, int *per_sm)
+{
+    std::lock_guard<std::mutex> lock(ctx->setup_mutex);
+    KernelSetup &ks = ctx->kernel_setup[reinterpret_cast<const void *>(kernel)];
+    cudaError_t err;
+    if (smem > ks.max_smem) {
+        if ((err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+        ks.max_smem = smem;
+    }
+    if (!ks.carveout) {
+        if ((err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) !=
+            cudaSuccess)
+            return err;
+        ks.carveout = true;
+    }
+    if (per_sm) {
+        if (ks.occ_threads != threads || ks.occ_smem != smem) {
+            int occ = 0;
+            if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem)) != cudaSuccess) return err;
+            ks.occ_threads = threads, ks.occ_smem = smem, ks.occ = occ;
+        }
+        *per_sm = ks.occ;
+    }
+    return cudaSuccess;
 }
 
 // RAII helper: records an event pair around one launch when profiling is enabled for `id`.

@@ -813,8 +813,7 @@ int launch_boundaries(aat_ctx *ctx, const aat_plan *plan, const float *mel, cons
     const size_t smem = sizeof(float) * (size_t)(2 * chunk + kRing) + sizeof(int) * (size_t)(2 * chunk) +
                         sizeof(longlong2) * (size_t)kSegQueue;
     auto kernel = boundaries_kernel_t<kChunk>;
-    AAT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AAT_MAX_SMEM_CARVEOUT(kernel);
+    AAT_CUDA_CHECK(prepare_kernel(ctx, kernel, 0, smem, nullptr));
     {
         ProfileScope prof(ctx, AAT_K_BOUNDARIES, stream);
         AAT_CUDA_CHECK(launch_pdl(kernel, dim3(plan->n_utts), dim3(kThreads), smem, stream, p));
@@ -852,8 +851,7 @@ int launch_segment_frame_csr(aat_ctx *ctx, const aat_plan *plan, const int64_t *
 {
     const size_t smem = sizeof(int64_t) * 2 * (size_t)(plan->n_utts + 1);
     AAT_REQUIRE(smem <= 200 * 1024, AAT_ERR_UNSUPPORTED, "aat_segment_frame_csr: at most 12799 utterances per plan");
-    AAT_CUDA_CHECK(
-        cudaFuncSetAttribute(segment_frame_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AAT_CUDA_CHECK(prepare_kernel(ctx, segment_frame_csr_kernel, 0, smem, nullptr));
     ProfileScope prof(ctx, AAT_K_FRAME_CSR, stream);
     segment_frame_csr_kernel<<<1, kCsrThreads, smem, stream>>>(plan->n_utts, plan->d_seg_slot_off, seg_len, seg_count,
                                                                seg_off, n_seg, utt_seg_off);

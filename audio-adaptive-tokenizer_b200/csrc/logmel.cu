@@ -647,10 +647,8 @@ int launch_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave, int wave
     const size_t smem = smem_layout(raw_elems(p.stage_pad, gap), wave_bytes, p.n_mels, p.n_weights).total;
     const bool znorm = znorm_stats != nullptr;
     auto kernel = wave_dtype == AAT_F32 ? pick_logmel_kernel<float>(hop160, znorm) : pick_logmel_kernel<double>(hop160, znorm);
-    AAT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AAT_MAX_SMEM_CARVEOUT(kernel);
     int per_sm = 0;
-    AAT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
+    AAT_CUDA_CHECK(prepare_kernel(ctx, kernel, kThreads, smem, &per_sm));
     AAT_REQUIRE(per_sm >= 1, AAT_ERR_UNSUPPORTED, "aat_logmel: kernel does not fit on an SM (%zu bytes of shared memory)", smem);
     int grid = ctx->num_sms * per_sm;
     // Tried and rejected (gpurun r2_b3 / r2_b4): leaving one CTA slot per utterance free on long streams, so that the

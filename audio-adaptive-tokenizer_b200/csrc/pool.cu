@@ -754,12 +754,9 @@ int launch_typed(aat_ctx *ctx, const PoolScratch &ps, PoolParams &p, size_t smem
 {
     const int threads = p.n_consumers + 32;
     auto kernel = colsum ? pool_kernel<EmbT, kSlabs, true> : pool_kernel<EmbT, kSlabs, false>;
-    AAT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AAT_MAX_SMEM_CARVEOUT(kernel);
-    // persistent grid: the cross-CTA carry needs every CTA resident at once, so size it from the
-    // occupancy the driver reports for this very instantiation
+    // persistent grid, sized from the occupancy the driver reports for this very instantiation
     int per_sm = 0;
-    AAT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    AAT_CUDA_CHECK(prepare_kernel(ctx, kernel, threads, smem, &per_sm));
     AAT_REQUIRE(per_sm >= 1, AAT_ERR_UNSUPPORTED, "aat_segment_mean_pool: kernel does not fit on an SM");
     if (per_sm > kMaxCtasPerSm) per_sm = kMaxCtasPerSm;
     int grid = ctx->num_sms * per_sm;
@@ -927,7 +924,6 @@ extern "C" __attribute__((visibility("default"))) int aat_debug_pool_trace(unsig
 
 int launch_colsum_accumulate(double *acc, const double *colsum, int32_t dim, cudaStream_t stream)
 {
-    AAT_MAX_SMEM_CARVEOUT(colsum_accumulate_kernel);
     colsum_accumulate_kernel<<<(dim + 1 + 127) / 128, 128, 0, stream>>>(acc, colsum, dim + 1);
     AAT_LAUNCH_CHECK();
     return AAT_OK;
