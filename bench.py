@@ -486,10 +486,14 @@ def measure_workload(torch, dist, w, steps, warmup, world, sample_every, no_cols
     launches = _cabi.launch_count() - launches0
     prof = _cabi.profile_summary(ctx_handle)
     _cabi.profile_enable(ctx_handle, ())
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
+    t = torch.tensor([elapsed_ms, host_us], dtype=torch.float64, device=dev)
+    by_rank = None
+    if world > 1:  # every rank's own clock (the job's time is the slowest rank's)
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        by_rank = {"ms_per_step": [float(p[0].item()) / steps for p in parts],
+                   "host_enqueue_us_per_step": [float(p[1].item()) for p in parts]}
+        elapsed_ms = max(float(p[0].item()) for p in parts)
 
     # ---- the collective's result against an independent reduction (A9): per-set pooled sums by torch, weighted by use
     # count, gathered from every rank and added in rank order (no NCCL reduction on the checking side)
@@ -529,7 +533,7 @@ def measure_workload(torch, dist, w, steps, warmup, world, sample_every, no_cols
     return {"elapsed_ms": elapsed_ms, "value": world * w.audio_hours_per_step * steps / (elapsed_ms / 1e3),
             "ms_per_step": elapsed_ms / steps, "launches": int(launches), "sampled_pool": prof["pool"],
             "kernel_us": kernel_us, "wall": (wall0, wall1), "dataset_mean_check": check, "depth": depth,
-            "host_enqueue_us_per_step": host_us}
+            "host_enqueue_us_per_step": host_us, "by_rank": by_rank}
 
 
 def schedule_note(depth):
@@ -767,6 +771,7 @@ def run_b200(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": m["launches"], "roofline": roofline,
         "kernel_us": m["kernel_us"], "dataset_mean_check": m["dataset_mean_check"],
         "schedule": schedule_note(m["depth"]), "host_enqueue_us_per_step": m["host_enqueue_us_per_step"],
+        "by_rank": m["by_rank"],
         "serial": {"value": serial["value"], "ms_per_step": serial["ms_per_step"], "schedule": schedule_note(1)},
     }
     if not args.no_configs and args.workload == "c2":
