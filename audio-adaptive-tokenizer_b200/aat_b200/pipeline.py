@@ -29,6 +29,7 @@ class _Slot:
         self.mean = DatasetMean(dim, device=dev.index)
         self.done = torch.cuda.Event()
         self.stats = None  # [B, 2] waveform statistics of the fused z-score (allocated on first use)
+        self.graphs = {}   # (input buffers, options) -> [times seen, captured CUDA graph of the step or None]
 
 
 class TokenizerPipeline:
@@ -53,7 +54,7 @@ class TokenizerPipeline:
 
     def __init__(self, tokenizer: AdaptiveAudioAmplitudeTokenizer, n_samples: Sequence[int], dim: int,
                  depth: Optional[int] = None, device=None, priorities: Optional[Sequence[int]] = None,
-                 fused_amp: bool = True):
+                 fused_amp: bool = True, graphs: bool = True):
         import torch
 
         if depth is None:
@@ -72,6 +73,11 @@ class TokenizerPipeline:
         # while the epilogue costs the log-mel kernel — the one kernel nothing hides — a CTA barrier and a serial
         # 64-term chain per tile.
         self.fused_amp = bool(fused_amp)
+        # A step is four kernel launches.  When a slot is handed the same input buffers again (a loader that rotates over a
+        # few device buffers, as any double-buffered loader does) the step is captured into a CUDA graph on its second
+        # appearance and replayed from then on: one graph launch instead of four kernel launches, which matters on hosts
+        # whose launch path is slow (104 us per step against 150 us of device time on the 8-GPU boxes of this pool).
+        self.graphs = bool(graphs)
         self._reduced = False  # dataset_mean() has folded (and allreduced) the sums: reset_sums() before the next pass
 
     def fork(self):
@@ -96,7 +102,31 @@ class TokenizerPipeline:
         self.submitted += 1
         if not inputs_ready:
             slot.stream.wait_stream(torch.cuda.current_stream(self.device))
-        b, st = slot.batch, slot.handle  # the slot's stream goes straight to the C ABI (no current-stream switch)
+        if self.graphs:
+            key = (wave.data_ptr(), emb.data_ptr(), int(emb.shape[0]), bool(colsum), bool(znorm), bool(rows_from_device))
+            entry = slot.graphs.get(key)
+            if entry is None:
+                if len(slot.graphs) >= 8:  # forget the oldest pattern: the cache is for a handful of rotating buffers
+                    slot.graphs.pop(next(iter(slot.graphs)))
+                entry = slot.graphs[key] = [0, None]
+            entry[0] += 1
+            if entry[1] is None and entry[0] == 2:  # second appearance (everything lazy is set up by now): capture
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=slot.stream, capture_error_mode="thread_local"):
+                    self._enqueue(slot, wave, emb, colsum, znorm, rows_from_device, None)  # None: the capturing stream
+                entry[1] = g
+            if entry[1] is not None:
+                with torch.cuda.stream(slot.stream):
+                    entry[1].replay()
+                slot.done.record(slot.stream)
+                return slot
+        self._enqueue(slot, wave, emb, colsum, znorm, rows_from_device, slot.handle)
+        slot.done.record(slot.stream)
+        return slot
+
+    def _enqueue(self, slot, wave, emb, colsum, znorm, rows_from_device, st):
+        """The launches of one step on stream handle ``st`` (None = torch's current stream, used while capturing)."""
+        b = slot.batch
         if self.fused_amp:  # the whole step in one foreign call
             b.step(wave, emb, slot.out, colsum=slot.mean.running_buffer() if colsum else None, accumulate=colsum,
                    znorm=znorm, rows_from_device=rows_from_device, stream=st)
@@ -111,8 +141,6 @@ class TokenizerPipeline:
             # the launch in front of the pool kernel is this slot's boundary scan, which does not write embeddings
             b.pool(emb, slot.out, colsum=slot.mean.running_buffer() if colsum else None, accumulate=colsum,
                    emb_ready=not rows_from_device, rows_from_device=rows_from_device, stream=st)
-        slot.done.record(slot.stream)
-        return slot
 
     def join(self):
         """Make the caller's current stream wait for everything submitted so far (no host synchronisation)."""

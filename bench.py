@@ -359,7 +359,9 @@ class Workload:
         # the step runs through the public pipeline object: `depth` plans on `depth` streams, so that the boundary scan
         # and the pool of one batch overlap the log-mel of the next (depth 1 = strictly serial, kept for the A/B)
         self.depth = depth = depth if depth > 0 else TokenizerPipeline.default_depth([self.N] * B)
-        self.pipes = {d: TokenizerPipeline(tok, [self.N] * B, D, depth=d, device=local_rank, fused_amp=fused_amp)
+        # the pipelined schedule replays each slot's step from a CUDA graph (the rotating input buffers come round again);
+        # the strictly serial one launches kernel by kernel, as round 1's step did (and so that kernels can be event-timed)
+        self.pipes = {d: TokenizerPipeline(tok, [self.N] * B, D, depth=d, device=local_rank, fused_amp=fused_amp, graphs=d > 1)
                       for d in sorted({1, depth})}
         self.audio_hours_per_step = B * self.N / 16000 / 3600
         self.pool_bytes = float(np.mean([r * D * 4 + s * D * 4 + (s + 1) * 8 for r, s in zip(self.n_rows, self.n_seg)]))
@@ -540,7 +542,7 @@ def schedule_note(depth):
     if depth == 1:
         return "one plan, one stream: log-mel -> boundaries -> pool strictly one after the other"
     return (f"aat_b200.pipeline.TokenizerPipeline, {depth} plans on {depth} streams: boundaries and pool of one batch overlap "
-            f"the log-mel of the next")
+            f"the log-mel of the next; steps on recurring input buffers are replayed from CUDA graphs")
 
 
 def pool_traffic(name):
@@ -625,7 +627,8 @@ def run_c5(torch, dist, tok, rank, local_rank, world, args):
     chunk = min(64, per_rank)  # 4096 utterances: 4.2 GB of waveforms + 10 GB of embeddings per chunk
     rows_ub = B * hubert_rows_upper_bound(N)
     batch = tok.plan([N] * B)  # generator layout + the audit's plan
-    pipe = TokenizerPipeline(tok, [N] * B, D, depth=args.depth if args.depth > 0 else None, device=local_rank)
+    # fresh buffers every chunk: nothing to replay, the steps are launched kernel by kernel
+    pipe = TokenizerPipeline(tok, [N] * B, D, depth=args.depth if args.depth > 0 else None, device=local_rank, graphs=False)
     waves = torch.empty(chunk, batch.total_samples, dtype=torch.float32, device=dev)
     embs = torch.empty(chunk, rows_ub, D, dtype=torch.float32, device=dev)
     out = torch.empty(batch.total_seg_slots, D, device=dev)

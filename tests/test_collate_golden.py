@@ -218,3 +218,29 @@ def test_gpu_w2v2_normalisation_against_the_live_feature_extractor():
         np.testing.assert_allclose(got[o0:o1].cpu().numpy(), live[b], rtol=2e-6, atol=2e-6)
         np.testing.assert_allclose(padded[b, : w.size].cpu().numpy(), live[b], rtol=2e-6, atol=2e-6)
         assert not padded[b, w.size:].any() and int(mask[b].sum()) == w.size
+
+
+@pytest.mark.gpu
+def test_gpu_mel_tiles_from_column_slices_match_the_port():
+    """aat_scatter_mel_tiles on VIEWS (first element, columns, row stride per utterance): the cropped mels of the n-word
+    path are column slices of the full ones (ref:src/aat/training/collate.py:208-212) and are not copied."""
+    from aat_b200 import AdaptiveAudioAmplitudeTokenizer
+
+    rng = np.random.default_rng(8)
+    tok = AdaptiveAudioAmplitudeTokenizer()
+    batch = tok.plan([16000])  # only lends its context and mel count
+    full = [rng.standard_normal((64, t)).astype(np.float32) for t in (500, 301, 777)]
+    rngs = [(17, 480), (0, 301), (400, 777)]
+    views = [m[:, lo:hi] for m, (lo, hi) in zip(full, rngs)]
+    boarders = [np.cumsum(rng.integers(2000, 20000, size=k)) for k in (4, 2, 5)]
+    # keep every slice inside its view: the last boarder // 160 must not exceed the view's columns
+    boarders = [b[b // 160 <= v.shape[1]] for b, v in zip(boarders, views)]
+    padded, _ = collate_port.make_padded_segments_boarders(boarders, 3)
+    n_max = int(padded.max())
+    _, _, want = collate_port.scatter_segments(torch.zeros(3, n_max), padded, 24000, items_melspecs=views)
+    flat = torch.cat([torch.from_numpy(m).reshape(-1) for m in full]).cuda()
+    base = np.concatenate([[0], np.cumsum([m.size for m in full])[:-1]])
+    dev = lambda v: torch.tensor(np.asarray(v), dtype=torch.int64, device="cuda")  # noqa: E731
+    got = collate.scatter_mel_tiles(batch, flat, dev([b + lo for b, (lo, _) in zip(base, rngs)]),
+                                    dev([hi - lo for lo, hi in rngs]), dev([m.shape[1] for m in full]), padded.cuda(), 24000)
+    assert np.array_equal(got.cpu().numpy(), want.numpy())

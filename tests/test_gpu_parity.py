@@ -740,8 +740,9 @@ def test_pool_flags_row_count_from_the_device_and_early_fetch(tok):
 
 def test_pipelined_steps_match_serial_steps(tok):
     """aat_b200.pipeline.TokenizerPipeline: with 2 or 3 plans on as many streams (boundaries and pool of one batch
-    overlapping the log-mel of the next) every step gives bit for bit what the strictly serial loop gives, with and
-    without the fused z-score; the dataset mean agrees to float64 rounding (the slots' sums are added in another order)."""
+    overlapping the log-mel of the next), steps replayed from CUDA graphs when their input buffers come round again,
+    every step gives bit for bit what the strictly serial, kernel-by-kernel loop gives, with and without the fused
+    z-score; the dataset mean agrees to float64 rounding (the slots' sums are added in another order)."""
     import torch
 
     from aat_b200 import synth
@@ -757,9 +758,9 @@ def test_pipelined_steps_match_serial_steps(tok):
     for znorm in (False, True):
         results = {}
         for depth in (1, 2, 3, -3):  # -3: three batches in flight, amplitude curve by the separate pass
-            pipe = TokenizerPipeline(tok, lengths, dim, depth=abs(depth), fused_amp=depth > 0)
+            pipe = TokenizerPipeline(tok, lengths, dim, depth=abs(depth), fused_amp=depth > 0, graphs=abs(depth) > 1)
             got = []
-            for it in range(11):
+            for it in range(21):  # every (slot, input set) pair comes round again: captured and replayed CUDA graphs
                 k = it % 5
                 slot = pipe.submit(sets[k], embs[k], znorm=znorm, rows_from_device=True, inputs_ready=True)
                 with torch.cuda.stream(slot.stream):  # copies ordered behind the step, ahead of the slot's reuse
