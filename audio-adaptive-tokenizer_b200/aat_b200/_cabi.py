@@ -70,6 +70,7 @@ SIGNATURES = {
     "aat_version": (ctypes.c_int, []),
     "aat_last_error": (ctypes.c_char_p, []),
     "aat_kernel_launch_count": (c_i64, []),
+    "aat_kernel_launch_count_add": (None, [c_i64]),
     "aat_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(AatConfig), c_void, c_void, ctypes.POINTER(c_void)]),
     "aat_destroy": (ctypes.c_int, [c_void]),
     "aat_profile_enable": (ctypes.c_int, [c_void, ctypes.c_uint32]),

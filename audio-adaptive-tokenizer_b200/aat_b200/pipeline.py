@@ -15,6 +15,7 @@ from __future__ import annotations
 import ctypes
 from typing import List, Optional, Sequence
 
+from . import _cabi
 from .pooling import DatasetMean
 from .tokenizer import AdaptiveAudioAmplitudeTokenizer, PackedBatch
 
@@ -108,16 +109,19 @@ class TokenizerPipeline:
             if entry is None:
                 if len(slot.graphs) >= 8:  # forget the oldest pattern: the cache is for a handful of rotating buffers
                     slot.graphs.pop(next(iter(slot.graphs)))
-                entry = slot.graphs[key] = [0, None]
+                entry = slot.graphs[key] = [0, None, 0]
             entry[0] += 1
             if entry[1] is None and entry[0] == 2:  # second appearance (everything lazy is set up by now): capture
                 g = torch.cuda.CUDAGraph()
+                before = _cabi.launch_count()
                 with torch.cuda.graph(g, stream=slot.stream, capture_error_mode="thread_local"):
                     self._enqueue(slot, wave, emb, colsum, znorm, rows_from_device, None)  # None: the capturing stream
-                entry[1] = g
+                entry[1], entry[2] = g, _cabi.launch_count() - before  # kernels of the library in the graph
+                _cabi.lib().aat_kernel_launch_count_add(-entry[2])      # captured, not run: every replay counts them
             if entry[1] is not None:
                 with torch.cuda.stream(slot.stream):
                     entry[1].replay()
+                _cabi.lib().aat_kernel_launch_count_add(entry[2])
                 slot.done.record(slot.stream)
                 return slot
         self._enqueue(slot, wave, emb, colsum, znorm, rows_from_device, slot.handle)

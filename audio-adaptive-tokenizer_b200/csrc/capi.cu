@@ -166,6 +166,7 @@ extern "C" {
 int aat_version(void) { return AAT_B200_VERSION; }
 const char *aat_last_error(void) { return g_error; }
 int64_t aat_kernel_launch_count(void) { return g_launch_count.load(); }
+void aat_kernel_launch_count_add(int64_t n) { g_launch_count.fetch_add(n); }
 
 int64_t aat_segment_capacity(const aat_config *cfg, int64_t n_samples)
 {

@@ -93,6 +93,9 @@ int aat_version(void);
 const char *aat_last_error(void);
 /* Number of CUDA kernels this library has launched in the calling process (bench.py's gpu_launches). */
 int64_t aat_kernel_launch_count(void);
+/* A caller that replays a CUDA graph holding n of the library's kernel launches (captured through these entry points,
+ * where they were counted once) reports the replay here, so that the count stays the number of kernels that RAN. */
+void aat_kernel_launch_count_add(int64_t n);
 
 /* ------------------------------------------------------------------ profiling
  * Optional CUDA-event timing of the library's own kernels, recorded on the launching stream
