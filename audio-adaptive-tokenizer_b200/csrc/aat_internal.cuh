@@ -304,6 +304,10 @@ struct ProfileScope {
     {
         Profiler &p = c->prof;
         if (((p.mask >> id) & 1u) && (p.seen[id]++ % p.every) == 0) {
+            // a launch that is being captured into a CUDA graph is not timed (a timing event recorded inside a capture
+            // is a graph node, not a time stamp)
+            cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+            if (cudaStreamIsCapturing(s, &capturing) != cudaSuccess || capturing != cudaStreamCaptureStatusNone) return;
             if (p.used < p.start.size()) {
                 slot = (long)p.used++;
                 p.kernel[slot] = id;

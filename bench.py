@@ -459,6 +459,8 @@ def measure_workload(torch, dist, w, steps, warmup, world, sample_every, no_cols
             dist.barrier()
         torch.cuda.synchronize()
 
+    if pipe.graphs:  # every (slot, buffer set) pair comes round twice in the warm-up: its graph is captured there
+        warmup = max(warmup, 2 * math.lcm(depth, w.R) + 2)
     for i in range(warmup):
         w.step(i, not no_colsum, depth)
     barrier()
