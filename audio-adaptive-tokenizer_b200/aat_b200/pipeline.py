@@ -55,7 +55,7 @@ class TokenizerPipeline:
 
     def __init__(self, tokenizer: AdaptiveAudioAmplitudeTokenizer, n_samples: Sequence[int], dim: int,
                  depth: Optional[int] = None, device=None, priorities: Optional[Sequence[int]] = None,
-                 fused_amp: bool = True, graphs: bool = True):
+                 fused_amp: bool = True, graphs: bool = False):
         import torch
 
         if depth is None:
@@ -74,10 +74,13 @@ class TokenizerPipeline:
         # while the epilogue costs the log-mel kernel — the one kernel nothing hides — a CTA barrier and a serial
         # 64-term chain per tile.
         self.fused_amp = bool(fused_amp)
-        # A step is four kernel launches.  When a slot is handed the same input buffers again (a loader that rotates over a
-        # few device buffers, as any double-buffered loader does) the step is captured into a CUDA graph on its second
-        # appearance and replayed from then on: one graph launch instead of four kernel launches, which matters on hosts
-        # whose launch path is slow (104 us per step against 150 us of device time on the 8-GPU boxes of this pool).
+        # A step is four kernel launches: 32 us of host time on a fast host, 80-104 us on the slower hosts of this pool,
+        # against 150 us of device time at 64 x 16 s.  With ``graphs=True``, when a slot is handed the same input buffers
+        # again (a loader that rotates over a few device buffers, as any double-buffered loader does) the step is captured
+        # into a CUDA graph on its second appearance and replayed from then on: 13 us of host time per step.  Off by
+        # default because the replayed step takes 3-5 % more DEVICE time (0.1556 vs 0.1507 ms at 64 x 16 s, 2.08 vs 1.99 ms
+        # on 30-min streams: the overlap of consecutive kernels by programmatic dependent launch does not survive the
+        # capture); switch it on where the host cannot keep the streams fed.
         self.graphs = bool(graphs)
         self._reduced = False  # dataset_mean() has folded (and allreduced) the sums: reset_sums() before the next pass
 

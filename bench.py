@@ -331,7 +331,7 @@ class Workload:
     """One BASELINE config resident on one GPU: R rotating buffer sets of distinct, device-generated utterances with
     the embeddings their own segmentation calls for, and the step that runs the path over one set."""
 
-    def __init__(self, torch, tok, name, rank, local_rank, rotate, depth=0, fused_amp=True):
+    def __init__(self, torch, tok, name, rank, local_rank, rotate, depth=0, fused_amp=True, graphs=False):
         from aat_b200 import synth
         from aat_b200.pipeline import TokenizerPipeline
 
@@ -359,9 +359,11 @@ class Workload:
         # the step runs through the public pipeline object: `depth` plans on `depth` streams, so that the boundary scan
         # and the pool of one batch overlap the log-mel of the next (depth 1 = strictly serial, kept for the A/B)
         self.depth = depth = depth if depth > 0 else TokenizerPipeline.default_depth([self.N] * B)
-        # the pipelined schedule replays each slot's step from a CUDA graph (the rotating input buffers come round again);
-        # the strictly serial one launches kernel by kernel, as round 1's step did (and so that kernels can be event-timed)
-        self.pipes = {d: TokenizerPipeline(tok, [self.N] * B, D, depth=d, device=local_rank, fused_amp=fused_amp, graphs=d > 1)
+        # with --graphs the pipelined schedule replays each slot's step from a CUDA graph (the rotating input buffers come
+        # round again); the strictly serial one always launches kernel by kernel, as round 1's step did (and so that
+        # kernels can be event-timed)
+        self.pipes = {d: TokenizerPipeline(tok, [self.N] * B, D, depth=d, device=local_rank, fused_amp=fused_amp,
+                                           graphs=d > 1 and graphs)
                       for d in sorted({1, depth})}
         self.audio_hours_per_step = B * self.N / 16000 / 3600
         self.pool_bytes = float(np.mean([r * D * 4 + s * D * 4 + (s + 1) * 8 for r, s in zip(self.n_rows, self.n_seg)]))
@@ -544,7 +546,7 @@ def schedule_note(depth):
     if depth == 1:
         return "one plan, one stream: log-mel -> boundaries -> pool strictly one after the other"
     return (f"aat_b200.pipeline.TokenizerPipeline, {depth} plans on {depth} streams: boundaries and pool of one batch overlap "
-            f"the log-mel of the next; steps on recurring input buffers are replayed from CUDA graphs")
+            f"the log-mel of the next")
 
 
 def pool_traffic(name):
@@ -558,7 +560,7 @@ def sub_record(torch, dist, tok, name, rank, local_rank, world, args):
     """configs[...] sub-record of another BASELINE config, same machinery as the headline at fewer steps."""
     from aat_b200 import _cabi
 
-    w = Workload(torch, tok, name, rank, local_rank, args.rotate, args.depth)
+    w = Workload(torch, tok, name, rank, local_rank, args.rotate, args.depth, graphs=args.graphs)
     steps = {"c3": 200, "c4": 60, "c2": 500}[name]
     m = measure_workload(torch, dist, w, steps, 5, world, args.pool_sample_every)
     serial = measure_workload(torch, dist, w, steps, 5, world, args.pool_sample_every, depth=1, breakdown=False)
@@ -748,7 +750,7 @@ def run_b200(args):
             os.close(saved)
 
     tok = AdaptiveAudioAmplitudeTokenizer(device=local_rank)
-    w = Workload(torch, tok, args.workload, rank, local_rank, args.rotate, args.depth, not args.unfused_amp)
+    w = Workload(torch, tok, args.workload, rank, local_rank, args.rotate, args.depth, not args.unfused_amp, args.graphs)
     sampler = ClockSampler(local_rank)
     sampler.start()
     m = measure_workload(torch, dist, w, args.steps, args.warmup, world, args.pool_sample_every, args.no_colsum, sampler)
@@ -941,6 +943,9 @@ def main():
     ap.add_argument("--depth", type=int, default=0,
                     help="batches in flight (plans x streams) of the step's pipeline; 1 = serial, 0 = the pipeline's own default")
     ap.add_argument("--unfused-amp", action="store_true", help="amplitude curve by the separate pass (aat_amplitude) instead of the log-mel kernel's epilogue")
+    ap.add_argument("--graphs", action="store_true",
+                    help="replay the pipelined steps from CUDA graphs (14 instead of 32-100 us of host time per step, 3 %% more "
+                         "device time: for hosts whose launch path cannot keep up)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-configs", action="store_true", help="skip the c1/c3/c4/c5 sub-records (profiling runs)")

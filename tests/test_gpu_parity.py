@@ -757,8 +757,10 @@ def test_pipelined_steps_match_serial_steps(tok):
     first_mel = {}
     for znorm in (False, True):
         results = {}
-        for depth in (1, 2, 3, -3):  # -3: three batches in flight, amplitude curve by the separate pass
-            pipe = TokenizerPipeline(tok, lengths, dim, depth=abs(depth), fused_amp=depth > 0, graphs=abs(depth) > 1)
+        # (batches in flight, amplitude curve from the fused epilogue, steps replayed from CUDA graphs)
+        variants = {1: (1, True, False), 2: (2, True, True), 3: (3, True, True), -3: (3, False, True), 4: (4, True, False)}
+        for depth, (n_slots, fused_amp, graphs) in variants.items():
+            pipe = TokenizerPipeline(tok, lengths, dim, depth=n_slots, fused_amp=fused_amp, graphs=graphs)
             got = []
             for it in range(21):  # every (slot, input set) pair comes round again: captured and replayed CUDA graphs
                 k = it % 5
@@ -777,7 +779,7 @@ def test_pipelined_steps_match_serial_steps(tok):
             torch.cuda.synchronize()
         ref_steps, ref_acc, ref_mean = results[1]
         assert int(ref_acc[dim].item()) == sum(int(g[4][0].item()) for g in ref_steps)
-        for depth in (2, 3, -3):
+        for depth in (2, 3, -3, 4):
             steps, acc, mean = results[depth]
             for it, (a, b) in enumerate(zip(ref_steps, steps)):
                 n_seg = int(a[4][0].item())
