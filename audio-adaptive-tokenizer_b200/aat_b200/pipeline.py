@@ -92,12 +92,13 @@ class TokenizerPipeline:
             slot.stream.wait_stream(cur)
 
     def submit(self, wave, emb, colsum: bool = True, znorm: bool = False, rows_from_device: bool = False,
-               inputs_ready: bool = False) -> _Slot:
+               inputs_ready: bool = False, record_done: bool = True) -> _Slot:
         """One step over one batch on the next slot's stream.  ``wave`` / ``emb`` must be ready on the CALLER's current
         stream: the slot's stream is made to wait for it, unless ``inputs_ready`` says they have been for long (resident
         inputs, or after :meth:`fork`) — an event wait between two steps of a slot costs the overlap of the second
         step's first kernel with the first step's last.  ``znorm`` applies the call sites' z-score inside the log-mel
-        kernel; ``rows_from_device`` as in :meth:`PackedBatch.pool`."""
+        kernel; ``rows_from_device`` as in :meth:`PackedBatch.pool`.  ``record_done=False`` skips the ``slot.done`` event for
+        callers that only consume the dataset mean (or order consumers with ``stream.wait_stream(slot.stream)``)."""
         torch = self.torch
         if colsum and self._reduced:
             raise RuntimeError("the running sums were folded and allreduced by dataset_mean(); call reset_sums() before "
@@ -125,10 +126,12 @@ class TokenizerPipeline:
                 with torch.cuda.stream(slot.stream):
                     entry[1].replay()
                 _cabi.lib().aat_kernel_launch_count_add(entry[2])
-                slot.done.record(slot.stream)
+                if record_done:
+                    slot.done.record(slot.stream)
                 return slot
         self._enqueue(slot, wave, emb, colsum, znorm, rows_from_device, slot.handle)
-        slot.done.record(slot.stream)
+        if record_done:
+            slot.done.record(slot.stream)
         return slot
 
     def _enqueue(self, slot, wave, emb, colsum, znorm, rows_from_device, st):

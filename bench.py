@@ -370,8 +370,9 @@ class Workload:
 
     def step(self, i, colsum=True, depth=None):
         s = i % self.R
+        # results stay on the device in this loop (that is what `value` measures; `e2e` reads them back): no per-step event
         self.pipes[self.depth if depth is None else depth].submit(self.wave_sets[s], self.emb_sets[s], colsum=colsum,
-                                                                   inputs_ready=True)
+                                                                   inputs_ready=True, record_done=False)
 
     def expected_sums(self, uses):
         """Independent reduction of what `steps` steps must have accumulated: the pooled vectors of every buffer set
@@ -650,7 +651,7 @@ def run_c5(torch, dist, tok, rank, local_rank, world, args):
         pipe.fork()  # the slots' streams start behind the generation (and behind the timing event)
         for k in range(n):
             # embeddings are an allocation of the upper-bound row count: the rows the segments cover are read on the device
-            pipe.submit(waves[k], embs[k], rows_from_device=True, inputs_ready=True)
+            pipe.submit(waves[k], embs[k], rows_from_device=True, inputs_ready=True, record_done=False)
         pipe.join()
 
     # warm-up on the first chunk's first batches (untimed), then reset the accumulators
