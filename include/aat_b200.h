@@ -242,6 +242,9 @@ int aat_segment_mean_pool(aat_ctx *ctx, const aat_plan *plan, const void *emb_de
                           float *out_dev, double *colsum_dev, int flags, void *stream);
 
 /* ------------------------------------------------------------------ one step in one call
+ * What the reference's offline job does per item — tokenize (ref:scripts/audio_tokenization.py:33-41, with the z-score of
+ * ref:scripts/audio_tokenization_melspec.py:40 when `znorm`) and pool its embeddings
+ * (ref:scripts/mean_hubert_embeddings.py:16-23) — for a whole batch:
  * aat_logmel (with the fused z-score when `znorm` is non-zero: statistics by aat_normalize into bufs->znorm_stats
  * first) -> aat_boundaries (with the packed frame CSR) -> aat_segment_mean_pool, enqueued back to back on `stream`:
  * exactly the launches the separate calls make, for loops that drive many steps per second from an interpreted host
