@@ -62,17 +62,23 @@ struct KernelSetup {
 
 // The dense (bins, mels) float64 filter bank in the banded form the log-mel kernel walks.  Every filter covers a
 // run of consecutive bins.  In the kernel thread (frame f, group q) evaluates the filters q, q + kMelGroups, ... of
-// its frame and keeps the sums in registers until their log10 is taken; the two groups that share a warp (q even and
-// q + 1) own neighbouring filters, whose runs are zero-padded to a common even length so that the fully unrolled
-// tap loops have warp-uniform trip counts.
+// its frame.  The taps of a group are ONE stream of chunks of four (weights zero-padded to whole chunks), so the kernel
+// runs a single rolled loop per thread with the next chunk's operands in flight, instead of dispatching on every
+// filter's length.  A chunk's descriptor says where the NEXT chunk's power values start and whether this chunk ends a
+// filter.  The two groups that share a warp (q even and q + 1) own neighbouring filters, which are padded to a common
+// chunk count so that the end-of-filter branch is warp-uniform.
 constexpr int kMelGroups = 10;    // thread groups of the mel phase (160 threads / 16 frames)
+constexpr int kMelChunk = 4;      // taps per chunk = independent FMA chains per filter
+constexpr int kMelDescHeader = 32; // uint16 header: per group q [3q] first chunk, [3q+1] chunks, [3q+2] first bin
+constexpr uint16_t kMelDescLast = 0x8000; // descriptor bit: the chunk is the last one of its filter (bits 0-7: next bin)
 constexpr int kMelMaxWeights = 1536; // padded weights that fit the kernel's shared-memory budget at two CTAs per SM
 struct MelSchedule {
     int n_mels = 0;
     int nnz = 0;        // total band length of the filters
-    int n_weights = 0;  // padded weights (doubles, even per filter)
-    uint32_t *filter_desc = nullptr; // device [n_mels]: (weight pair offset << 16) | (tap pairs << 8) | first bin
-    double *weight = nullptr;        // device [n_weights]
+    int n_weights = 0;  // padded weights (doubles): kMelChunk per chunk, one chunk of padding at the end
+    int n_desc = 0;     // uint16 entries of chunk_desc: header + one per chunk + 2 of padding
+    uint16_t *chunk_desc = nullptr; // device [n_desc]
+    double *weight = nullptr;       // device [n_weights], group-major chunk streams
 };
 
 // One tile (kMelFramesPerTile consecutive frames of one utterance) of the log-mel kernel.

@@ -97,8 +97,8 @@ struct Arena {
     }
 };
 
-// dense (bins, mels) -> banded rows (see MelSchedule).  Filter m covers bins [first_m, last_m] (its first and last
-// non-zero weight; interior zeros are kept so the run stays contiguous).
+// dense (bins, mels) -> per-group chunk streams (see MelSchedule).  Filter m covers bins [first_m, last_m] (its first
+// and last non-zero weight; interior zeros are kept so the run stays contiguous), zero-padded to whole chunks of four taps.
 int build_mel_schedule(aat_ctx *ctx, const double *filters)
 {
     const int M = ctx->cfg.num_mel_filters;
@@ -114,33 +114,51 @@ int build_mel_schedule(aat_ctx *ctx, const double *filters)
     }
     // an empty filter (band above Nyquist) is one zero tap at bin 0: 0 * NaN stays NaN as in the reference's dense product
     auto len_of = [&](int m) { return lo[m] < 0 ? 1 : hi[m] - lo[m] + 1; };
-    std::vector<uint32_t> desc(M, 0);
+    std::vector<uint16_t> desc(kMelDescHeader, 0);
     std::vector<double> weights;
-    for (int m = 0; m < M; ++m) {
-        // the filter evaluated by the other half of the warp: groups q (even) and q + 1 sit in one warp
-        const int q = m % kMelGroups;
-        const int partner = (q % 2 == 0) ? m + 1 : m - 1;
-        int L = len_of(m);
-        if (partner >= 0 && partner < M && partner / kMelGroups == m / kMelGroups && len_of(partner) > L) L = len_of(partner);
-        L = (L + 1) & ~1;
-        const int first = lo[m] < 0 ? 0 : lo[m];
-        const int start = (first + L <= kBins) ? first : kBins - L;
-        AAT_REQUIRE(start >= 0, AAT_ERR_UNSUPPORTED, "aat_create: mel filter %d is wider than the spectrum", m);
-        const size_t at = weights.size();
-        weights.resize(at + L, 0.0);
-        if (lo[m] >= 0)
-            for (int k = lo[m]; k <= hi[m]; ++k) weights[at + (k - start)] = filters[(size_t)k * M + m];
-        AAT_REQUIRE(weights.size() <= (size_t)kMelMaxWeights, AAT_ERR_UNSUPPORTED,
-                    "aat_create: the mel filter bank is too dense for the log-mel kernel (more than %d banded weights)",
-                    kMelMaxWeights);
-        desc[m] = ((uint32_t)(at / 2) << 16) | ((uint32_t)(L / 2) << 8) | (uint32_t)start;
+    for (int q = 0; q < kMelGroups; ++q) {
+        const size_t first_chunk = weights.size() / kMelChunk;
+        int prev_desc = -1; // index of the last chunk written for this group: it learns where the next chunk starts
+        for (int m = q; m < M; m += kMelGroups) {
+            // the filter evaluated by the other half of the warp: groups q (even) and q + 1 sit in one warp
+            const int partner = (q % 2 == 0) ? m + 1 : m - 1;
+            int L = len_of(m);
+            if (partner >= 0 && partner < M && partner / kMelGroups == m / kMelGroups && len_of(partner) > L) L = len_of(partner);
+            L = (L + kMelChunk - 1) / kMelChunk * kMelChunk;
+            const int first = lo[m] < 0 ? 0 : lo[m];
+            // padding taps must read this frame's own (finite) power values: a run that would cross the last bin moves left
+            const int start = (first + L <= kBins) ? first : kBins - L;
+            AAT_REQUIRE(start >= 0, AAT_ERR_UNSUPPORTED, "aat_create: mel filter %d is wider than the spectrum", m);
+            const size_t at = weights.size();
+            weights.resize(at + L, 0.0);
+            if (lo[m] >= 0)
+                for (int k = lo[m]; k <= hi[m]; ++k) weights[at + (k - start)] = filters[(size_t)k * M + m];
+            for (int c = 0; c < L / kMelChunk; ++c) {
+                const int bin = start + c * kMelChunk;
+                if (prev_desc < 0)
+                    desc[3 * q + 2] = (uint16_t)bin;
+                else
+                    desc[prev_desc] |= (uint16_t)bin;
+                prev_desc = (int)desc.size();
+                desc.push_back(c + 1 == L / kMelChunk ? kMelDescLast : 0);
+            }
+        }
+        desc[3 * q + 0] = (uint16_t)first_chunk;
+        desc[3 * q + 1] = (uint16_t)(weights.size() / kMelChunk - first_chunk);
     }
+    // the kernel fetches one chunk (and its descriptor) ahead of the one it is adding up
+    weights.resize(weights.size() + kMelChunk, 0.0);
+    desc.resize(desc.size() + 2, 0);
+    AAT_REQUIRE(weights.size() <= (size_t)kMelMaxWeights, AAT_ERR_UNSUPPORTED,
+                "aat_create: the mel filter bank is too dense for the log-mel kernel (more than %d banded weights)",
+                kMelMaxWeights);
     MelSchedule &ms = ctx->mel;
     ms.n_mels = M;
     ms.nnz = nnz;
     ms.n_weights = (int)weights.size();
+    ms.n_desc = (int)desc.size();
     int rc;
-    if ((rc = upload(&ms.filter_desc, desc.data(), desc.size()))) return rc;
+    if ((rc = upload(&ms.chunk_desc, desc.data(), desc.size()))) return rc;
     if ((rc = upload(&ms.weight, weights.data(), weights.size()))) return rc;
     return AAT_OK;
 }
@@ -257,7 +275,7 @@ int aat_destroy(aat_ctx *ctx)
     cudaFree(ctx->window_half);
     cudaFree(ctx->twiddle);
     cudaFree(ctx->log_table);
-    cudaFree(ctx->mel.filter_desc);
+    cudaFree(ctx->mel.chunk_desc);
     cudaFree(ctx->mel.weight);
     pool_scratch_free(&ctx->pool);
     if (ctx->pool_done) cudaEventDestroy(ctx->pool_done);

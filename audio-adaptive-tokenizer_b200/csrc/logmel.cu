@@ -194,12 +194,13 @@ struct LogmelParams {
     const double *window_half;
     const double2 *twiddle;
     const double2 *log_table;
-    const uint32_t *filter_desc;
+    const uint16_t *chunk_desc;
     const double *mel_weight;
     int n_tiles;
     int hop;
     int n_mels;
     int n_weights;
+    int n_desc;    // uint16 entries of chunk_desc
     int stage_len; // (kFrames - 1) * hop + 400
     int stage_pad; // stage_len rounded up to 16 bytes worth of samples
     int *sched;    // [2] dynamic tile counter, exit counter (both left at zero by the last CTA to exit)
@@ -221,7 +222,7 @@ struct SmemLayout {
     size_t ex, raw, tw, logt, mw, fdesc, tiles, next, mel, acc, total;
 };
 
-__host__ __device__ inline SmemLayout smem_layout(int raw_elems, int wave_bytes, int n_mels, int n_weights)
+__host__ __device__ inline SmemLayout smem_layout(int raw_elems, int wave_bytes, int n_desc, int n_weights)
 {
     SmemLayout L{};
     size_t o = 0;
@@ -239,7 +240,7 @@ __host__ __device__ inline SmemLayout smem_layout(int raw_elems, int wave_bytes,
     L.tw = take(sizeof(double2) * kTwiddles);
     L.logt = take(sizeof(double2) * kLogTable * kLogCopies);
     L.mw = take(sizeof(double) * n_weights);
-    L.fdesc = take(sizeof(uint32_t) * n_mels);
+    L.fdesc = take(sizeof(uint16_t) * n_desc);
     L.tiles = take(sizeof(MelTile) * kTileRing);
     L.next = take(sizeof(int)); // the tile id thread 0 grabbed during the current tile
     L.total = o;
@@ -249,65 +250,6 @@ static_assert(sizeof(double) * kFrames * kPowStride + sizeof(float) * kFrames * 
                       sizeof(double) * ((kMaxMels + kMelGroups - 1) / kMelGroups) * kThreads <=
                   sizeof(double2) * kPairs * kPairStride,
               "power spectra + float32 mel tile + staged filter sums must fit in the exchange matrix");
-
-// One band of kTapPairs * 2 taps: four independent FMA chains (explicit _rn: no contraction of the final additions,
-// so the sum does not depend on the compiler's mood).
-template <int kTapPairs>
-__device__ __forceinline__ double band(const double2 *__restrict__ w2, const double *__restrict__ pw)
-{
-    double2 w = w2[0];
-    double a0 = __dmul_rn(w.x, pw[0]), a1 = __dmul_rn(w.y, pw[1]);
-    if (kTapPairs == 1) return __dadd_rn(a0, a1);
-    w = w2[1];
-    double a2 = __dmul_rn(w.x, pw[2]), a3 = __dmul_rn(w.y, pw[3]);
-#pragma unroll
-    for (int i = 2; i < kTapPairs; ++i) {
-        w = w2[i];
-        if (i & 1) {
-            a2 = fma(w.x, pw[2 * i], a2);
-            a3 = fma(w.y, pw[2 * i + 1], a3);
-        } else {
-            a0 = fma(w.x, pw[2 * i], a0);
-            a1 = fma(w.y, pw[2 * i + 1], a1);
-        }
-    }
-    return __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
-}
-
-// Runtime tap count (warp-uniform by construction of the schedule) -> the unrolled instance.  One call site (a rolled
-// loop over the thread's filters): ten unrolled bodies per slot of the unrolled log batch would not fit the instruction
-// cache, and an out-of-line function costs ~25 instructions of argument / live-register shuffling per call.
-__device__ __forceinline__ double band_sum(int tap_pairs, const double2 *__restrict__ w2, const double *__restrict__ pw)
-{
-    switch (tap_pairs) {
-    case 1: return band<1>(w2, pw);
-    case 2: return band<2>(w2, pw);
-    case 3: return band<3>(w2, pw);
-    case 4: return band<4>(w2, pw);
-    case 5: return band<5>(w2, pw);
-    case 6: return band<6>(w2, pw);
-    case 7: return band<7>(w2, pw);
-    case 8: return band<8>(w2, pw);
-    case 9: return band<9>(w2, pw);
-    case 10: return band<10>(w2, pw);
-    default: break;
-    }
-    // wider filters (coarse banks): same four chains, rolled
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    for (int i = 0; i + 1 < tap_pairs; i += 2) {
-        const double2 w = w2[i], u = w2[i + 1];
-        a0 = fma(w.x, pw[2 * i], a0);
-        a1 = fma(w.y, pw[2 * i + 1], a1);
-        a2 = fma(u.x, pw[2 * i + 2], a2);
-        a3 = fma(u.y, pw[2 * i + 3], a3);
-    }
-    if (tap_pairs & 1) {
-        const double2 w = w2[tap_pairs - 1];
-        a0 = fma(w.x, pw[2 * tap_pairs - 2], a0);
-        a1 = fma(w.y, pw[2 * tap_pairs - 1], a1);
-    }
-    return __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
-}
 
 // First / last tiles of an utterance (and unaligned ones): element-wise copies with np.pad(mode="reflect")
 // index arithmetic (TF:audio_utils.py:769-771).  Rare, so out of line: the 64-bit modulo is bulky.
@@ -329,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int kGap = kHop160 ? raw_gap<WaveT>() : 0;
-    const SmemLayout L = smem_layout(raw_elems(p.stage_pad, kGap), (int)sizeof(WaveT), p.n_mels, p.n_weights);
+    const SmemLayout L = smem_layout(raw_elems(p.stage_pad, kGap), (int)sizeof(WaveT), p.n_desc, p.n_weights);
     double2 *s_ex = reinterpret_cast<double2 *>(smem_raw + L.ex);
     double *s_pow = reinterpret_cast<double *>(smem_raw + L.ex);
     WaveT *s_rawbuf = reinterpret_cast<WaveT *>(smem_raw + L.raw);
@@ -337,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
     double2 *s_tw = reinterpret_cast<double2 *>(smem_raw + L.tw);
     double2 *s_logt = reinterpret_cast<double2 *>(smem_raw + L.logt);
     double *s_mw = reinterpret_cast<double *>(smem_raw + L.mw);
-    uint32_t *s_fdesc = reinterpret_cast<uint32_t *>(smem_raw + L.fdesc);
+    uint16_t *s_cdesc = reinterpret_cast<uint16_t *>(smem_raw + L.fdesc);
     MelTile *s_tiles = reinterpret_cast<MelTile *>(smem_raw + L.tiles);
     int *s_next = reinterpret_cast<int *>(smem_raw + L.next);
     float *s_mel = reinterpret_cast<float *>(smem_raw + L.mel);
@@ -366,8 +308,20 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
             const int64_t src = d.src;
             if (d.interior && wave_aligned && (src & (kVec - 1)) == 0) {
                 const WaveT *from = wave + src;
-                for (int i = tid * kVec; i < p.stage_pad; i += kThreads * kVec)
-                    cp_async<16>(s_rawbuf + i + kGap * (i / kRawBlock), from + i);
+                if constexpr (kHop160) {
+                    // 2 800 samples: the trip count and the gap of every copy are known at compile time
+                    constexpr int kStage = (kFrames - 1) * 160 + kNfft;
+                    constexpr int kPerBlock = kRawBlock / kVec; // 16-byte copies per 320-sample block
+                    static_assert(kStage % kVec == 0 && kThreads % kPerBlock == 0, "staging geometry");
+                    const int at = tid * kVec + kGap * (tid / kPerBlock);
+#pragma unroll
+                    for (int k = 0; k * kThreads * kVec < kStage; ++k)
+                        if ((k + 1) * kThreads * kVec <= kStage || (tid + k * kThreads) * kVec < kStage)
+                            cp_async<16>(s_rawbuf + at + k * (kThreads * kVec + kGap * (kThreads / kPerBlock)),
+                                         from + (tid + k * kThreads) * kVec);
+                } else {
+                    for (int i = tid * kVec; i < p.stage_pad; i += kThreads * kVec) cp_async<16>(s_rawbuf + i, from + i);
+                }
             } else {
                 fetch_edge_tile<WaveT>(s_rawbuf, wave + d.wave_off, src - d.wave_off, d.n, p.stage_len, kGap, tid);
             }
@@ -382,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
     for (int i = tid; i < kTwiddles; i += kThreads) s_tw[i] = p.twiddle[i];
     for (int i = tid; i < kLogTable * kLogCopies; i += kThreads) s_logt[i] = p.log_table[i / kLogCopies];
     for (int i = tid; i < p.n_weights; i += kThreads) s_mw[i] = p.mel_weight[i];
-    for (int i = tid; i < p.n_mels; i += kThreads) s_fdesc[i] = p.filter_desc[i];
+    for (int i = tid; i < p.n_desc; i += kThreads) s_cdesc[i] = p.chunk_desc[i];
     cp_async_wait<0>();
     __syncthreads();
     // everything above reads tables that no kernel writes; the samples may come from the previous kernel
@@ -519,22 +473,50 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
             constexpr int kMaxPerThread = (kMaxMels + kMelGroups - 1) / kMelGroups;
             constexpr int kBatch = 7; // filters whose logs are evaluated together (7 x 10 groups covers 64..70 filters)
             const double *pw = s_pow + f * kPowStride;
-            const double2 *w2 = reinterpret_cast<const double2 *>(s_mw);
             float *dst = p.mel + cur.mel_off + f;
             const bool live = f < cur.valid;
             const size_t T = (size_t)cur.T;
             float *smel = s_mel + f * mel_stride;
-            // projection: a rolled loop (one copy of the unrolled tap bodies); the floored sums wait in the thread's own
-            // shared-memory slots for the unrolled log batch below
-            double *my_acc = s_acc + tid;
-            uint32_t d_next = n_mine > 0 ? s_fdesc[q] : 0u; // descriptors run one filter ahead of the taps
-#pragma unroll 1
-            for (int i = 0; i < n_mine; ++i) {
-                const uint32_t d = d_next;
-                if (i + 1 < n_mine) d_next = s_fdesc[q + (i + 1) * kMelGroups];
-                const double acc = band_sum((int)((d >> 8) & 0xffu), w2 + (d >> 16), pw + (d & 0xffu));
-                my_acc[i * kThreads] = (acc < 1e-10) ? 1e-10 : acc; // np.maximum(mel_floor, .): NaN propagates
+            // projection: ONE rolled loop over the chunk stream of this thread's group (four taps per chunk = four
+            // independent FMA chains, explicit fma / _rn so that the sums do not depend on the compiler's mood).  The
+            // operands of chunk c + 1 are fetched before chunk c is added up; a chunk that ends a filter reduces the
+            // chains ((a0 + a1) + (a2 + a3)), floors the sum and parks it in the thread's own shared-memory slot for
+            // the unrolled log batch below.  Zero weights pad a filter to whole chunks: they read this frame's own
+            // power values, so they add exact zeros (or keep a NaN frame NaN).
+            {
+                double *my_acc = s_acc + tid;
+                const uint32_t first_chunk = s_cdesc[3 * q], n_chunks = s_cdesc[3 * q + 1];
+                const uint16_t *cd = s_cdesc + kMelDescHeader + first_chunk;
+                const double2 *w2 = reinterpret_cast<const double2 *>(s_mw) + 2 * first_chunk;
+                const double *pp = pw + s_cdesc[3 * q + 2];
+                double2 wa = w2[0], wb = w2[1];
+                double p0 = pp[0], p1 = pp[1], p2 = pp[2], p3 = pp[3];
+                uint32_t d = cd[0];
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 2
+                for (uint32_t c = 0; c < n_chunks; ++c) {
+                    w2 += 2;
+                    ++cd;
+                    const double2 nwa = w2[0], nwb = w2[1];
+                    const double *pn = pw + (d & 0xffu);
+                    const double n0 = pn[0], n1 = pn[1], n2 = pn[2], n3 = pn[3];
+                    const uint32_t dn = cd[0];
+                    a0 = fma(wa.x, p0, a0);
+                    a1 = fma(wa.y, p1, a1);
+                    a2 = fma(wb.x, p2, a2);
+                    a3 = fma(wb.y, p3, a3);
+                    if (d & kMelDescLast) {
+                        const double acc = __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
+                        *my_acc = (acc < 1e-10) ? 1e-10 : acc; // np.maximum(mel_floor, .): NaN propagates
+                        my_acc += kThreads;
+                        a0 = a1 = a2 = a3 = 0.0;
+                    }
+                    wa = nwa, wb = nwb;
+                    p0 = n0, p1 = n1, p2 = n2, p3 = n3;
+                    d = dn;
+                }
             }
+            const double *my_acc = s_acc + tid;
 #pragma unroll
             for (int i0 = 0; i0 < kMaxPerThread; i0 += kBatch) {
                 if (i0 < n_mine) {
@@ -573,9 +555,22 @@ __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams 
         if (p.amp != nullptr) {
             __syncthreads();
             if (tid < kFrames && tid < cur.valid) {
+                // The additions are one dependent chain, the loads are not: batches of 21 loads are in flight together
+                // (64 filters = the first term + three batches); a rolled loop paid a shared-memory round trip every
+                // four terms.  -0.8 us per config-2 launch (profiles/r2_logmel_ab.txt).
                 const float *col = s_mel + tid * mel_stride;
+                const int n = p.n_mels;
                 float acc = col[0];
-                for (int m = 1; m < p.n_mels; ++m) acc = __fadd_rn(acc, col[m]);
+                int m = 1;
+#pragma unroll 1
+                for (; m + 21 <= n; m += 21) {
+                    float v[21];
+#pragma unroll
+                    for (int k = 0; k < 21; ++k) v[k] = col[m + k];
+#pragma unroll
+                    for (int k = 0; k < 21; ++k) acc = __fadd_rn(acc, v[k]);
+                }
+                for (; m < n; ++m) acc = __fadd_rn(acc, col[m]);
                 const float mean = __fdiv_rn(acc, (float)p.n_mels);
                 p.amp[cur.amp_off + tid] = __fmul_rn(-10.0f, mean);
             }
@@ -630,12 +625,13 @@ int launch_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave, int wave
     p.window_half = ctx->window_half;
     p.twiddle = ctx->twiddle;
     p.log_table = ctx->log_table;
-    p.filter_desc = ctx->mel.filter_desc;
+    p.chunk_desc = ctx->mel.chunk_desc;
     p.mel_weight = ctx->mel.weight;
     p.n_tiles = plan->mel_tiles;
     p.hop = ctx->cfg.hop_length;
     p.n_mels = ctx->mel.n_mels;
     p.n_weights = ctx->mel.n_weights;
+    p.n_desc = ctx->mel.n_desc;
     p.K = kLogmelConsts;
     p.sched = plan->d_mel_sched;
     p.stage_len = (kFrames - 1) * p.hop + kNfft;
@@ -644,7 +640,7 @@ int launch_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave, int wave
     p.stage_pad = (p.stage_len + vec - 1) / vec * vec;
     const bool hop160 = p.hop == 160;
     const int gap = hop160 ? (wave_dtype == AAT_F32 ? raw_gap<float>() : raw_gap<double>()) : 0;
-    const size_t smem = smem_layout(raw_elems(p.stage_pad, gap), wave_bytes, p.n_mels, p.n_weights).total;
+    const size_t smem = smem_layout(raw_elems(p.stage_pad, gap), wave_bytes, p.n_desc, p.n_weights).total;
     const bool znorm = znorm_stats != nullptr;
     auto kernel = wave_dtype == AAT_F32 ? pick_logmel_kernel<float>(hop160, znorm) : pick_logmel_kernel<double>(hop160, znorm);
     int per_sm = 0;
