@@ -39,6 +39,7 @@
 #include <cuda_fp16.h>
 
 #include "aat_internal.cuh"
+#include <cstdlib>
 
 namespace aat {
 
@@ -769,6 +770,10 @@ int launch_typed(aat_ctx *ctx, const PoolScratch &ps, PoolParams &p, size_t smem
     const int64_t min_rows = 2 * (int64_t)p.rows_per_stage;
     const int64_t by_rows = (p.n_rows + min_rows - 1) / min_rows;
     if (by_rows < grid) grid = by_rows < 1 ? 1 : (int)by_rows;
+#ifdef AAT_EXPERIMENTS
+    if (const char *e = getenv("AAT_POOL_GRID")) // profiles/pool_grid.py: what a few SMs alone can stream
+        if (atoi(e) > 0 && atoi(e) < grid) grid = atoi(e);
+#endif
     *grid_out = grid;
     ProfileScope prof(ctx, AAT_K_POOL, stream); // the streaming kernel alone (not the colsum reduce)
     AAT_CUDA_CHECK(launch_pdl(kernel, dim3(grid), dim3(threads), smem, stream, p));
