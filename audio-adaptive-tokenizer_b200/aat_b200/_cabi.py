@@ -24,7 +24,7 @@ AAT_ERR_TAIL = -5
 
 AAT_F32, AAT_F64, AAT_F16, AAT_BF16 = 0, 1, 2, 3
 AAT_NORM_ZSCORE, AAT_NORM_W2V2 = 0, 1
-AAT_POOL_ACCUMULATE, AAT_POOL_EMB_READY, AAT_POOL_ROWS_FROM_DEVICE = 1, 2, 4
+AAT_POOL_ACCUMULATE, AAT_POOL_EMB_READY, AAT_POOL_ROWS_FROM_DEVICE, AAT_POOL_SHARE_SMS = 1, 2, 4, 8
 
 c_i32 = ctypes.c_int32
 c_i64 = ctypes.c_int64

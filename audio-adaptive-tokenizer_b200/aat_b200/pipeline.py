@@ -55,7 +55,7 @@ class TokenizerPipeline:
 
     def __init__(self, tokenizer: AdaptiveAudioAmplitudeTokenizer, n_samples: Sequence[int], dim: int,
                  depth: Optional[int] = None, device=None, priorities: Optional[Sequence[int]] = None,
-                 fused_amp: bool = True, graphs: bool = False):
+                 fused_amp: bool = True, graphs: bool = False, share_sms: Optional[bool] = None):
         import torch
 
         if depth is None:
@@ -67,6 +67,14 @@ class TokenizerPipeline:
         pr = list(priorities) if priorities is not None else [0] * depth
         self.slots: List[_Slot] = [_Slot(torch, tokenizer, n_samples, self.dim, device, pr[k]) for k in range(depth)]
         self.device = self.slots[0].batch.device
+        # Several batches in flight: the pool kernels launch one CTA per SM (AAT_POOL_SHARE_SMS).  In steady state the
+        # hardware runs the `depth` log-mel kernels of a round back to back and then the `depth` pool kernels
+        # (profiles/r2_step_timeline.txt); with half grids two of those pools, or a pool and the first CTAs of the next
+        # log-mel, share the SMs, and the ramp and tail of every pool launch are covered: -1.4 % (config 2), -0.3 %
+        # (config 3), -2.7 % (config 4) per step, although the pool kernel alone is 20 % slower that way.  The flag
+        # moves the CTA tile borders and with them the order of the additions: means may differ in the last bit from
+        # share_sms=False (deterministic either way).
+        self.share_sms = depth > 1 if share_sms is None else bool(share_sms)
         self.submitted = 0
         # True: the log-mel kernel also emits the amplitude curve the boundary scan starts from (its fused epilogue);
         # False: a separate, fully parallel pass over the mel (aat_amplitude) does, between the two kernels.  Bit-identical
@@ -139,7 +147,7 @@ class TokenizerPipeline:
         b = slot.batch
         if self.fused_amp:  # the whole step in one foreign call
             b.step(wave, emb, slot.out, colsum=slot.mean.running_buffer() if colsum else None, accumulate=colsum,
-                   znorm=znorm, rows_from_device=rows_from_device, stream=st)
+                   znorm=znorm, rows_from_device=rows_from_device, share_sms=self.share_sms, stream=st)
         else:
             if znorm:
                 slot.stats = b.waveform_stats(wave, out=slot.stats, stream=st)
@@ -150,7 +158,7 @@ class TokenizerPipeline:
             b.boundaries(stream=st)
             # the launch in front of the pool kernel is this slot's boundary scan, which does not write embeddings
             b.pool(emb, slot.out, colsum=slot.mean.running_buffer() if colsum else None, accumulate=colsum,
-                   emb_ready=not rows_from_device, rows_from_device=rows_from_device, stream=st)
+                   emb_ready=not rows_from_device, rows_from_device=rows_from_device, share_sms=self.share_sms, stream=st)
 
     def join(self):
         """Make the caller's current stream wait for everything submitted so far (no host synchronisation)."""

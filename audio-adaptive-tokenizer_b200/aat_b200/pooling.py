@@ -31,7 +31,7 @@ def _torch_dtype_code(dtype) -> int:
 
 
 def _pool_device(ctx: Context, emb, seg_off, n_seg: int, n_seg_dev, out, colsum, stream, accumulate: bool = False,
-                 plan=None, emb_ready: bool = False, rows_from_device: bool = False):
+                 plan=None, emb_ready: bool = False, rows_from_device: bool = False, share_sms: bool = False):
     """Raw K4 launch on CUDA tensors (no allocation, no sync).  ``plan`` is an ``aat_plan`` handle (its scratch is
     used, so launches on different plans may overlap) or None (the context's scratch; such launches are serialised)."""
     if emb.dim() != 2 or not emb.is_contiguous():
@@ -39,7 +39,8 @@ def _pool_device(ctx: Context, emb, seg_off, n_seg: int, n_seg_dev, out, colsum,
     if out.dtype.is_floating_point is False or out.element_size() != 4 or not out.is_contiguous():
         raise TypeError("out must be a contiguous float32 tensor")
     flags = ((_cabi.AAT_POOL_ACCUMULATE if accumulate else 0) | (_cabi.AAT_POOL_EMB_READY if emb_ready else 0) |
-             (_cabi.AAT_POOL_ROWS_FROM_DEVICE if rows_from_device else 0))
+             (_cabi.AAT_POOL_ROWS_FROM_DEVICE if rows_from_device else 0) |
+             (_cabi.AAT_POOL_SHARE_SMS if share_sms else 0))
     _cabi.check(_cabi.lib().aat_segment_mean_pool(
         ctx.handle, plan, emb.data_ptr(), _torch_dtype_code(emb.dtype), int(emb.shape[0]), int(emb.shape[1]),
         seg_off.data_ptr(), int(n_seg), n_seg_dev.data_ptr() if n_seg_dev is not None else None, out.data_ptr(),

@@ -413,22 +413,26 @@ class PackedBatch:
         return self.seg_off, self.n_seg
 
     def pool(self, emb, out, colsum=None, accumulate: bool = False, emb_ready: bool = False,
-             rows_from_device: bool = False, stream=None):
+             rows_from_device: bool = False, share_sms: bool = False, stream=None):
         """K4 with the device-resident CSR of :meth:`frame_csr`.  ``out`` is [capacity, D] float32; ``colsum``
         ([D+1] float64) receives the column sums of the pooled vectors, added to its content when ``accumulate``.
 
         emb_ready        : the previous launch on this stream is this batch's :meth:`boundaries` (or anything else that
                            does not write ``emb``): the kernel may start fetching embeddings before that launch ends
         rows_from_device : ``emb`` is an allocation of at least as many rows as the segments cover; the covered row
-                           count is taken from the device (written by :meth:`boundaries`) instead of ``emb.shape[0]``"""
+                           count is taken from the device (written by :meth:`boundaries`) instead of ``emb.shape[0]``
+        share_sms        : other batches are in flight on other streams: one CTA per SM instead of two, so that two pool
+                           kernels (or a pool kernel and a log-mel CTA) fit on an SM together (``AAT_POOL_SHARE_SMS``;
+                           the order of the additions follows the CTA tiles: means may differ in the last bit from a launch
+                           without it)"""
         from .pooling import _pool_device
 
         return _pool_device(self.ctx, emb, self.seg_off, int(out.shape[0]), self.n_seg, out, colsum,
                             self._stream(stream), accumulate, plan=self.handle, emb_ready=emb_ready,
-                            rows_from_device=rows_from_device)
+                            rows_from_device=rows_from_device, share_sms=share_sms)
 
     def step(self, wave, emb, out, colsum=None, accumulate: bool = False, znorm: bool = False, emb_ready: bool = True,
-             rows_from_device: bool = False, stream=None):
+             rows_from_device: bool = False, share_sms: bool = False, stream=None):
         """:meth:`logmel` (with the fused z-score when ``znorm``) -> :meth:`boundaries` -> :meth:`pool` in ONE call
         through the C ABI (``aat_tokenize_and_pool``): the same launches, a third of the host time per step, for loops
         that run thousands of steps per second.  Arguments as in the three methods; no validation beyond the C side's."""
@@ -449,7 +453,8 @@ class PackedBatch:
             raise TypeError("wave must be the plan's packed float32/float64 tensor, emb a [T, D] float32/16/bfloat16 tensor")
         flags = ((_cabi.AAT_POOL_ACCUMULATE if accumulate else 0) |
                  (_cabi.AAT_POOL_EMB_READY if emb_ready and not rows_from_device else 0) |
-                 (_cabi.AAT_POOL_ROWS_FROM_DEVICE if rows_from_device else 0))
+                 (_cabi.AAT_POOL_ROWS_FROM_DEVICE if rows_from_device else 0) |
+                 (_cabi.AAT_POOL_SHARE_SMS if share_sms else 0))
         _cabi.check(_cabi.lib().aat_tokenize_and_pool(
             self.ctx.handle, self.handle, ctypes.byref(bufs), wave.data_ptr(), wdt, 1 if znorm else 0, emb.data_ptr(), edt,
             int(emb.shape[0]), int(emb.shape[1]), out.data_ptr(), int(out.shape[0]),

@@ -220,6 +220,52 @@ void pool_scratch_free(PoolScratch *ps);
 
 constexpr int kMelFramesPerTile = 16; // frames one CTA of the log-mel kernel produces
 
+// -DAAT_TIMELINE (the timeline build of profiles/step_timeline.py, never the product library): thread 0 of every CTA of
+// the three path kernels records {start, end, SM << 32 | CTA} of its life (global timer, ns) in a ring of its file.
+#ifdef AAT_TIMELINE
+constexpr unsigned kTimelineRing = 1u << 16;
+struct TimelineScope {
+    unsigned long long t0;
+    unsigned long long *ring;
+    unsigned *count;
+    __device__ static unsigned long long now()
+    {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        return t;
+    }
+    __device__ TimelineScope(unsigned long long *r, unsigned *c) : t0(now()), ring(r), count(c) {}
+    __device__ ~TimelineScope()
+    {
+        if (threadIdx.x == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            const unsigned i = atomicAdd(count, 1u) & (kTimelineRing - 1);
+            ring[3 * i] = t0, ring[3 * i + 1] = now(), ring[3 * i + 2] = ((unsigned long long)smid << 32) | blockIdx.x;
+        }
+    }
+};
+#define AAT_TIMELINE_STORAGE(name)                                     \
+    __device__ unsigned long long g_tl_ring_##name[3 * kTimelineRing]; \
+    __device__ unsigned g_tl_count_##name;
+// at the end of the file, outside every namespace (NS = the namespaces the storage sits in)
+#define AAT_TIMELINE_EXPORT(name, NS)                                                                                         \
+    extern "C" __attribute__((visibility("default"))) int aat_debug_timeline_##name(unsigned long long *out_host,            \
+                                                                                    unsigned *count_host)                    \
+    {                                                                                                                         \
+        if (cudaMemcpyFromSymbol(count_host, NS g_tl_count_##name, sizeof(unsigned)) != cudaSuccess) return -1;               \
+        return (int)cudaMemcpyFromSymbol(out_host, NS g_tl_ring_##name, sizeof(unsigned long long) * 3 * aat::kTimelineRing); \
+    }
+#define AAT_TIMELINE_SCOPE(name) TimelineScope tl_scope__(g_tl_ring_##name, &g_tl_count_##name)
+#else
+#define AAT_TIMELINE_STORAGE(name)
+#define AAT_TIMELINE_EXPORT(name, NS)
+#define AAT_TIMELINE_SCOPE(name) \
+    do {                         \
+    } while (0)
+#endif
+
+
 // Programmatic dependent launch (PDL) between the kernels of a step.  A kernel launched through launch_pdl may
 // start while its predecessor in the stream is still running; it must call pdl_wait() before it touches
 // anything the predecessor writes (and before it writes anything the predecessor reads), and calls

@@ -393,9 +393,11 @@ __device__ unsigned long long g_bnd_trace[256 * 32];
 
 __device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(kWorkers) : "memory"); }
 
+AAT_TIMELINE_STORAGE(boundaries)
 template <int kChunk>
 __global__ void __launch_bounds__(kThreads) boundaries_kernel_t(const BoundaryParams p)
 {
+    AAT_TIMELINE_SCOPE(boundaries);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *s_amp = reinterpret_cast<float *>(smem_raw);          // [2][kChunk]
     float *s_cs = s_amp + 2 * kChunk;                             // [kRing]: cs index g lives at s_cs[g & (kRing - 1)]
@@ -860,3 +862,5 @@ int launch_segment_frame_csr(aat_ctx *ctx, const aat_plan *plan, const int64_t *
 }
 
 } // namespace aat
+
+AAT_TIMELINE_EXPORT(boundaries, aat::)

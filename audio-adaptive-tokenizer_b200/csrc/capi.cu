@@ -549,7 +549,7 @@ int aat_segment_mean_pool(aat_ctx *ctx, const aat_plan *plan, const void *emb_de
 {
     AAT_REQUIRE(ctx, AAT_ERR_INVALID, "aat_segment_mean_pool: NULL context");
     AAT_REQUIRE(plan == nullptr || plan->ctx == ctx, AAT_ERR_INVALID, "aat_segment_mean_pool: plan belongs to another context");
-    AAT_REQUIRE((flags & ~(AAT_POOL_ACCUMULATE | AAT_POOL_EMB_READY | AAT_POOL_ROWS_FROM_DEVICE)) == 0, AAT_ERR_INVALID,
+    AAT_REQUIRE((flags & ~(AAT_POOL_ACCUMULATE | AAT_POOL_EMB_READY | AAT_POOL_ROWS_FROM_DEVICE | AAT_POOL_SHARE_SMS)) == 0, AAT_ERR_INVALID,
                 "aat_segment_mean_pool: unknown flag bits 0x%x", flags);
     AAT_DEVICE_GUARD(ctx);
     return launch_mean_pool(ctx, plan, emb_dev, emb_dtype, n_rows, dim, seg_off_dev, n_seg, n_seg_dev, out_dev,
@@ -566,7 +566,7 @@ int aat_tokenize_and_pool(aat_ctx *ctx, const aat_plan *plan, const aat_step_buf
                     bufs->seg_off && bufs->n_seg,
                 AAT_ERR_INVALID, "aat_tokenize_and_pool: a required step buffer is NULL");
     AAT_REQUIRE(!znorm || bufs->znorm_stats, AAT_ERR_INVALID, "aat_tokenize_and_pool: znorm needs bufs->znorm_stats");
-    AAT_REQUIRE((pool_flags & ~(AAT_POOL_ACCUMULATE | AAT_POOL_EMB_READY | AAT_POOL_ROWS_FROM_DEVICE)) == 0, AAT_ERR_INVALID,
+    AAT_REQUIRE((pool_flags & ~(AAT_POOL_ACCUMULATE | AAT_POOL_EMB_READY | AAT_POOL_ROWS_FROM_DEVICE | AAT_POOL_SHARE_SMS)) == 0, AAT_ERR_INVALID,
                 "aat_tokenize_and_pool: unknown flag bits 0x%x", pool_flags);
     AAT_DEVICE_GUARD(ctx);
     cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -266,9 +266,11 @@ __device__ __noinline__ void fetch_edge_tile(WaveT *dst, const WaveT *utt, int64
 // ref:scripts/audio_tokenization_melspec.py:40) in float64, applied where a sample is widened for the transform, so a
 // normalised copy of the waveform is never written or re-read: the Znorm functor of aat_internal.cuh (correctly rounded
 // quotient in three FP64 operations), the very one aat_normalize applies, so fused and separate passes agree bit for bit.
+AAT_TIMELINE_STORAGE(logmel)
 template <typename WaveT, bool kHop160, bool kZnorm>
 __global__ void __launch_bounds__(kThreads, 3) logmel_kernel(const LogmelParams p)
 {
+    AAT_TIMELINE_SCOPE(logmel);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int kGap = kHop160 ? raw_gap<WaveT>() : 0;
     const SmemLayout L = smem_layout(raw_elems(p.stage_pad, kGap), (int)sizeof(WaveT), p.n_desc, p.n_weights);
@@ -659,3 +661,5 @@ int launch_logmel(aat_ctx *ctx, const aat_plan *plan, const void *wave, int wave
 }
 
 } // namespace aat
+
+AAT_TIMELINE_EXPORT(logmel, aat::)

@@ -280,9 +280,11 @@ __device__ __forceinline__ OffWindow first_window(const int64_t *seg_off, int64_
     return w;
 }
 
+AAT_TIMELINE_STORAGE(pool)
 template <typename EmbT, int kSlabs, bool kColsum>
 __global__ void __launch_bounds__(kMaxConsumers + 32) pool_kernel(const PoolParams p)
 {
+    AAT_TIMELINE_SCOPE(pool);
     using S = Slab<EmbT>;
     constexpr int kCols = S::kCols;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -750,8 +752,8 @@ __global__ void colsum_finalize_kernel(const double *acc, int dim, float *mean)
 }
 
 template <typename EmbT, int kSlabs>
-int launch_typed(aat_ctx *ctx, const PoolScratch &ps, PoolParams &p, size_t smem, bool colsum, cudaStream_t stream,
-                 int *grid_out)
+int launch_typed(aat_ctx *ctx, const PoolScratch &ps, PoolParams &p, size_t smem, bool colsum, int ctas_per_sm,
+                 cudaStream_t stream, int *grid_out)
 {
     const int threads = p.n_consumers + 32;
     auto kernel = colsum ? pool_kernel<EmbT, kSlabs, true> : pool_kernel<EmbT, kSlabs, false>;
@@ -759,7 +761,7 @@ int launch_typed(aat_ctx *ctx, const PoolScratch &ps, PoolParams &p, size_t smem
     int per_sm = 0;
     AAT_CUDA_CHECK(prepare_kernel(ctx, kernel, threads, smem, &per_sm));
     AAT_REQUIRE(per_sm >= 1, AAT_ERR_UNSUPPORTED, "aat_segment_mean_pool: kernel does not fit on an SM");
-    if (per_sm > kMaxCtasPerSm) per_sm = kMaxCtasPerSm;
+    if (per_sm > ctas_per_sm) per_sm = ctas_per_sm;
     int grid = ctx->num_sms * per_sm;
     if (grid > ps.max_ctas) grid = ps.max_ctas;
     // (More, smaller CTAs handed out in waves by the hardware, as a cheap form of dynamic balancing, were tried:
@@ -782,13 +784,13 @@ int launch_typed(aat_ctx *ctx, const PoolScratch &ps, PoolParams &p, size_t smem
 }
 
 template <typename EmbT>
-int launch_slabs(aat_ctx *ctx, const PoolScratch &ps, PoolParams &p, int slabs, size_t smem, bool colsum,
+int launch_slabs(aat_ctx *ctx, const PoolScratch &ps, PoolParams &p, int slabs, size_t smem, bool colsum, int ctas_per_sm,
                  cudaStream_t stream, int *grid_out)
 {
     switch (slabs) {
-    case 1: return launch_typed<EmbT, 1>(ctx, ps, p, smem, colsum, stream, grid_out);
-    case 2: return launch_typed<EmbT, 2>(ctx, ps, p, smem, colsum, stream, grid_out);
-    default: return launch_typed<EmbT, 4>(ctx, ps, p, smem, colsum, stream, grid_out);
+    case 1: return launch_typed<EmbT, 1>(ctx, ps, p, smem, colsum, ctas_per_sm, stream, grid_out);
+    case 2: return launch_typed<EmbT, 2>(ctx, ps, p, smem, colsum, ctas_per_sm, stream, grid_out);
+    default: return launch_typed<EmbT, 4>(ctx, ps, p, smem, colsum, ctas_per_sm, stream, grid_out);
     }
 }
 
@@ -877,12 +879,14 @@ static int launch_mean_pool_on(aat_ctx *ctx, const PoolScratch &ps, const void *
 
     int rc, grid = 0;
     const bool want_colsum = colsum != nullptr;
+    // AAT_POOL_SHARE_SMS: half the persistent grid, so that two launches (or a launch and a log-mel CTA) share an SM
+    const int ctas_per_sm = (flags & AAT_POOL_SHARE_SMS) ? 1 : kMaxCtasPerSm;
     if (emb_dtype == AAT_F32)
-        rc = launch_slabs<float>(ctx, ps, p, slabs, smem, want_colsum, stream, &grid);
+        rc = launch_slabs<float>(ctx, ps, p, slabs, smem, want_colsum, ctas_per_sm, stream, &grid);
     else if (emb_dtype == AAT_F16)
-        rc = launch_slabs<__half>(ctx, ps, p, slabs, smem, want_colsum, stream, &grid);
+        rc = launch_slabs<__half>(ctx, ps, p, slabs, smem, want_colsum, ctas_per_sm, stream, &grid);
     else
-        rc = launch_slabs<__nv_bfloat16>(ctx, ps, p, slabs, smem, want_colsum, stream, &grid);
+        rc = launch_slabs<__nv_bfloat16>(ctx, ps, p, slabs, smem, want_colsum, ctas_per_sm, stream, &grid);
     if (rc != AAT_OK) return rc;
     if (want_colsum) {
         AAT_MAX_SMEM_CARVEOUT(colsum_reduce_kernel);
@@ -942,3 +946,5 @@ int launch_colsum_finalize(const double *acc, int32_t dim, float *mean, cudaStre
 }
 
 } // namespace aat
+
+AAT_TIMELINE_EXPORT(pool, aat::)

@@ -374,16 +374,17 @@ class Workload:
         self.pipes[self.depth if depth is None else depth].submit(self.wave_sets[s], self.emb_sets[s], colsum=colsum,
                                                                    inputs_ready=True, record_done=False)
 
-    def expected_sums(self, uses):
+    def expected_sums(self, uses, share_sms=False):
         """Independent reduction of what `steps` steps must have accumulated: the pooled vectors of every buffer set
-        are summed by torch in float64 and weighted with how often the set was used."""
+        are summed by torch in float64 and weighted with how often the set was used.  `share_sms`: pool with the grid
+        the pipeline under test uses (the flag moves the CTA tile borders, hence the last bit of some means)."""
         torch = self.torch
         acc = torch.zeros(self.D + 1, dtype=torch.float64, device=self.dev)
         for s in range(self.R):
             if uses[s] == 0:
                 continue
             self.batch.logmel(self.wave_sets[s]), self.batch.boundaries()
-            self.batch.pool(self.emb_sets[s], self.out)
+            self.batch.pool(self.emb_sets[s], self.out, share_sms=share_sms)
             torch.cuda.synchronize()
             n_seg = int(self.batch.n_seg.item())
             acc[: self.D] += uses[s] * self.out[:n_seg].double().sum(dim=0)
@@ -507,7 +508,7 @@ def measure_workload(torch, dist, w, steps, warmup, world, sample_every, no_cols
     check = None
     if not no_colsum:
         uses = [len(range(s, steps, w.R)) for s in range(w.R)]
-        mine = w.expected_sums(uses)
+        mine = w.expected_sums(uses, share_sms=pipe.share_sms)
         if world > 1:
             parts = [torch.empty_like(mine) for _ in range(world)]
             dist.all_gather(parts, mine)

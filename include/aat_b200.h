@@ -233,9 +233,16 @@ typedef enum aat_pool_flags {
                                       then request embedding rows before it waits for that predecessor.  Without the
                                       flag nothing is read before the wait, so any producer of emb_dev may precede
                                       the call, including kernels that trigger their dependents early */
-    AAT_POOL_ROWS_FROM_DEVICE = 4  /* n_rows is an upper bound (the allocation); the rows the CSR covers are read
+    AAT_POOL_ROWS_FROM_DEVICE = 4, /* n_rows is an upper bound (the allocation); the rows the CSR covers are read
                                       from n_seg_dev[1] as written by aat_boundaries / aat_segment_frame_csr, and
                                       nothing beyond them is streamed */
+    AAT_POOL_SHARE_SMS = 8         /* several batches are in flight (other plans on other streams): launch ONE CTA per
+                                      SM instead of two, so that the pool kernels of two batches, or a pool kernel and a
+                                      log-mel CTA, fit on an SM together.  The kernel alone is ~20 % slower that way,
+                                      a pipelined schedule 0.3-2.7 % faster (profiles/r2_pipeline_ab.txt).  The order in
+                                      which a segment's rows are added follows the CTA tiles, and the flag halves the
+                                      number of tiles: a mean may differ in the last float32 bit from a launch without
+                                      the flag (either way deterministic, and far inside the 1e-5 bound) */
 } aat_pool_flags;
 int aat_segment_mean_pool(aat_ctx *ctx, const aat_plan *plan, const void *emb_dev, int emb_dtype, int64_t n_rows,
                           int32_t dim, const int64_t *seg_off_dev, int64_t n_seg, const int64_t *n_seg_dev,

@@ -706,7 +706,8 @@ def test_pool_launches_without_a_plan_are_serialised_across_streams(c_oracle):
 
 def test_pool_flags_row_count_from_the_device_and_early_fetch(tok):
     """AAT_POOL_ROWS_FROM_DEVICE: the embedding tensor is an allocation larger than what the segments cover and the
-    covered row count comes from the boundary kernel; AAT_POOL_EMB_READY only changes when rows are requested."""
+    covered row count comes from the boundary kernel; AAT_POOL_EMB_READY only changes when rows are requested;
+    AAT_POOL_SHARE_SMS halves the grid."""
     import torch
 
     from aat_b200 import synth
@@ -730,6 +731,19 @@ def test_pool_flags_row_count_from_the_device_and_early_fetch(tok):
         got = batch.pool(src, out, **kw)[:n_seg]
         torch.cuda.synchronize()
         assert torch.equal(got, want), kw
+    # AAT_POOL_SHARE_SMS: one CTA per SM.  The CTA tile borders move, and with them the order in which a segment's rows
+    # are added (rows pair up from the tile's first row): equal to float32 rounding, bit-identical among launches
+    # with the flag, same under the other flags.
+    shared = None
+    for kw in (dict(share_sms=True), dict(share_sms=True, rows_from_device=True), dict(share_sms=True, emb_ready=True)):
+        out.zero_()
+        src = big if kw.get("rows_from_device") else exact
+        batch.logmel(wave), batch.boundaries()
+        got = batch.pool(src, out, **kw)[:n_seg].clone()
+        torch.cuda.synchronize()
+        assert torch.allclose(got, want, rtol=1e-6, atol=1e-7), kw
+        shared = got if shared is None else shared
+        assert torch.equal(got, shared), kw
     cs = torch.zeros(769, dtype=torch.float64, device="cuda")
     batch.logmel(wave), batch.boundaries()
     batch.pool(big, out, colsum=cs, rows_from_device=True)
@@ -760,7 +774,10 @@ def test_pipelined_steps_match_serial_steps(tok):
         # (batches in flight, amplitude curve from the fused epilogue, steps replayed from CUDA graphs)
         variants = {1: (1, True, False), 2: (2, True, True), 3: (3, True, True), -3: (3, False, True), 4: (4, True, False)}
         for depth, (n_slots, fused_amp, graphs) in variants.items():
-            pipe = TokenizerPipeline(tok, lengths, dim, depth=n_slots, fused_amp=fused_amp, graphs=graphs)
+            # the pool grid of the pipelined variants (one CTA per SM, AAT_POOL_SHARE_SMS) for the serial reference too:
+            # the flag moves the CTA tile borders, hence the last bit of segments that straddle one
+            pipe = TokenizerPipeline(tok, lengths, dim, depth=n_slots, fused_amp=fused_amp, graphs=graphs, share_sms=True)
+            assert pipe.share_sms
             got = []
             for it in range(21):  # every (slot, input set) pair comes round again: captured and replayed CUDA graphs
                 k = it % 5
