@@ -47,11 +47,12 @@ class TokenizerPipeline:
 
     @staticmethod
     def default_depth(n_samples: Sequence[int], sampling_rate: int = 16000) -> int:
-        """Batches in flight when the caller does not say: 4, or 6 for long streams (>= 200 s), whose boundary scan is a
-        long serial chain on a handful of CTAs and needs more neighbours to hide behind (measured on a B200,
-        profiles/r2_pipeline_ab.txt: 64 x 16 s is best at 4, 8 x 30 min keeps gaining up to 6)."""
-        longest = max((int(n) for n in n_samples), default=0)
-        return 6 if longest >= 200 * sampling_rate else 4
+        """Batches in flight when the caller does not say: 6.  The hardware runs the log-mel kernels of a round back to
+        back and then the round's pool kernels (profiles/r2_step_timeline.txt); with the pools at one CTA per SM
+        (AAT_POOL_SHARE_SMS) longer rounds keep gaining up to five or six batches (measured on a B200,
+        profiles/r2_pipeline_ab.txt: 64 x 16 s 0.1450 ms at 4, 0.1415 at 5, 0.1418 at 6, 0.1421 at 8; 256 x 20 s
+        0.7164 at 4, 0.7092 at 6; 8 x 30 min 1.983 at 4, 1.889 at 6, 1.917 at 8)."""
+        return 6
 
     def __init__(self, tokenizer: AdaptiveAudioAmplitudeTokenizer, n_samples: Sequence[int], dim: int,
                  depth: Optional[int] = None, device=None, priorities: Optional[Sequence[int]] = None,
