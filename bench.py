@@ -356,8 +356,9 @@ class Workload:
             synth.device_normal(emb, 1234 + 97 * rank + s)
             self.wave_sets.append(wave), self.emb_sets.append(emb), self.n_seg.append(n_seg), self.n_rows.append(n_rows)
         self.out = torch.empty(self.batch.total_seg_slots, D, device=self.dev)
-        # the step runs through the public pipeline object: `depth` plans on `depth` streams, so that the boundary scan
-        # and the pool of one batch overlap the log-mel of the next (depth 1 = strictly serial, kept for the A/B)
+        # the step runs through the public pipeline object: `depth` plans on `depth` streams, so that consecutive log-mel
+        # kernels cover each other's ramp and tail, the boundary scans hide beside them and the pools share the SMs
+        # (profiles/r2_step_timeline.txt; depth 1 = strictly serial, kept for the A/B)
         self.depth = depth = depth if depth > 0 else TokenizerPipeline.default_depth([self.N] * B)
         # with --graphs the pipelined schedule replays each slot's step from a CUDA graph (the rotating input buffers come
         # round again); the strictly serial one always launches kernel by kernel, as round 1's step did (and so that
@@ -547,8 +548,8 @@ def measure_workload(torch, dist, w, steps, warmup, world, sample_every, no_cols
 def schedule_note(depth):
     if depth == 1:
         return "one plan, one stream: log-mel -> boundaries -> pool strictly one after the other"
-    return (f"aat_b200.pipeline.TokenizerPipeline, {depth} plans on {depth} streams: boundaries and pool of one batch overlap "
-            f"the log-mel of the next")
+    return (f"aat_b200.pipeline.TokenizerPipeline, {depth} plans on {depth} streams: the log-mel kernels of a round run back "
+            f"to back, the boundary scans beside them, the round's pool kernels share the SMs (one CTA per SM each)")
 
 
 def pool_traffic(name):
