@@ -65,13 +65,18 @@ __device__ __forceinline__ unsigned long long trace_now()
     } while (0)
 #endif
 
+// Ring geometry.  Every stage costs a fixed ~0.45 us of hand-shaking (consumers release it, the producer thread sees the
+// release, issues the bulk copy, the data crosses the chip, the consumers see it land), so FEW, BIG stages win: two
+// stages of 48 KB instead of four of 24 KB in the same 96 KB stream 5-7 % faster at every size (config 2: 29.7 ->
+// 28.0 us back to back, configs 3 / 4: 167 -> 161 / 350 -> 336 us; profiles/r2_pool_ring_grid.txt), and many small stages
+// are far worse (7 x 9 KB: 72 us).
 #ifndef AAT_POOL_STAGES
-#define AAT_POOL_STAGES 4
-#define AAT_POOL_STAGE_KB 24
+#define AAT_POOL_STAGES 2
+#define AAT_POOL_STAGE_KB 48
 #define AAT_POOL_CTAS 2
 #endif
 constexpr int kStages = AAT_POOL_STAGES;
-constexpr int kStageBytes = AAT_POOL_STAGE_KB * 1024; // 24 KB: 8 rows of 768 fp32, 6 rows of 1024 fp32
+constexpr int kStageBytes = AAT_POOL_STAGE_KB * 1024; // 48 KB: 16 rows of 768 fp32, 12 rows of 1024 fp32
 constexpr int kMaxConsumers = 256;
 constexpr int kMaxSlabs = 4; // 16-byte column slabs per consumer thread -> dim*e <= 16 KB
 constexpr int kMaxCtasPerSm = AAT_POOL_CTAS;
