@@ -71,8 +71,8 @@ class TokenizerPipeline:
         # Several batches in flight: the pool kernels launch one CTA per SM (AAT_POOL_SHARE_SMS).  In steady state the
         # hardware runs the `depth` log-mel kernels of a round back to back and then the `depth` pool kernels
         # (profiles/r2_step_timeline.txt); with half grids two of those pools, or a pool and the first CTAs of the next
-        # log-mel, share the SMs, and the ramp and tail of every pool launch are covered: -1.4 % (config 2), -0.3 %
-        # (config 3), -2.7 % (config 4) per step, although the pool kernel alone is 20 % slower that way.  The flag
+        # log-mel, share the SMs, and the ramp and tail of every pool launch are covered: -2.2 % (config 2), -2.2 %
+        # (config 3), -2.8 % (config 4) per step, although the pool kernel alone is 8 % slower that way.  The flag
         # moves the CTA tile borders and with them the order of the additions: means may differ in the last bit from
         # share_sms=False (deterministic either way).
         self.share_sms = depth > 1 if share_sms is None else bool(share_sms)

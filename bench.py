@@ -331,7 +331,7 @@ class Workload:
     """One BASELINE config resident on one GPU: R rotating buffer sets of distinct, device-generated utterances with
     the embeddings their own segmentation calls for, and the step that runs the path over one set."""
 
-    def __init__(self, torch, tok, name, rank, local_rank, rotate, depth=0, fused_amp=True, graphs=False):
+    def __init__(self, torch, tok, name, rank, local_rank, rotate, depth=0, fused_amp=True, graphs=False, share_sms=None):
         from aat_b200 import synth
         from aat_b200.pipeline import TokenizerPipeline
 
@@ -364,7 +364,7 @@ class Workload:
         # round again); the strictly serial one always launches kernel by kernel, as round 1's step did (and so that
         # kernels can be event-timed)
         self.pipes = {d: TokenizerPipeline(tok, [self.N] * B, D, depth=d, device=local_rank, fused_amp=fused_amp,
-                                           graphs=d > 1 and graphs)
+                                           graphs=d > 1 and graphs, share_sms=share_sms if d > 1 else None)
                       for d in sorted({1, depth})}
         self.audio_hours_per_step = B * self.N / 16000 / 3600
         self.pool_bytes = float(np.mean([r * D * 4 + s * D * 4 + (s + 1) * 8 for r, s in zip(self.n_rows, self.n_seg)]))
@@ -753,7 +753,8 @@ def run_b200(args):
             os.close(saved)
 
     tok = AdaptiveAudioAmplitudeTokenizer(device=local_rank)
-    w = Workload(torch, tok, args.workload, rank, local_rank, args.rotate, args.depth, not args.unfused_amp, args.graphs)
+    w = Workload(torch, tok, args.workload, rank, local_rank, args.rotate, args.depth, not args.unfused_amp, args.graphs,
+                 False if args.no_share_sms else None)
     sampler = ClockSampler(local_rank)
     sampler.start()
     m = measure_workload(torch, dist, w, args.steps, args.warmup, world, args.pool_sample_every, args.no_colsum, sampler)
@@ -945,6 +946,7 @@ def main():
     ap.add_argument("--rotate", type=int, default=DEFAULT_ROTATE)
     ap.add_argument("--depth", type=int, default=0,
                     help="batches in flight (plans x streams) of the step's pipeline; 1 = serial, 0 = the pipeline's own default")
+    ap.add_argument("--no-share-sms", action="store_true", help="A/B: pool kernels of the pipelined schedule with the full grid (two CTAs per SM) instead of AAT_POOL_SHARE_SMS")
     ap.add_argument("--unfused-amp", action="store_true", help="amplitude curve by the separate pass (aat_amplitude) instead of the log-mel kernel's epilogue")
     ap.add_argument("--graphs", action="store_true",
                     help="replay the pipelined steps from CUDA graphs (14 instead of 32-100 us of host time per step, 3 %% more "

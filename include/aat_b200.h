@@ -238,8 +238,8 @@ typedef enum aat_pool_flags {
                                       nothing beyond them is streamed */
     AAT_POOL_SHARE_SMS = 8         /* several batches are in flight (other plans on other streams): launch ONE CTA per
                                       SM instead of two, so that the pool kernels of two batches, or a pool kernel and a
-                                      log-mel CTA, fit on an SM together.  The kernel alone is ~20 % slower that way,
-                                      a pipelined schedule 0.3-2.7 % faster (profiles/r2_pipeline_ab.txt).  The order in
+                                      log-mel CTA, fit on an SM together.  The kernel alone is ~8 % slower that way,
+                                      a pipelined schedule 2-3 % faster (profiles/r2_pipeline_ab.txt).  The order in
                                       which a segment's rows are added follows the CTA tiles, and the flag halves the
                                       number of tiles: a mean may differ in the last float32 bit from a launch without
                                       the flag (either way deterministic, and far inside the 1e-5 bound) */
