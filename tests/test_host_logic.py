@@ -148,3 +148,21 @@ def test_synth_is_deterministic():
     a = synth.bursty_speech(16000, 5)
     b = synth.bursty_speech(16000, 5)
     assert a.dtype == np.float32 and np.array_equal(a, b) and not np.array_equal(a, synth.bursty_speech(16000, 6))
+
+
+def test_pipeline_defaults_and_pool_flag_values():
+    """Host-side constants of the pipelined schedule: six batches in flight whatever the shape, and the flag bits of
+    ``aat_pool_flags`` as the header declares them (the pipeline passes AAT_POOL_SHARE_SMS when depth > 1)."""
+    import re
+
+    from aat_b200 import _cabi
+    from aat_b200.pipeline import TokenizerPipeline
+
+    assert TokenizerPipeline.default_depth([256000] * 64) == 6
+    assert TokenizerPipeline.default_depth([28800000] * 8) == 6
+    assert TokenizerPipeline.default_depth([]) == 6
+    header = open(os.path.join(ROOT, "include", "aat_b200.h")).read()
+    for name in ("AAT_POOL_ACCUMULATE", "AAT_POOL_EMB_READY", "AAT_POOL_ROWS_FROM_DEVICE", "AAT_POOL_SHARE_SMS"):
+        m = re.search(name + r"\s*=\s*(\d+)", header)
+        assert m and int(m.group(1)) == getattr(_cabi, name), name
+
