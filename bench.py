@@ -435,7 +435,10 @@ class Workload:
                 "bytes_per_launch": self.pool_bytes, "us_per_launch": best, "launches_timed": reps,
                 "method": f"{reps} back-to-back launches over the {self.R} rotating input sets inside one CUDA-event "
                           f"pair, best of 3 (no column-sum epilogue: the reduce kernel is a separate launch)",
-                "peak_source": peak_src}
+                "peak_source": peak_src,
+                "peak_note": "the peak is a COPY figure (read + write); this kernel is 96 % reads, and a pure read stream "
+                             "through the same ring reaches 7.26 TB/s on this chip (profiles/r2_ubench_tma2d.txt), so "
+                             "frac can pass 1 at the large configs without the bytes being wrong (traffic = ncu DRAM bytes)"}
         if sampled is not None:
             n, ms = sampled
             if n:
