@@ -25,6 +25,13 @@
  *     (AAT_POOL_EMB_READY).  A plan may have one launch of each in flight at a time (use one plan per stream): the
  *     plan owns the kernels' device-side scheduling state (tile counter, completion ticket, look-back words, the
  *     pool kernel's cross-CTA partial sums).  Plans on different streams are independent and may run concurrently.
+ *     Forward progress when persistent grids of several launches share the GPU: a CTA only ever waits for CTAs of
+ *     its own launch, and the hardware hands out the CTAs of a launch in index order.  The boundary kernel looks back
+ *     (lower indices: resident or done).  A pool CTA publishes its pieces before it waits for anything and waits for
+ *     higher indices only, so of the resident CTAs of a partly resident launch at most the last ones wait for a CTA
+ *     that has no slot yet; the others leave, and their slots go to the CTAs waited for.  Partly resident launches
+ *     therefore cannot block each other for good (exercised by the tests with two to four plans in flight and by
+ *     every bench run with six).
  *   - device entry points run on the context's device whatever the calling thread's current device is; `stream`
  *     must belong to that device.
  *
