@@ -43,7 +43,7 @@ def launches(rec, grid):
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "c2"
     depth = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-    steps = 120
+    steps = 132
     tok = AdaptiveAudioAmplitudeTokenizer()
     w = bench.Workload(torch, tok, name, 0, 0, 4, depth)
     pipe = w.pipes[w.depth]
@@ -57,26 +57,28 @@ def main():
     grid = {k: int((rec[k][:, 2] & 0xffffffff).max()) + 1 for k in rec}
     # keep the records of the timed loop only: the last `steps` launches of every kernel
     L = {k: launches(rec[k][-steps * grid[k]:], grid[k]) for k in rec}
-    t0 = L["logmel"][steps - 12][:, 0].min()
-    print(f"# {name}, {w.depth} batches in flight, grids {grid}; times in us relative to the first CTA start of log-mel launch {steps - 12}")
+    first = steps - 36  # well inside the steady state, well before the drain at the end of the loop
+    t0 = L["logmel"][first][:, 0].min()
+    print(f"# {name}, {w.depth} batches in flight, grids {grid}; times in us relative to the first CTA start of log-mel launch {first}")
     print("# launch: first start, last start | first end, last end   (duration of the launch = last end - first start)")
     events = []
     for k in L:
         for j, r in enumerate(L[k]):
             events.append((r[:, 0].min(), k, j, r))
     events.sort(key=lambda e: e[0])
-    for first, k, j, r in events:
-        if steps - 12 <= j <= steps - 8:
+    starts = np.array([r[:, 0].min() for r in L["logmel"]])
+    t1 = starts[min(first + 2 * w.depth, steps - 1)]  # two rounds of the pipeline
+    for begin, k, j, r in events:
+        if t0 <= begin < t1:
             us = lambda t: (t - t0) / 1e3
             sms = len(set((r[:, 2] >> 32).tolist()))
-            print(f"{k:10s} #{j:2d}  start {us(r[:, 0].min()):8.1f} .. {us(r[:, 0].max()):8.1f} | end {us(r[:, 1].min()):8.1f} .. {us(r[:, 1].max()):8.1f}"
+            print(f"{k:10s} #{j:3d}  start {us(r[:, 0].min()):8.1f} .. {us(r[:, 0].max()):8.1f} | end {us(r[:, 1].min()):8.1f} .. {us(r[:, 1].max()):8.1f}"
                   f"   ({(r[:, 1].max() - r[:, 0].min()) / 1e3:6.1f} us, CTA lifetime median {np.median(r[:, 1] - r[:, 0]) / 1e3:6.1f} us, on {sms} SMs)")
     # steady-state step = distance between consecutive log-mel launches
-    starts = np.array([r[:, 0].min() for r in L["logmel"]])
     period = np.diff(starts)[steps // 2:-4].mean() / 1e3
     print(f"# steady-state period (first start of a log-mel launch to the next): {period:.1f} us")
     # share of the SM x time area covered by CTAs of each kernel within one period (a CTA slot counts 1/slots-per-SM)
-    a, b = starts[steps - 12], starts[steps - 11]
+    a, b = starts[first], starts[first + 1]
     slots = {"logmel": 3, "pool": max(1, grid["pool"] // 148), "boundaries": 1}
     for k in rec:
         r = rec[k]
