@@ -1,5 +1,6 @@
 """What the pool kernel streams when it runs on a FEW SMs only (grid capped by AAT_POOL_GRID, experiments build:
-`make -C audio-adaptive-tokenizer_b200/csrc EXTRA_NVCCFLAGS=-DAAT_EXPERIMENTS`, library under profiles/_build/):
+`make -C audio-adaptive-tokenizer_b200/csrc experiments` -> profiles/_build/libaat_b200_exp.so; ring variants with
+EXTRA_NVCCFLAGS="-DAAT_POOL_STAGES=S -DAAT_POOL_STAGE_KB=KB -DAAT_POOL_CTAS=C", as in profiles/r2_pool_ring_grid.txt):
 the question behind "give the HBM-bound pool 8-32 SMs of its own beside the FP64-bound log-mel kernel".
 
     AAT_B200_LIB=profiles/_build/libaat_b200_exp.so AAT_POOL_GRID=16 python profiles/pool_grid.py"""
