@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AAT_B200_LIB") or os.path.join(_HERE, "libaat_b200.so")  # override: profiles/ experiments
 CSRC_DIR = os.path.join(os.path.dirname(_HERE), "csrc")
 
-ABI_VERSION = 200  # AAT_B200_VERSION of include/aat_b200.h this binding was written against
+ABI_VERSION = 201  # AAT_B200_VERSION of include/aat_b200.h this binding was written against
 AAT_OK = 0
 AAT_ERR_INVALID = -1
 AAT_ERR_UNSUPPORTED = -2
@@ -88,6 +88,7 @@ SIGNATURES = {
     "aat_boundaries": (ctypes.c_int, [c_void] * 14),
     "aat_process_boarders": (ctypes.c_int, [c_void, c_i64, c_void, c_i64, c_void, c_void, c_i64, c_void, c_void, c_void]),
     "aat_segment_frame_csr": (ctypes.c_int, [c_void] * 8),
+    "aat_utterance_frame_csr": (ctypes.c_int, [c_void] * 8),
     "aat_segment_mean_pool": (ctypes.c_int, [c_void, c_void, c_void, ctypes.c_int, c_i64, c_i32, c_void, c_i64, c_void,
                                              c_void, c_void, ctypes.c_int, c_void]),
     "aat_tokenize_and_pool": (ctypes.c_int, [c_void, c_void, ctypes.POINTER(AatStepBuffers), c_void, ctypes.c_int, ctypes.c_int,

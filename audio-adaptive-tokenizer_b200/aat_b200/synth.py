@@ -15,6 +15,8 @@ counter-based RNG through the C ABI (``aat_synth_*``), for the benchmark's datas
 * ``segment_frame_offsets`` – CSR frame offsets for a list of segment lengths
   under the per-segment-encode convention that
   ref:scripts/mean_hubert_embeddings.py:18-20 consumes.
+* ``utterance_frame_offsets`` – the same for one whole-utterance encoding
+  (convention (ii)).
 """
 from __future__ import annotations
 
@@ -74,6 +76,21 @@ def segment_frame_offsets(segment_lengths) -> np.ndarray:
     off = np.zeros(n.size + 1, dtype=np.int64)
     np.cumsum(n, out=off[1:])
     return off
+
+
+def utterance_frame_offsets(segment_lengths, n_samples: int) -> np.ndarray:
+    """CSR offsets (S+1,) int64 over the rows of ONE whole-utterance encoding (convention (ii)): the
+    encoder ran once over the ``n_samples`` samples (``T = hubert_frames(n_samples)`` rows) and the segment that starts
+    at sample ``s`` starts at row ``min(s // 320, T)`` — the collator's ``// hop_length``
+    (ref:src/aat/training/collate.py:340) with the encoder's stride.  The lengths add up to at least ``n_samples``
+    (ref:src/aat/tokenizer.py:195), so the last offset is ``T``.  Host-side twin of ``aat_utterance_frame_csr``."""
+    lengths = np.asarray(segment_lengths, dtype=np.int64).reshape(-1)
+    if int(lengths.sum()) < int(n_samples):
+        raise ValueError("segment lengths must cover the utterance (sum >= n_samples)")
+    rows = int(hubert_frames(n_samples))
+    starts = np.zeros(lengths.size + 1, dtype=np.int64)
+    np.cumsum(lengths, out=starts[1:])
+    return np.minimum(starts // 320, rows)
 
 
 def mel_frames(n_samples: int, hop_length: int = 160) -> int:

@@ -412,9 +412,28 @@ class PackedBatch:
             self.n_seg.data_ptr(), self.utt_seg_off.data_ptr(), self._stream()))
         return self.seg_off, self.n_seg
 
+    def utterance_frame_csr(self, stream=None):
+        """Packed CSR of the WHOLE-UTTERANCE encode convention, for :meth:`pool` with ``csr=``: the
+        encoder ran once over each utterance, ``emb`` holds ``(N_b - 400) // 320 + 1`` rows per utterance back to back,
+        and the segment that starts at sample ``s`` starts at row ``min(s // 320, T_b)`` of its utterance (the collator's
+        ``// hop_length``, ref:src/aat/training/collate.py:340).  Needs :meth:`boundaries` (with its CSR) before it on the
+        stream.  Returns ``(seg_off, totals)`` — buffers of their own, so the per-segment CSR stays valid beside them;
+        ``totals`` is ``{segments, rows}``."""
+        import torch
+
+        if getattr(self, "_utt_csr", None) is None:  # allocated on first use (before any graph capture)
+            self._utt_csr = (torch.zeros(self.total_seg_slots + 1, dtype=torch.int64, device=self.device),
+                             torch.zeros(2, dtype=torch.int64, device=self.device))
+        seg_off, totals = self._utt_csr
+        _cabi.check(_cabi.lib().aat_utterance_frame_csr(
+            self.ctx.handle, self.handle, self.seg_start.data_ptr(), self.seg_count.data_ptr(), self.utt_seg_off.data_ptr(),
+            seg_off.data_ptr(), totals.data_ptr(), self._stream(stream)))
+        return seg_off, totals
+
     def pool(self, emb, out, colsum=None, accumulate: bool = False, emb_ready: bool = False,
-             rows_from_device: bool = False, share_sms: bool = False, stream=None):
-        """K4 with the device-resident CSR of :meth:`frame_csr`.  ``out`` is [capacity, D] float32; ``colsum``
+             rows_from_device: bool = False, share_sms: bool = False, stream=None, csr=None):
+        """K4 with the device-resident CSR of :meth:`frame_csr` (or ``csr=(seg_off, totals)`` from
+        :meth:`utterance_frame_csr`).  ``out`` is [capacity, D] float32; ``colsum``
         ([D+1] float64) receives the column sums of the pooled vectors, added to its content when ``accumulate``.
 
         emb_ready        : the previous launch on this stream is this batch's :meth:`boundaries` (or anything else that
@@ -427,7 +446,8 @@ class PackedBatch:
                            without it)"""
         from .pooling import _pool_device
 
-        return _pool_device(self.ctx, emb, self.seg_off, int(out.shape[0]), self.n_seg, out, colsum,
+        seg_off, totals = (self.seg_off, self._csr_totals) if csr is None else csr
+        return _pool_device(self.ctx, emb, seg_off, int(out.shape[0]), totals, out, colsum,
                             self._stream(stream), accumulate, plan=self.handle, emb_ready=emb_ready,
                             rows_from_device=rows_from_device, share_sms=share_sms)
 

@@ -189,6 +189,8 @@ int launch_process_boarders(aat_ctx *ctx, int64_t n_samples, const int64_t *boar
                             int32_t *status, cudaStream_t stream);
 int launch_segment_frame_csr(aat_ctx *ctx, const aat_plan *plan, const int64_t *seg_len, const int32_t *seg_count,
                              int64_t *seg_off, int64_t *n_seg, int64_t *utt_seg_off, cudaStream_t stream);
+int launch_utterance_frame_csr(const aat_plan *plan, const int64_t *seg_start, const int32_t *seg_count,
+                               const int64_t *utt_seg_off, int64_t *seg_off, int64_t *n_seg, cudaStream_t stream);
 int launch_mean_pool(aat_ctx *ctx, const aat_plan *plan, const void *emb, int emb_dtype, int64_t n_rows, int32_t dim,
                      const int64_t *seg_off, int64_t n_seg, const int64_t *n_seg_dev, float *out, double *colsum,
                      int flags, cudaStream_t stream);

@@ -543,6 +543,18 @@ int aat_segment_frame_csr(aat_ctx *ctx, const aat_plan *plan, const int64_t *seg
                                     static_cast<cudaStream_t>(stream));
 }
 
+int aat_utterance_frame_csr(aat_ctx *ctx, const aat_plan *plan, const int64_t *seg_start_dev,
+                            const int32_t *seg_count_dev, const int64_t *utt_seg_off_dev, int64_t *seg_off_dev,
+                            int64_t *n_seg_dev, void *stream)
+{
+    AAT_REQUIRE(ctx && plan && seg_start_dev && seg_count_dev && utt_seg_off_dev && seg_off_dev && n_seg_dev,
+                AAT_ERR_INVALID, "aat_utterance_frame_csr: NULL argument");
+    AAT_REQUIRE(plan->ctx == ctx, AAT_ERR_INVALID, "aat_utterance_frame_csr: plan belongs to another context");
+    AAT_DEVICE_GUARD(ctx);
+    return launch_utterance_frame_csr(plan, seg_start_dev, seg_count_dev, utt_seg_off_dev, seg_off_dev, n_seg_dev,
+                                      static_cast<cudaStream_t>(stream));
+}
+
 int aat_segment_mean_pool(aat_ctx *ctx, const aat_plan *plan, const void *emb_dev, int emb_dtype, int64_t n_rows,
                           int32_t dim, const int64_t *seg_off_dev, int64_t n_seg, const int64_t *n_seg_dev,
                           float *out_dev, double *colsum_dev, int flags, void *stream)

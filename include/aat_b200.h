@@ -57,7 +57,8 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define AAT_B200_VERSION 200 /* 0.2.0: aat_segment_mean_pool takes a plan and flags; n_seg_dev holds {S, frames} */
+#define AAT_B200_VERSION 201 /* 0.2.1: + aat_utterance_frame_csr; 0.2.0: aat_segment_mean_pool takes a plan and flags;
+                                n_seg_dev holds {S, frames} */
 
 typedef enum aat_status {
     AAT_OK = 0,
@@ -215,6 +216,23 @@ int aat_process_boarders(aat_ctx *ctx, int64_t n_samples, const int64_t *boarder
 int aat_segment_frame_csr(aat_ctx *ctx, const aat_plan *plan, const int64_t *seg_len_dev,
                           const int32_t *seg_count_dev, int64_t *seg_off_dev, int64_t *n_seg_dev,
                           int64_t *utt_seg_off_dev, void *stream);
+
+/* The same CSR for the WHOLE-UTTERANCE encode convention (convention (ii)): the encoder ran once
+ * over every utterance and emb_dev holds the T_b = max(0, (N_b - 400) / 320 + 1) rows of utterance b back to back (plan
+ * order).  The segment that starts at sample s of utterance b starts at row min(s / 320, T_b) of that utterance — the
+ * integer division by the encoder's stride that the collator applies to mel frames with `// hop_length`
+ * (ref:src/aat/training/collate.py:340) — and the last segment of an utterance ends at T_b (the lengths add up to at
+ * least N_b, ref:src/aat/tokenizer.py:195), so every encoder row belongs to exactly one segment.  A padded tail that
+ * starts behind the last encoder row is an empty segment (NaN mean, like torch's mean of no rows).
+ * seg_start_dev / seg_count_dev / utt_seg_off_dev : as written by aat_boundaries (utt_seg_off_dev also by
+ *                 aat_segment_frame_csr)
+ * seg_off_dev   : int64 [total_seg_slots + 1]; entries [0, S] are written — a buffer of its own if the per-segment CSR
+ *                 of the same batch is still needed
+ * n_seg_dev     : int64 [2]; {S, sum of T_b}
+ * Feed both to aat_segment_mean_pool (n_rows = sum of T_b, or AAT_POOL_ROWS_FROM_DEVICE). */
+int aat_utterance_frame_csr(aat_ctx *ctx, const aat_plan *plan, const int64_t *seg_start_dev,
+                            const int32_t *seg_count_dev, const int64_t *utt_seg_off_dev, int64_t *seg_off_dev,
+                            int64_t *n_seg_dev, void *stream);
 
 /* ------------------------------------------------------------------ K4: ragged mean-pool
  * Replaces `torch.cat([x.mean(dim=1, keepdim=True).to(float32) for x in embs], dim=1)`

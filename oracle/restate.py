@@ -194,3 +194,20 @@ def mean_pool_csr_f64(emb, seg_off):
         seg = emb[off[i] : off[i + 1]].astype(np.float64)
         out[i] = seg.sum(axis=0) / seg.shape[0] if seg.shape[0] else np.nan
     return out
+
+
+def utterance_frame_offsets_loop(segment_lengths, n_samples):
+    """Frame CSR of ONE whole-utterance encoding (convention (ii)), as a plain loop: the encoder
+    (receptive field 400, stride 320: TF:models/hubert/modeling_hubert.py:675-688) yields T rows for the utterance; a
+    segment that starts at sample s starts at row min(s // 320, T), like the collator's `// hop_length`
+    (ref:src/aat/training/collate.py:340).  There is no reference code for this convention; this loop DEFINES it for
+    the tests (parity unpinned by construction)."""
+    n_samples = int(n_samples)
+    rows = 0 if n_samples < 400 else (n_samples - 400) // 320 + 1
+    off, start = [], 0
+    for length in segment_lengths:
+        off.append(min(start // 320, rows))
+        start += int(length)
+    assert start >= n_samples
+    off.append(min(start // 320, rows))
+    return np.asarray(off, dtype=np.int64)

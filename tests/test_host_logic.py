@@ -133,6 +133,28 @@ def test_hubert_frame_formula_and_offsets():
     assert off.tolist() == [0, 6, 80, 80]
 
 
+def test_whole_utterance_frame_offsets_match_the_oracle_loop():
+    """SURVEY.md §8d convention (ii): host twin of aat_utterance_frame_csr against the oracle's loop, on the oracle
+    port's segmentations of real (synthetic) audio and on the edge lengths of the golden set."""
+    from oracle import ref_port, restate
+
+    ref = ref_port.RefTokenizer()
+    cases = [(n, ref.segment_lengths(synth.bursty_speech(n, 900 + i))[0])
+             for i, n in enumerate((100, 399, 400, 719, 720, 1999, 2000, 2080, 24000, 24001, 25999, 50000, 256000))]
+    cases += [(32000, [24000, 8000]), (25000, [23000, 2000]), (100, [2000]), (0, [])]
+    for n, lengths in cases:
+        off = synth.utterance_frame_offsets(lengths, n)
+        assert off.dtype == np.int64 and off.shape == (len(lengths) + 1,)
+        assert np.array_equal(off, restate.utterance_frame_offsets_loop(lengths, n)), (n, lengths)
+        rows = int(synth.hubert_frames(n))
+        assert off[0] == 0 and off[-1] == rows and np.all(np.diff(off) >= 0)  # every encoder row in exactly one segment
+    # known answers: 16 s, cuts at 2 s and 9.99 s; a padded tail behind the last encoder row is an empty segment
+    assert synth.utterance_frame_offsets([32000, 127840, 96160], 256000).tolist() == [0, 100, 499, 799]
+    assert synth.utterance_frame_offsets([2000, 2000], 2080).tolist() == [0, 6, 6]
+    with pytest.raises(ValueError):
+        synth.utterance_frame_offsets([2000], 4000)
+
+
 def test_sharding_balances_samples():
     rng = np.random.default_rng(0)
     n = rng.integers(16000, 480000, size=257)
